@@ -1,0 +1,146 @@
+/* subrosadg_b200.h — C ABI of the B200-native (sm_100a) DG residual + explicit SSP-RK path.
+ *
+ * The reference (SubrosaDG) has no FFI: its seam is the C++ class SubrosaDG::Solver<SimulationControl>
+ * (src/Solver/SolveControl.cpp:327-436) driven by System<SC>::solve() (src/Utils/SystemControl.cpp:159-195).
+ * Every entry point below replaces one member of that class (cited per function); the header-only shim
+ * include/SubrosaDG_b200/Solver.hpp maps the reference's template configuration surface onto this ABI.
+ *
+ * Conventions: plain pointers and sizes, caller-owned HOST buffers unless the name says `_device`; every function
+ * returns 0 on success and non-zero on failure with the message available from sdg_last_error().  NaNs in the state
+ * propagate into `relative_error` (the reference's only run-time failure signal, SystemControl.cpp:185-191).
+ * There is no CPU fallback: sdg_create fails when no CUDA device is usable.
+ *
+ * Data order at the seam (identical to the reference):
+ *   element types      ElementEnum values (src/Utils/Enum.cpp:28-36): 1 line, 2 triangle, 3 quadrangle, 6 hexahedron
+ *   node coordinates   [n][nn][D], gmsh node order of Lagrange order `geom_order` (PerElementMesh::node_coordinate_,
+ *                      src/Mesh/ReadControl.cpp:86-92)
+ *   modal state        [n][Nb][Nv] = Eigen::Matrix<Real,Nv,Nb> column-major per element (SolveControl.cpp:45-58),
+ *                      conserved order rho, rho u.., rho E (VariableConvertor.cpp:28-68)
+ *   quadrature arrays  [n][Nq][..]  volume points in the reference's "Gauss{2p}" order (src/Mesh/Quadrature.cpp:27-34)
+ *   face records       interior faces first, then boundary faces (AdjacencyElementMesh, ReadControl.cpp:72-83,143-155)
+ */
+#ifndef SUBROSADG_B200_H
+#define SUBROSADG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdg_ctx sdg_ctx;
+
+/* POD image of SimulationControl<...> (src/Solver/SimulationControl.cpp:1197-1279); integer fields carry the enum
+ * values of src/Utils/Enum.cpp. */
+typedef struct sdg_config {
+  int32_t dim;        /* DimensionEnum 1..3 (2 and 3 implemented on the device) */
+  int32_t p;          /* PolynomialOrderEnum 1..5 */
+  int32_t model;      /* EquationModelEnum: 0 CompresibleEuler 1 CompresibleNS 2 IncompresibleEuler 3 IncompresibleNS */
+  int32_t eos;        /* EquationOfStateEnum: 0 IdealGas 1 WeakCompressibleFluid */
+  int32_t transport;  /* TransportModelEnum: 0 None 1 Constant 2 Sutherland */
+  int32_t conv_flux;  /* ConvectiveFluxEnum: 0 Central 1 LaxFriedrichs 2 HLLC 3 Roe 4 Exact */
+  int32_t visc_flux;  /* ViscousFluxEnum: 0 None 1 BR1 2 BR2 */
+  int32_t source;     /* SourceTermEnum: 0 None 1 Boussinesq */
+  int32_t rk;         /* TimeIntegrationEnum: 0 ForwardEuler 1 HeunRK2 2 SSPRK3 */
+  int32_t device;     /* CUDA device ordinal */
+  int32_t chunk;      /* elements per thread block (0 = automatic) */
+  int32_t reorder;    /* 1: internal space-filling-curve element order (invisible at the seam); 0: keep caller order */
+  double cp, cv;      /* ThermodynamicModel<Constant>, PhysicalModel.cpp:26-38 */
+  double mu;          /* TransportModel dynamic viscosity (reference value for Sutherland), PhysicalModel.cpp:83-123 */
+  double c0, rho0;    /* EquationOfState<WeakCompressibleFluid>, PhysicalModel.cpp:57-78 */
+  double beta, t_ref; /* SourceTerm<Boussinesq>, SourceTerm.cpp:29-58 */
+} sdg_config;
+
+const char* sdg_last_error(void);
+int sdg_version(void);
+
+/* System<SC>() + setters (SystemControl.cpp:55-140) collapsed into one POD. */
+int sdg_create(const sdg_config* cfg, sdg_ctx** out);
+void sdg_destroy(sdg_ctx* ctx);
+
+/* Mesh<SC>::readMeshElement output for one element type (src/Mesh/Element.cpp:31-70): node coordinates only; Jacobians,
+ * M^-1 and normals (src/Mesh/Geometry.cpp) are recomputed by the library and kept resident in HBM.
+ * The last `n_ghost` elements are halo copies owned by another rank: they are read as neighbours, never advanced. */
+int sdg_add_elements(sdg_ctx* ctx, int32_t type, int32_t n, int32_t n_ghost, int32_t geom_order, const double* coords);
+
+/* AdjacencyElementMesh records (src/Mesh/Adjacency.cpp:330-430): parent_index_each_type_ (le/re),
+ * parent_gmsh_type_number_ as ElementEnum (lt/rt), adjacency_sequence_in_parent_ (lf/rf), adjacency_right_rotation_,
+ * boundary_condition_type_ (BoundaryConditionEnum), gmsh_physical_index_.  right_* are ignored for boundary faces. */
+int sdg_set_faces(sdg_ctx* ctx, int32_t n_int, int32_t n_bnd, const int32_t* le, const int32_t* lt, const int32_t* lf,
+                  const int32_t* re, const int32_t* rt, const int32_t* rf, const int32_t* rot, const int32_t* bc,
+                  const int32_t* phys);
+
+/* System::synchronize() (SystemControl.cpp:142-157): geometry, index flattening, upload. */
+int sdg_finalize(sdg_ctx* ctx);
+
+/* out[8] = n, Nb, Nq, Nf, Naq, nn, Nqf, Nv   (SimulationControl.cpp:74-97,243-379,1143-1151) */
+int sdg_sizes(sdg_ctx* ctx, int32_t type, int32_t* out);
+
+/* quadrature_node_coordinate_ of elements [n][Nq][D] / of boundary faces [n_bnd][Nqf][D] (Geometry.cpp:44-86): the
+ * points at which the host evaluates the user's InitialCondition / BoundaryCondition callbacks. */
+int sdg_get_quadrature_coordinates(sdg_ctx* ctx, int32_t type, double* xq);
+int sdg_get_boundary_quadrature_coordinates(sdg_ctx* ctx, double* xb);
+
+/* Solver::initializeSolver (InitialCondition.cpp:85-149): user primitive values (rho, u.., T) at the volume
+ * quadrature points [n][Nq][Nv] -> least-squares projection; at the boundary-face points [n_bnd][Nqf][Nv] ->
+ * boundary_dummy_variable_.  sdg_set_boundary_primitive is also Solver::updateBoundaryVariable
+ * (BoundaryCondition.cpp:29-74) for BoundaryTimeEnum::TimeVarying. */
+int sdg_set_state_from_primitive(sdg_ctx* ctx, int32_t type, const double* prim);
+int sdg_set_boundary_primitive(sdg_ctx* ctx, const double* prim);
+
+/* variable_basis_function_coefficient_ in the reference's modal (H1Legendre) basis, [n][Nb][Nv]
+ * (what Solver::writeRawBinary serialises, src/View/RawBinary.cpp:75-88). */
+int sdg_set_state(sdg_ctx* ctx, int32_t type, const double* U);
+int sdg_get_state(sdg_ctx* ctx, int32_t type, double* U);
+/* conserved variables / total gradient at the volume quadrature points, [n][Nq][Nv] / [n][Nq][Nv*D] (row var*D+dir) */
+int sdg_get_state_at_quadrature(sdg_ctx* ctx, int32_t type, double* Uq);
+int sdg_get_gradient_at_quadrature(sdg_ctx* ctx, int32_t type, double* Gq);
+
+/* Solver::calculateDeltaTime (TimeIntegration.cpp:104-179) */
+int sdg_compute_dt(sdg_ctx* ctx, double cfl, double* dt);
+
+/* Solver::stepSolver x n_steps (TimeIntegration.cpp:326-350); relative_error[Nv] = Solver::relative_error_ of the last
+ * step (TimeIntegration.cpp:279-324), may be NULL. */
+int sdg_step(sdg_ctx* ctx, double dt, int32_t n_steps, double* relative_error);
+
+/* Parity hook: one residual evaluation of the current state.  Rmodal [n][Nb][Nv] = variable_residual_
+ * (SpatialDiscrete.cpp:1016-1032); rhsq [n][Nq][Nv] = (R M^-1) Phi^T, i.e. dU/dt at the quadrature points.
+ * Either may be NULL. */
+int sdg_residual(sdg_ctx* ctx, int32_t type, double* Rmodal, double* rhsq);
+
+/* ---- element-block partitioning across the GPUs of one box (one context per rank) --------------------------------
+ * Device-resident halo staging: sdg_halo_pack gathers the states of the `n_send` local elements listed by
+ * sdg_set_halo_send into a contiguous device buffer; the ghost elements of sdg_add_elements form one contiguous
+ * device range that NCCL receives into directly.  `what`: 0 conserved state, 1 volume-gradient state (NS).
+ * The pointers are device addresses on cfg.device; `stream` is a cudaStream_t (0 = the context's stream). */
+int sdg_set_halo_send(sdg_ctx* ctx, int32_t type, int32_t n_send, const int32_t* elems);
+int sdg_halo_pack(sdg_ctx* ctx, int32_t type, int32_t what, void* stream);
+int sdg_halo_buffers_device(sdg_ctx* ctx, int32_t type, int32_t what, void** send, int64_t* send_doubles, void** recv,
+                            int64_t* recv_doubles);
+/* Split stepping used by the multi-GPU driver: stage `s` of the current step, restricted to thread blocks that do not
+ * (part 0) / do (part 1) touch ghost elements; part -1 = all.  sdg_step_begin / sdg_step_end bracket one step. */
+int sdg_step_begin(sdg_ctx* ctx, double dt);
+int sdg_stage_pass(sdg_ctx* ctx, int32_t stage, int32_t pass, int32_t part, void* stream);
+int sdg_step_end(sdg_ctx* ctx, double* relative_error_sum /* Nv sums over OWNED elements, not yet divided */);
+int sdg_num_passes(sdg_ctx* ctx);     /* passes per stage: 1 (Euler) or 2 (NS: gradient pass, residual pass) */
+int sdg_num_stages(sdg_ctx* ctx);
+void* sdg_stream(sdg_ctx* ctx);       /* the context's cudaStream_t */
+int sdg_synchronize(sdg_ctx* ctx);
+
+/* Device-resident access for callers that already hold the state in HBM (bench.py's `value` leg):
+ * modal state buffer [n][Nb][Nv] <-> internal representation, both on the device. */
+int sdg_set_state_device(sdg_ctx* ctx, int32_t type, const void* U_device);
+int sdg_get_state_device(sdg_ctx* ctx, int32_t type, void* U_device);
+
+/* Diagnostics (host plan, no device needed): copies one of the flattened arrays and/or returns its length.
+ * what: 0 geoE  1 invjw  2 minEdge  3 geoF (doubles);  10 perm  11 chunkFaceOff  12 faceRec  13 chunkInterior  14 chunkBoundary
+ *       15 {affine, K, nChunks, nOwned} (int32).  Element arrays are in INTERNAL order (position perm[e]). */
+int sdg_debug_plan(sdg_ctx* ctx, int32_t what, double* out_d, int32_t* out_i, int64_t* count);
+
+/* counters: number of kernels this library launched since creation (bench.py's gpu_launches) */
+int64_t sdg_launch_count(sdg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,608 @@
+// sdg_api.cu — C ABI (include/subrosadg_b200.h) over the sm_100a kernels: context, uploads, stage sequencing.
+//
+// Mirrors what System<SC>::solve() asks of Solver<SC> (src/Utils/SystemControl.cpp:159-195): initializeSolver,
+// calculateDeltaTime, stepSolver, relative_error_.  There is no CPU fallback anywhere in this file: without a CUDA
+// device every compute entry point fails with an error message.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <memory>
+#include <mutex>
+
+#include "../../include/subrosadg_b200.h"
+#include "host_plan.hpp"
+#include "tensor_kernels.cuh"
+
+using namespace sdg;
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CUDA_OK(x)                                                                                              \
+  do {                                                                                                          \
+    cudaError_t e_ = (x);                                                                                       \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  void alloc(size_t count) { release(); n = count; if (count) CUDA_OK(cudaMalloc(&p, count * sizeof(T))); }
+  void upload(const std::vector<T>& v, cudaStream_t s = 0) { alloc(v.size()); if (!v.empty()) { CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s)); CUDA_OK(cudaStreamSynchronize(s)); } }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+using StageFn = void (*)(const StageArgs&, int nBlocks, cudaStream_t);
+
+template <int D, int N, int K, bool AFFINE, int PH>
+void launchEuler(const StageArgs& a, int nBlocks, cudaStream_t s) {
+  using L = Layout<D, N, K>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(eulerStageKernel<D, N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+    configured = true;
+  }
+  eulerStageKernel<D, N, K, AFFINE, PH><<<nBlocks, kThreads, L::bytes, s>>>(a);
+}
+
+// chunk sizes: bricks of 2^D .. elements, sized so that two blocks fit an SM
+template <int D, int N> struct ChunkOf;
+template <> struct ChunkOf<2, 2> { static constexpr int K = 64; };
+template <> struct ChunkOf<2, 3> { static constexpr int K = 32; };
+template <> struct ChunkOf<2, 4> { static constexpr int K = 16; };
+template <> struct ChunkOf<3, 2> { static constexpr int K = 32; };
+template <> struct ChunkOf<3, 3> { static constexpr int K = 8; };
+template <> struct ChunkOf<3, 4> { static constexpr int K = 8; };
+
+template <int D, int N>
+StageFn pickEuler(bool affine, int ph) {
+  constexpr int K = ChunkOf<D, N>::K;
+  if (affine) return ph ? launchEuler<D, N, K, true, 1> : launchEuler<D, N, K, true, 0>;
+  return ph ? launchEuler<D, N, K, false, 1> : launchEuler<D, N, K, false, 0>;
+}
+StageFn pickEulerFn(int D, int N, bool affine, int ph, int& K) {
+  if (D == 2 && N == 2) { K = ChunkOf<2, 2>::K; return pickEuler<2, 2>(affine, ph); }
+  if (D == 2 && N == 3) { K = ChunkOf<2, 3>::K; return pickEuler<2, 3>(affine, ph); }
+  if (D == 2 && N == 4) { K = ChunkOf<2, 4>::K; return pickEuler<2, 4>(affine, ph); }
+  if (D == 3 && N == 2) { K = ChunkOf<3, 2>::K; return pickEuler<3, 2>(affine, ph); }
+  if (D == 3 && N == 3) { K = ChunkOf<3, 3>::K; return pickEuler<3, 3>(affine, ph); }
+  if (D == 3 && N == 4) { K = ChunkOf<3, 4>::K; return pickEuler<3, 4>(affine, ph); }
+  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..3");
+}
+
+}  // namespace
+
+struct sdg_ctx {
+  sdg_config cfg{};
+  PhysParams phys{};
+  int D = 0, NV = 0, nStages = 3;
+  double rkc[3][3]{};
+  bool hasDevice = false, finalized = false;
+  MeshPlan plan;
+  bool haveBlock = false, haveFaces = false;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+
+  // device state
+  DevBuf<double> U[3], geoE, invjw, minEdge, geoF, dummy, Phi, PhiInv, PhiT, normPartial, normOut, dtPartial, scratch, sendBuf;
+  DevBuf<int> perm, faceRec, chunkOff, chunkInterior, chunkBoundary, sendList;
+  DevBuf<TensorDev> tab;
+  int cur = 0;          // index of the buffer holding the current state
+  int latest = 0;       // buffer written last (halo source / target)
+  StageFn eulerFn = nullptr;
+  double stepDt = 0.0;
+  int nSend = 0;
+  std::vector<double> hostNorm;
+
+  size_t stateDoubles() const { return (size_t)plan.blk.n * NV * plan.blk.T.NN; }
+  size_t elemDoubles() const { return (size_t)NV * plan.blk.T.NN; }
+};
+
+namespace {
+
+void needDevice(sdg_ctx* c) { if (!c->hasDevice) throw std::runtime_error("no CUDA device bound to this context (plan-only context); the product has no CPU path"); }
+void needFinal(sdg_ctx* c) { if (!c->finalized) throw std::runtime_error("sdg_finalize has not been called"); }
+void needType(sdg_ctx* c, int type) { if (!c->haveBlock || c->plan.blk.type != type) throw std::runtime_error("no element block of this type"); }
+
+void fillArgs(sdg_ctx* c, StageArgs& a) {
+  const BlockPlan& B = c->plan.blk;
+  a = StageArgs{};
+  a.geoE = c->geoE.p; a.invjw = c->invjw.p; a.geoF = c->geoF.p;
+  a.faceRec = reinterpret_cast<const int4*>(c->faceRec.p); a.chunkFaceOff = c->chunkOff.p; a.chunkList = nullptr;
+  a.dummy = c->dummy.p; a.tab = c->tab.p; a.normPartial = nullptr;
+  a.nOwned = B.nOwned; a.nInt = c->plan.F.nInt; a.mode = 0; a.phys = c->phys;
+}
+
+// one pass of one stage over a subset of the chunks
+void runStage(sdg_ctx* c, const StageArgs& base, int part, cudaStream_t s) {
+  const BlockPlan& B = c->plan.blk;
+  StageArgs a = base;
+  int nBlocks = B.nChunks;
+  if (part == 0) { a.chunkList = c->chunkInterior.p; nBlocks = (int)B.chunkInterior.size(); }
+  else if (part == 1) { a.chunkList = c->chunkBoundary.p; nBlocks = (int)B.chunkBoundary.size(); }
+  if (nBlocks == 0) return;
+  c->eulerFn(a, nBlocks, s);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+}
+
+// buffers of stage s: in / out indices (SSP-RK tables TimeIntegration.cpp:45-65 realised with three rotating buffers)
+void stageBuffers(sdg_ctx* c, int s, int& in, int& out) {
+  const int cur = c->cur, a = (cur + 1) % 3, b = (cur + 2) % 3;
+  if (c->nStages == 1) { in = cur; out = a; return; }
+  if (s == 0) { in = cur; out = a; }
+  else if (s == c->nStages - 1) { in = (s == 1) ? a : b; out = cur; }
+  else { in = a; out = b; }
+}
+
+void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st) {
+  int in, out; stageBuffers(c, s, in, out);
+  StageArgs a; fillArgs(c, a);
+  a.Uin = c->U[in].p; a.Ulast = c->U[c->cur].p; a.Uout = c->U[out].p;
+  a.aLast = s == 0 ? 0.0 : c->rkc[s][0];
+  a.aCur = s == 0 ? 1.0 : c->rkc[s][1];
+  a.bdt = c->rkc[s][2] * c->stepDt;
+  a.normPartial = s == c->nStages - 1 ? c->normPartial.p : nullptr;
+  runStage(c, a, part, st);
+  c->latest = out;
+}
+
+void finishStep(sdg_ctx* c) { if (c->nStages == 1) c->cur = (c->cur + 1) % 3; c->latest = c->cur; }
+
+void reduceNorm(sdg_ctx* c, double* sums) {
+  normReduceKernel<<<c->NV, 256, 0, c->stream>>>(c->normPartial.p, c->plan.blk.nChunks, c->NV, c->normOut.p);
+  c->launches++;
+  CUDA_OK(cudaMemcpyAsync(c->hostNorm.data(), c->normOut.p, sizeof(double) * c->NV, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int v = 0; v < c->NV; v++) sums[v] = c->hostNorm[v];
+}
+
+}  // namespace
+
+#define SDG_TRY try {
+#define SDG_CATCH                                                          \
+  }                                                                        \
+  catch (const std::exception& ex) { g_err = ex.what(); return 1; }        \
+  catch (...) { g_err = "unknown error"; return 1; }                       \
+  return 0;
+
+extern "C" {
+
+const char* sdg_last_error(void) { return g_err.c_str(); }
+int sdg_version(void) { return 100; }
+
+int sdg_create(const sdg_config* cfg, sdg_ctx** out) {
+  SDG_TRY
+  if (!cfg || !out) throw std::runtime_error("null argument");
+  auto c = std::make_unique<sdg_ctx>();
+  c->cfg = *cfg;
+  if (cfg->dim < 2 || cfg->dim > 3) throw std::runtime_error("dim must be 2 or 3 on the device path");
+  if (cfg->p < 1 || cfg->p > 3) throw std::runtime_error("polynomial order must be 1..3 on the device path");
+  c->D = cfg->dim; c->NV = cfg->dim + 2;
+  PhysParams& P = c->phys;
+  P.model = cfg->model; P.eos = cfg->eos; P.transport = cfg->transport; P.conv = cfg->conv_flux; P.visc = cfg->visc_flux; P.source = cfg->source;
+  P.compressible = (cfg->model == kCompresibleEuler || cfg->model == kCompresibleNS) ? 1 : 0;
+  P.ns = (cfg->model == kCompresibleNS || cfg->model == kIncompresibleNS) ? 1 : 0;
+  P.cp = cfg->cp; P.cv = cfg->cv; P.gamma = 1.4;  // EquationOfState<IdealGas>::kSpecificHeatRatio, PhysicalModel.cpp:45
+  P.mu0 = cfg->mu; P.k0 = cfg->cp * cfg->mu / 0.71;  // Pr = 0.71, PhysicalModel.cpp:152-156
+  P.c0 = cfg->c0; P.rho0 = cfg->rho0; P.padd = 0.01 * cfg->rho0 * cfg->c0 * cfg->c0;  // :63-66
+  P.beta = cfg->beta; P.tref = cfg->t_ref;
+  if (cfg->model < 0 || cfg->model > 3) throw std::runtime_error("equation model not supported");
+  if (P.ns && (cfg->visc_flux != kBR1 && cfg->visc_flux != kBR2)) throw std::runtime_error("Navier-Stokes needs ViscousFluxEnum::BR1 or BR2");
+  if (!P.ns) P.visc = kViscNone;
+  if ((cfg->conv_flux == kHLLC || cfg->conv_flux == kRoe) && cfg->eos != kIdealGas) throw std::runtime_error("HLLC/Roe need the ideal-gas EOS (reference uses kSpecificHeatRatio)");
+  if (cfg->conv_flux < 0 || cfg->conv_flux > 4) throw std::runtime_error("bad convective flux");
+  // TimeIntegrationData, TimeIntegration.cpp:45-65: {a_last, a_cur, b}
+  const double FE[1][3] = {{1.0, 0.0, 1.0}};
+  const double H2[2][3] = {{1.0, 0.0, 1.0}, {0.5, 0.5, 0.5}};
+  const double S3[3][3] = {{1.0, 0.0, 1.0}, {3.0 / 4.0, 1.0 / 4.0, 1.0 / 4.0}, {1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0}};
+  if (cfg->rk == kForwardEuler) { c->nStages = 1; std::memcpy(c->rkc, FE, sizeof(FE)); }
+  else if (cfg->rk == kHeunRK2) { c->nStages = 2; std::memcpy(c->rkc, H2, sizeof(H2)); }
+  else if (cfg->rk == kSSPRK3) { c->nStages = 3; std::memcpy(c->rkc, S3, sizeof(S3)); }
+  else throw std::runtime_error("bad time integration scheme");
+  if (cfg->device >= 0) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= cfg->device) throw std::runtime_error(std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") + " — this library has no CPU path");
+    CUDA_OK(cudaSetDevice(cfg->device));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->hasDevice = true;
+  }
+  c->hostNorm.assign(8, 0.0);
+  *out = c.release();
+  SDG_CATCH
+}
+
+void sdg_destroy(sdg_ctx* c) {
+  if (!c) return;
+  if (c->hasDevice) { cudaSetDevice(c->cfg.device); cudaDeviceSynchronize(); }
+  cudaStream_t s = c->stream; const bool dev = c->hasDevice;
+  delete c;
+  if (dev && s) cudaStreamDestroy(s);
+}
+
+int sdg_add_elements(sdg_ctx* c, int32_t type, int32_t n, int32_t n_ghost, int32_t geom_order, const double* coords) {
+  SDG_TRY
+  if (c->finalized) throw std::runtime_error("context already finalized");
+  if (!(type == kQuadrangle || type == kHexahedron)) throw std::runtime_error("device path implements quadrangle and hexahedron blocks (triangle blocks: not yet)");
+  if (elemDim(type) != c->D) throw std::runtime_error("element dimension mismatch");
+  if (c->haveBlock) throw std::runtime_error("one element block per context on the device path");
+  if (n <= 0 || n_ghost < 0 || n_ghost >= n || geom_order < 1 || geom_order > 5) throw std::runtime_error("bad element block arguments");
+  BlockPlan& B = c->plan.blk;
+  B.type = type; B.D = c->D; B.p = c->cfg.p; B.g = geom_order; B.n = n; B.nGhost = n_ghost; B.nOwned = n - n_ghost;
+  B.T = buildTensorTables(type, c->cfg.p);
+  B.nn = (int)gmshNodeLattice(type, geom_order).size();
+  B.X.assign(coords, coords + (size_t)n * B.nn * c->D);
+  c->plan.D = c->D; c->plan.p = c->cfg.p;
+  c->haveBlock = true;
+  SDG_CATCH
+}
+
+int sdg_set_faces(sdg_ctx* c, int32_t n_int, int32_t n_bnd, const int32_t* le, const int32_t* lt, const int32_t* lf, const int32_t* re,
+                  const int32_t* rt, const int32_t* rf, const int32_t* rot, const int32_t* bc, const int32_t* phys) {
+  SDG_TRY
+  if (c->finalized) throw std::runtime_error("context already finalized");
+  FaceInput& F = c->plan.F;
+  const int nf = n_int + n_bnd;
+  F.nInt = n_int; F.nBnd = n_bnd;
+  F.le.assign(le, le + nf); F.lt.assign(lt, lt + nf); F.lf.assign(lf, lf + nf);
+  F.re.assign(re, re + nf); F.rt.assign(rt, rt + nf); F.rf.assign(rf, rf + nf);
+  F.rot.assign(rot, rot + nf); F.bc.assign(bc, bc + nf); F.phys.assign(phys, phys + nf);
+  c->haveFaces = true;
+  SDG_CATCH
+}
+
+int sdg_finalize(sdg_ctx* c) {
+  SDG_TRY
+  if (c->finalized) throw std::runtime_error("context already finalized");
+  if (!c->haveBlock || !c->haveFaces) throw std::runtime_error("elements and faces must be set before sdg_finalize");
+  MeshPlan& M = c->plan; BlockPlan& B = M.blk; const FaceInput& F = M.F;
+  const int nf = F.nInt + F.nBnd;
+  for (int i = 0; i < nf; i++) {
+    const bool interior = i < F.nInt;
+    if (F.lt[i] != B.type || F.le[i] < 0 || F.le[i] >= B.n || F.lf[i] < 0 || F.lf[i] >= B.T.NF) throw std::runtime_error("face record out of range (left parent)");
+    if (interior && (F.rt[i] != B.type || F.re[i] < 0 || F.re[i] >= B.n || F.rf[i] < 0 || F.rf[i] >= B.T.NF || F.rot[i] < 0 || F.rot[i] > 3)) throw std::runtime_error("face record out of range (right parent)");
+    if (!interior && (F.bc[i] < 0 || F.bc[i] > 5)) throw std::runtime_error("boundary face without a boundary condition (Periodic is not a boundary type)");
+  }
+  const int N = B.T.N;
+  int K = 0;
+  const int ph = (c->phys.compressible && c->phys.eos == kIdealGas && c->phys.conv == kHLLC) ? 1 : 0;
+  // decide the affine flag first (needs geometry), then the kernel
+  M.buildBlock(c->cfg.reorder, 1);  // provisional chunk size; chunking is redone below once K is known
+  c->eulerFn = pickEulerFn(c->D, N, B.affine, ph, K);
+  if (c->cfg.chunk > 0 && c->cfg.chunk != K) throw std::runtime_error("chunk override not available: kernels are compiled for K = " + std::to_string(K));
+  B.K = K; B.nChunks = (B.nOwned + K - 1) / K;
+  M.buildFaces(nullptr, false);
+  M.buildChunkFaces();
+  // the compile-time face direction / side tables of the kernels must agree with the numerically derived ones
+  for (int f = 0; f < B.T.NF; f++) {
+    const int dirRef = c->D == 2 ? ((0x1 | 0x0 << 2 | 0x1 << 4 | 0x0 << 6) >> (2 * f)) & 3 : ((0x2 | 0x1 << 2 | 0x0 << 4 | 0x0 << 6 | 0x1 << 8 | 0x2 << 10) >> (2 * f)) & 3;
+    const int sideRef = c->D == 2 ? ((0x6 >> f) & 1) : (f >= 3);
+    if (dirRef != B.T.faceDir[f] || sideRef != B.T.faceSide[f]) throw std::runtime_error("internal: face direction table mismatch");
+  }
+  if (c->hasDevice) {
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t nd = c->stateDoubles();
+    for (int i = 0; i < 3; i++) { c->U[i].alloc(nd); CUDA_OK(cudaMemsetAsync(c->U[i].p, 0, nd * sizeof(double), c->stream)); }
+    c->geoE.upload(B.geoE, c->stream); c->invjw.upload(B.invjw, c->stream); c->minEdge.upload(B.minEdge, c->stream);
+    c->geoF.upload(M.geoF, c->stream);
+    c->dummy.alloc((size_t)std::max(F.nBnd, 1) * (c->D + 3) * B.T.NQF);
+    CUDA_OK(cudaMemsetAsync(c->dummy.p, 0, c->dummy.n * sizeof(double), c->stream));
+    c->perm.upload(B.perm, c->stream);
+    c->faceRec.upload(B.faceRec, c->stream); c->chunkOff.upload(B.chunkFaceOff, c->stream);
+    c->chunkInterior.upload(B.chunkInterior, c->stream); c->chunkBoundary.upload(B.chunkBoundary, c->stream);
+    c->Phi.upload(B.T.Phi, c->stream); c->PhiInv.upload(B.T.PhiInv, c->stream);
+    { std::vector<double> PT(B.T.Phi.size()); const int NN = B.T.NN; for (int q = 0; q < NN; q++) for (int b = 0; b < NN; b++) PT[(size_t)b * NN + q] = B.T.Phi[(size_t)q * NN + b]; c->PhiT.upload(PT, c->stream); }
+    c->normPartial.alloc((size_t)B.nChunks * c->NV); c->normOut.alloc(8); c->dtPartial.alloc(1024);
+    CUDA_OK(cudaMemsetAsync(c->normPartial.p, 0, c->normPartial.n * sizeof(double), c->stream));
+    std::vector<TensorDev> td(1);
+    TensorDev& t = td[0]; std::memset(&t, 0, sizeof(t));
+    for (int i = 0; i < N * N; i++) { t.Dm[i] = B.T.Dm[i]; t.K1[i] = B.T.K1[i]; }
+    for (int i = 0; i < 2 * N; i++) t.Lend[i] = B.T.Lend[i];
+    for (int i = 0; i < B.T.NN; i++) t.wq[i] = B.T.wq[i];
+    for (int i = 0; i < B.T.NQF; i++) t.wf[i] = B.T.wf[i];
+    for (int f = 0; f < B.T.NF; f++) { t.faceDir[f] = B.T.faceDir[f]; t.faceSide[f] = B.T.faceSide[f]; }
+    for (int i = 0; i < B.T.NF * B.T.NQF; i++) t.faceBase[i] = B.T.faceBase[i];
+    for (int i = 0; i < B.T.NF * B.T.NN; i++) t.nodeFacePt[i] = (unsigned char)B.T.nodeFacePt[i];
+    const int ft = faceType(B.type);
+    for (int r = 0; r < 4; r++) {
+      std::vector<int> s = faceSequence(ft, N, ft == kLine ? 0 : r);
+      for (int j = 0; j < B.T.NQF; j++) t.seq[r * B.T.NQF + j] = s[j];
+    }
+    c->tab.upload(td, c->stream);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  c->finalized = true;
+  SDG_CATCH
+}
+
+int sdg_sizes(sdg_ctx* c, int32_t type, int32_t* out) {
+  SDG_TRY
+  needType(c, type);
+  const BlockPlan& B = c->plan.blk;
+  out[0] = B.n; out[1] = B.T.NN; out[2] = B.T.NN; out[3] = B.T.NF; out[4] = B.T.NF * B.T.NQF; out[5] = B.nn; out[6] = B.T.NQF; out[7] = c->NV;
+  SDG_CATCH
+}
+
+int sdg_get_quadrature_coordinates(sdg_ctx* c, int32_t type, double* xq) {
+  SDG_TRY
+  needType(c, type);
+  c->plan.quadratureCoordinates(xq);
+  SDG_CATCH
+}
+
+int sdg_get_boundary_quadrature_coordinates(sdg_ctx* c, double* xb) {
+  SDG_TRY
+  if (!c->haveBlock || !c->haveFaces) throw std::runtime_error("elements and faces must be set first");
+  MeshPlan tmp = c->plan;  // coordinates only; leaves the finalized plan untouched
+  tmp.buildFaces(xb, true);
+  SDG_CATCH
+}
+
+int sdg_set_state_from_primitive(sdg_ctx* c, int32_t type, const double* prim) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  const size_t nd = c->stateDoubles();
+  c->scratch.alloc(nd);
+  CUDA_OK(cudaMemcpyAsync(c->scratch.p, prim, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const int blocks = (int)std::min<size_t>(((size_t)B.n * B.T.NN + 255) / 256, 148 * 16);
+  if (c->D == 2) primitiveToStateKernel<2><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
+  else primitiveToStateKernel<3><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->scratch.release();
+  c->latest = c->cur;
+  SDG_CATCH
+}
+
+int sdg_set_boundary_primitive(sdg_ctx* c, const double* prim) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk; const int nb = c->plan.F.nBnd;
+  if (nb == 0) return 0;
+  DevBuf<double> tmp; tmp.alloc((size_t)nb * B.T.NQF * c->NV);
+  CUDA_OK(cudaMemcpyAsync(tmp.p, prim, tmp.n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const int blocks = (nb * B.T.NQF + 255) / 256;
+  if (c->D == 2) boundaryPrimitiveKernel<2><<<blocks, 256, 0, c->stream>>>(tmp.p, c->dummy.p, nb, B.T.NQF, c->phys);
+  else boundaryPrimitiveKernel<3><<<blocks, 256, 0, c->stream>>>(tmp.p, c->dummy.p, nb, B.T.NQF, c->phys);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  SDG_CATCH
+}
+
+static void transformModal(sdg_ctx* c, const double* in, double* out, const double* M, int dir) {
+  const BlockPlan& B = c->plan.blk;
+  seamTransformKernel<<<B.n, 128, sizeof(double) * c->NV * B.T.NN, c->stream>>>(in, out, M, c->perm.p, B.n, c->NV, B.T.NN, dir);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+}
+
+int sdg_set_state_device(sdg_ctx* c, int32_t type, const void* U_device) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  transformModal(c, (const double*)U_device, c->U[c->cur].p, c->Phi.p, 0);
+  c->latest = c->cur;
+  SDG_CATCH
+}
+int sdg_get_state_device(sdg_ctx* c, int32_t type, void* U_device) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  transformModal(c, c->U[c->cur].p, (double*)U_device, c->PhiInv.p, 1);
+  SDG_CATCH
+}
+
+int sdg_set_state(sdg_ctx* c, int32_t type, const double* U) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const size_t nd = c->stateDoubles();
+  const int s = (c->cur + 1) % 3;  // scratch: a stage buffer that holds no live data between steps
+  CUDA_OK(cudaMemcpyAsync(c->U[s].p, U, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  transformModal(c, c->U[s].p, c->U[c->cur].p, c->Phi.p, 0);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->latest = c->cur;
+  SDG_CATCH
+}
+int sdg_get_state(sdg_ctx* c, int32_t type, double* U) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const size_t nd = c->stateDoubles();
+  const int s = (c->cur + 1) % 3;
+  transformModal(c, c->U[c->cur].p, c->U[s].p, c->PhiInv.p, 1);
+  CUDA_OK(cudaMemcpyAsync(U, c->U[s].p, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  SDG_CATCH
+}
+
+int sdg_get_state_at_quadrature(sdg_ctx* c, int32_t type, double* Uq) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  const size_t nd = c->stateDoubles();
+  const int s = (c->cur + 1) % 3;
+  seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->U[c->cur].p, c->U[s].p, c->perm.p, B.n, c->NV, B.T.NN, 1);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(Uq, c->U[s].p, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  SDG_CATCH
+}
+
+int sdg_get_gradient_at_quadrature(sdg_ctx* c, int32_t type, double* Gq) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  (void)Gq;
+  throw std::runtime_error("gradient state exists for Navier-Stokes models only");
+  SDG_CATCH
+}
+
+int sdg_compute_dt(sdg_ctx* c, double cfl, double* dt) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  const int blocks = (int)std::min<size_t>(((size_t)B.nOwned * B.T.NN + 255) / 256, 1024);
+  if (c->D == 2) deltaTimeKernel<2><<<blocks, 256, 0, c->stream>>>(c->U[c->cur].p, c->minEdge.p, B.nOwned, B.T.NN, c->cfg.p, cfl, c->phys, c->dtPartial.p);
+  else deltaTimeKernel<3><<<blocks, 256, 0, c->stream>>>(c->U[c->cur].p, c->minEdge.p, B.nOwned, B.T.NN, c->cfg.p, cfl, c->phys, c->dtPartial.p);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  std::vector<double> h(blocks);
+  CUDA_OK(cudaMemcpyAsync(h.data(), c->dtPartial.p, sizeof(double) * blocks, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  double best = 1.7976931348623157e308;
+  for (double v : h) best = std::min(best, v);
+  *dt = best;
+  SDG_CATCH
+}
+
+int sdg_num_stages(sdg_ctx* c) { return c->nStages; }
+int sdg_num_passes(sdg_ctx* c) { return c->phys.ns ? 2 : 1; }
+void* sdg_stream(sdg_ctx* c) { return (void*)c->stream; }
+int64_t sdg_launch_count(sdg_ctx* c) { return c->launches; }
+
+int sdg_synchronize(sdg_ctx* c) {
+  SDG_TRY
+  needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  SDG_CATCH
+}
+
+int sdg_step_begin(sdg_ctx* c, double dt) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  c->stepDt = dt;
+  SDG_CATCH
+}
+
+int sdg_stage_pass(sdg_ctx* c, int32_t stage, int32_t pass, int32_t part, void* stream) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  if (stage < 0 || stage >= c->nStages || pass < 0 || pass >= sdg_num_passes(c) || part < -1 || part > 1) throw std::runtime_error("bad stage/pass/part");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  stageLaunch(c, stage, part, stream ? (cudaStream_t)stream : c->stream);
+  SDG_CATCH
+}
+
+int sdg_step_end(sdg_ctx* c, double* sums) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  finishStep(c);
+  if (sums) reduceNorm(c, sums);
+  SDG_CATCH
+}
+
+int sdg_step(sdg_ctx* c, double dt, int32_t n_steps, double* relative_error) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  c->stepDt = dt;
+  for (int it = 0; it < n_steps; it++) {
+    for (int s = 0; s < c->nStages; s++) stageLaunch(c, s, -1, c->stream);
+    finishStep(c);
+  }
+  if (relative_error) {
+    double sums[8];
+    reduceNorm(c, sums);
+    for (int v = 0; v < c->NV; v++) relative_error[v] = sums[v] / c->plan.blk.nOwned;  // TimeIntegration.cpp:323
+  } else {
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  SDG_CATCH
+}
+
+int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  const size_t nd = c->stateDoubles();
+  const int a = (c->cur + 1) % 3, b = (c->cur + 2) % 3;
+  for (int mode = 1; mode <= 2; mode++) {
+    double* host = mode == 1 ? rhsq : Rmodal;
+    if (!host) continue;
+    StageArgs args; fillArgs(c, args);
+    args.Uin = c->U[c->cur].p; args.Ulast = c->U[c->cur].p; args.Uout = c->U[a].p; args.mode = mode;
+    args.aLast = 0.0; args.aCur = 0.0; args.bdt = 1.0;
+    CUDA_OK(cudaMemsetAsync(c->U[a].p, 0, nd * sizeof(double), c->stream));
+    runStage(c, args, -1, c->stream);
+    if (mode == 1) {
+      seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->U[a].p, c->U[b].p, c->perm.p, B.n, c->NV, B.T.NN, 1);
+      c->launches++;
+    } else {
+      transformModal(c, c->U[a].p, c->U[b].p, c->PhiT.p, 1);
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(host, c->U[b].p, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  SDG_CATCH
+}
+
+int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int64_t* count) {
+  SDG_TRY
+  needFinal(c);
+  const BlockPlan& B = c->plan.blk;
+  const std::vector<double>* d = nullptr; const std::vector<int>* i = nullptr;
+  std::vector<int> misc = {B.affine ? 1 : 0, B.K, B.nChunks, B.nOwned};
+  switch (what) {
+    case 0: d = &B.geoE; break; case 1: d = &B.invjw; break; case 2: d = &B.minEdge; break; case 3: d = &c->plan.geoF; break;
+    case 10: i = &B.perm; break; case 11: i = &B.chunkFaceOff; break; case 12: i = &B.faceRec; break;
+    case 13: i = &B.chunkInterior; break; case 14: i = &B.chunkBoundary; break; case 15: i = &misc; break;
+    default: throw std::runtime_error("bad diagnostics id");
+  }
+  if (d) { if (count) *count = (int64_t)d->size(); if (out_d) std::memcpy(out_d, d->data(), d->size() * sizeof(double)); }
+  if (i) { if (count) *count = (int64_t)i->size(); if (out_i) std::memcpy(out_i, i->data(), i->size() * sizeof(int)); }
+  SDG_CATCH
+}
+
+int sdg_set_halo_send(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* elems) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  std::vector<int> pos(n_send);
+  for (int i = 0; i < n_send; i++) { if (elems[i] < 0 || elems[i] >= B.nOwned) throw std::runtime_error("halo send element out of range"); pos[i] = B.perm[elems[i]]; }
+  c->sendList.upload(pos, c->stream);
+  c->nSend = n_send;
+  c->sendBuf.alloc((size_t)std::max(n_send, 1) * c->elemDoubles() * (c->phys.ns ? c->D : 1));
+  SDG_CATCH
+}
+
+int sdg_halo_pack(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  if (what != 0) throw std::runtime_error("gradient halo: Navier-Stokes only");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (c->nSend == 0) return 0;
+  const int stride = (int)c->elemDoubles();
+  const int blocks = (int)std::min<size_t>(((size_t)c->nSend * stride + 255) / 256, 148 * 8);
+  haloPackKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(c->U[c->latest].p, c->sendList.p, c->nSend, stride, c->sendBuf.p);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  SDG_CATCH
+}
+
+int sdg_halo_buffers_device(sdg_ctx* c, int32_t type, int32_t what, void** send, int64_t* send_doubles, void** recv, int64_t* recv_doubles) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  if (what != 0) throw std::runtime_error("gradient halo: Navier-Stokes only");
+  const BlockPlan& B = c->plan.blk;
+  *send = c->sendBuf.p; *send_doubles = (int64_t)c->nSend * (int64_t)c->elemDoubles();
+  *recv = c->U[c->latest].p + (size_t)B.nOwned * c->elemDoubles(); *recv_doubles = (int64_t)B.nGhost * (int64_t)c->elemDoubles();
+  SDG_CATCH
+}
+
+}  // extern "C"

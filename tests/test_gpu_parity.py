@@ -1,0 +1,90 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical meshes / initial conditions.
+Tolerances are BASELINE.json's: per-stage residual rel-L2 <= 1e-12, conserved fields after N steps <= 1e-10 (fp64)."""
+import numpy as np
+import pytest
+
+import cases
+from subrosadg_b200 import mesh as M
+
+pytestmark = pytest.mark.gpu
+
+TOL_RES = 1e-12
+TOL_STATE = 1e-10
+
+
+def compare(O, S, dt, nsteps, tol_res=TOL_RES, tol_state=TOL_STATE, label=""):
+    t = S.types[0]
+    # modal coefficients after the IC projection (same H1Legendre convention on both sides)
+    assert cases.rel_l2(S.get_state(t), O.get_state(t)) < 1e-12, label
+    Ro, qo = O.residual()[t]
+    Rs, qs = S.residual()[t]
+    e_q, e_R = cases.rel_l2(qs, qo), cases.rel_l2(Rs, Ro)
+    assert e_q < tol_res, f"{label}: dU/dt at quadrature points rel-L2 {e_q:.3e}"
+    assert e_R < tol_res, f"{label}: modal residual rel-L2 {e_R:.3e}"
+    err_o = O.step(dt, nsteps)
+    err_s = S.stepSolver(dt, nsteps)
+    e_u = cases.rel_l2(S.state_at_quadrature(t), O.state_at_quadrature(t))
+    assert e_u < tol_state, f"{label}: state after {nsteps} steps rel-L2 {e_u:.3e}"
+    assert cases.rel_l2(S.get_state(t), O.get_state(t)) < tol_state, label
+    assert np.allclose(err_s, err_o, rtol=1e-9, atol=1e-300), f"{label}: relative_error_ {err_s} vs {err_o}"
+    return e_q, e_R, e_u
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_periodic_2d_ceuler(built, p):
+    """config 1: examples/periodic_2d_ceuler.cpp (10x10 quads on [0,2]^2, HLLC, SSPRK3, dt = 1e-3)"""
+    mesh = M.periodic_box(2, 10)
+    O, S = cases.make_pair(dict(p=p, conv_flux=2, rk=2), mesh, cases.ic_density_wave([0.7, 0.3]))
+    assert abs(S.calculateDeltaTime(1.0) - O.compute_dt(1.0)) <= 1e-14 * O.compute_dt(1.0)
+    compare(O, S, 1e-3, 10, label=f"periodic_2d p{p}")
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_periodic_3d_ceuler(built, p):
+    """config 4 (scaled down): periodic hex box, HLLC, SSPRK3"""
+    mesh = M.periodic_box_fast(3, 6)
+    O, S = cases.make_pair(dict(p=p, conv_flux=2, rk=2), mesh, cases.ic_density_wave([0.5, 0.3, 0.2]))
+    compare(O, S, 1e-3, 5, label=f"periodic_3d p{p}")
+
+
+@pytest.mark.parametrize("flux", [0, 1, 2, 3])
+@pytest.mark.parametrize("rk", [0, 1, 2])
+def test_fluxes_and_rk(built, flux, rk):
+    mesh = M.periodic_box(2, 6)
+    O, S = cases.make_pair(dict(p=2, conv_flux=flux, rk=rk), mesh, cases.ic_density_wave([0.7, 0.3]))
+    compare(O, S, 5e-4, 4, label=f"flux {flux} rk {rk}")
+
+
+def test_curved_box_farfield_2d(built):
+    warp = lambda x: x + 0.04 * np.sin(np.pi * x[:, ::-1])
+    mesh = M.box(2, (6, 5), 0.0, 1.0, geom_order=3, warp=warp)
+    ic = cases.ic_perturbed_freestream(0.63, 2.0, 2)
+    O, S = cases.make_pair(dict(p=3, conv_flux=2, rk=2), mesh, ic, cases.bc_freestream(0.63, 2.0, 2, wall_phys=()))
+    compare(O, S, 1e-3, 5, label="curved box farfield")
+
+
+def test_naca0012_2d_ceuler(built):
+    """config 2 (scaled down): curved P3 quads, HLLC, Riemann far field + slip wall, M = 0.63, alpha = 2 deg"""
+    mesh = M.naca0012(nr=8, nt=24)
+    ic = cases.ic_perturbed_freestream(0.63, 2.0, 2, amp=1e-3)
+    O, S = cases.make_pair(dict(p=3, conv_flux=2, rk=2), mesh, ic, cases.bc_freestream(0.63, 2.0, 2))
+    dt = O.compute_dt(0.5)
+    assert abs(S.calculateDeltaTime(0.5) - dt) <= 1e-13 * dt
+    compare(O, S, dt, 5, label="naca0012")
+
+
+def test_curved_hex_box_farfield_3d(built):
+    warp = lambda x: x + 0.03 * np.sin(np.pi * np.roll(x, 1, axis=1))
+    mesh = M.box(3, (3, 4, 3), 0.0, 1.0, geom_order=2, warp=warp)
+    ic = cases.ic_perturbed_freestream(0.5, 3.0, 3)
+    O, S = cases.make_pair(dict(p=2, conv_flux=3, rk=2), mesh, ic, cases.bc_freestream(0.5, 3.0, 3, wall_phys=()))
+    compare(O, S, 1e-3, 4, label="curved hex box")
+
+
+def test_modal_state_roundtrip(built):
+    mesh = M.periodic_box(2, 6)
+    O, S = cases.make_pair(dict(p=3), mesh, cases.ic_density_wave([0.7, 0.3]))
+    t = S.types[0]
+    U = O.get_state(t)
+    S.set_state(t, U * 1.25)
+    assert cases.rel_l2(S.get_state(t), U * 1.25) < 1e-14
