@@ -1,0 +1,213 @@
+#!/usr/bin/env python
+"""bench.py — GDOF·stage/s of the DG residual + RK stage (fp64) on BASELINE.json's config 4
+(periodic_3d_ceuler: synthetic structured hex mesh, 128^3 = 2,097,152 elements, p = 3, HLLC, SSPRK3).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells C] [--p P]
+
+`value`  : scalar-DOF stage updates per second (Ne*Nb*Nv*stages*steps / device time) with the state resident in HBM.
+`e2e`    : the same metric through the reference-facing calls with HOST buffers every step
+           (sdg_set_state -> sdg_step -> sdg_get_state; the host<->device copies are inside the timed region).
+`roofline`: algorithmic bytes (24 B per scalar DOF·stage = read U, read U_last, write U) over the stage
+           kernel's mean duration (CUDA events on the library's stream) against the measured HBM copy bandwidth.
+`cpu_baseline` / `--impl reference`: the CPU oracle (restatement of the reference's oneTBB path, OpenMP, all host cores)
+           timed on a bounded sample (a smaller cube of the same family, same p / flux / RK).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "GDOF·stage/s per RK stage (fp64)"
+UNIT = "GDOF·stage/s"
+BYTES_PER_DOF_STAGE = 24.0  # 3*S per element per stage for the inviscid path
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def ic_config4(x):
+    """examples/periodic_3d_ceuler.cpp:33-35"""
+    rho = 1.0 + 0.2 * np.sin(np.pi * (x[..., 0] + x[..., 1] + x[..., 2]))
+    out = np.empty(x.shape[:-1] + (5,))
+    out[..., 0] = rho; out[..., 1] = 0.5; out[..., 2] = 0.3; out[..., 3] = 0.2; out[..., 4] = 1.4 / rho
+    return out
+
+
+CFG = dict(p=3, model=0, conv_flux=2, rk=2)
+
+
+def run_oracle(cells, p, steps, warmup, threads=None):
+    """CPU restatement of the reference path on a cells^3 cube; returns (GDOF·stage/s, seconds, cores)."""
+    import oracle
+    from subrosadg_b200 import mesh as M
+    mesh = M.periodic_box_fast(3, cells)
+    cfg = dict(CFG); cfg["p"] = p
+    O = oracle.Oracle(cfg, mesh, threads=threads)
+    O.initialize(ic_config4)
+    dt = 1e-4
+    if warmup:
+        O.step(dt, warmup)
+    t0 = time.perf_counter()
+    O.step(dt, steps)
+    sec = time.perf_counter() - t0
+    s = O.sizes(6)
+    dof = s.n * s.Nb * s.Nv
+    return dof * 3 * steps / sec / 1e9, sec, oracle.max_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cells", type=int, default=128)
+    ap.add_argument("--p", type=int, default=3)
+    ap.add_argument("--cpu-cells", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    workload = f"periodic_3d_ceuler synthetic structured hex mesh {a.cells}^3, p={a.p}, CompresibleEuler, HLLC, SSPRK3 (BASELINE configs[3])"
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import __graft_entry__ as g
+        g.build()
+        # bounded sample of the same workload: a cpu_cells^3 cube of the same family; per-DOF rate is size independent
+        val, sec, cores = run_oracle(a.cpu_cells, a.p, max(1, a.steps), a.warmup)
+        sample = f"{a.cpu_cells}^3 hexes p={a.p}, {max(1, a.steps)} steps x 3 stages, {sec:.1f} s (CPU restatement of the reference algorithm incl. its dense M^-1 and gradient sweeps; the reference itself cannot be built here)"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": 1e3 * sec / max(1, a.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": workload, "timed_sample": sample},
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    if world > 1:
+        from subrosadg_b200 import parallel
+        parallel.bench_main(a, workload, METRIC, UNIT, BYTES_PER_DOF_STAGE, peaks, ClockSampler, ic_config4, CFG)
+        return
+
+    from subrosadg_b200 import mesh as M
+    from subrosadg_b200.solver import Solver
+    torch.cuda.init()
+    mesh = M.periodic_box_fast(3, a.cells)
+    cfg = dict(CFG); cfg["p"] = a.p
+    S = Solver(cfg, mesh, device=0)
+    S.initializeSolver(ic_config4)
+    t = S.types[0]
+    sz = S.sizes(t)
+    dof = sz.n * sz.Nb * sz.Nv
+    nst = 3
+    dt = S.calculateDeltaTime(1.0)
+    S.step_timed(dt, warmup)
+    clocks = ClockSampler(); clocks.start()
+    l0 = S.launch_count
+    torch.cuda.synchronize()
+    err, ms = S.step_timed(dt, a.steps)
+    torch.cuda.synchronize()
+    launches = S.launch_count - l0
+    ck = clocks.stop()
+    sec = ms * 1e-3
+    value = dof * nst * a.steps / sec / 1e9
+    hbm, how = peaks()
+    stage_ms = ms / (a.steps * nst)
+    achieved = BYTES_PER_DOF_STAGE * dof / (stage_ms * 1e-3) / 1e9
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": warmup, "ms_per_step": ms / a.steps,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload, "elements": sz.n, "scalar_dof": dof, "dt": dt, "l2": f"state {dof * 8 / 1e9:.2f} GB per buffer >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                      "relative_error": [float(x) for x in err]},
+           "gpu_launches": int(launches), "clocks": ck,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                        "kernel": "eulerStageKernel<3,4,8,affine,HLLC>", "kernel_ms": stage_ms, "algorithmic_bytes_per_launch": BYTES_PER_DOF_STAGE * dof,
+                        "peak_source": how}}
+
+    if not a.no_e2e:
+        # end to end through the C ABI with host buffers: modal state in, step, modal state out (pinned host memory)
+        U = torch.empty((sz.n, sz.Nb, sz.Nv), dtype=torch.float64).pin_memory()
+        Un = U.numpy()
+        Un[...] = S.get_state(t)
+        n_e2e = max(1, min(a.steps, 3))
+        S.set_state(t, Un); S.stepSolver(dt, 1); Un[...] = S.get_state(t)  # warm
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            S.set_state(t, Un)
+            e = S.stepSolver(dt, 1)
+            S_out = S.get_state(t)
+        torch.cuda.synchronize()
+        sec_e = time.perf_counter() - t0
+        out["e2e"] = {"value": dof * nst * n_e2e / sec_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(dof * 8), "d2h_bytes_per_step": int(dof * 8 + 8 * sz.Nv),
+                      "steps": n_e2e, "note": "host modal coefficients -> sdg_set_state -> sdg_step -> sdg_get_state (+ relative_error_) every step"}
+        del S_out, e
+    if not a.no_cpu:
+        import __graft_entry__ as g
+        g.build()
+        val, sec_c, cores = run_oracle(a.cpu_cells, a.p, 1, 0)
+        out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{a.cpu_cells}^3 hexes p={a.p}, 1 step x 3 stages, {sec_c:.1f} s; CPU restatement of the reference algorithm (dense per-element M^-1, gradient sweeps included), OpenMP on all host cores"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,9 @@ int sdg_compute_dt(sdg_ctx* ctx, double cfl, double* dt);
  * step (TimeIntegration.cpp:279-324), may be NULL. */
 int sdg_step(sdg_ctx* ctx, double dt, int32_t n_steps, double* relative_error);
 
+/* Same as sdg_step, additionally returning the device time of the n_steps (CUDA events on the context's stream). */
+int sdg_step_timed(sdg_ctx* ctx, double dt, int32_t n_steps, double* relative_error, float* milliseconds);
+
 /* Parity hook: one residual evaluation of the current state.  Rmodal [n][Nb][Nv] = variable_residual_
  * (SpatialDiscrete.cpp:1016-1032); rhsq [n][Nq][Nv] = (R M^-1) Phi^T, i.e. dU/dt at the quadrature points.
  * Either may be NULL. */

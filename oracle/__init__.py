@@ -32,7 +32,7 @@ def build(force: bool = False) -> str:
 
 class _Config(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("dim", "p", "model", "eos", "transport", "conv_flux", "visc_flux", "source", "rk", "dead_gradient")] + \
+                ("dim", "p", "model", "eos", "transport", "conv_flux", "visc_flux", "source", "rk", "dead_gradient", "accurate")] + \
                [(n, ctypes.c_double) for n in ("cp", "cv", "mu", "c0", "rho0", "beta", "t_ref")]
 
 
@@ -94,7 +94,7 @@ class Oracle:
     def __init__(self, cfg: dict, mesh, threads: int | None = None):
         c = _Config()
         defaults = dict(dim=mesh.dim, p=cfg["p"], model=0, eos=0, transport=0, conv_flux=2, visc_flux=0, source=0, rk=2,
-                        dead_gradient=1, cp=2.5, cv=25.0 / 14.0, mu=0.0, c0=1.0, rho0=1.0, beta=0.0, t_ref=0.0)
+                        dead_gradient=1, accurate=1, cp=2.5, cv=25.0 / 14.0, mu=0.0, c0=1.0, rho0=1.0, beta=0.0, t_ref=0.0)
         defaults.update(cfg)
         for k, v in defaults.items():
             setattr(c, k, v)

@@ -53,11 +53,24 @@ static inline void gemmNT(int m, int n, int k, double alpha, const double* A, in
   }
 }
 
+// C(m x n) = alpha * A(m x k) * B(k x n) + beta * C with extended-precision accumulation (accurate mode: keeps the
+// ill-conditioned modal M^-1 / least-squares products at round-off of the RESULT, so that the checker is not the noisier side)
+template <class TB>
+static inline void gemmLD(int m, int n, int k, double alpha, const double* A, int lda, const TB* B, int ldb, double beta,
+                          double* C, int ldc) {
+  for (int j = 0; j < n; j++) for (int i = 0; i < m; i++) {
+    long double s = 0.0L;
+    for (int l = 0; l < k; l++) s += (long double)A[i + (size_t)l * lda] * (long double)B[l + (size_t)j * ldb];
+    C[i + (size_t)j * ldc] = (double)((long double)alpha * s + (beta == 0.0 ? 0.0L : (long double)beta * (long double)C[i + (size_t)j * ldc]));
+  }
+}
+
 // Per element type: ElementBasisFunction + ElementQuadrature (src/Mesh/BasisFunction.cpp:136-230, Quadrature.cpp:36-52)
 struct ElemTable {
   int type = 0, D = 0, p = 0, g = 1, Nb = 0, Nq = 0, Nf = 0, Naq = 0, nn = 0;
   std::vector<int> off, nqf;
   Quadrature quad, fquad;
+  std::vector<long double> LSinvL;  // extended-precision copy of LSinv (accurate mode)
   std::vector<double> Phi, dPhi, PhiF, LSinv;   // modal_value_, modal_gradient_value_ (row q*D+d), modal_adjacency_value_
   std::vector<double> GN, dGN;                  // geometry Lagrange basis at volume points: Nq x nn, (Nq*D) x nn
   std::vector<double> GNf, dGNf;                // at face points (parent coordinates): Naq x nn, (Naq*D) x nn
@@ -89,8 +102,8 @@ struct ElemTable {
     }
     // modal_least_squares_inverse_ = (Phi^T Phi)^-1, BasisFunction.cpp:217
     LSinv.assign((size_t)Nb * Nb, 0);
-    for (int a = 0; a < Nb; a++) for (int b = 0; b < Nb; b++) { double s = 0; for (int q = 0; q < Nq; q++) s += Phi[(size_t)a * Nq + q] * Phi[(size_t)b * Nq + q]; LSinv[(size_t)b * Nb + a] = s; }
-    invertInPlace(LSinv, Nb);
+    for (int a = 0; a < Nb; a++) for (int b = 0; b < Nb; b++) { long double s = 0; for (int q = 0; q < Nq; q++) s += (long double)Phi[(size_t)a * Nq + q] * (long double)Phi[(size_t)b * Nq + q]; LSinv[(size_t)b * Nb + a] = (double)s; }
+    invertInPlace(LSinv, Nb, &LSinvL);
     // face tables: parent basis at face points through the P1 map of the face corners, BasisFunction.cpp:76-111,149-197
     PhiF.assign((size_t)Naq * Nb, 0); GNf.assign((size_t)Naq * nn, 0); dGNf.assign((size_t)Naq * D * nn, 0);
     ftan.assign((size_t)Nf * std::max(D - 1, 1) * D, 0); fxi.assign((size_t)Naq * 3, 0);
@@ -121,6 +134,7 @@ struct ElemBlock {
   int type = 0, n = 0;
   ElemTable tab;
   std::vector<double> X;                         // node_coordinate_: n x nn x D (gmsh node order)
+  std::vector<long double> MinvL;  // extended-precision copy of Minv (accurate mode only)
   std::vector<double> xq, jw, mt, Minv, minEdge; // quadrature_node_coordinate_, detJ*w, (J^T)^-1 detJ w, M^-1, minimum_edge_
   // solver state (column-major per element, rows = variables)
   std::vector<double> coef, coefLast, vq, vaq, res, sq;
@@ -141,6 +155,7 @@ struct Oracle {
   Phys P;
   int p = 1, rk = kSSPRK3;
   bool deadGradient = true;  // run G1-G4 for Euler like the reference does
+  bool accurate = false;     // extended-precision accumulation in the M^-1 / least-squares products (checker mode)
   std::unique_ptr<ElemBlock> blk[7];
   FaceSet F;
   bool finalized = false;
@@ -167,11 +182,12 @@ static double det_inv(int D, const double* Jt /*row-major k,l*/, double* inv /*r
   return det;
 }
 
-static void elementGeometry(ElemBlock& B) {
+static void elementGeometry(ElemBlock& B, bool accurate) {
   const ElemTable& T = B.tab;
   const int D = T.D, Nq = T.Nq, nn = T.nn, Nb = T.Nb;
   B.xq.assign((size_t)B.n * Nq * D, 0); B.jw.assign((size_t)B.n * Nq, 0); B.mt.assign((size_t)B.n * Nq * D * D, 0);
   B.Minv.assign((size_t)B.n * Nb * Nb, 0); B.minEdge.assign(B.n, 0);
+  if (accurate) B.MinvL.assign((size_t)B.n * Nb * Nb, 0.0L);
   bool bad = false;
 #pragma omp parallel for schedule(static)
   for (int e = 0; e < B.n; e++) {
@@ -195,11 +211,13 @@ static void elementGeometry(ElemBlock& B) {
     // calculateElementLocalMassMatrixInverse, Geometry.cpp:88-100: M = Phi^T diag(detJ w) Phi
     std::vector<double> M((size_t)Nb * Nb);
     for (int a = 0; a < Nb; a++) for (int b = a; b < Nb; b++) {
-      double s = 0; for (int q = 0; q < Nq; q++) s += T.Phi[(size_t)a * Nq + q] * B.jw[(size_t)e * Nq + q] * T.Phi[(size_t)b * Nq + q];
-      M[(size_t)b * Nb + a] = s; M[(size_t)a * Nb + b] = s;
+      long double s = 0; for (int q = 0; q < Nq; q++) s += (long double)T.Phi[(size_t)a * Nq + q] * (long double)B.jw[(size_t)e * Nq + q] * (long double)T.Phi[(size_t)b * Nq + q];
+      M[(size_t)b * Nb + a] = (double)s; M[(size_t)a * Nb + b] = (double)s;
     }
-    invertInPlace(M, Nb);
+    std::vector<long double> ML;
+    invertInPlace(M, Nb, B.MinvL.empty() ? nullptr : &ML);
     std::memcpy(&B.Minv[(size_t)e * Nb * Nb], M.data(), sizeof(double) * Nb * Nb);
+    if (!B.MinvL.empty()) std::copy(ML.begin(), ML.end(), B.MinvL.begin() + (size_t)e * Nb * Nb);
     // getElementQuality "minEdge", Geometry.cpp:29-42: shortest straight distance between the end vertices of an edge
     double me = 1e300;
     auto dist = [&](int a, int b) { double s = 0; for (int l = 0; l < D; l++) { double d = X[a * D + l] - X[b * D + l]; s += d * d; } return std::sqrt(s); };
@@ -552,7 +570,8 @@ static void sweepR4(Oracle& O, ElemBlock& B, const double* c, double dt) {
     const double* UL = &B.coefLast[(size_t)e * s.Nv * s.Nb];
     for (int k = 0; k < s.Nv * s.Nb; k++) U[k] *= c[1];
     for (int k = 0; k < s.Nv * s.Nb; k++) U[k] += c[0] * UL[k];
-    gemm(s.Nv, s.Nb, s.Nb, c[2] * dt, &B.res[(size_t)e * s.Nv * s.Nb], s.Nv, &B.Minv[(size_t)e * s.Nb * s.Nb], s.Nb, 1.0, U, s.Nv);
+    if (O.accurate) gemmLD(s.Nv, s.Nb, s.Nb, c[2] * dt, &B.res[(size_t)e * s.Nv * s.Nb], s.Nv, &B.MinvL[(size_t)e * s.Nb * s.Nb], s.Nb, 1.0, U, s.Nv);
+    else gemm(s.Nv, s.Nb, s.Nb, c[2] * dt, &B.res[(size_t)e * s.Nv * s.Nb], s.Nv, &B.Minv[(size_t)e * s.Nb * s.Nb], s.Nb, 1.0, U, s.Nv);
   }
 }
 
@@ -613,7 +632,7 @@ static void step(Oracle& O, double dt) {
 using namespace orc;
 
 struct orc_config {
-  int32_t dim, p, model, eos, transport, conv_flux, visc_flux, source, rk, dead_gradient;
+  int32_t dim, p, model, eos, transport, conv_flux, visc_flux, source, rk, dead_gradient, accurate;
   double cp, cv, mu, c0, rho0, beta, t_ref;
 };
 
@@ -633,7 +652,7 @@ int orc_create(const orc_config* c, void** out) {
   P.k0 = c->cp * c->mu / 0.71;  // calculateThermalConductivityFromDynamicViscosity, PhysicalModel.cpp:152-156 (Pr = 0.71)
   P.c0 = c->c0; P.rho0 = c->rho0; P.padd = 0.01 * c->rho0 * c->c0 * c->c0;  // PhysicalModel.cpp:63-66
   P.beta = c->beta; P.Tref = c->t_ref;
-  O->p = c->p; O->rk = c->rk; O->deadGradient = c->dead_gradient != 0;
+  O->p = c->p; O->rk = c->rk; O->deadGradient = c->dead_gradient != 0; O->accurate = c->accurate != 0;
   if (P.ns() && P.visc == kViscNone) throw std::runtime_error("oracle: NS model needs BR1 or BR2");
   if (!P.ns()) P.visc = kViscNone;
   if (c->p < 1 || c->p > 5 || c->dim < 1 || c->dim > 3) throw std::runtime_error("oracle: dim/p out of range");
@@ -675,7 +694,7 @@ int orc_finalize(void* h) {
   if (ft < 0) throw std::runtime_error("oracle: no elements");
   O.F.ftype = ft;
   O.F.Nqf = makeQuadrature(ft, 2 * O.p + 1).n;
-  for (auto& b : O.blk) if (b) { elementGeometry(*b); allocSolver(O, *b); }
+  for (auto& b : O.blk) if (b) { elementGeometry(*b, O.accurate); allocSolver(O, *b); }
   const int nf = O.F.nInt + O.F.nBnd;
   for (int i = 0; i < nf; i++) {
     for (int s = 0; s < (i < O.F.nInt ? 2 : 1); s++) {
@@ -786,8 +805,15 @@ int orc_set_state_from_primitive(void* h, int type, const double* prim) {
       consFromPrim(O.P, v);
       for (int k = 0; k < s.Nv; k++) uq[(size_t)q * s.Nv + k] = v.cons[k];
     }
-    gemm(s.Nv, s.Nb, s.Nq, 1.0, uq.data(), s.Nv, T.Phi.data(), s.Nq, 0.0, t.data(), s.Nv);
-    gemm(s.Nv, s.Nb, s.Nb, 1.0, t.data(), s.Nv, T.LSinv.data(), s.Nb, 0.0, &B.coef[(size_t)e * s.Nv * s.Nb], s.Nv);
+    if (O.accurate) {
+      // Uq Phi (Phi^T Phi)^-1 with every product accumulated in extended precision
+      std::vector<long double> tl((size_t)s.Nv * s.Nb);
+      for (int b = 0; b < s.Nb; b++) for (int v = 0; v < s.Nv; v++) { long double a = 0; for (int q = 0; q < s.Nq; q++) a += (long double)uq[(size_t)q * s.Nv + v] * (long double)T.Phi[(size_t)b * s.Nq + q]; tl[(size_t)b * s.Nv + v] = a; }
+      for (int b = 0; b < s.Nb; b++) for (int v = 0; v < s.Nv; v++) { long double a = 0; for (int l = 0; l < s.Nb; l++) a += tl[(size_t)l * s.Nv + v] * T.LSinvL[(size_t)b * s.Nb + l]; B.coef[((size_t)e * s.Nb + b) * s.Nv + v] = (double)a; }
+    } else {
+      gemm(s.Nv, s.Nb, s.Nq, 1.0, uq.data(), s.Nv, T.Phi.data(), s.Nq, 0.0, t.data(), s.Nv);
+      gemm(s.Nv, s.Nb, s.Nb, 1.0, t.data(), s.Nv, T.LSinv.data(), s.Nb, 0.0, &B.coef[(size_t)e * s.Nv * s.Nb], s.Nv);
+    }
   }
   ORC_CATCH
 }
@@ -879,7 +905,8 @@ int orc_fetch_residual(void* h, int type, double* Rmodal, double* rhsq) {
 #pragma omp parallel for schedule(static)
     for (int e = 0; e < B.n; e++) {
       std::vector<double> t((size_t)s.Nv * s.Nb);
-      gemm(s.Nv, s.Nb, s.Nb, 1.0, &B.res[(size_t)e * s.Nv * s.Nb], s.Nv, &B.Minv[(size_t)e * s.Nb * s.Nb], s.Nb, 0.0, t.data(), s.Nv);
+      if (O.accurate) gemmLD(s.Nv, s.Nb, s.Nb, 1.0, &B.res[(size_t)e * s.Nv * s.Nb], s.Nv, &B.MinvL[(size_t)e * s.Nb * s.Nb], s.Nb, 0.0, t.data(), s.Nv);
+      else gemm(s.Nv, s.Nb, s.Nb, 1.0, &B.res[(size_t)e * s.Nv * s.Nb], s.Nv, &B.Minv[(size_t)e * s.Nb * s.Nb], s.Nb, 0.0, t.data(), s.Nv);
       gemmNT(s.Nv, s.Nq, s.Nb, 1.0, t.data(), s.Nv, B.tab.Phi.data(), s.Nq, 0.0, &rhsq[(size_t)e * s.Nq * s.Nv], s.Nv);
     }
   }

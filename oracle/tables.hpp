@@ -432,22 +432,25 @@ inline std::vector<int> faceQuadratureSequence(int ftype, int p, int rotation) {
 }
 
 // small dense helpers (column-major, A(r,c) = a[c*ld + r]) -----------------------------------------------------------
-inline void invertInPlace(std::vector<double>& A, int n) {  // Gauss-Jordan with partial pivoting (Eigen .inverse() stand-in)
-  std::vector<double> I(n * n, 0.0);
-  for (int i = 0; i < n; i++) I[i * n + i] = 1.0;
+inline void invertInPlace(std::vector<double>& Ain, int n, std::vector<long double>* keep = nullptr) {  // Gauss-Jordan with partial pivoting in extended precision
+  // (stand-in for Eigen's .inverse(); extended precision so that the inverse itself is correctly rounded for the
+  // moderately ill-conditioned modal mass / least-squares matrices)
+  std::vector<long double> A(Ain.begin(), Ain.end()), I((size_t)n * n, 0.0L);
+  for (int i = 0; i < n; i++) I[i * n + i] = 1.0L;
   for (int c = 0; c < n; c++) {
     int piv = c;
-    for (int r = c + 1; r < n; r++) if (std::fabs(A[c * n + r]) > std::fabs(A[c * n + piv])) piv = r;
-    if (A[c * n + piv] == 0.0) throw std::runtime_error("oracle: singular matrix");
+    for (int r = c + 1; r < n; r++) if (std::fabs((double)A[c * n + r]) > std::fabs((double)A[c * n + piv])) piv = r;
+    if (A[c * n + piv] == 0.0L) throw std::runtime_error("oracle: singular matrix");
     if (piv != c) for (int k = 0; k < n; k++) { std::swap(A[k * n + c], A[k * n + piv]); std::swap(I[k * n + c], I[k * n + piv]); }
-    double d = 1.0 / A[c * n + c];
+    long double d = 1.0L / A[c * n + c];
     for (int k = 0; k < n; k++) { A[k * n + c] *= d; I[k * n + c] *= d; }
     for (int r = 0; r < n; r++) if (r != c) {
-      double f = A[c * n + r];
-      if (f != 0.0) for (int k = 0; k < n; k++) { A[k * n + r] -= f * A[k * n + c]; I[k * n + r] -= f * I[k * n + c]; }
+      long double f = A[c * n + r];
+      if (f != 0.0L) for (int k = 0; k < n; k++) { A[k * n + r] -= f * A[k * n + c]; I[k * n + r] -= f * I[k * n + c]; }
     }
   }
-  A = I;
+  for (size_t i = 0; i < Ain.size(); i++) Ain[i] = (double)I[i];
+  if (keep) *keep = I;
 }
 
 }  // namespace orc

@@ -57,7 +57,7 @@ __device__ __forceinline__ double dotn(const double* c, const double* n) { doubl
 
 // Variable::calculateComputationalFromConserved, VariableConvertor.cpp:315-339
 template <int D, int PH>
-__device__ __forceinline__ void compFromCons(const Phys<PH>& ph, const double* cons, double* comp) {
+__device__ __forceinline__ double compFromCons(const Phys<PH>& ph, const double* cons, double* comp) {
   const double rho = cons[0];
   const double ir = 1.0 / rho;
   comp[0] = rho;
@@ -67,6 +67,7 @@ __device__ __forceinline__ void compFromCons(const Phys<PH>& ph, const double* c
   if (ph.comp()) e -= 0.5 * vsq<D>(comp);
   comp[D + 1] = e;
   comp[D + 2] = ph.pressure(rho, e);
+  return ir;
 }
 // calculateConservedFromComputational, :291-313
 template <int D, int PH>
@@ -113,47 +114,53 @@ __device__ __forceinline__ void convNormalFlux(const Phys<PH>& ph, const double*
   Fn[D + 1] = ph.comp() ? (rho * (comp[D + 1] + 0.5 * vsq<D>(comp)) + p) * un : rho * comp[D + 1] * un;
 }
 
-// calculateConvectiveHLLCFlux, :137-238 (pressure estimate without the 1/2 on the velocity jump, p* in the star energy)
+// calculateConvectiveHLLCFlux, :137-238 (pressure estimate without the 1/2 on the velocity jump, p* in the star energy).
+// Restated branch-free (the reference's early returns S_L >= 0 -> F_L, S_R <= 0 -> F_R become selects, so a warp never
+// diverges) and with the wave-speed factor folded into the sound speed:
+//   c_K q_K = sqrt(g p_K/rho_K) sqrt(1 + (g+1)/(2g) (p*/p_K - 1)) = sqrt(g/rho_K (p_K + (g+1)/(2g) max(p* - p_K, 0)))
+// which is the same number up to round-off and costs one square root instead of two divisions and two square roots.
+// irL/irR = 1/rho of the two states (already known from the conserved -> computational conversion).
 template <int D, int PH>
-__device__ __forceinline__ void hllcFlux(const Phys<PH>& ph, const double* n, const double* consL, const double* compL,
-                                         const double* consR, const double* compR, double* F) {
+__device__ __forceinline__ void hllcFlux(const Phys<PH>& ph, const double* n, const double* consL, const double* compL, double irL,
+                                         const double* consR, const double* compR, double irR, double* F) {
   constexpr int NV = D + 2;
   const double g = ph.P.gamma;
   const double rL = compL[0], rR = compR[0], pL = compL[D + 2], pR = compR[D + 2];
   const double unL = dotn<D>(compL, n), unR = dotn<D>(compR, n);
-  const double cL = ph.sound(rL, pL), cR = ph.sound(rR, pR);
+  const double cL = sqrt(g * pL * irL), cR = sqrt(g * pR * irR);
   const double ps = fmax(0.0, 0.5 * (pL + pR) - (unR - unL) * (0.5 * (rL + rR)) * (0.5 * (cL + cR)));
   const double kg = 0.5 * (g + 1.0) / g;
-  const double SL = unL - cL * (ps <= pL ? 1.0 : sqrt(1.0 + kg * (ps / pL - 1.0)));
-  if (SL >= 0.0) { convNormalFlux<D>(ph, n, compL, F); return; }
-  const double SR = unR + cR * (ps <= pR ? 1.0 : sqrt(1.0 + kg * (ps / pR - 1.0)));
-  if (SR <= 0.0) { convNormalFlux<D>(ph, n, compR, F); return; }
-  const double Ss = (pR - pL + rL * unL * (SL - unL) - rR * unR * (SR - unR)) / (rL * (SL - unL) - rR * (SR - unR));
-  // select the side facing the contact wave
-  const bool left = Ss >= 0.0;
-  const double* comp = left ? compL : compR;
-  const double* cons = left ? consL : consR;
-  const double S = left ? SL : SR, un = left ? unL : unR, r = left ? rL : rR, p = left ? pL : pR;
+  const double SL = unL - sqrt(g * irL * (pL + kg * fmax(ps - pL, 0.0)));
+  const double SR = unR + sqrt(g * irR * (pR + kg * fmax(ps - pR, 0.0)));
+  const double mL = rL * (SL - unL), mR = rR * (SR - unR);
+  const double Ss = (pR - pL + mL * unL - mR * unR) / (mL - mR);
+  const bool left = SL >= 0.0 ? true : (SR <= 0.0 ? false : Ss >= 0.0);
+  const bool pure = SL >= 0.0 || SR <= 0.0;
+  const double S = left ? SL : SR, un = left ? unL : unR, p = left ? pL : pR, m = left ? mL : mR;
+  double comp[D + 3], cons[NV];
+#pragma unroll
+  for (int k = 0; k < D + 3; k++) comp[k] = left ? compL[k] : compR[k];
+#pragma unroll
+  for (int v = 0; v < NV; v++) cons[v] = left ? consL[v] : consR[v];
   double FK[NV];
   convNormalFlux<D>(ph, n, comp, FK);
   const double inv = 1.0 / (S - Ss);
-  const double m = (S - un) * r;
   double Us[NV];
   Us[0] = m * inv;
 #pragma unroll
   for (int d = 0; d < D; d++) Us[1 + d] = (m * comp[1 + d] + (ps - p) * n[d]) * inv;
   Us[D + 1] = (m * (comp[D + 1] + 0.5 * vsq<D>(comp)) - p * un + ps * Ss) * inv;
 #pragma unroll
-  for (int v = 0; v < NV; v++) F[v] = FK[v] + S * (Us[v] - cons[v]);
+  for (int v = 0; v < NV; v++) F[v] = pure ? FK[v] : FK[v] + S * (Us[v] - cons[v]);
 }
 
 // calculateConvectiveFlux dispatch, :417-439
 template <int D, int PH>
-__device__ __forceinline__ void convFlux(const Phys<PH>& ph, const double* n, const double* consL, const double* compL,
-                                         const double* consR, const double* compR, double* F) {
+__device__ __forceinline__ void convFlux(const Phys<PH>& ph, const double* n, const double* consL, const double* compL, double irL,
+                                         const double* consR, const double* compR, double irR, double* F) {
   constexpr int NV = D + 2;
   const int kind = ph.conv();
-  if (kind == kHLLC) { hllcFlux<D>(ph, n, consL, compL, consR, compR, F); return; }
+  if (kind == kHLLC) { hllcFlux<D>(ph, n, consL, compL, irL, consR, compR, irR, F); return; }
   if constexpr (PH == 0) {
     double FL[NV], FR[NV];
     if (kind == kCentral) {  // :94-104

@@ -86,7 +86,7 @@ struct sdg_ctx {
   int64_t launches = 0;
 
   // device state
-  DevBuf<double> U[3], geoE, invjw, minEdge, geoF, dummy, Phi, PhiInv, PhiT, normPartial, normOut, dtPartial, scratch, sendBuf;
+  DevBuf<double> U[3], geoE, invjw, minEdge, geoF, dummy, Phi, PhiInv, PhiT, normPartial, normOut, dtPartial, scratch, sendBuf, cfGeo;
   DevBuf<int> perm, faceRec, chunkOff, chunkInterior, chunkBoundary, sendList;
   DevBuf<TensorDev> tab;
   int cur = 0;          // index of the buffer holding the current state
@@ -109,7 +109,7 @@ void needType(sdg_ctx* c, int type) { if (!c->haveBlock || c->plan.blk.type != t
 void fillArgs(sdg_ctx* c, StageArgs& a) {
   const BlockPlan& B = c->plan.blk;
   a = StageArgs{};
-  a.geoE = c->geoE.p; a.invjw = c->invjw.p; a.geoF = c->geoF.p;
+  a.geoE = c->geoE.p; a.invjw = c->invjw.p; a.geoF = c->geoF.p; a.cfGeo = c->cfGeo.p;
   a.faceRec = reinterpret_cast<const int4*>(c->faceRec.p); a.chunkFaceOff = c->chunkOff.p; a.chunkList = nullptr;
   a.dummy = c->dummy.p; a.tab = c->tab.p; a.normPartial = nullptr;
   a.nOwned = B.nOwned; a.nInt = c->plan.F.nInt; a.mode = 0; a.phys = c->phys;
@@ -286,7 +286,21 @@ int sdg_finalize(sdg_ctx* c) {
     CUDA_OK(cudaSetDevice(c->cfg.device));
     const size_t nd = c->stateDoubles();
     for (int i = 0; i < 3; i++) { c->U[i].alloc(nd); CUDA_OK(cudaMemsetAsync(c->U[i].p, 0, nd * sizeof(double), c->stream)); }
-    c->geoE.upload(B.geoE, c->stream); c->invjw.upload(B.invjw, c->stream); c->minEdge.upload(B.minEdge, c->stream);
+    if (B.affine) {
+      // device images for the TMA staging of the stage kernel: element metric records padded to an even number of doubles,
+      // face geometry duplicated per chunk-face entry (one contiguous 16-byte-granular range per thread block)
+      const int DD = c->D * c->D, REC = (DD + 2) & ~1;
+      std::vector<double> ge((size_t)B.n * REC, 0.0);
+      for (int pos = 0; pos < B.n; pos++) for (int k = 0; k <= DD; k++) ge[(size_t)pos * REC + k] = B.geoE[(size_t)pos * (DD + 1) + k];
+      c->geoE.upload(ge, c->stream);
+      const size_t ncf = B.faceRec.size() / 4;
+      std::vector<double> cf(std::max<size_t>(ncf, 1) * 4, 0.0);
+      for (size_t k = 0; k < ncf; k++) for (int l = 0; l <= c->D; l++) cf[k * 4 + l] = M.geoF[(size_t)B.faceRec[k * 4 + 2] * (c->D + 1) + l];
+      c->cfGeo.upload(cf, c->stream);
+    } else {
+      c->geoE.upload(B.geoE, c->stream);
+    }
+    c->invjw.upload(B.invjw, c->stream); c->minEdge.upload(B.minEdge, c->stream);
     c->geoF.upload(M.geoF, c->stream);
     c->dummy.alloc((size_t)std::max(F.nBnd, 1) * (c->D + 3) * B.T.NQF);
     CUDA_OK(cudaMemsetAsync(c->dummy.p, 0, c->dummy.n * sizeof(double), c->stream));
@@ -519,6 +533,31 @@ int sdg_step(sdg_ctx* c, double dt, int32_t n_steps, double* relative_error) {
     for (int v = 0; v < c->NV; v++) relative_error[v] = sums[v] / c->plan.blk.nOwned;  // TimeIntegration.cpp:323
   } else {
     CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  SDG_CATCH
+}
+
+int sdg_step_timed(sdg_ctx* c, double dt, int32_t n_steps, double* relative_error, float* milliseconds) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+  c->stepDt = dt;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaEventRecord(e0, c->stream));
+  for (int it = 0; it < n_steps; it++) {
+    for (int s = 0; s < c->nStages; s++) stageLaunch(c, s, -1, c->stream);
+    finishStep(c);
+  }
+  CUDA_OK(cudaEventRecord(e1, c->stream));
+  CUDA_OK(cudaEventSynchronize(e1));
+  if (milliseconds) CUDA_OK(cudaEventElapsedTime(milliseconds, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (relative_error) {
+    double sums[8];
+    reduceNorm(c, sums);
+    for (int v = 0; v < c->NV; v++) relative_error[v] = sums[v] / c->plan.blk.nOwned;
   }
   SDG_CATCH
 }

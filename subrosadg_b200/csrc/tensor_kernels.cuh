@@ -51,9 +51,10 @@ struct StageArgs {
   double* Uout;
   const double* Gvol;     // NS residual pass: volume gradient [nTotal][NV*D][NN]
   double* Gout;           // NS gradient pass output
-  const double* geoE;     // affine: [n][D*D+1]; curved: [n][D*D][NN]
+  const double* geoE;     // affine: [n][REC] (REC = D*D+1 rounded up to even: {(J^T)^-1 detJ rows, detJ}); curved: [n][D*D][NN]
   const double* invjw;    // curved: [n][NN]
   const double* geoF;     // affine: [nf][D+1]; curved: [nf][D+1][NQF]
+  const double* cfGeo;    // affine: per chunk-face entry {n[D], |J| scale} padded to 4 doubles (same order as faceRec)
   const int4* faceRec;    // per chunk, the faces touching it
   const int* chunkFaceOff;
   const int* chunkList;   // chunk ids handled by this launch
@@ -69,48 +70,102 @@ struct StageArgs {
 template <int N, int D> struct Pow { static constexpr int v = N * Pow<N, D - 1>::v; };
 template <int N> struct Pow<N, 0> { static constexpr int v = 1; };
 
+#ifndef SDG_MIN_BLOCKS
+#define SDG_MIN_BLOCKS 3
+#endif
+
 template <int D, int N, int K>
 struct Layout {
   static constexpr int NV = D + 2, NN = Pow<N, D>::v, NQF = NN / N, NF = 2 * D, NAQ = NF * NQF;
-  static constexpr int oU = 0;                              // [K][NV][NN]
-  static constexpr int oF = oU + K * NV * NN;               // [K][D][NV][NN]
-  static constexpr int oFlux = oF + K * D * NV * NN;        // [K][NV][NAQ]
+  static constexpr int oU = 0;                              // [K][NV][NN]   staged states
+  static constexpr int oF = oU + K * NV * NN;               // [K][NV][NN]   contravariant flux of ONE reference direction
+  static constexpr int oFlux = oF + K * NV * NN;            // [K][NV][NAQ]  face-flux slots
   static constexpr int oTab = oFlux + K * NV * NAQ;         // Dm, Lend, K1, wq, wf
-  static constexpr int nTabD = 2 * N * N + 2 * N + NN + NQF;
-  static constexpr int nDoubles = oTab + nTabD;
-  static constexpr int nInts = NF * NQF + 4 * NQF + NF * NN;
-  static constexpr size_t bytes = sizeof(double) * nDoubles + sizeof(int) * nInts + 64;
+  static constexpr int nTabD = 2 * N * N + 2 * N + NN + NQF + ((NN + NQF) & 1);   // kept even: what follows is 16-byte aligned
+  static constexpr int REC = (D * D + 2) & ~1;                // per-element affine metric record
+  static constexpr int MAXF = K * NF;                         // faces touching a chunk (upper bound)
+  static constexpr int oGeoE = oTab + nTabD;                  // [K][REC]
+  static constexpr int oCf = oGeoE + K * REC;                 // [MAXF][4]
+  static constexpr int oRec = oCf + MAXF * 4;                 // [MAXF] int4
+  static constexpr int nDoubles = oRec + MAXF * 2;
+  static constexpr int nBytesTab = NF * NQF + 4 * NQF + NF * NN;   // faceBase, seq, nodeFacePt as bytes
+  static constexpr size_t bytes = sizeof(double) * nDoubles + ((nBytesTab + 15) / 16) * 16;
+  static constexpr int ITERS = (K * NN + kThreads - 1) / kThreads;
 };
 
+// ---- mbarrier + TMA bulk copy (global -> shared::cta), sm_90+ PTX ---------------------------------------------------------
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dstShared, const void* srcGlobal, unsigned bytes, unsigned long long* bar) {
+  if (bytes == 0) return;
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstShared)),
+               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smemAddr(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+
 template <int N, int D>
-__device__ __forceinline__ int strideOf(int d) { int s = 1; for (int k = D - 1; k > d; k--) s *= N; return s; }
+__device__ __forceinline__ constexpr int strideOf(int d) { int s = 1; for (int k = D - 1; k > d; k--) s *= N; return s; }
 // Normal axis / side of the gmsh local faces (getElementPerAdjacencyNodeIndex, SimulationControl.cpp:177-216, with the gmsh
 // reference corners): quadrangle faces (eta-,xi+,eta+,xi-), hexahedron faces (zeta-,eta-,xi-,xi+,eta+,zeta+).
 // sdg_finalize checks these against the numerically derived tables of host_tables.hpp.
 template <int D>
-__device__ __forceinline__ int faceDirOf(int f) {
+__device__ __forceinline__ constexpr int faceDirOf(int f) {
   return D == 2 ? ((0x1 | 0x0 << 2 | 0x1 << 4 | 0x0 << 6) >> (2 * f)) & 3 : ((0x2 | 0x1 << 2 | 0x0 << 4 | 0x0 << 6 | 0x1 << 8 | 0x2 << 10) >> (2 * f)) & 3;
 }
 template <int D>
-__device__ __forceinline__ int faceSideOf(int f) { return D == 2 ? (0x6 >> f) & 1 : (f >= 3 ? 1 : 0); }
+__device__ __forceinline__ constexpr int faceSideOf(int f) { return D == 2 ? (0x6 >> f) & 1 : (f >= 3 ? 1 : 0); }
 
 // Trace of the conserved variables of one element at one face point: U·Φ_f[face]ᵀ (AdjacencyElementVariable::get,
 // VariableConvertor.cpp:432-485) = end-point interpolation along the face-normal line.
 template <int N, int NV, int NN>
 __device__ __forceinline__ void lineTrace(const double* __restrict__ src, int base, int stride, const double* __restrict__ lend, double* out) {
+  double val[NV][N];
+#pragma unroll
+  for (int v = 0; v < NV; v++)
+#pragma unroll
+    for (int a = 0; a < N; a++) val[v][a] = src[v * NN + base + a * stride];
 #pragma unroll
   for (int v = 0; v < NV; v++) {
     double s = 0.0;
 #pragma unroll
-    for (int a = 0; a < N; a++) s += lend[a] * src[v * NN + base + a * stride];
+    for (int a = 0; a < N; a++) s += lend[a] * val[v][a];
     out[v] = s;
   }
 }
 
+// Contravariant convective flux of reference direction dd at one node:  F(U)·m  with m = row dd of (J^T)^-1 detJ w
+// (calculateConvectiveRawFlux, ConvectiveFlux.cpp:28-57, contracted like SpatialDiscrete.cpp:229-232).
+template <int D, int PH>
+__device__ __forceinline__ void contravariantFlux(const Phys<PH>& ph, const double* cons, const double* comp, const double* m, double* Ft) {
+  double um = 0.0;
+#pragma unroll
+  for (int c = 0; c < D; c++) um += comp[1 + c] * m[c];
+  const double p = comp[D + 2];
+  Ft[0] = cons[0] * um;
+#pragma unroll
+  for (int k = 0; k < D; k++) Ft[1 + k] = cons[1 + k] * um + p * m[k];
+  Ft[D + 1] = ph.comp() ? (cons[D + 1] + p) * um : cons[D + 1] * um;
+}
+
 template <int D, int N, int K, bool AFFINE, int PH>
-__global__ void __launch_bounds__(kThreads) eulerStageKernel(const __grid_constant__ StageArgs A) {
+__global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(const __grid_constant__ StageArgs A) {
   using L = Layout<D, N, K>;
-  constexpr int NV = L::NV, NN = L::NN, NQF = L::NQF, NF = L::NF, NAQ = L::NAQ;
+  constexpr int NV = L::NV, NN = L::NN, NQF = L::NQF, NF = L::NF, NAQ = L::NAQ, ITERS = L::ITERS;
   extern __shared__ __align__(16) double smem[];
   double* sU = smem + L::oU;
   double* sF = smem + L::oF;
@@ -120,214 +175,268 @@ __global__ void __launch_bounds__(kThreads) eulerStageKernel(const __grid_consta
   double* sK1 = sLend + 2 * N;
   double* sWq = sK1 + N * N;
   double* sWf = sWq + NN;
-  int* sFaceBase = reinterpret_cast<int*>(smem + L::nDoubles);
-  int* sSeq = sFaceBase + NF * NQF;
-  int* sNodePt = sSeq + 4 * NQF;
+  unsigned char* sFaceBase = reinterpret_cast<unsigned char*>(smem + L::nDoubles);
+  unsigned char* sSeq = sFaceBase + NF * NQF;
+  unsigned char* sNodePt = sSeq + 4 * NQF;
 
   const int tid = threadIdx.x;
   const int chunk = A.chunkList ? A.chunkList[blockIdx.x] : blockIdx.x;
   const int e0 = chunk * K;
   const int ne = min(K, A.nOwned - e0);
+  const int nNodes = ne * NN;
+  // when the block size is a multiple of the nodes per element every thread keeps the same node q in all its iterations
+  constexpr bool FIXQ = (kThreads % NN) == 0;
+  constexpr int EL_STEP = kThreads / NN;
+  const int q0 = tid % NN, el0 = tid / NN;
   const Phys<PH> ph(A.phys);
   const TensorDev& T = *A.tab;
 
+  // Stage everything the chunk owns with TMA bulk copies (cp.async.bulk -> UBLKCP): its states, its affine metric
+  // records and the records + geometry of the faces touching it are each ONE contiguous range in global memory.
+  // One thread arms an mbarrier with the byte count and issues the copies; the block meets them at mbarWait below.
+  double* sGeoE = smem + L::oGeoE;
+  double* sCf = smem + L::oCf;
+  const int4* sRec = reinterpret_cast<const int4*>(smem + L::oRec);
+  __shared__ __align__(8) unsigned long long mbar;
+  const int f0 = A.chunkFaceOff[chunk], nfc = A.chunkFaceOff[chunk + 1] - f0;
+  const unsigned bytesU = (unsigned)(ne * NV * NN * sizeof(double));
+  const bool bulkU = (bytesU & 15u) == 0;   // 16-byte granularity of the bulk copy engine
+  if (tid == 0) { mbarInit(&mbar, 1); }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned total = (unsigned)(nfc * sizeof(int4)) + (bulkU ? bytesU : 0u);
+    if constexpr (AFFINE) total += (unsigned)(ne * L::REC * sizeof(double)) + (unsigned)(nfc * 4 * sizeof(double));
+    mbarExpectTx(&mbar, total);
+    if (bulkU) bulkLoad(sU, A.Uin + (size_t)e0 * NV * NN, bytesU, &mbar);
+    bulkLoad(smem + L::oRec, A.faceRec + f0, (unsigned)(nfc * sizeof(int4)), &mbar);
+    if constexpr (AFFINE) {
+      bulkLoad(sGeoE, A.geoE + (size_t)e0 * L::REC, (unsigned)(ne * L::REC * sizeof(double)), &mbar);
+      bulkLoad(sCf, A.cfGeo + (size_t)f0 * 4, (unsigned)(nfc * 4 * sizeof(double)), &mbar);
+    }
+  }
+  if (!bulkU) {
+    const double* src = A.Uin + (size_t)e0 * NV * NN;
+    for (int i = tid; i < ne * NV * NN; i += kThreads) sU[i] = src[i];
+  }
   for (int i = tid; i < N * N; i += kThreads) { sDm[i] = T.Dm[i]; sK1[i] = T.K1[i]; }
   for (int i = tid; i < 2 * N; i += kThreads) sLend[i] = T.Lend[i];
   for (int i = tid; i < NN; i += kThreads) sWq[i] = T.wq[i];
   for (int i = tid; i < NQF; i += kThreads) sWf[i] = T.wf[i];
-  for (int i = tid; i < NF * NQF; i += kThreads) sFaceBase[i] = T.faceBase[i];
-  for (int i = tid; i < 4 * NQF; i += kThreads) sSeq[i] = T.seq[i];
+  for (int i = tid; i < NF * NQF; i += kThreads) sFaceBase[i] = (unsigned char)T.faceBase[i];
+  for (int i = tid; i < 4 * NQF; i += kThreads) sSeq[i] = (unsigned char)T.seq[i];
   for (int i = tid; i < NF * NN; i += kThreads) sNodePt[i] = T.nodeFacePt[i];
-  {  // stage the chunk's states (contiguous in global memory)
-    const double* src = A.Uin + (size_t)e0 * NV * NN;
-    for (int i = tid; i < ne * NV * NN; i += kThreads) sU[i] = src[i];
+
+  // U_last of the thread's own nodes: issued now, consumed in R4, so the latency hides behind the whole stage
+  double ulast[ITERS][NV];
+  if (A.mode == 0 && A.aLast != 0.0) {
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+      const int nd = tid + it * kThreads;
+      if (nd < nNodes) {
+        const int el = FIXQ ? el0 + it * EL_STEP : nd / NN, q = FIXQ ? q0 : nd - el * NN;
+        const double* g = A.Ulast + ((size_t)(e0 + el) * NV) * NN + q;
+#pragma unroll
+        for (int v = 0; v < NV; v++) ulast[it][v] = g[(size_t)v * NN];
+      }
+    }
   }
   __syncthreads();
-
-  // ---- R1: volume flux at the nodes, contracted with (J^T)^-1 detJ w ---------------------------------------------------
-  for (int nd = tid; nd < ne * NN; nd += kThreads) {
-    const int el = nd / NN, q = nd - el * NN;
-    double cons[NV], comp[D + 3], F[NV * D];
-#pragma unroll
-    for (int v = 0; v < NV; v++) cons[v] = sU[(el * NV + v) * NN + q];
-    compFromCons<D>(ph, cons, comp);
-    convRawFlux<D>(ph, comp, F);
-    double mt[D * D];
-    if constexpr (AFFINE) {
-      const double* g = A.geoE + (size_t)(e0 + el) * (D * D + 1);
-      const double w = sWq[q];
-#pragma unroll
-      for (int k = 0; k < D * D; k++) mt[k] = g[k] * w;
-    } else {
-      const double* g = A.geoE + (size_t)(e0 + el) * (D * D) * NN + q;
-#pragma unroll
-      for (int k = 0; k < D * D; k++) mt[k] = g[k * NN];
-    }
-#pragma unroll
-    for (int dd = 0; dd < D; dd++)
-#pragma unroll
-      for (int v = 0; v < NV; v++) {
-        double t = 0.0;
-#pragma unroll
-        for (int c = 0; c < D; c++) t += F[v * D + c] * mt[dd * D + c];
-        sF[((el * D + dd) * NV + v) * NN + q] = t;
-      }
-  }
+  mbarWait(&mbar, 0);
 
   // ---- R2: face fluxes, once per face of the chunk ------------------------------------------------------------------------
   {
-    const int f0 = A.chunkFaceOff[chunk], nfc = A.chunkFaceOff[chunk + 1] - f0;
     for (int fp = tid; fp < nfc * NQF; fp += kThreads) {
       const int fi = fp / NQF, j = fp - fi * NQF;
-      const int4 rec = A.faceRec[f0 + fi];
+      const int4 rec = sRec[fi];
       const int eL = rec.x, eR = rec.y, faceId = rec.z;
       const int lfL = rec.w & 15, lfR = (rec.w >> 4) & 15, rot = (rec.w >> 8) & 15, bc = (rec.w >> 12) & 15;
       double n[D], jw;
       if constexpr (AFFINE) {
-        const double* g = A.geoF + (size_t)faceId * (D + 1);
+        const double* g = sCf + fi * 4;
 #pragma unroll
         for (int d = 0; d < D; d++) n[d] = g[d];
         jw = g[D] * sWf[j];
       } else {
         const double* g = A.geoF + (size_t)faceId * (D + 1) * NQF + j;
 #pragma unroll
-        for (int d = 0; d < D; d++) n[d] = g[d * NQF];
-        jw = g[D * NQF];
+        for (int d = 0; d < D; d++) n[d] = __ldg(g + d * NQF);
+        jw = __ldg(g + D * NQF);
       }
-      double consL[NV], compL[D + 3], Fn[NV];
+      double consL[NV], compL[D + 3], consR[NV], compR[D + 3], Fn[NV];
+      const int locL = eL - e0, locR = eR - e0;
+      const bool inL = locL >= 0 && locL < ne, inR = eR >= 0 && locR >= 0 && locR < ne;
       {
         const int dn = faceDirOf<D>(lfL), side = faceSideOf<D>(lfL);
         const int base = sFaceBase[lfL * NQF + j], stride = strideOf<N, D>(dn);
-        const int loc = eL - e0;
-        if (loc >= 0 && loc < ne) lineTrace<N, NV, NN>(sU + loc * NV * NN, base, stride, sLend + side * N, consL);
+        if (inL) lineTrace<N, NV, NN>(sU + locL * NV * NN, base, stride, sLend + side * N, consL);
         else lineTrace<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, sLend + side * N, consL);
       }
-      compFromCons<D>(ph, consL, compL);
+      const double irL = compFromCons<D>(ph, consL, compL);
       int jr = j;
       if (eR >= 0) {
-        double consR[NV], compR[D + 3];
         jr = sSeq[rot * NQF + j];
         const int dn = faceDirOf<D>(lfR), side = faceSideOf<D>(lfR);
         const int base = sFaceBase[lfR * NQF + jr], stride = strideOf<N, D>(dn);
-        const int loc = eR - e0;
-        if (loc >= 0 && loc < ne) lineTrace<N, NV, NN>(sU + loc * NV * NN, base, stride, sLend + side * N, consR);
+        if (inR) lineTrace<N, NV, NN>(sU + locR * NV * NN, base, stride, sLend + side * N, consR);
         else lineTrace<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, sLend + side * N, consR);
-        compFromCons<D>(ph, consR, compR);
-        convFlux<D>(ph, n, consL, compL, consR, compR, Fn);
+        const double irR = compFromCons<D>(ph, consR, compR);
+        convFlux<D>(ph, n, consL, compL, irL, consR, compR, irR, Fn);
       } else {
         // boundary face: normal flux of the BC-constructed state, no Riemann solve (SpatialDiscrete.cpp:797-803)
-        double compR[D + 3], b[D + 3];
+        double b[D + 3];
         const double* dm = A.dummy + (size_t)(faceId - A.nInt) * (D + 3) * NQF + j;
 #pragma unroll
         for (int k = 0; k < D + 3; k++) compR[k] = dm[k * NQF];
         bcBoundaryVariable<D>(ph, bc, n, compL, compR, b);
         convNormalFlux<D>(ph, n, b, Fn);
       }
-      {
-        const int loc = eL - e0;
-        if (loc >= 0 && loc < ne) {
+      if (inL) {
 #pragma unroll
-          for (int v = 0; v < NV; v++) sFlux[(loc * NV + v) * NAQ + lfL * NQF + j] = Fn[v] * jw;
-        }
+        for (int v = 0; v < NV; v++) sFlux[(locL * NV + v) * NAQ + lfL * NQF + j] = Fn[v] * jw;
       }
-      if (eR >= 0) {
-        const int loc = eR - e0;
-        if (loc >= 0 && loc < ne) {
+      if (inR) {
 #pragma unroll
-          for (int v = 0; v < NV; v++) sFlux[(loc * NV + v) * NAQ + lfR * NQF + jr] = -Fn[v] * jw;
-        }
+        for (int v = 0; v < NV; v++) sFlux[(locR * NV + v) * NAQ + lfR * NQF + jr] = -Fn[v] * jw;
       }
     }
   }
-  __syncthreads();
 
-  // ---- R3 + R4: residual by sum factorisation, mass inverse, RK update ------------------------------------------------------
-  const bool wantNorm = A.normPartial != nullptr;
-  double* sR = sFlux;  // reused for the norm: [K][NV][NN] fits in [K][NV][NAQ] when NAQ >= NN (2D: 4N >= N^2 for N<=4; 3D: 6N^2 >= N^3 for N<=6)
-  constexpr int ITERS = (K * NN + kThreads - 1) / kThreads;
-  double Rkeep[ITERS][NV];
+  // ---- R1 + R3: volume term, one reference direction at a time (sum factorisation) ------------------------------------------
+  double R[ITERS][NV];
+#pragma unroll
+  for (int it = 0; it < ITERS; it++)
+#pragma unroll
+    for (int v = 0; v < NV; v++) R[it][v] = 0.0;
+  double velp[ITERS][D + 1];  // velocity and pressure of the thread's nodes, reused by the D direction passes
 #pragma unroll
   for (int it = 0; it < ITERS; it++) {
     const int nd = tid + it * kThreads;
-    if (nd >= ne * NN) break;
-    const int el = nd / NN, q = nd - el * NN;
-    double R[NV];
+    if (nd < nNodes) {
+      const int el = FIXQ ? el0 + it * EL_STEP : nd / NN, q = FIXQ ? q0 : nd - el * NN;
+      double cons[NV], comp[D + 3];
 #pragma unroll
-    for (int v = 0; v < NV; v++) R[v] = 0.0;
-#pragma unroll
-    for (int dd = 0; dd < D; dd++) {
-      const int st = strideOf<N, D>(dd);
-      const int id = (q / st) % N;
-      const int qb = q - id * st;
-      const double* f = sF + ((el * D + dd) * NV) * NN + qb;
-#pragma unroll
-      for (int a = 0; a < N; a++) {
-        const double dm = sDm[a * N + id];
-#pragma unroll
-        for (int v = 0; v < NV; v++) R[v] += f[v * NN + a * st] * dm;
-      }
-    }
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-      const int dn = faceDirOf<D>(f), side = faceSideOf<D>(f);
-      const int st = strideOf<N, D>(dn);
-      const int id = (q / st) % N;
-      const double cf = sLend[side * N + id];
-      const int j = sNodePt[f * NN + q];
-      const double* fl = sFlux + (el * NV) * NAQ + f * NQF + j;
-#pragma unroll
-      for (int v = 0; v < NV; v++) R[v] -= cf * fl[v * NAQ];
-    }
-    double cons[NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) cons[v] = sU[(el * NV + v) * NN + q];
-    double ijw;
-    if constexpr (AFFINE) ijw = 1.0 / (A.geoE[(size_t)(e0 + el) * (D * D + 1) + D * D] * sWq[q]);
-    else ijw = A.invjw[(size_t)(e0 + el) * NN + q];
-    if (A.phys.source == kBoussinesq) {  // SpatialDiscrete.cpp:254-262 + :1016-1032 (source·detJ w, times Φ)
-      double comp[D + 3];
+      for (int v = 0; v < NV; v++) cons[v] = sU[(el * NV + v) * NN + q];
       compFromCons<D>(ph, cons, comp);
-      R[D] += boussinesqSource<D>(ph, comp) / ijw;
-    }
-    const size_t g = ((size_t)(e0 + el) * NV) * NN + q;
-    if (A.mode == 0) {
 #pragma unroll
-      for (int v = 0; v < NV; v++) {
-        double u = A.aCur * cons[v] + A.bdt * (R[v] * ijw);
-        if (A.aLast != 0.0) u += A.aLast * A.Ulast[g + (size_t)v * NN];
-        A.Uout[g + (size_t)v * NN] = u;
+      for (int c = 0; c < D; c++) velp[it][c] = comp[1 + c];
+      velp[it][D] = comp[D + 2];
+    }
+  }
+#pragma unroll
+  for (int dd = 0; dd < D; dd++) {
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+      const int nd = tid + it * kThreads;
+      if (nd < nNodes) {
+        const int el = FIXQ ? el0 + it * EL_STEP : nd / NN, q = FIXQ ? q0 : nd - el * NN;
+        double cons[NV], comp[D + 3], m[D], Ft[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) cons[v] = sU[(el * NV + v) * NN + q];
+#pragma unroll
+        for (int c = 0; c < D; c++) comp[1 + c] = velp[it][c];
+        comp[D + 2] = velp[it][D];
+        if constexpr (AFFINE) {
+          const double* g = sGeoE + el * L::REC + dd * D;
+          const double w = sWq[q];
+#pragma unroll
+          for (int c = 0; c < D; c++) m[c] = g[c] * w;
+        } else {
+          const double* g = A.geoE + ((size_t)(e0 + el) * (D * D) + dd * D) * NN + q;
+#pragma unroll
+          for (int c = 0; c < D; c++) m[c] = __ldg(g + c * NN);
+        }
+        contravariantFlux<D>(ph, cons, comp, m, Ft);
+#pragma unroll
+        for (int v = 0; v < NV; v++) sF[(el * NV + v) * NN + q] = Ft[v];
       }
-    } else {
-#pragma unroll
-      for (int v = 0; v < NV; v++) A.Uout[g + (size_t)v * NN] = A.mode == 1 ? R[v] * ijw : R[v];
     }
+    __syncthreads();   // (first pass: also orders the face-flux slot writes before their use below)
+    const int st = strideOf<N, D>(dd);
 #pragma unroll
-    for (int v = 0; v < NV; v++) Rkeep[it][v] = R[v];
+    for (int it = 0; it < ITERS; it++) {
+      const int nd = tid + it * kThreads;
+      if (nd < nNodes) {
+        const int el = FIXQ ? el0 + it * EL_STEP : nd / NN, q = FIXQ ? q0 : nd - el * NN;
+        const int id = (q / st) % N;
+        const double* f = sF + (el * NV) * NN + (q - id * st);
+#pragma unroll
+        for (int a = 0; a < N; a++) {
+          const double dm = sDm[a * N + id];
+#pragma unroll
+          for (int v = 0; v < NV; v++) R[it][v] += f[v * NN + a * st] * dm;
+        }
+      }
+    }
+    if (dd + 1 < D) __syncthreads();
+  }
+
+  // ---- R3 (face part) + R4: lifting of the face fluxes, mass inverse, RK update ---------------------------------------------
+#pragma unroll
+  for (int it = 0; it < ITERS; it++) {
+    const int nd = tid + it * kThreads;
+    if (nd < nNodes) {
+      const int el = FIXQ ? el0 + it * EL_STEP : nd / NN, q = FIXQ ? q0 : nd - el * NN;
+#pragma unroll
+      for (int f = 0; f < NF; f++) {
+        const int dn = faceDirOf<D>(f), side = faceSideOf<D>(f);
+        const int st = strideOf<N, D>(dn);
+        const int id = (q / st) % N;
+        const double cf = sLend[side * N + id];
+        const int j = sNodePt[f * NN + q];
+        const double* fl = sFlux + (el * NV) * NAQ + f * NQF + j;
+#pragma unroll
+        for (int v = 0; v < NV; v++) R[it][v] -= cf * fl[v * NAQ];
+      }
+      double cons[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) cons[v] = sU[(el * NV + v) * NN + q];
+      double ijw;
+      if constexpr (AFFINE) ijw = 1.0 / (sGeoE[el * L::REC + D * D] * sWq[q]);
+      else ijw = __ldg(A.invjw + (size_t)(e0 + el) * NN + q);
+      if (A.phys.source == kBoussinesq) {  // SpatialDiscrete.cpp:254-262 + :1016-1032 (source·detJ w, times Φ)
+        double comp[D + 3];
+        compFromCons<D>(ph, cons, comp);
+        R[it][D] += boussinesqSource<D>(ph, comp) / ijw;
+      }
+      const size_t g = ((size_t)(e0 + el) * NV) * NN + q;
+      if (A.mode == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          double u = A.aCur * cons[v] + A.bdt * (R[it][v] * ijw);
+          if (A.aLast != 0.0) u += A.aLast * ulast[it][v];
+          A.Uout[g + (size_t)v * NN] = u;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < NV; v++) A.Uout[g + (size_t)v * NN] = A.mode == 1 ? R[it][v] * ijw : R[it][v];
+      }
+    }
   }
 
   // ---- K: relative error = mean_q |R_modal Φᵀ| = mean_q |(K1⊗…⊗K1) R_nodal|, summed over the chunk's elements --------------
-  if (wantNorm) {
-    double* bufA = sF;                   // [K][NV][NN]
-    double* bufB = sF + K * NV * NN;     // D >= 2 so sF holds at least two such buffers
+  if (A.normPartial != nullptr) {
+    double* bufA = sF;      // [K][NV][NN]
+    double* bufB = sFlux;   // [K][NV][NAQ] >= [K][NV][NN]  (2D: 4N >= N^2 for N <= 4; 3D: 6N^2 >= N^3 for N <= 6)
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
       const int nd = tid + it * kThreads;
-      if (nd < ne * NN) {
-        const int el = nd / NN, q = nd - el * NN;
+      if (nd < nNodes) {
+        const int el = FIXQ ? el0 + it * EL_STEP : nd / NN, q = FIXQ ? q0 : nd - el * NN;
 #pragma unroll
-        for (int v = 0; v < NV; v++) bufA[(el * NV + v) * NN + q] = Rkeep[it][v];
+        for (int v = 0; v < NV; v++) bufA[(el * NV + v) * NN + q] = R[it][v];
       }
     }
     double acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; v++) acc[v] = 0.0;
+#pragma unroll
     for (int dd = 0; dd < D; dd++) {
       __syncthreads();
       const double* in = (dd & 1) ? bufB : bufA;
       double* out = (dd & 1) ? bufA : bufB;
       const int st = strideOf<N, D>(dd);
-      for (int nd = tid; nd < ne * NN; nd += kThreads) {
+      for (int nd = tid; nd < nNodes; nd += kThreads) {
         const int el = nd / NN, q = nd - el * NN;
         const int id = (q / st) % N, qb = q - id * st;
 #pragma unroll
@@ -341,7 +450,7 @@ __global__ void __launch_bounds__(kThreads) eulerStageKernel(const __grid_consta
     }
     __syncthreads();
     // deterministic block reduction: warp shuffle, then one thread sums the warp partials in order
-    double* red = sFlux;
+    double* red = sU;
 #pragma unroll
     for (int v = 0; v < NV; v++) {
       double s = acc[v];
@@ -355,7 +464,6 @@ __global__ void __launch_bounds__(kThreads) eulerStageKernel(const __grid_consta
       A.normPartial[(size_t)chunk * NV + tid] = s / NN;
     }
   }
-  (void)sR;
 }
 
 // ---- seam / utility kernels -------------------------------------------------------------------------------------------------

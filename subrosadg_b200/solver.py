@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsubrosadg_b200.so")
+LIB_PATH = os.environ.get("SDG_LIB", os.path.join(_HERE, "libsubrosadg_b200.so"))  # SDG_LIB: A/B builds of the same ABI
 
 POINT, LINE, TRIANGLE, QUADRANGLE, TETRAHEDRON, PYRAMID, HEXAHEDRON = range(7)
 
@@ -42,7 +42,7 @@ EXPORTS = [
     "sdg_last_error", "sdg_version", "sdg_create", "sdg_destroy", "sdg_add_elements", "sdg_set_faces", "sdg_finalize", "sdg_sizes",
     "sdg_get_quadrature_coordinates", "sdg_get_boundary_quadrature_coordinates", "sdg_set_state_from_primitive",
     "sdg_set_boundary_primitive", "sdg_set_state", "sdg_get_state", "sdg_get_state_at_quadrature", "sdg_get_gradient_at_quadrature",
-    "sdg_compute_dt", "sdg_step", "sdg_residual", "sdg_set_halo_send", "sdg_halo_pack", "sdg_halo_buffers_device", "sdg_step_begin",
+    "sdg_compute_dt", "sdg_step", "sdg_step_timed", "sdg_residual", "sdg_set_halo_send", "sdg_halo_pack", "sdg_halo_buffers_device", "sdg_step_begin",
     "sdg_stage_pass", "sdg_step_end", "sdg_num_passes", "sdg_num_stages", "sdg_stream", "sdg_synchronize", "sdg_set_state_device",
     "sdg_get_state_device", "sdg_launch_count", "sdg_debug_plan",
 ]
@@ -217,6 +217,14 @@ class Solver:
         if want_error:
             self.relative_error_ = err
         return err
+
+    def step_timed(self, dt, nsteps=1):
+        """stepSolver x nsteps; returns (relative_error_, device milliseconds measured with CUDA events on the stream)."""
+        err = np.zeros(self.Nv)
+        ms = ctypes.c_float(0)
+        _chk(load_library().sdg_step_timed(self.h, ctypes.c_double(dt), int(nsteps), _dp(err), ctypes.byref(ms)))
+        self.relative_error_ = err
+        return err, float(ms.value)
 
     def step(self, dt, nsteps=1):
         return self.stepSolver(dt, nsteps)
