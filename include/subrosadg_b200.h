@@ -136,8 +136,10 @@ int sdg_set_state_device(sdg_ctx* ctx, int32_t type, const void* U_device);
 int sdg_get_state_device(sdg_ctx* ctx, int32_t type, void* U_device);
 
 /* Diagnostics (host plan, no device needed): copies one of the flattened arrays and/or returns its length.
- * what: 0 geoE  1 invjw  2 minEdge  3 geoF (doubles);  10 perm  11 chunkFaceOff  12 faceRec  13 chunkInterior  14 chunkBoundary
- *       15 {affine, K, nChunks, nOwned} (int32).  Element arrays are in INTERNAL order (position perm[e]). */
+ * what: 0 geoE  1 invjw  2 minEdge  3 geoF  4 Phi[Nq][Nb]  5 1-D differentiation matrix  6 end-point interpolation
+ *       7 Gauss abscissae  8 Gauss weights (doubles);  10 perm  11 chunkFaceOff  12 faceRec  13 chunkInterior
+ *       14 chunkBoundary  15 {affine, K, nChunks, nOwned}  16 face-point permutations [4][Nqf]  17 faceBase  18 nodeFacePt
+ *       19 modal function index triples (int32).  Element arrays are in INTERNAL order (position perm[e]). */
 int sdg_debug_plan(sdg_ctx* ctx, int32_t what, double* out_d, int32_t* out_i, int64_t* count);
 
 /* counters: number of kernels this library launched since creation (bench.py's gpu_launches) */

@@ -596,10 +596,18 @@ int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int6
   const BlockPlan& B = c->plan.blk;
   const std::vector<double>* d = nullptr; const std::vector<int>* i = nullptr;
   std::vector<int> misc = {B.affine ? 1 : 0, B.K, B.nChunks, B.nOwned};
+  std::vector<int> seqs, midx;
+  {  // right-side face-point permutations for rotations 0..3 (the table the kernels stage), modal function index triples
+    const int ft = faceType(B.type);
+    for (int r = 0; r < 4; r++) { std::vector<int> q = faceSequence(ft, B.T.N, ft == kLine ? 0 : r); seqs.insert(seqs.end(), q.begin(), q.end()); }
+    for (auto& t : B.T.modalIdx) for (int k = 0; k < 3; k++) midx.push_back(t[k]);
+  }
   switch (what) {
     case 0: d = &B.geoE; break; case 1: d = &B.invjw; break; case 2: d = &B.minEdge; break; case 3: d = &c->plan.geoF; break;
     case 10: i = &B.perm; break; case 11: i = &B.chunkFaceOff; break; case 12: i = &B.faceRec; break;
     case 13: i = &B.chunkInterior; break; case 14: i = &B.chunkBoundary; break; case 15: i = &misc; break;
+    case 16: i = &seqs; break; case 17: i = &B.T.faceBase; break; case 18: i = &B.T.nodeFacePt; break; case 19: i = &midx; break;
+    case 4: d = &B.T.Phi; break; case 5: d = &B.T.Dm; break; case 6: d = &B.T.Lend; break; case 7: d = &B.T.x; break; case 8: d = &B.T.w; break;
     default: throw std::runtime_error("bad diagnostics id");
   }
   if (d) { if (count) *count = (int64_t)d->size(); if (out_d) std::memcpy(out_d, d->data(), d->size() * sizeof(double)); }
