@@ -11,6 +11,7 @@
 
 #include "../../include/subrosadg_b200.h"
 #include "host_plan.hpp"
+#include "ns_kernels.cuh"
 #include "tensor_kernels.cuh"
 
 using namespace sdg;
@@ -45,6 +46,44 @@ void launchEuler(const StageArgs& a, int nBlocks, cudaStream_t s) {
     configured = true;
   }
   eulerStageKernel<D, N, K, AFFINE, PH><<<nBlocks, kThreads, L::bytes, s>>>(a);
+}
+
+template <int D, int N, int K, bool AFFINE>
+void launchNsGrad(const StageArgs& a, int nBlocks, cudaStream_t s) {
+  using L = NsLayout<D, N, K>;
+  static bool configured = false;
+  if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsGradKernel<D, N, K, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
+  nsGradKernel<D, N, K, AFFINE><<<nBlocks, kThreads, L::bytes, s>>>(a);
+}
+template <int D, int N, int K, bool AFFINE, int PH>
+void launchNsStage(const StageArgs& a, int nBlocks, cudaStream_t s) {
+  using L = NsLayout<D, N, K>;
+  static bool configured = false;
+  if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsStageKernel<D, N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
+  nsStageKernel<D, N, K, AFFINE, PH><<<nBlocks, kThreads, L::bytes, s>>>(a);
+}
+template <int D, int N> struct NsChunkOf;
+template <> struct NsChunkOf<2, 2> { static constexpr int K = 32; };
+template <> struct NsChunkOf<2, 3> { static constexpr int K = 16; };
+template <> struct NsChunkOf<2, 4> { static constexpr int K = 16; };
+template <> struct NsChunkOf<3, 2> { static constexpr int K = 16; };
+template <> struct NsChunkOf<3, 3> { static constexpr int K = 8; };
+template <> struct NsChunkOf<3, 4> { static constexpr int K = 4; };
+template <int D, int N>
+void pickNs(bool affine, int ph, StageFn& grad, StageFn& stage, int& K) {
+  constexpr int KK = NsChunkOf<D, N>::K;
+  K = KK;
+  if (affine) { grad = launchNsGrad<D, N, KK, true>; stage = ph ? launchNsStage<D, N, KK, true, 1> : launchNsStage<D, N, KK, true, 0>; }
+  else { grad = launchNsGrad<D, N, KK, false>; stage = ph ? launchNsStage<D, N, KK, false, 1> : launchNsStage<D, N, KK, false, 0>; }
+}
+void pickNsFn(int D, int N, bool affine, int ph, StageFn& grad, StageFn& stage, int& K) {
+  if (D == 2 && N == 2) return pickNs<2, 2>(affine, ph, grad, stage, K);
+  if (D == 2 && N == 3) return pickNs<2, 3>(affine, ph, grad, stage, K);
+  if (D == 2 && N == 4) return pickNs<2, 4>(affine, ph, grad, stage, K);
+  if (D == 3 && N == 2) return pickNs<3, 2>(affine, ph, grad, stage, K);
+  if (D == 3 && N == 3) return pickNs<3, 3>(affine, ph, grad, stage, K);
+  if (D == 3 && N == 4) return pickNs<3, 4>(affine, ph, grad, stage, K);
+  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..3");
 }
 
 // chunk sizes: bricks of 2^D .. elements, sized so that two blocks fit an SM
@@ -91,7 +130,8 @@ struct sdg_ctx {
   DevBuf<TensorDev> tab;
   int cur = 0;          // index of the buffer holding the current state
   int latest = 0;       // buffer written last (halo source / target)
-  StageFn eulerFn = nullptr;
+  StageFn eulerFn = nullptr, nsGradFn = nullptr, nsStageFn = nullptr;
+  DevBuf<double> G, G2;   // NS: gradient field [n][NV*D][NN] (+ scratch for diagnostics)
   double stepDt = 0.0;
   int nSend = 0;
   std::vector<double> hostNorm;
@@ -116,14 +156,16 @@ void fillArgs(sdg_ctx* c, StageArgs& a) {
 }
 
 // one pass of one stage over a subset of the chunks
-void runStage(sdg_ctx* c, const StageArgs& base, int part, cudaStream_t s) {
+void runStage(sdg_ctx* c, const StageArgs& base, int part, cudaStream_t s, int pass = -1) {
   const BlockPlan& B = c->plan.blk;
   StageArgs a = base;
   int nBlocks = B.nChunks;
   if (part == 0) { a.chunkList = c->chunkInterior.p; nBlocks = (int)B.chunkInterior.size(); }
   else if (part == 1) { a.chunkList = c->chunkBoundary.p; nBlocks = (int)B.chunkBoundary.size(); }
   if (nBlocks == 0) return;
-  c->eulerFn(a, nBlocks, s);
+  if (!c->phys.ns) c->eulerFn(a, nBlocks, s);
+  else if (pass == 0) c->nsGradFn(a, nBlocks, s);
+  else c->nsStageFn(a, nBlocks, s);
   c->launches++;
   CUDA_OK(cudaGetLastError());
 }
@@ -137,15 +179,19 @@ void stageBuffers(sdg_ctx* c, int s, int& in, int& out) {
   else { in = a; out = b; }
 }
 
-void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st) {
+// pass: -1 = every pass of the stage (single GPU); 0 = gradient pass (NS); 1 = residual pass (the only pass for Euler)
+void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st, int pass = -1) {
   int in, out; stageBuffers(c, s, in, out);
   StageArgs a; fillArgs(c, a);
   a.Uin = c->U[in].p; a.Ulast = c->U[c->cur].p; a.Uout = c->U[out].p;
+  a.Gvol = c->G.p; a.Gout = c->G.p;
+  if (c->phys.ns && (pass == -1 || pass == 0)) { runStage(c, a, part, st, 0); if (pass == 0) return; }
+  if (!c->phys.ns && pass == 0) return;
   a.aLast = s == 0 ? 0.0 : c->rkc[s][0];
   a.aCur = s == 0 ? 1.0 : c->rkc[s][1];
   a.bdt = c->rkc[s][2] * c->stepDt;
   a.normPartial = s == c->nStages - 1 ? c->normPartial.p : nullptr;
-  runStage(c, a, part, st);
+  runStage(c, a, part, st, 1);
   c->latest = out;
 }
 
@@ -271,7 +317,8 @@ int sdg_finalize(sdg_ctx* c) {
   const int ph = (c->phys.compressible && c->phys.eos == kIdealGas && c->phys.conv == kHLLC) ? 1 : 0;
   // decide the affine flag first (needs geometry), then the kernel
   M.buildBlock(c->cfg.reorder, 1);  // provisional chunk size; chunking is redone below once K is known
-  c->eulerFn = pickEulerFn(c->D, N, B.affine, ph, K);
+  if (c->phys.ns) pickNsFn(c->D, N, B.affine, ph, c->nsGradFn, c->nsStageFn, K);
+  else c->eulerFn = pickEulerFn(c->D, N, B.affine, ph, K);
   if (c->cfg.chunk > 0 && c->cfg.chunk != K) throw std::runtime_error("chunk override not available: kernels are compiled for K = " + std::to_string(K));
   B.K = K; B.nChunks = (B.nOwned + K - 1) / K;
   M.buildFaces(nullptr, false);
@@ -309,6 +356,7 @@ int sdg_finalize(sdg_ctx* c) {
     c->chunkInterior.upload(B.chunkInterior, c->stream); c->chunkBoundary.upload(B.chunkBoundary, c->stream);
     c->Phi.upload(B.T.Phi, c->stream); c->PhiInv.upload(B.T.PhiInv, c->stream);
     { std::vector<double> PT(B.T.Phi.size()); const int NN = B.T.NN; for (int q = 0; q < NN; q++) for (int b = 0; b < NN; b++) PT[(size_t)b * NN + q] = B.T.Phi[(size_t)q * NN + b]; c->PhiT.upload(PT, c->stream); }
+    if (c->phys.ns) { c->G.alloc((size_t)B.n * c->NV * c->D * B.T.NN); CUDA_OK(cudaMemsetAsync(c->G.p, 0, c->G.n * sizeof(double), c->stream)); }
     c->normPartial.alloc((size_t)B.nChunks * c->NV); c->normOut.alloc(8); c->dtPartial.alloc(1024);
     CUDA_OK(cudaMemsetAsync(c->normPartial.p, 0, c->normPartial.n * sizeof(double), c->stream));
     std::vector<TensorDev> td(1);
@@ -456,8 +504,23 @@ int sdg_get_state_at_quadrature(sdg_ctx* c, int32_t type, double* Uq) {
 int sdg_get_gradient_at_quadrature(sdg_ctx* c, int32_t type, double* Gq) {
   SDG_TRY
   needFinal(c); needDevice(c); needType(c, type);
-  (void)Gq;
-  throw std::runtime_error("gradient state exists for Navier-Stokes models only");
+  if (!c->phys.ns) throw std::runtime_error("gradient state exists for Navier-Stokes models only");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  const int NG = c->NV * c->D;
+  c->G2.alloc(c->G.n);
+  DevBuf<double> tmp; tmp.alloc(c->G.n);
+  StageArgs args; fillArgs(c, args);
+  args.Uin = c->U[c->cur].p; args.Ulast = c->U[c->cur].p; args.Uout = c->U[(c->cur + 1) % 3].p;
+  args.Gvol = c->G.p; args.Gout = c->G.p;
+  runStage(c, args, -1, c->stream, 0);
+  if (c->phys.visc == kBR2) { args.Gout = c->G2.p; args.mode = 3; runStage(c, args, -1, c->stream, 1); }
+  seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->phys.visc == kBR2 ? c->G2.p : c->G.p, tmp.p, c->perm.p, B.n, NG, B.T.NN, 1);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(Gq, tmp.p, c->G.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->G2.release();
   SDG_CATCH
 }
 
@@ -505,7 +568,7 @@ int sdg_stage_pass(sdg_ctx* c, int32_t stage, int32_t pass, int32_t part, void* 
   needFinal(c); needDevice(c);
   if (stage < 0 || stage >= c->nStages || pass < 0 || pass >= sdg_num_passes(c) || part < -1 || part > 1) throw std::runtime_error("bad stage/pass/part");
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  stageLaunch(c, stage, part, stream ? (cudaStream_t)stream : c->stream);
+  stageLaunch(c, stage, part, stream ? (cudaStream_t)stream : c->stream, c->phys.ns ? pass : 1);
   SDG_CATCH
 }
 
@@ -576,7 +639,9 @@ int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
     args.Uin = c->U[c->cur].p; args.Ulast = c->U[c->cur].p; args.Uout = c->U[a].p; args.mode = mode;
     args.aLast = 0.0; args.aCur = 0.0; args.bdt = 1.0;
     CUDA_OK(cudaMemsetAsync(c->U[a].p, 0, nd * sizeof(double), c->stream));
-    runStage(c, args, -1, c->stream);
+    args.Gvol = c->G.p; args.Gout = c->G.p;
+    if (c->phys.ns) runStage(c, args, -1, c->stream, 0);
+    runStage(c, args, -1, c->stream, 1);
     if (mode == 1) {
       seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->U[a].p, c->U[b].p, c->perm.p, B.n, c->NV, B.T.NN, 1);
       c->launches++;

@@ -94,3 +94,74 @@ def test_modal_state_roundtrip(built):
     U = O.get_state(t)
     S.set_state(t, U * 1.25)
     assert cases.rel_l2(S.get_state(t), U * 1.25) < 1e-14
+
+
+# ---- Navier-Stokes (BR1 / BR2) ----------------------------------------------------------------------------------------------
+NS = dict(model=1, transport=1, mu=1.4 * 0.2 / 200.0)   # examples/sphere_3d_cns.cpp:57-60 (Re = 200)
+
+
+def compare_ns(O, S, dt, nsteps, label):
+    t = S.types[0]
+    S.set_state(t, O.get_state(t))
+    Ro, qo = O.residual()[t]
+    go = O.gradient_at_quadrature(t)
+    gs = S.gradient_at_quadrature(t)
+    Rs, qs = S.residual()[t]
+    e_g = cases.rel_l2(gs, go)
+    assert e_g < 1e-11, f"{label}: total gradient at quadrature points rel-L2 {e_g:.3e}"
+    e_R, e_q = cases.rel_l2(Rs, Ro), cases.rel_l2(qs, qo)
+    assert e_R < TOL_RES, f"{label}: modal residual rel-L2 {e_R:.3e}"
+    assert e_q < TOL_RHS, f"{label}: dU/dt rel-L2 {e_q:.3e}"
+    err_o = O.step(dt, nsteps)
+    err_s = S.stepSolver(dt, nsteps)
+    e_u = cases.rel_l2(S.state_at_quadrature(t), O.state_at_quadrature(t))
+    assert e_u < TOL_STATE, f"{label}: state after {nsteps} steps rel-L2 {e_u:.3e}"
+    assert np.allclose(err_s, err_o, rtol=1e-8, atol=1e-300), f"{label}: relative_error_ {err_s} vs {err_o}"
+
+
+@pytest.mark.parametrize("visc,transport", [(2, 1), (1, 1), (2, 2)])
+@pytest.mark.parametrize("p", [2, 3])
+def test_periodic_2d_cns(built, visc, transport, p):
+    mesh = M.periodic_box(2, 6)
+    cfg = dict(NS, p=p, visc_flux=visc, transport=transport, mu=0.01)
+    O, S = cases.make_pair(cfg, mesh, cases.ic_density_wave([0.7, 0.3]))
+    compare_ns(O, S, 5e-4, 4, f"periodic_2d_cns visc{visc} transport{transport} p{p}")
+
+
+@pytest.mark.parametrize("visc", [1, 2])
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_periodic_3d_cns(built, visc, p):
+    mesh = M.periodic_box_fast(3, 4)
+    cfg = dict(NS, p=p, visc_flux=visc, mu=0.01)
+    O, S = cases.make_pair(cfg, mesh, cases.ic_density_wave([0.5, 0.3, 0.2]))
+    compare_ns(O, S, 5e-4, 3, f"periodic_3d_cns visc{visc} p{p}")
+
+
+@pytest.mark.parametrize("wall", [M.ADIABATIC_NONSLIP_WALL, M.ISOTHERMAL_NONSLIP_WALL, M.ADIABATIC_SLIP_WALL])
+def test_walls_2d_cns(built, wall):
+    """flat-plate style box: wall on the bottom (physical 3), far field elsewhere (examples/blasius_2d_cns.cpp family)"""
+    mesh = M.box(2, (6, 5), 0.0, 1.0, phys_bc={1: M.RIEMANN_FARFIELD, 2: M.RIEMANN_FARFIELD, 3: wall, 4: M.RIEMANN_FARFIELD})
+    cfg = dict(NS, p=3, visc_flux=2, mu=0.005)
+    ic = cases.ic_perturbed_freestream(0.3, 0.0, 2)
+    O, S = cases.make_pair(cfg, mesh, ic, cases.bc_freestream(0.3, 0.0, 2, wall_phys=(3,)))
+    compare_ns(O, S, 2e-4, 4, f"walls wall{wall}")
+
+
+def test_karman_like_quads_2d_cns(built):
+    """config 3 without its triangles: curved P3 quad ring around a cylinder, BR2, Sutherland, no-slip wall + far field"""
+    mesh = M.annulus(5, 16, r0=0.5, r1=4.0, geom_order=3, stretch=1.5, phys_bc={1: M.RIEMANN_FARFIELD, 2: M.ADIABATIC_NONSLIP_WALL})
+    cfg = dict(NS, p=3, visc_flux=2, transport=2)
+    ic = cases.ic_perturbed_freestream(0.2, 0.0, 2, amp=1e-3)
+    O, S = cases.make_pair(cfg, mesh, ic, cases.bc_freestream(0.2, 0.0, 2, wall_phys=(2,)))
+    dt = 0.3 * O.compute_dt(1.0)
+    compare_ns(O, S, dt, 3, "karman quads")
+
+
+def test_sphere_3d_cns(built):
+    """config 5 (scaled down): curved P3 hexahedra around a sphere, BR2, constant viscosity, no-slip wall + far field"""
+    mesh = M.cubed_sphere_shell(3, 3, r0=0.5, r1=4.0, geom_order=3)
+    cfg = dict(NS, p=3, visc_flux=2)
+    ic = cases.ic_perturbed_freestream(0.2, 0.0, 3, amp=1e-3)
+    O, S = cases.make_pair(cfg, mesh, ic, cases.bc_freestream(0.2, 0.0, 3, wall_phys=(2,)))
+    dt = 0.3 * O.compute_dt(1.0)
+    compare_ns(O, S, dt, 2, "sphere_3d_cns")
