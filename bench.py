@@ -90,14 +90,17 @@ def ic_config4(x):
 
 
 CFG = dict(p=3, model=0, conv_flux=2, rk=2)
+# north_star's Navier-Stokes throughput target: same cube, CompresibleNS, HLLC, BR2, constant mu = 1.4e-3
+CFG_NS = dict(p=3, model=1, conv_flux=2, rk=2, visc_flux=2, transport=1, mu=1.4 * 0.2 / 200.0)
+BYTES_PER_DOF_STAGE_NS = 144.0  # 3S + 2DS + 16 Nv D Naq per element = 46,080 B per P3 hexahedron
 
 
-def run_oracle(cells, p, steps, warmup, threads=None):
+def run_oracle(cells, p, steps, warmup, threads=None, base=None):
     """CPU restatement of the reference path on a cells^3 cube; returns (GDOF·stage/s, seconds, cores)."""
     import oracle
     from subrosadg_b200 import mesh as M
     mesh = M.periodic_box_fast(3, cells)
-    cfg = dict(CFG); cfg["p"] = p
+    cfg = dict(base or CFG); cfg["p"] = p
     O = oracle.Oracle(cfg, mesh, threads=threads)
     O.initialize(ic_config4)
     dt = 1e-4
@@ -119,14 +122,22 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cells", type=int, default=128)
     ap.add_argument("--p", type=int, default=3)
-    ap.add_argument("--cpu-cells", type=int, default=16)
+    ap.add_argument("--cpu-cells", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--model", default="euler", choices=["euler", "ns"], help="euler: BASELINE configs[3] (the metric's config); ns: north_star's NS-BR2 target cube")
     a = ap.parse_args()
+    base_cfg = CFG if a.model == "euler" else CFG_NS
+    bytes_per_dof = BYTES_PER_DOF_STAGE if a.model == "euler" else BYTES_PER_DOF_STAGE_NS
+    if a.model == "ns" and a.cells == 128:
+        a.cells = 96   # N = 96 so that the NS buffers fit comfortably
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
-    workload = f"periodic_3d_ceuler synthetic structured hex mesh {a.cells}^3, p={a.p}, CompresibleEuler, HLLC, SSPRK3 (BASELINE configs[3])"
+    if a.model == "euler":
+        workload = f"periodic_3d_ceuler synthetic structured hex mesh {a.cells}^3, p={a.p}, CompresibleEuler, HLLC, SSPRK3 (BASELINE configs[3])"
+    else:
+        workload = f"periodic cube of configs[3] with CompresibleNS, HLLC, BR2, constant mu=1.4e-3, {a.cells}^3 hexes, p={a.p}, SSPRK3 (north_star NS target)"
 
     if a.impl == "reference":
         if rank != 0:
@@ -134,7 +145,7 @@ def main():
         import __graft_entry__ as g
         g.build()
         # bounded sample of the same workload: a cpu_cells^3 cube of the same family; per-DOF rate is size independent
-        val, sec, cores = run_oracle(a.cpu_cells, a.p, max(1, a.steps), a.warmup)
+        val, sec, cores = run_oracle(a.cpu_cells, a.p, max(1, a.steps), a.warmup, base=base_cfg)
         sample = f"{a.cpu_cells}^3 hexes p={a.p}, {max(1, a.steps)} steps x 3 stages, {sec:.1f} s (CPU restatement of the reference algorithm incl. its dense M^-1 and gradient sweeps; the reference itself cannot be built here)"
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": 1e3 * sec / max(1, a.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -146,14 +157,14 @@ def main():
     import torch
     if world > 1:
         from subrosadg_b200 import parallel
-        parallel.bench_main(a, workload, METRIC, UNIT, BYTES_PER_DOF_STAGE, peaks, ClockSampler, ic_config4, CFG)
+        parallel.bench_main(a, workload, METRIC, UNIT, bytes_per_dof, peaks, ClockSampler, ic_config4, base_cfg)
         return
 
     from subrosadg_b200 import mesh as M
     from subrosadg_b200.solver import Solver
     torch.cuda.init()
     mesh = M.periodic_box_fast(3, a.cells)
-    cfg = dict(CFG); cfg["p"] = a.p
+    cfg = dict(base_cfg); cfg["p"] = a.p
     S = Solver(cfg, mesh, device=0)
     S.initializeSolver(ic_config4)
     t = S.types[0]
@@ -173,14 +184,15 @@ def main():
     value = dof * nst * a.steps / sec / 1e9
     hbm, how = peaks()
     stage_ms = ms / (a.steps * nst)
-    achieved = BYTES_PER_DOF_STAGE * dof / (stage_ms * 1e-3) / 1e9
+    achieved = bytes_per_dof * dof / (stage_ms * 1e-3) / 1e9
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": warmup, "ms_per_step": ms / a.steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload, "elements": sz.n, "scalar_dof": dof, "dt": dt, "l2": f"state {dof * 8 / 1e9:.2f} GB per buffer >> 126 MB L2 (inputs larger than L2, no flush needed)",
                       "relative_error": [float(x) for x in err]},
            "gpu_launches": int(launches), "clocks": ck,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                        "kernel": "eulerStageKernel<3,4,8,affine,HLLC>", "kernel_ms": stage_ms, "algorithmic_bytes_per_launch": BYTES_PER_DOF_STAGE * dof,
+                        "kernel": "eulerStageKernel<3,4,8,affine,HLLC>" if a.model == "euler" else "nsGradKernel<3,4,8,affine> + nsStageKernel<3,4,8,affine,HLLC> (one stage = both launches)",
+                        "kernel_ms": stage_ms, "algorithmic_bytes_per_launch": bytes_per_dof * dof,
                         "peak_source": how}}
 
     if not a.no_e2e:
@@ -203,7 +215,7 @@ def main():
     if not a.no_cpu:
         import __graft_entry__ as g
         g.build()
-        val, sec_c, cores = run_oracle(a.cpu_cells, a.p, 1, 0)
+        val, sec_c, cores = run_oracle(a.cpu_cells, a.p, 1, 0, base=base_cfg)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"{a.cpu_cells}^3 hexes p={a.p}, 1 step x 3 stages, {sec_c:.1f} s; CPU restatement of the reference algorithm (dense per-element M^-1, gradient sweeps included), OpenMP on all host cores"}
     print(json.dumps(out))
