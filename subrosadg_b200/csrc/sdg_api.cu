@@ -696,12 +696,13 @@ int sdg_set_halo_send(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* e
 int sdg_halo_pack(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
   SDG_TRY
   needFinal(c); needDevice(c); needType(c, type);
-  if (what != 0) throw std::runtime_error("gradient halo: Navier-Stokes only");
+  if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
   CUDA_OK(cudaSetDevice(c->cfg.device));
   if (c->nSend == 0) return 0;
-  const int stride = (int)c->elemDoubles();
+  const int stride = (int)c->elemDoubles() * (what == 1 ? c->D : 1);
+  const double* src = what == 1 ? c->G.p : c->U[c->latest].p;
   const int blocks = (int)std::min<size_t>(((size_t)c->nSend * stride + 255) / 256, 148 * 8);
-  haloPackKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(c->U[c->latest].p, c->sendList.p, c->nSend, stride, c->sendBuf.p);
+  haloPackKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(src, c->sendList.p, c->nSend, stride, c->sendBuf.p);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   SDG_CATCH
@@ -710,10 +711,12 @@ int sdg_halo_pack(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
 int sdg_halo_buffers_device(sdg_ctx* c, int32_t type, int32_t what, void** send, int64_t* send_doubles, void** recv, int64_t* recv_doubles) {
   SDG_TRY
   needFinal(c); needDevice(c); needType(c, type);
-  if (what != 0) throw std::runtime_error("gradient halo: Navier-Stokes only");
+  if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
   const BlockPlan& B = c->plan.blk;
-  *send = c->sendBuf.p; *send_doubles = (int64_t)c->nSend * (int64_t)c->elemDoubles();
-  *recv = c->U[c->latest].p + (size_t)B.nOwned * c->elemDoubles(); *recv_doubles = (int64_t)B.nGhost * (int64_t)c->elemDoubles();
+  const int64_t per = (int64_t)c->elemDoubles() * (what == 1 ? c->D : 1);
+  double* base = what == 1 ? c->G.p : c->U[c->latest].p;
+  *send = c->sendBuf.p; *send_doubles = (int64_t)c->nSend * per;
+  *recv = base + (size_t)B.nOwned * per; *recv_doubles = (int64_t)B.nGhost * per;
   SDG_CATCH
 }
 

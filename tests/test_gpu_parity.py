@@ -165,3 +165,28 @@ def test_sphere_3d_cns(built):
     O, S = cases.make_pair(cfg, mesh, ic, cases.bc_freestream(0.2, 0.0, 3, wall_phys=(2,)))
     dt = 0.3 * O.compute_dt(1.0)
     compare_ns(O, S, dt, 2, "sphere_3d_cns")
+
+
+# ---- element-block partitions (multi-rank path on one device) -----------------------------------------------------------------
+@pytest.mark.parametrize("dim,n,world,model", [(2, 8, 2, {}), (3, 6, 3, {}), (3, 4, 2, dict(NS, visc_flux=2, mu=0.01)), (2, 8, 4, dict(NS, visc_flux=1, mu=0.01))])
+def test_two_contexts_match_single_context(built, dim, n, world, model):
+    """`world` contexts with ghost elements, pack kernel and part-0 / part-1 launches (the N>1 path of bench.py, with
+    device copies in place of NCCL) must reproduce the single-context run element for element."""
+    from subrosadg_b200.parallel import InProcessCluster
+    from subrosadg_b200.solver import Solver
+    mesh = M.periodic_box_fast(dim, n)
+    cfg = dict(p=3 if dim == 2 else 2, conv_flux=2, rk=2)
+    cfg.update(model)
+    vel = [0.7, 0.3] if dim == 2 else [0.5, 0.3, 0.2]
+    ic = cases.ic_density_wave(vel)
+    S = Solver(dict(cfg), mesh, device=0)
+    S.initializeSolver(ic)
+    C = InProcessCluster(dict(cfg), mesh, world, device=0)
+    C.initializeSolver(ic)
+    t = S.types[0]
+    assert abs(C.calculateDeltaTime(1.0) - S.calculateDeltaTime(1.0)) == 0.0
+    err_s = S.stepSolver(5e-4, 3)
+    err_c = C.stepSolver(5e-4, 3)
+    a, b = C.state_at_quadrature(), S.state_at_quadrature(t)
+    assert cases.rel_l2(a, b) < 1e-14, f"partitioned vs single context: {cases.rel_l2(a, b):.3e}"
+    assert np.allclose(err_c, err_s, rtol=1e-11, atol=1e-300)

@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Per-CUDA-source-line summary of `ncu -i X.ncu-rep --page source --csv --print-source cuda,sass`:
 stall samples, instructions, shared-memory wavefronts (actual / ideal), global sectors, top stall reasons.
-usage: python tools/ncu_src.py dump.csv [top_n] [kernel_instance]"""
+usage: python tools/ncu_src.py dump.csv [top_n] [kernel_instance] [function-name substring]"""
 import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 want = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+filt = sys.argv[4] if len(sys.argv) > 4 else ""
 tables, cur = [], None
 for r in rows:
     if r and r[0] == "File Path":
@@ -20,7 +21,7 @@ for t in tables:
     fn = t["rows"][0][1] if t["rows"] and t["rows"][0][0] == "Function Name" else "?"
     hdr = t["rows"][1] if len(t["rows"]) > 1 else []
     col = {h: i for i, h in enumerate(hdr)}
-    if "Line No" not in col:
+    if "Line No" not in col or filt not in fn:
         continue
     if (fn, t["file"]) in seen:
         kidx += 1
