@@ -16,86 +16,124 @@
 // face-normal lines, i.e.  G_f(node) = invjw(node) · l_{a(node)}(±1) · [n ⊗ ½(U_R−U_L) |J|w](face point of that line).
 // It is rank one per face point, so it is never stored: pass R rebuilds  trace_f(G_vol + G_f)  and  G_vol + Σ_f G_f  from
 // the face jumps it needs anyway.  The 6 extra M^-1 applications and the Nf coefficient blocks of the reference disappear.
+//
+// v2 (round 1): the chunk's states / gradients / metric and face records arrive by TMA bulk copies; the face-trace gathers
+// walk the normal line in a per-lane rotated order (bank-conflict free for N = 4); the volume fluxes of all D directions
+// are written once into the (dead) gradient tile, so the pass needs one barrier instead of D; affine meshes keep one
+// normal per (element, face) and a precomputed lifting table, so no division is left in the face loop besides 1/rho.
 #pragma once
 #include "tensor_kernels.cuh"
 
 namespace sdg {
 
-template <int D, int N, int K>
+template <int D, int N, int K, bool AFFINE, bool WITHG>
 struct NsLayout {
   static constexpr int NV = D + 2, NG = NV * D, NN = Pow<N, D>::v, NQF = NN / N, NF = 2 * D, NAQ = NF * NQF;
-  static constexpr int oU = 0;                          // [K][NV][NN]
-  static constexpr int oG = oU + K * NV * NN;           // [K][NG][NN]   gradient field of the chunk's own elements (pass R)
-  static constexpr int oF = oG + K * NG * NN;           // [K][NV][NN]   contravariant flux of one direction
-  static constexpr int oFlux = oF + K * NV * NN;        // [K][NV][NAQ]  flux slots (pass G: {U} |J|w slots)
-  static constexpr int oB = oFlux + K * NV * NAQ;       // [K][NV][NAQ]  jump slots  ½(U_R−U_L)|J|w  /  (U_b−U_L)|J|w
-  static constexpr int oN = oB + K * NV * NAQ;          // [K][D][NAQ]   face normal at every slot
-  static constexpr int oTab = oN + K * D * NAQ;
-  static constexpr int nTabD = 2 * N * N + 2 * N + NN + NQF;
-  static constexpr int nDoubles = oTab + nTabD;
+  static constexpr int REC = (D * D + 2) & ~1;
+  static constexpr int MAXF = K * NF;
+  static constexpr int oU = 0;                                      // [K][NV][NN]
+  static constexpr int oG = oU + K * NV * NN;                       // [K][NG][NN]   gradient tile (pass R), later the volume fluxes
+  static constexpr int oFlux = oG + (WITHG ? K * NG * NN : 0);      // [K][NV][NAQ]  flux slots (pass G: {U} |J|w slots)
+  static constexpr int oB = oFlux + K * NV * NAQ;                   // [K][NV][NAQ]  jump slots  ½(U_R−U_L)|J|w  /  (U_b−U_L)|J|w
+  static constexpr int oN = oB + K * NV * NAQ;                      // affine: [K][NF][D]; curved: [K][D][NAQ]
+  static constexpr int nN = AFFINE ? ((K * NF * D + 1) & ~1) : K * D * NAQ;
+  static constexpr int oTab = oN + nN;                              // Dm, K1, Lend, Wq, InvWq, Wf, LiftC
+  static constexpr int nTab = (2 * N * N + 2 * N + 2 * NN + NQF + NF * NQF + 1) & ~1;
+  static constexpr int oGeoE = oTab + nTab;                         // affine: [K][REC]
+  static constexpr int oInvDet = oGeoE + (AFFINE ? K * REC : 0);    // affine: [K]
+  static constexpr int oCf = oInvDet + ((K + 1) & ~1);              // affine: [MAXF][kCF]
+  static constexpr int oRec = oCf + (AFFINE ? MAXF * kCF : 0);      // [MAXF] int4
+  static constexpr int nDoubles = oRec + MAXF * 2;
   static constexpr int nBytesTab = NF * NQF + 4 * NQF + NF * NN;
   static constexpr size_t bytes = sizeof(double) * nDoubles + ((nBytesTab + 15) / 16) * 16;
   static constexpr int ITERS = (K * NN + kThreads - 1) / kThreads;
 };
 
-template <int D, int N, int K>
+template <int D, int N, int K, bool AFFINE, bool WITHG>
 struct NsShared {
-  using L = NsLayout<D, N, K>;
-  double *sU, *sG, *sF, *sFlux, *sB, *sN, *sDm, *sLend, *sK1, *sWq, *sWf;
+  using L = NsLayout<D, N, K, AFFINE, WITHG>;
+  double *sU, *sG, *sFlux, *sB, *sN, *sDm, *sK1, *sLend, *sWq, *sInvWq, *sWf, *sLiftC, *sGeoE, *sInvDet, *sCf;
+  const int4* sRec;
   unsigned char *sFaceBase, *sSeq, *sNodePt;
   __device__ __forceinline__ void carve(double* smem) {
-    sU = smem + L::oU; sG = smem + L::oG; sF = smem + L::oF; sFlux = smem + L::oFlux; sB = smem + L::oB; sN = smem + L::oN;
-    sDm = smem + L::oTab; sLend = sDm + N * N; sK1 = sLend + 2 * N; sWq = sK1 + N * N; sWf = sWq + L::NN;
+    sU = smem + L::oU; sG = smem + L::oG; sFlux = smem + L::oFlux; sB = smem + L::oB; sN = smem + L::oN;
+    sDm = smem + L::oTab; sK1 = sDm + N * N; sLend = sK1 + N * N; sWq = sLend + 2 * N; sInvWq = sWq + L::NN; sWf = sInvWq + L::NN; sLiftC = sWf + L::NQF;
+    sGeoE = smem + L::oGeoE; sInvDet = smem + L::oInvDet; sCf = smem + L::oCf;
+    sRec = reinterpret_cast<const int4*>(smem + L::oRec);
     sFaceBase = reinterpret_cast<unsigned char*>(smem + L::nDoubles); sSeq = sFaceBase + L::NF * L::NQF; sNodePt = sSeq + 4 * L::NQF;
   }
   __device__ __forceinline__ void loadTables(const TensorDev& T, int tid) {
     for (int i = tid; i < N * N; i += kThreads) { sDm[i] = T.Dm[i]; sK1[i] = T.K1[i]; }
     for (int i = tid; i < 2 * N; i += kThreads) sLend[i] = T.Lend[i];
-    for (int i = tid; i < L::NN; i += kThreads) sWq[i] = T.wq[i];
+    for (int i = tid; i < L::NN; i += kThreads) { const double w = T.wq[i]; sWq[i] = w; sInvWq[i] = 1.0 / w; }
     for (int i = tid; i < L::NQF; i += kThreads) sWf[i] = T.wf[i];
-    for (int i = tid; i < L::NF * L::NQF; i += kThreads) sFaceBase[i] = (unsigned char)T.faceBase[i];
+    for (int i = tid; i < L::NF * L::NQF; i += kThreads) {
+      // trace of the rank-one BR2 lift at its own face, without the 1/detJ:  Σ_a l_a(±1)^2 / w(node(a, j))
+      const int f = i / L::NQF, dn = faceDirOf<D>(f), side = faceSideOf<D>(f), base = T.faceBase[i], st = strideOf<N, D>(dn);
+      double s = 0.0;
+      for (int a = 0; a < N; a++) { const double l = T.Lend[side * N + a]; s += l * l / T.wq[base + a * st]; }
+      sLiftC[i] = s;
+      sFaceBase[i] = (unsigned char)base;
+    }
     for (int i = tid; i < 4 * L::NQF; i += kThreads) sSeq[i] = (unsigned char)T.seq[i];
     for (int i = tid; i < L::NF * L::NN; i += kThreads) sNodePt[i] = T.nodeFacePt[i];
   }
 };
 
-// face geometry at one face point: unit normal (outward from the LEFT parent) and |J|·w
-template <int D, int NQF, bool AFFINE>
-__device__ __forceinline__ void faceGeometryAt(const StageArgs& A, int faceId, int j, const double* sWf, double* n, double& jw) {
-  if constexpr (AFFINE) {
-    const double* g = A.geoF + (size_t)faceId * (D + 1);
+// entry [dd][c] of (J^T)^-1 detJ w at node q of element e (curved meshes: read from HBM / L2)
+template <int D, int NN>
+__device__ __forceinline__ double metricCurved(const StageArgs& A, int e, int q, int dd, int c) {
+  return __ldg(A.geoE + ((size_t)e * (D * D) + dd * D + c) * NN + q);
+}
+// lifting factor of a face point on curved meshes:  Σ_a l_a(±1)^2 / (detJ w)(node(a, j))
+template <int D, int N, int NN>
+__device__ __forceinline__ double liftTraceFactorCurved(const StageArgs& A, int e, int base, int stride, const double* lend) {
+  double s = 0.0;
 #pragma unroll
-    for (int d = 0; d < D; d++) n[d] = __ldg(g + d);
-    jw = __ldg(g + D) * sWf[j];
-  } else {
-    const double* g = A.geoF + (size_t)faceId * (D + 1) * NQF + j;
-#pragma unroll
-    for (int d = 0; d < D; d++) n[d] = __ldg(g + d * NQF);
-    jw = __ldg(g + D * NQF);
+  for (int a = 0; a < N; a++) s += lend[a] * lend[a] * __ldg(A.invjw + (size_t)e * NN + base + a * stride);
+  return s;
+}
+
+// stages the chunk-owned contiguous ranges with TMA bulk copies; returns after the data has landed
+template <class SH, int D, int N, int K, bool AFFINE, bool WITHG>
+__device__ __forceinline__ void nsStageIn(const StageArgs& A, SH& S, unsigned long long* mbar, int tid, int chunk, int e0, int ne, int f0, int nfc) {
+  using L = NsLayout<D, N, K, AFFINE, WITHG>;
+  constexpr int NV = L::NV, NG = L::NG, NN = L::NN;
+  const unsigned bytesU = (unsigned)(ne * NV * NN * sizeof(double));
+  const unsigned bytesG = WITHG ? (unsigned)(ne * NG * NN * sizeof(double)) : 0u;
+  const bool bulkU = (bytesU & 15u) == 0, bulkG = (bytesG & 15u) == 0;
+  if (tid == 0) mbarInit(mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned total = (unsigned)(nfc * sizeof(int4)) + (bulkU ? bytesU : 0u) + (bulkG ? bytesG : 0u);
+    if constexpr (AFFINE) total += (unsigned)(ne * L::REC * sizeof(double)) + (unsigned)(nfc * kCF * sizeof(double));
+    mbarExpectTx(mbar, total);
+    if (bulkU) bulkLoad(S.sU, A.Uin + (size_t)e0 * NV * NN, bytesU, mbar);
+    if constexpr (WITHG) { if (bulkG) bulkLoad(S.sG, A.Gvol + (size_t)e0 * NG * NN, bytesG, mbar); }
+    bulkLoad(const_cast<int4*>(S.sRec), A.faceRec + f0, (unsigned)(nfc * sizeof(int4)), mbar);
+    if constexpr (AFFINE) {
+      bulkLoad(S.sGeoE, A.geoE + (size_t)e0 * L::REC, (unsigned)(ne * L::REC * sizeof(double)), mbar);
+      bulkLoad(S.sCf, A.cfGeo + (size_t)f0 * kCF, (unsigned)(nfc * kCF * sizeof(double)), mbar);
+    }
   }
-}
-// 1 / (detJ w) at node q of element e (the diagonal inverse mass matrix, Geometry.cpp:88-100 in the collocation basis)
-template <int D, int NN, bool AFFINE>
-__device__ __forceinline__ double invJwAt(const StageArgs& A, int e, int q, const double* sWq) {
-  if constexpr (AFFINE) return 1.0 / (__ldg(A.geoE + (size_t)e * ((D * D + 2) & ~1) + D * D) * sWq[q]);
-  else return __ldg(A.invjw + (size_t)e * NN + q);
-}
-// entry [dd][c] of (J^T)^-1 detJ w at node q of element e
-template <int D, int NN, bool AFFINE>
-__device__ __forceinline__ double metricAt(const StageArgs& A, int e, int q, int dd, int c, const double* sWq) {
-  if constexpr (AFFINE) return __ldg(A.geoE + (size_t)e * ((D * D + 2) & ~1) + dd * D + c) * sWq[q];
-  else return __ldg(A.geoE + ((size_t)e * (D * D) + dd * D + c) * NN + q);
+  if (!bulkU) { const double* src = A.Uin + (size_t)e0 * NV * NN; for (int i = tid; i < ne * NV * NN; i += kThreads) S.sU[i] = src[i]; }
+  if constexpr (WITHG) { if (!bulkG) { const double* src = A.Gvol + (size_t)e0 * NG * NN; for (int i = tid; i < ne * NG * NN; i += kThreads) S.sG[i] = src[i]; } }
+  S.loadTables(*A.tab, tid);
+  mbarWait(mbar, 0);
+  if constexpr (AFFINE) { if (tid < ne) S.sInvDet[tid] = 1.0 / S.sGeoE[tid * L::REC + D * D]; }
+  __syncthreads();
 }
 
 // =====================================================================================================================
 // pass G
 // =====================================================================================================================
 template <int D, int N, int K, bool AFFINE>
-__global__ void __launch_bounds__(kThreads, 1) nsGradKernel(const __grid_constant__ StageArgs A) {
-  using L = NsLayout<D, N, K>;
-  constexpr int NV = L::NV, NG = L::NG, NN = L::NN, NQF = L::NQF, NF = L::NF, NAQ = L::NAQ, ITERS = L::ITERS;
+__global__ void __launch_bounds__(kThreads, 2) nsGradKernel(const __grid_constant__ StageArgs A) {
+  using L = NsLayout<D, N, K, AFFINE, false>;
+  constexpr int NV = L::NV, NG = L::NG, NN = L::NN, NQF = L::NQF, NF = L::NF, NAQ = L::NAQ;
   extern __shared__ __align__(16) double smem[];
-  NsShared<D, N, K> S; S.carve(smem);
+  __shared__ __align__(8) unsigned long long mbar;
+  NsShared<D, N, K, AFFINE, false> S; S.carve(smem);
   const int tid = threadIdx.x;
   const int chunk = A.chunkList ? A.chunkList[blockIdx.x] : blockIdx.x;
   const int e0 = chunk * K;
@@ -103,30 +141,36 @@ __global__ void __launch_bounds__(kThreads, 1) nsGradKernel(const __grid_constan
   const int nNodes = ne * NN;
   const Phys<0> ph(A.phys);
   const bool br1 = A.phys.visc == kBR1;
-  {
-    const double* src = A.Uin + (size_t)e0 * NV * NN;
-    for (int i = tid; i < ne * NV * NN; i += kThreads) S.sU[i] = src[i];
-  }
-  S.loadTables(*A.tab, tid);
-  __syncthreads();
+  const int f0 = A.chunkFaceOff[chunk], nfc = A.chunkFaceOff[chunk + 1] - f0;
+  nsStageIn<decltype(S), D, N, K, AFFINE, false>(A, S, &mbar, tid, chunk, e0, ne, f0, nfc);
 
   // ---- G2: {U} n |J|w (volume-gradient flux) and ½(U_R−U_L) n |J|w (interface-gradient flux) at the face points -----------
-  const int f0 = A.chunkFaceOff[chunk], nfc = A.chunkFaceOff[chunk + 1] - f0;
   for (int fp = tid; fp < nfc * NQF; fp += kThreads) {
     const int fi = fp / NQF, j = fp - fi * NQF;
-    const int4 rec = __ldg(A.faceRec + f0 + fi);
+    const int4 rec = S.sRec[fi];
     const int eL = rec.x, eR = rec.y, faceId = rec.z;
     const int lfL = rec.w & 15, lfR = (rec.w >> 4) & 15, rot = (rec.w >> 8) & 15, bc = (rec.w >> 12) & 15;
+    const int rl = (j / N + fi) % N;
     double n[D], jw;
-    faceGeometryAt<D, NQF, AFFINE>(A, faceId, j, S.sWf, n, jw);
+    if constexpr (AFFINE) {
+      const double* g = S.sCf + fi * kCF;
+#pragma unroll
+      for (int d = 0; d < D; d++) n[d] = g[d];
+      jw = g[D] * S.sWf[j];
+    } else {
+      const double* g = A.geoF + (size_t)faceId * (D + 1) * NQF + j;
+#pragma unroll
+      for (int d = 0; d < D; d++) n[d] = __ldg(g + d * NQF);
+      jw = __ldg(g + D * NQF);
+    }
     double consL[NV], avg[NV], jump[NV];
     const int locL = eL - e0, locR = eR - e0;
     const bool inL = locL >= 0 && locL < ne, inR = eR >= 0 && locR >= 0 && locR < ne;
     {
       const int dn = faceDirOf<D>(lfL), side = faceSideOf<D>(lfL);
       const int base = S.sFaceBase[lfL * NQF + j], stride = strideOf<N, D>(dn);
-      if (inL) lineTrace<N, NV, NN>(S.sU + locL * NV * NN, base, stride, S.sLend + side * N, consL);
-      else lineTrace<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, S.sLend + side * N, consL);
+      if (inL) lineTraceRot<N, NV, NN>(S.sU + locL * NV * NN, base, stride, S.sLend + side * N, rl, consL);
+      else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, S.sLend + side * N, rl, consL);
     }
     int jr = j;
     if (eR >= 0) {
@@ -134,8 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1) nsGradKernel(const __grid_constan
       jr = S.sSeq[rot * NQF + j];
       const int dn = faceDirOf<D>(lfR), side = faceSideOf<D>(lfR);
       const int base = S.sFaceBase[lfR * NQF + jr], stride = strideOf<N, D>(dn);
-      if (inR) lineTrace<N, NV, NN>(S.sU + locR * NV * NN, base, stride, S.sLend + side * N, consR);
-      else lineTrace<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, S.sLend + side * N, consR);
+      if (inR) lineTraceRot<N, NV, NN>(S.sU + locR * NV * NN, base, stride, S.sLend + side * N, rl, consR);
+      else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, S.sLend + side * N, rl, consR);
 #pragma unroll
       for (int v = 0; v < NV; v++) { avg[v] = (consL[v] + consR[v]) / 2.0; jump[v] = (consR[v] - consL[v]) / 2.0; }  // ViscousFlux.cpp:33-56
     } else {
@@ -150,15 +194,29 @@ __global__ void __launch_bounds__(kThreads, 1) nsGradKernel(const __grid_constan
       const int slot = lfL * NQF + j;
 #pragma unroll
       for (int v = 0; v < NV; v++) { S.sFlux[(locL * NV + v) * NAQ + slot] = avg[v] * jw; S.sB[(locL * NV + v) * NAQ + slot] = jump[v] * jw; }
+      if constexpr (AFFINE) {
+        if (j == 0) {
 #pragma unroll
-      for (int d = 0; d < D; d++) S.sN[(locL * D + d) * NAQ + slot] = n[d];
+          for (int d = 0; d < D; d++) S.sN[(locL * NF + lfL) * D + d] = n[d];
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; d++) S.sN[(locL * D + d) * NAQ + slot] = n[d];
+      }
     }
     if (inR) {  // right parent: volume-gradient flux changes sign, interface-gradient flux does not (SpatialDiscrete.cpp:885-906)
       const int slot = lfR * NQF + jr;
 #pragma unroll
       for (int v = 0; v < NV; v++) { S.sFlux[(locR * NV + v) * NAQ + slot] = -avg[v] * jw; S.sB[(locR * NV + v) * NAQ + slot] = jump[v] * jw; }
+      if constexpr (AFFINE) {
+        if (j == 0) {
 #pragma unroll
-      for (int d = 0; d < D; d++) S.sN[(locR * D + d) * NAQ + slot] = n[d];
+          for (int d = 0; d < D; d++) S.sN[(locR * NF + lfR) * D + d] = n[d];
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; d++) S.sN[(locR * D + d) * NAQ + slot] = n[d];
+      }
     }
   }
   __syncthreads();
@@ -176,18 +234,38 @@ __global__ void __launch_bounds__(kThreads, 1) nsGradKernel(const __grid_constan
     for (int dd = 0; dd < D; dd++) {
       const int st = strideOf<N, D>(dd);
       const int id = (q / st) % N, qb = q - id * st;
+      if constexpr (AFFINE) {
+        // metric = g[dd][c] * w(node): contract the line first, then the D x D metric
+        double t[NV];
 #pragma unroll
-      for (int a = 0; a < N; a++) {
-        const int qa = qb + a * st;
-        const double dcoef = S.sDm[a * N + id];
-        double u[NV];
+        for (int v = 0; v < NV; v++) t[v] = 0.0;
 #pragma unroll
-        for (int v = 0; v < NV; v++) u[v] = S.sU[(el * NV + v) * NN + qa];
+        for (int a = 0; a < N; a++) {
+          const int qa = qb + a * st;
+          const double dw = S.sDm[a * N + id] * S.sWq[qa];
+#pragma unroll
+          for (int v = 0; v < NV; v++) t[v] += dw * S.sU[(el * NV + v) * NN + qa];
+        }
 #pragma unroll
         for (int c = 0; c < D; c++) {
-          const double mc = metricAt<D, NN, AFFINE>(A, e, qa, dd, c, S.sWq) * dcoef;
+          const double g = S.sGeoE[el * L::REC + dd * D + c];
 #pragma unroll
-          for (int v = 0; v < NV; v++) G[v][c] -= mc * u[v];
+          for (int v = 0; v < NV; v++) G[v][c] -= g * t[v];
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < N; a++) {
+          const int qa = qb + a * st;
+          const double dcoef = S.sDm[a * N + id];
+          double u[NV];
+#pragma unroll
+          for (int v = 0; v < NV; v++) u[v] = S.sU[(el * NV + v) * NN + qa];
+#pragma unroll
+          for (int c = 0; c < D; c++) {
+            const double mc = metricCurved<D, NN>(A, e, qa, dd, c) * dcoef;
+#pragma unroll
+            for (int v = 0; v < NV; v++) G[v][c] -= mc * u[v];
+          }
         }
       }
     }
@@ -198,16 +276,21 @@ __global__ void __launch_bounds__(kThreads, 1) nsGradKernel(const __grid_constan
       const int id = (q / st) % N;
       const double cf = S.sLend[side * N + id];
       const int slot = f * NQF + S.sNodePt[f * NN + q];
+      double nn[D];
+#pragma unroll
+      for (int c = 0; c < D; c++) nn[c] = AFFINE ? S.sN[(el * NF + f) * D + c] : S.sN[(el * D + c) * NAQ + slot];
 #pragma unroll
       for (int v = 0; v < NV; v++) {
         double a = S.sFlux[(el * NV + v) * NAQ + slot];
         if (br1) a += S.sB[(el * NV + v) * NAQ + slot];   // BR1: single lifting block, G = G_vol + G_lift (TimeIntegration.cpp:208-215)
         a *= cf;
 #pragma unroll
-        for (int c = 0; c < D; c++) G[v][c] += a * S.sN[(el * D + c) * NAQ + slot];
+        for (int c = 0; c < D; c++) G[v][c] += a * nn[c];
       }
     }
-    const double ijw = invJwAt<D, NN, AFFINE>(A, e, q, S.sWq);
+    double ijw;
+    if constexpr (AFFINE) ijw = S.sInvDet[el] * S.sInvWq[q];
+    else ijw = __ldg(A.invjw + (size_t)e * NN + q);
     double* out = A.Gout + ((size_t)e * NG) * NN + q;
 #pragma unroll
     for (int v = 0; v < NV; v++)
@@ -216,24 +299,16 @@ __global__ void __launch_bounds__(kThreads, 1) nsGradKernel(const __grid_constan
   }
 }
 
-// lifting factor of a face point:  Σ_a l_a(±1)^2 / (detJ w)(node(a, j))   (trace of the rank-one BR2 lift at its own face)
-template <int D, int N, int NN, bool AFFINE>
-__device__ __forceinline__ double liftTraceFactor(const StageArgs& A, int e, int base, int stride, const double* lend, const double* sWq) {
-  double s = 0.0;
-#pragma unroll
-  for (int a = 0; a < N; a++) s += lend[a] * lend[a] * invJwAt<D, NN, AFFINE>(A, e, base + a * stride, sWq);
-  return s;
-}
-
 // =====================================================================================================================
 // pass R
 // =====================================================================================================================
 template <int D, int N, int K, bool AFFINE, int PH>
-__global__ void __launch_bounds__(kThreads, 1) nsStageKernel(const __grid_constant__ StageArgs A) {
-  using L = NsLayout<D, N, K>;
+__global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_constant__ StageArgs A) {
+  using L = NsLayout<D, N, K, AFFINE, true>;
   constexpr int NV = L::NV, NG = L::NG, NN = L::NN, NQF = L::NQF, NF = L::NF, NAQ = L::NAQ, ITERS = L::ITERS;
   extern __shared__ __align__(16) double smem[];
-  NsShared<D, N, K> S; S.carve(smem);
+  __shared__ __align__(8) unsigned long long mbar;
+  NsShared<D, N, K, AFFINE, true> S; S.carve(smem);
   const int tid = threadIdx.x;
   const int chunk = A.chunkList ? A.chunkList[blockIdx.x] : blockIdx.x;
   const int e0 = chunk * K;
@@ -241,78 +316,108 @@ __global__ void __launch_bounds__(kThreads, 1) nsStageKernel(const __grid_consta
   const int nNodes = ne * NN;
   const Phys<PH> ph(A.phys);
   const bool br2 = A.phys.visc == kBR2;
-  {
-    const double* src = A.Uin + (size_t)e0 * NV * NN;
-    for (int i = tid; i < ne * NV * NN; i += kThreads) S.sU[i] = src[i];
-    const double* gsrc = A.Gvol + (size_t)e0 * NG * NN;
-    for (int i = tid; i < ne * NG * NN; i += kThreads) S.sG[i] = gsrc[i];
+  const int f0 = A.chunkFaceOff[chunk], nfc = A.chunkFaceOff[chunk + 1] - f0;
+  if (A.mode == 0 && A.aLast != 0.0) {   // U_last is consumed at the very end: pull its lines into L2 now
+    const char* p = reinterpret_cast<const char*>(A.Ulast + (size_t)e0 * NV * NN);
+    const int bytes = ne * NV * NN * (int)sizeof(double);
+    for (int o = tid * 128; o < bytes; o += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
   }
-  S.loadTables(*A.tab, tid);
-  __syncthreads();
+  nsStageIn<decltype(S), D, N, K, AFFINE, true>(A, S, &mbar, tid, chunk, e0, ne, f0, nfc);
 
   // ---- R2: Riemann flux minus averaged viscous normal flux at the face points ------------------------------------------------------
-  const int f0 = A.chunkFaceOff[chunk], nfc = A.chunkFaceOff[chunk + 1] - f0;
   for (int fp = tid; fp < nfc * NQF; fp += kThreads) {
     const int fi = fp / NQF, j = fp - fi * NQF;
-    const int4 rec = __ldg(A.faceRec + f0 + fi);
+    const int4 rec = S.sRec[fi];
     const int eL = rec.x, eR = rec.y, faceId = rec.z;
     const int lfL = rec.w & 15, lfR = (rec.w >> 4) & 15, rot = (rec.w >> 8) & 15, bc = (rec.w >> 12) & 15;
-    double n[D], jw;
-    faceGeometryAt<D, NQF, AFFINE>(A, faceId, j, S.sWf, n, jw);
-    double consL[NV], compL[D + 3], gL[NG], jump[NV], Fn[NV];
+    const int rl = (j / N + fi) % N;
+    double n[D], jw, invDetL = 0.0, invDetR = 0.0;
+    if constexpr (AFFINE) {
+      const double* g = S.sCf + fi * kCF;
+#pragma unroll
+      for (int d = 0; d < D; d++) n[d] = g[d];
+      jw = g[D] * S.sWf[j];
+      invDetL = g[D + 1]; invDetR = g[D + 2];
+    } else {
+      const double* g = A.geoF + (size_t)faceId * (D + 1) * NQF + j;
+#pragma unroll
+      for (int d = 0; d < D; d++) n[d] = __ldg(g + d * NQF);
+      jw = __ldg(g + D * NQF);
+    }
     const int locL = eL - e0, locR = eR - e0;
     const bool inL = locL >= 0 && locL < ne, inR = eR >= 0 && locR >= 0 && locR < ne;
-    double lamL;
-    {
-      const int dn = faceDirOf<D>(lfL), side = faceSideOf<D>(lfL);
-      const int base = S.sFaceBase[lfL * NQF + j], stride = strideOf<N, D>(dn);
-      if (inL) { lineTrace<N, NV, NN>(S.sU + locL * NV * NN, base, stride, S.sLend + side * N, consL); lineTrace<N, NG, NN>(S.sG + locL * NG * NN, base, stride, S.sLend + side * N, gL); }
-      else { lineTrace<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, S.sLend + side * N, consL); lineTrace<N, NG, NN>(A.Gvol + (size_t)eL * NG * NN, base, stride, S.sLend + side * N, gL); }
-      lamL = br2 ? liftTraceFactor<D, N, NN, AFFINE>(A, eL, base, stride, S.sLend + side * N, S.sWq) : 0.0;
-    }
+    const int dnL = faceDirOf<D>(lfL), sideL = faceSideOf<D>(lfL);
+    const int baseL = S.sFaceBase[lfL * NQF + j], strideL = strideOf<N, D>(dnL);
+    double consL[NV], compL[D + 3], jump[NV], Fn[NV], va[NV];
+    if (inL) lineTraceRot<N, NV, NN>(S.sU + locL * NV * NN, baseL, strideL, S.sLend + sideL * N, rl, consL);
+    else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, baseL, strideL, S.sLend + sideL * N, rl, consL);
     const double irL = compFromCons<D>(ph, consL, compL);
+    double lamL = 0.0;
+    if (br2) {
+      if constexpr (AFFINE) lamL = S.sLiftC[lfL * NQF + j] * invDetL;
+      else lamL = liftTraceFactorCurved<D, N, NN>(A, eL, baseL, strideL, S.sLend + sideL * N);
+    }
     int jr = j;
     if (eR >= 0) {
-      double consR[NV], compR[D + 3], gR[NG];
+      double consR[NV], compR[D + 3];
       jr = S.sSeq[rot * NQF + j];
-      const int dn = faceDirOf<D>(lfR), side = faceSideOf<D>(lfR);
-      const int base = S.sFaceBase[lfR * NQF + jr], stride = strideOf<N, D>(dn);
-      if (inR) { lineTrace<N, NV, NN>(S.sU + locR * NV * NN, base, stride, S.sLend + side * N, consR); lineTrace<N, NG, NN>(S.sG + locR * NG * NN, base, stride, S.sLend + side * N, gR); }
-      else { lineTrace<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, S.sLend + side * N, consR); lineTrace<N, NG, NN>(A.Gvol + (size_t)eR * NG * NN, base, stride, S.sLend + side * N, gR); }
+      const int dnR = faceDirOf<D>(lfR), sideR = faceSideOf<D>(lfR);
+      const int baseR = S.sFaceBase[lfR * NQF + jr], strideR = strideOf<N, D>(dnR);
+      if (inR) lineTraceRot<N, NV, NN>(S.sU + locR * NV * NN, baseR, strideR, S.sLend + sideR * N, rl, consR);
+      else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, baseR, strideR, S.sLend + sideR * N, rl, consR);
       const double irR = compFromCons<D>(ph, consR, compR);
 #pragma unroll
       for (int v = 0; v < NV; v++) jump[v] = (consR[v] - consL[v]) / 2.0 * jw;
-      if (br2) {  // trace of (G_vol + G_f) on both sides, VariableConvertor.cpp:674-688
-        const double lamR = liftTraceFactor<D, N, NN, AFFINE>(A, eR, base, stride, S.sLend + side * N, S.sWq);
-#pragma unroll
-        for (int v = 0; v < NV; v++)
-#pragma unroll
-          for (int c = 0; c < D; c++) { gL[v * D + c] += lamL * n[c] * jump[v]; gR[v * D + c] += lamR * n[c] * jump[v]; }
-      }
-      double pL[NG], pR[NG], va[NV], vb[NV];
-      primGradFromConsGrad<D>(ph, consL, compL, gL, pL);
-      primGradFromConsGrad<D>(ph, consR, compR, gR, pR);
       convFlux<D>(ph, n, consL, compL, irL, consR, compR, irR, Fn);
-      viscNormalFlux<D>(ph, n, compL, pL, va);   // calculateViscousFlux, ViscousFlux.cpp:139-153: average of both sides
-      viscNormalFlux<D>(ph, n, compR, pR, vb);
+      {  // left side: trace of (G_vol + G_f), VariableConvertor.cpp:674-688, then its normal viscous flux
+        double g[NG], gp[NG];
+        if (inL) lineTraceRot<N, NG, NN>(S.sG + locL * NG * NN, baseL, strideL, S.sLend + sideL * N, rl, g);
+        else lineTraceRot<N, NG, NN>(A.Gvol + (size_t)eL * NG * NN, baseL, strideL, S.sLend + sideL * N, rl, g);
+        if (br2) {
 #pragma unroll
-      for (int v = 0; v < NV; v++) Fn[v] -= (va[v] + vb[v]) / 2.0;
+          for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int c = 0; c < D; c++) g[v * D + c] += lamL * n[c] * jump[v];
+        }
+        primGradFromConsGrad<D>(ph, consL, compL, g, gp);
+        viscNormalFlux<D>(ph, n, compL, gp, va);   // calculateViscousFlux, ViscousFlux.cpp:139-153: average of both sides
+      }
+      {
+        double g[NG], gp[NG], vb[NV];
+        if (inR) lineTraceRot<N, NG, NN>(S.sG + locR * NG * NN, baseR, strideR, S.sLend + sideR * N, rl, g);
+        else lineTraceRot<N, NG, NN>(A.Gvol + (size_t)eR * NG * NN, baseR, strideR, S.sLend + sideR * N, rl, g);
+        if (br2) {
+          double lamR;
+          if constexpr (AFFINE) lamR = S.sLiftC[lfR * NQF + jr] * invDetR;
+          else lamR = liftTraceFactorCurved<D, N, NN>(A, eR, baseR, strideR, S.sLend + sideR * N);
+#pragma unroll
+          for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int c = 0; c < D; c++) g[v * D + c] += lamR * n[c] * jump[v];
+        }
+        primGradFromConsGrad<D>(ph, consR, compR, g, gp);
+        viscNormalFlux<D>(ph, n, compR, gp, vb);
+#pragma unroll
+        for (int v = 0; v < NV; v++) Fn[v] -= (va[v] + vb[v]) / 2.0;
+      }
     } else {
-      double compR[D + 3], b[D + 3], volCons[NV], intCons[NV];
+      double compR[D + 3], b[D + 3], volCons[NV], intCons[NV], g[NG];
       const double* dm = A.dummy + (size_t)(faceId - A.nInt) * (D + 3) * NQF + j;
 #pragma unroll
       for (int k = 0; k < D + 3; k++) compR[k] = dm[k * NQF];
       bcBoundaryGradientVariable<D>(ph, bc, n, consL, compL, compR, volCons, intCons);
 #pragma unroll
       for (int v = 0; v < NV; v++) jump[v] = intCons[v] * jw;
+      if (inL) lineTraceRot<N, NG, NN>(S.sG + locL * NG * NN, baseL, strideL, S.sLend + sideL * N, rl, g);
+      else lineTraceRot<N, NG, NN>(A.Gvol + (size_t)eL * NG * NN, baseL, strideL, S.sLend + sideL * N, rl, g);
       if (br2) {
 #pragma unroll
         for (int v = 0; v < NV; v++)
 #pragma unroll
-          for (int c = 0; c < D; c++) gL[v * D + c] += lamL * n[c] * jump[v];
+          for (int c = 0; c < D; c++) g[v * D + c] += lamL * n[c] * jump[v];
       }
-      double pL[NG], gb[NG], va[NV], vb[NV];
-      primGradFromConsGrad<D>(ph, consL, compL, gL, pL);        // from the UNMODIFIED interior trace (SpatialDiscrete.cpp:792-796)
+      double pL[NG], gb[NG], vb[NV];
+      primGradFromConsGrad<D>(ph, consL, compL, g, pL);        // from the UNMODIFIED interior trace (SpatialDiscrete.cpp:792-796)
       bcBoundaryVariable<D>(ph, bc, n, compL, compR, b);
       convNormalFlux<D>(ph, n, b, Fn);                          // :797-803
       // modifyBoundaryVariable (BoundaryCondition.cpp:299-307,443-452,490-501,535-546): walls overwrite the interior computational
@@ -336,35 +441,52 @@ __global__ void __launch_bounds__(kThreads, 1) nsStageKernel(const __grid_consta
       const int slot = lfL * NQF + j;
 #pragma unroll
       for (int v = 0; v < NV; v++) { S.sFlux[(locL * NV + v) * NAQ + slot] = Fn[v] * jw; S.sB[(locL * NV + v) * NAQ + slot] = jump[v]; }
+      if constexpr (AFFINE) {
+        if (j == 0) {
 #pragma unroll
-      for (int d = 0; d < D; d++) S.sN[(locL * D + d) * NAQ + slot] = n[d];
+          for (int d = 0; d < D; d++) S.sN[(locL * NF + lfL) * D + d] = n[d];
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; d++) S.sN[(locL * D + d) * NAQ + slot] = n[d];
+      }
     }
     if (inR) {
       const int slot = lfR * NQF + jr;
 #pragma unroll
       for (int v = 0; v < NV; v++) { S.sFlux[(locR * NV + v) * NAQ + slot] = -Fn[v] * jw; S.sB[(locR * NV + v) * NAQ + slot] = jump[v]; }
+      if constexpr (AFFINE) {
+        if (j == 0) {
 #pragma unroll
-      for (int d = 0; d < D; d++) S.sN[(locR * D + d) * NAQ + slot] = n[d];
+          for (int d = 0; d < D; d++) S.sN[(locR * NF + lfR) * D + d] = n[d];
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; d++) S.sN[(locR * D + d) * NAQ + slot] = n[d];
+      }
     }
   }
   __syncthreads();
 
-  // ---- R1: convective minus viscous flux at the nodes; total gradient = G_vol + Σ_f G_f (BR2) -----------------------------------------
-  double R[ITERS][NV], Fv[ITERS][NG], velp[ITERS][D + 1];
+  // ---- R1: convective minus viscous flux at the nodes; total gradient = G_vol + Σ_f G_f (BR2).  The contravariant fluxes of
+  //      all D directions overwrite the node's own entries of the gradient tile (dead after this point). ---------------------
+  double ijwv[ITERS];
 #pragma unroll
   for (int it = 0; it < ITERS; it++) {
     const int nd = tid + it * kThreads;
-#pragma unroll
-    for (int v = 0; v < NV; v++) R[it][v] = 0.0;
+    ijwv[it] = 0.0;
     if (nd < nNodes) {
       const int el = nd / NN, q = nd - el * NN;
-      double cons[NV], comp[D + 3], g[NG], gp[NG];
+      double cons[NV], comp[D + 3], g[NG], gp[NG], Fv[NG];
 #pragma unroll
       for (int v = 0; v < NV; v++) cons[v] = S.sU[(el * NV + v) * NN + q];
 #pragma unroll
       for (int r = 0; r < NG; r++) g[r] = S.sG[(el * NG + r) * NN + q];
+      double ijw;
+      if constexpr (AFFINE) ijw = S.sInvDet[el] * S.sInvWq[q];
+      else ijw = __ldg(A.invjw + (size_t)(e0 + el) * NN + q);
+      ijwv[it] = ijw;
       if (br2) {
-        const double ijw = invJwAt<D, NN, AFFINE>(A, e0 + el, q, S.sWq);
 #pragma unroll
         for (int f = 0; f < NF; f++) {
           const int dn = faceDirOf<D>(f), side = faceSideOf<D>(f);
@@ -372,11 +494,14 @@ __global__ void __launch_bounds__(kThreads, 1) nsStageKernel(const __grid_consta
           const int id = (q / st) % N;
           const double cf = S.sLend[side * N + id] * ijw;
           const int slot = f * NQF + S.sNodePt[f * NN + q];
+          double nn[D];
+#pragma unroll
+          for (int c = 0; c < D; c++) nn[c] = (AFFINE ? S.sN[(el * NF + f) * D + c] : S.sN[(el * D + c) * NAQ + slot]) * cf;
 #pragma unroll
           for (int v = 0; v < NV; v++) {
-            const double a = cf * S.sB[(el * NV + v) * NAQ + slot];
+            const double a = S.sB[(el * NV + v) * NAQ + slot];
 #pragma unroll
-            for (int c = 0; c < D; c++) g[v * D + c] += a * S.sN[(el * D + c) * NAQ + slot];
+            for (int c = 0; c < D; c++) g[v * D + c] += a * nn[c];
           }
         }
       }
@@ -384,50 +509,47 @@ __global__ void __launch_bounds__(kThreads, 1) nsStageKernel(const __grid_consta
         double* out = A.Gout + ((size_t)(e0 + el) * NG) * NN + q;
 #pragma unroll
         for (int r = 0; r < NG; r++) out[(size_t)r * NN] = g[r];
-      }
-      compFromCons<D>(ph, cons, comp);
-      primGradFromConsGrad<D>(ph, cons, comp, g, gp);
-      viscRawFlux<D>(ph, comp, gp, Fv[it]);
+      } else {
+        compFromCons<D>(ph, cons, comp);
+        primGradFromConsGrad<D>(ph, cons, comp, g, gp);
+        viscRawFlux<D>(ph, comp, gp, Fv);
 #pragma unroll
-      for (int c = 0; c < D; c++) velp[it][c] = comp[1 + c];
-      velp[it][D] = comp[D + 2];
-    }
-  }
-  if (A.mode == 3) return;
+        for (int dd = 0; dd < D; dd++) {
+          double m[D], Ft[NV];
 #pragma unroll
-  for (int dd = 0; dd < D; dd++) {
+          for (int c = 0; c < D; c++) {
+            if constexpr (AFFINE) m[c] = S.sGeoE[el * L::REC + dd * D + c] * S.sWq[q];
+            else m[c] = metricCurved<D, NN>(A, e0 + el, q, dd, c);
+          }
+          contravariantFlux<D>(ph, cons, comp, m, Ft);
 #pragma unroll
-    for (int it = 0; it < ITERS; it++) {
-      const int nd = tid + it * kThreads;
-      if (nd < nNodes) {
-        const int el = nd / NN, q = nd - el * NN;
-        double cons[NV], comp[D + 3], m[D], Ft[NV];
+          for (int v = 0; v < NV; v++) {
+            double s = 0.0;
 #pragma unroll
-        for (int v = 0; v < NV; v++) cons[v] = S.sU[(el * NV + v) * NN + q];
-#pragma unroll
-        for (int c = 0; c < D; c++) comp[1 + c] = velp[it][c];
-        comp[D + 2] = velp[it][D];
-#pragma unroll
-        for (int c = 0; c < D; c++) m[c] = metricAt<D, NN, AFFINE>(A, e0 + el, q, dd, c, S.sWq);
-        contravariantFlux<D>(ph, cons, comp, m, Ft);
-#pragma unroll
-        for (int v = 0; v < NV; v++) {
-          double s = 0.0;
-#pragma unroll
-          for (int c = 0; c < D; c++) s += Fv[it][v * D + c] * m[c];
-          S.sF[(el * NV + v) * NN + q] = Ft[v] - s;   // SpatialDiscrete.cpp:216-232: (F_c − F_v)ᵀ (J^T)^-1 detJ w
+            for (int c = 0; c < D; c++) s += Fv[v * D + c] * m[c];
+            S.sG[(el * NG + dd * NV + v) * NN + q] = Ft[v] - s;   // SpatialDiscrete.cpp:216-232: (F_c − F_v)ᵀ (J^T)^-1 detJ w
+          }
         }
       }
     }
-    __syncthreads();
-    const int st = strideOf<N, D>(dd);
+  }
+  if (A.mode == 3) return;
+  __syncthreads();
+
+  // ---- R3 + R4: R = Q·∇Φ − A·Φ_f, mass inverse, RK update ----------------------------------------------------------------------------
+  double R[ITERS][NV];
 #pragma unroll
-    for (int it = 0; it < ITERS; it++) {
-      const int nd = tid + it * kThreads;
-      if (nd < nNodes) {
-        const int el = nd / NN, q = nd - el * NN;
+  for (int it = 0; it < ITERS; it++) {
+    const int nd = tid + it * kThreads;
+#pragma unroll
+    for (int v = 0; v < NV; v++) R[it][v] = 0.0;
+    if (nd < nNodes) {
+      const int el = nd / NN, q = nd - el * NN;
+#pragma unroll
+      for (int dd = 0; dd < D; dd++) {
+        const int st = strideOf<N, D>(dd);
         const int id = (q / st) % N;
-        const double* f = S.sF + (el * NV) * NN + (q - id * st);
+        const double* f = S.sG + (el * NG + dd * NV) * NN + (q - id * st);
 #pragma unroll
         for (int a = 0; a < N; a++) {
           const double dm = S.sDm[a * N + id];
@@ -435,16 +557,6 @@ __global__ void __launch_bounds__(kThreads, 1) nsStageKernel(const __grid_consta
           for (int v = 0; v < NV; v++) R[it][v] += f[v * NN + a * st] * dm;
         }
       }
-    }
-    if (dd + 1 < D) __syncthreads();
-  }
-
-  // ---- R3 (face part) + R4 -------------------------------------------------------------------------------------------------------
-#pragma unroll
-  for (int it = 0; it < ITERS; it++) {
-    const int nd = tid + it * kThreads;
-    if (nd < nNodes) {
-      const int el = nd / NN, q = nd - el * NN;
 #pragma unroll
       for (int f = 0; f < NF; f++) {
         const int dn = faceDirOf<D>(f), side = faceSideOf<D>(f);
@@ -458,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) nsStageKernel(const __grid_consta
       double cons[NV];
 #pragma unroll
       for (int v = 0; v < NV; v++) cons[v] = S.sU[(el * NV + v) * NN + q];
-      const double ijw = invJwAt<D, NN, AFFINE>(A, e0 + el, q, S.sWq);
+      const double ijw = ijwv[it];
       if (A.phys.source == kBoussinesq) {
         double comp[D + 3];
         compFromCons<D>(ph, cons, comp);
@@ -481,8 +593,8 @@ __global__ void __launch_bounds__(kThreads, 1) nsStageKernel(const __grid_consta
 
   // ---- K: relative error (same reduction as the Euler kernel) -------------------------------------------------------------------------
   if (A.normPartial != nullptr) {
-    double* bufA = S.sF;
-    double* bufB = S.sFlux;
+    double* bufA = S.sG;      // >= [K][NV][NN]
+    double* bufB = S.sFlux;   // [K][NV][NAQ] >= [K][NV][NN]
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {

@@ -50,14 +50,14 @@ void launchEuler(const StageArgs& a, int nBlocks, cudaStream_t s) {
 
 template <int D, int N, int K, bool AFFINE>
 void launchNsGrad(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  using L = NsLayout<D, N, K>;
+  using L = NsLayout<D, N, K, AFFINE, false>;
   static bool configured = false;
   if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsGradKernel<D, N, K, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
   nsGradKernel<D, N, K, AFFINE><<<nBlocks, kThreads, L::bytes, s>>>(a);
 }
 template <int D, int N, int K, bool AFFINE, int PH>
 void launchNsStage(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  using L = NsLayout<D, N, K>;
+  using L = NsLayout<D, N, K, AFFINE, true>;
   static bool configured = false;
   if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsStageKernel<D, N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
   nsStageKernel<D, N, K, AFFINE, PH><<<nBlocks, kThreads, L::bytes, s>>>(a);
@@ -341,8 +341,13 @@ int sdg_finalize(sdg_ctx* c) {
       for (int pos = 0; pos < B.n; pos++) for (int k = 0; k <= DD; k++) ge[(size_t)pos * REC + k] = B.geoE[(size_t)pos * (DD + 1) + k];
       c->geoE.upload(ge, c->stream);
       const size_t ncf = B.faceRec.size() / 4;
-      std::vector<double> cf(std::max<size_t>(ncf, 1) * 4, 0.0);
-      for (size_t k = 0; k < ncf; k++) for (int l = 0; l <= c->D; l++) cf[k * 4 + l] = M.geoF[(size_t)B.faceRec[k * 4 + 2] * (c->D + 1) + l];
+      std::vector<double> cf(std::max<size_t>(ncf, 1) * kCF, 0.0);
+      for (size_t k = 0; k < ncf; k++) {
+        for (int l = 0; l <= c->D; l++) cf[k * kCF + l] = M.geoF[(size_t)B.faceRec[k * 4 + 2] * (c->D + 1) + l];
+        const int pL = B.faceRec[k * 4 + 0], pR = B.faceRec[k * 4 + 1];
+        cf[k * kCF + c->D + 1] = 1.0 / B.geoE[(size_t)pL * (DD + 1) + DD];
+        cf[k * kCF + c->D + 2] = pR >= 0 ? 1.0 / B.geoE[(size_t)pR * (DD + 1) + DD] : 0.0;
+      }
       c->cfGeo.upload(cf, c->stream);
     } else {
       c->geoE.upload(B.geoE, c->stream);

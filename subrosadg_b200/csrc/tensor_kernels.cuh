@@ -31,6 +31,7 @@ namespace sdg {
 
 constexpr int kThreads = 256;
 constexpr int kMaxN = 4;
+constexpr int kCF = 6;   // chunk-face geometry record (affine meshes): {n[D], |J|, 1/detJ_left, 1/detJ_right}, padded to 6 doubles
 
 // Device image of TensorTables (host_tables.hpp); lives in global memory, staged into shared memory by every block.
 struct TensorDev {
@@ -54,7 +55,7 @@ struct StageArgs {
   const double* geoE;     // affine: [n][REC] (REC = D*D+1 rounded up to even: {(J^T)^-1 detJ rows, detJ}); curved: [n][D*D][NN]
   const double* invjw;    // curved: [n][NN]
   const double* geoF;     // affine: [nf][D+1]; curved: [nf][D+1][NQF]
-  const double* cfGeo;    // affine: per chunk-face entry {n[D], |J| scale} padded to 4 doubles (same order as faceRec)
+  const double* cfGeo;    // affine: per chunk-face entry {n[D], |J| scale, 1/detJ_L, 1/detJ_R} padded to kCF doubles (same order as faceRec)
   const int4* faceRec;    // per chunk, the faces touching it
   const int* chunkFaceOff;
   const int* chunkList;   // chunk ids handled by this launch
@@ -85,8 +86,8 @@ struct Layout {
   static constexpr int REC = (D * D + 2) & ~1;                // per-element affine metric record
   static constexpr int MAXF = K * NF;                         // faces touching a chunk (upper bound)
   static constexpr int oGeoE = oTab + nTabD;                  // [K][REC]
-  static constexpr int oCf = oGeoE + K * REC;                 // [MAXF][4]
-  static constexpr int oRec = oCf + MAXF * 4;                 // [MAXF] int4
+  static constexpr int oCf = oGeoE + K * REC;                 // [MAXF][kCF]
+  static constexpr int oRec = oCf + MAXF * kCF;               // [MAXF] int4
   static constexpr int nDoubles = oRec + MAXF * 2;
   static constexpr int nBytesTab = NF * NQF + 4 * NQF + NF * NN;   // faceBase, seq, nodeFacePt as bytes
   static constexpr size_t bytes = sizeof(double) * nDoubles + ((nBytesTab + 15) / 16) * 16;
@@ -148,6 +149,24 @@ __device__ __forceinline__ void lineTrace(const double* __restrict__ src, int ba
   }
 }
 
+// Same trace with the N nodes of the line visited starting at `rot`: the lanes of a warp (consecutive face points, several
+// faces) then hit different shared-memory banks (N = 4: the plain order is 3-4 way conflicted on the faces whose normal is not
+// the slowest axis).  Summation order differs per lane; parity is tolerance based (1e-12).
+template <int N, int NFLD, int NN>
+__device__ __forceinline__ void lineTraceRot(const double* __restrict__ src, int base, int stride, const double* __restrict__ lend, int rot, double* out) {
+#pragma unroll
+  for (int v = 0; v < NFLD; v++) out[v] = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    int a = k + rot;
+    a = a >= N ? a - N : a;
+    const double l = lend[a];
+    const double* s = src + base + a * stride;
+#pragma unroll
+    for (int v = 0; v < NFLD; v++) out[v] += l * s[v * NN];
+  }
+}
+
 // Contravariant convective flux of reference direction dd at one node:  F(U)·m  with m = row dd of (J^T)^-1 detJ w
 // (calculateConvectiveRawFlux, ConvectiveFlux.cpp:28-57, contracted like SpatialDiscrete.cpp:229-232).
 template <int D, int PH>
@@ -205,13 +224,13 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
   __syncthreads();
   if (tid == 0) {
     unsigned total = (unsigned)(nfc * sizeof(int4)) + (bulkU ? bytesU : 0u);
-    if constexpr (AFFINE) total += (unsigned)(ne * L::REC * sizeof(double)) + (unsigned)(nfc * 4 * sizeof(double));
+    if constexpr (AFFINE) total += (unsigned)(ne * L::REC * sizeof(double)) + (unsigned)(nfc * kCF * sizeof(double));
     mbarExpectTx(&mbar, total);
     if (bulkU) bulkLoad(sU, A.Uin + (size_t)e0 * NV * NN, bytesU, &mbar);
     bulkLoad(smem + L::oRec, A.faceRec + f0, (unsigned)(nfc * sizeof(int4)), &mbar);
     if constexpr (AFFINE) {
       bulkLoad(sGeoE, A.geoE + (size_t)e0 * L::REC, (unsigned)(ne * L::REC * sizeof(double)), &mbar);
-      bulkLoad(sCf, A.cfGeo + (size_t)f0 * 4, (unsigned)(nfc * 4 * sizeof(double)), &mbar);
+      bulkLoad(sCf, A.cfGeo + (size_t)f0 * kCF, (unsigned)(nfc * kCF * sizeof(double)), &mbar);
     }
   }
   if (!bulkU) {
@@ -252,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
       const int lfL = rec.w & 15, lfR = (rec.w >> 4) & 15, rot = (rec.w >> 8) & 15, bc = (rec.w >> 12) & 15;
       double n[D], jw;
       if constexpr (AFFINE) {
-        const double* g = sCf + fi * 4;
+        const double* g = sCf + fi * kCF;
 #pragma unroll
         for (int d = 0; d < D; d++) n[d] = g[d];
         jw = g[D] * sWf[j];
@@ -263,13 +282,14 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
         jw = __ldg(g + D * NQF);
       }
       double consL[NV], compL[D + 3], consR[NV], compR[D + 3], Fn[NV];
+      const int rl = (j / N + fi) % N;
       const int locL = eL - e0, locR = eR - e0;
       const bool inL = locL >= 0 && locL < ne, inR = eR >= 0 && locR >= 0 && locR < ne;
       {
         const int dn = faceDirOf<D>(lfL), side = faceSideOf<D>(lfL);
         const int base = sFaceBase[lfL * NQF + j], stride = strideOf<N, D>(dn);
-        if (inL) lineTrace<N, NV, NN>(sU + locL * NV * NN, base, stride, sLend + side * N, consL);
-        else lineTrace<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, sLend + side * N, consL);
+        if (inL) lineTraceRot<N, NV, NN>(sU + locL * NV * NN, base, stride, sLend + side * N, rl, consL);
+        else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, sLend + side * N, rl, consL);
       }
       const double irL = compFromCons<D>(ph, consL, compL);
       int jr = j;
@@ -277,8 +297,8 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
         jr = sSeq[rot * NQF + j];
         const int dn = faceDirOf<D>(lfR), side = faceSideOf<D>(lfR);
         const int base = sFaceBase[lfR * NQF + jr], stride = strideOf<N, D>(dn);
-        if (inR) lineTrace<N, NV, NN>(sU + locR * NV * NN, base, stride, sLend + side * N, consR);
-        else lineTrace<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, sLend + side * N, consR);
+        if (inR) lineTraceRot<N, NV, NN>(sU + locR * NV * NN, base, stride, sLend + side * N, rl, consR);
+        else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, sLend + side * N, rl, consR);
         const double irR = compFromCons<D>(ph, consR, compR);
         convFlux<D>(ph, n, consL, compL, irL, consR, compR, irR, Fn);
       } else {
