@@ -264,26 +264,31 @@ struct MeshPlan {
   void buildChunkFaces() {
     BlockPlan& B = blk;
     const int nf = F.nInt + F.nBnd;
-    std::vector<int> count(B.nChunks + 1, 0);
+    // Within a chunk's list the faces that need a parent from OUTSIDE the chunk (a long-latency gather) come first and the
+    // cheap ones (both parents in the chunk, or boundary faces) last, so that the tail of the kernels' face loop is short.
+    std::vector<int> count(B.nChunks + 1, 0), countCheap(B.nChunks + 1, 0);
     std::vector<char> touchesGhost(B.nChunks, 0);
     auto chunkOf = [&](int pos) { return pos < B.nOwned ? pos / B.K : -1; };
     for (int pass = 0; pass < 2; pass++) {
-      std::vector<int> cursor;
+      std::vector<int> cursor, cursorCheap;
       if (pass == 1) {
         B.chunkFaceOff.assign(B.nChunks + 1, 0);
         for (int c = 0; c < B.nChunks; c++) B.chunkFaceOff[c + 1] = B.chunkFaceOff[c] + count[c];
         B.faceRec.assign((size_t)B.chunkFaceOff[B.nChunks] * 4, 0);
         cursor.assign(B.chunkFaceOff.begin(), B.chunkFaceOff.end() - 1);
+        cursorCheap.resize(B.nChunks);
+        for (int c = 0; c < B.nChunks; c++) cursorCheap[c] = B.chunkFaceOff[c + 1] - countCheap[c];
       }
       for (int i = 0; i < nf; i++) {
         const bool interior = i < F.nInt;
         const int pL = B.perm[F.le[i]], pR = interior ? B.perm[F.re[i]] : -1;
         const int cL = chunkOf(pL), cR = interior ? chunkOf(pR) : -1;
         const int packed = F.lf[i] | ((interior ? F.rf[i] : 0) << 4) | ((interior ? F.rot[i] : 0) << 8) | ((F.bc[i] & 15) << 12);
+        const bool cheap = !interior || cL == cR;
         int targets[2] = {cL, (cR != cL) ? cR : -1};
         for (int t : targets) if (t >= 0) {
-          if (pass == 0) { count[t]++; if (pL >= B.nOwned || (interior && pR >= B.nOwned)) touchesGhost[t] = 1; }
-          else { int* r = &B.faceRec[(size_t)cursor[t]++ * 4]; r[0] = pL; r[1] = pR; r[2] = i; r[3] = packed; }
+          if (pass == 0) { count[t]++; if (cheap) countCheap[t]++; if (pL >= B.nOwned || (interior && pR >= B.nOwned)) touchesGhost[t] = 1; }
+          else { int* r = &B.faceRec[(size_t)(cheap ? cursorCheap[t]++ : cursor[t]++) * 4]; r[0] = pL; r[1] = pR; r[2] = i; r[3] = packed; }
         }
       }
     }

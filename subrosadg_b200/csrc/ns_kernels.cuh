@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsGradKernel(const __grid_constan
       const int dn = faceDirOf<D>(lfL), side = faceSideOf<D>(lfL);
       const int base = S.sFaceBase[lfL * NQF + j], stride = strideOf<N, D>(dn);
       if (inL) lineTraceRot<N, NV, NN>(S.sU + locL * NV * NN, base, stride, S.sLend + side * N, rl, consL);
-      else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, S.sLend + side * N, rl, consL);
+      else lineTraceGlobal<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, S.sLend + side * N, consL);
     }
     int jr = j;
     if (eR >= 0) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsGradKernel(const __grid_constan
       const int dn = faceDirOf<D>(lfR), side = faceSideOf<D>(lfR);
       const int base = S.sFaceBase[lfR * NQF + jr], stride = strideOf<N, D>(dn);
       if (inR) lineTraceRot<N, NV, NN>(S.sU + locR * NV * NN, base, stride, S.sLend + side * N, rl, consR);
-      else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, S.sLend + side * N, rl, consR);
+      else lineTraceGlobal<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, S.sLend + side * N, consR);
 #pragma unroll
       for (int v = 0; v < NV; v++) { avg[v] = (consL[v] + consR[v]) / 2.0; jump[v] = (consR[v] - consL[v]) / 2.0; }  // ViscousFlux.cpp:33-56
     } else {
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
     const int baseL = S.sFaceBase[lfL * NQF + j], strideL = strideOf<N, D>(dnL);
     double consL[NV], compL[D + 3], jump[NV], Fn[NV], va[NV];
     if (inL) lineTraceRot<N, NV, NN>(S.sU + locL * NV * NN, baseL, strideL, S.sLend + sideL * N, rl, consL);
-    else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, baseL, strideL, S.sLend + sideL * N, rl, consL);
+    else lineTraceGlobal<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, baseL, strideL, S.sLend + sideL * N, consL);
     const double irL = compFromCons<D>(ph, consL, compL);
     double lamL = 0.0;
     if (br2) {
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
       const int dnR = faceDirOf<D>(lfR), sideR = faceSideOf<D>(lfR);
       const int baseR = S.sFaceBase[lfR * NQF + jr], strideR = strideOf<N, D>(dnR);
       if (inR) lineTraceRot<N, NV, NN>(S.sU + locR * NV * NN, baseR, strideR, S.sLend + sideR * N, rl, consR);
-      else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, baseR, strideR, S.sLend + sideR * N, rl, consR);
+      else lineTraceGlobal<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, baseR, strideR, S.sLend + sideR * N, consR);
       const double irR = compFromCons<D>(ph, consR, compR);
 #pragma unroll
       for (int v = 0; v < NV; v++) jump[v] = (consR[v] - consL[v]) / 2.0 * jw;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
       {  // left side: trace of (G_vol + G_f), VariableConvertor.cpp:674-688, then its normal viscous flux
         double g[NG], gp[NG];
         if (inL) lineTraceRot<N, NG, NN>(S.sG + locL * NG * NN, baseL, strideL, S.sLend + sideL * N, rl, g);
-        else lineTraceRot<N, NG, NN>(A.Gvol + (size_t)eL * NG * NN, baseL, strideL, S.sLend + sideL * N, rl, g);
+        else lineTraceGlobal<N, NG, NN>(A.Gvol + (size_t)eL * NG * NN, baseL, strideL, S.sLend + sideL * N, g);
         if (br2) {
 #pragma unroll
           for (int v = 0; v < NV; v++)
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
       {
         double g[NG], gp[NG], vb[NV];
         if (inR) lineTraceRot<N, NG, NN>(S.sG + locR * NG * NN, baseR, strideR, S.sLend + sideR * N, rl, g);
-        else lineTraceRot<N, NG, NN>(A.Gvol + (size_t)eR * NG * NN, baseR, strideR, S.sLend + sideR * N, rl, g);
+        else lineTraceGlobal<N, NG, NN>(A.Gvol + (size_t)eR * NG * NN, baseR, strideR, S.sLend + sideR * N, g);
         if (br2) {
           double lamR;
           if constexpr (AFFINE) lamR = S.sLiftC[lfR * NQF + jr] * invDetR;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
 #pragma unroll
       for (int v = 0; v < NV; v++) jump[v] = intCons[v] * jw;
       if (inL) lineTraceRot<N, NG, NN>(S.sG + locL * NG * NN, baseL, strideL, S.sLend + sideL * N, rl, g);
-      else lineTraceRot<N, NG, NN>(A.Gvol + (size_t)eL * NG * NN, baseL, strideL, S.sLend + sideL * N, rl, g);
+      else lineTraceGlobal<N, NG, NN>(A.Gvol + (size_t)eL * NG * NN, baseL, strideL, S.sLend + sideL * N, g);
       if (br2) {
 #pragma unroll
         for (int v = 0; v < NV; v++)
@@ -545,6 +545,12 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
     for (int v = 0; v < NV; v++) R[it][v] = 0.0;
     if (nd < nNodes) {
       const int el = nd / NN, q = nd - el * NN;
+      const size_t g = ((size_t)(e0 + el) * NV) * NN + q;
+      double ul[NV];   // issued now, consumed after the contraction below
+      if (A.mode == 0 && A.aLast != 0.0) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) ul[v] = __ldg(A.Ulast + g + (size_t)v * NN);
+      }
 #pragma unroll
       for (int dd = 0; dd < D; dd++) {
         const int st = strideOf<N, D>(dd);
@@ -576,12 +582,11 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
         compFromCons<D>(ph, cons, comp);
         R[it][D] += boussinesqSource<D>(ph, comp) / ijw;
       }
-      const size_t g = ((size_t)(e0 + el) * NV) * NN + q;
       if (A.mode == 0) {
 #pragma unroll
         for (int v = 0; v < NV; v++) {
           double u = A.aCur * cons[v] + A.bdt * (R[it][v] * ijw);
-          if (A.aLast != 0.0) u += A.aLast * A.Ulast[g + (size_t)v * NN];
+          if (A.aLast != 0.0) u += A.aLast * ul[v];
           A.Uout[g + (size_t)v * NN] = u;
         }
       } else {

@@ -167,6 +167,35 @@ __device__ __forceinline__ void lineTraceRot(const double* __restrict__ src, int
   }
 }
 
+// Global-memory variant for a neighbour outside the chunk: no bank concern, so the line is read in natural order, and a
+// stride-1 line (face normal = fastest axis) is read with 16-byte loads when N is even (each lane then touches every 32-byte
+// sector once or twice instead of N times).
+template <int N, int NFLD, int NN>
+__device__ __forceinline__ void lineTraceGlobal(const double* __restrict__ src, int base, int stride, const double* __restrict__ lend, double* out) {
+  if ((N % 2 == 0) && stride == 1) {
+#pragma unroll
+    for (int v = 0; v < NFLD; v++) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < N; a += 2) {
+        const double2 x = __ldg(reinterpret_cast<const double2*>(src + v * NN + base + a));
+        s += lend[a] * x.x + lend[a + 1] * x.y;
+      }
+      out[v] = s;
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < NFLD; v++) out[v] = 0.0;
+#pragma unroll
+    for (int a = 0; a < N; a++) {
+      const double l = lend[a];
+      const double* s = src + base + a * stride;
+#pragma unroll
+      for (int v = 0; v < NFLD; v++) out[v] += l * __ldg(s + v * NN);
+    }
+  }
+}
+
 // Contravariant convective flux of reference direction dd at one node:  F(U)·m  with m = row dd of (J^T)^-1 detJ w
 // (calculateConvectiveRawFlux, ConvectiveFlux.cpp:28-57, contracted like SpatialDiscrete.cpp:229-232).
 template <int D, int PH>
@@ -245,19 +274,11 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
   for (int i = tid; i < 4 * NQF; i += kThreads) sSeq[i] = (unsigned char)T.seq[i];
   for (int i = tid; i < NF * NN; i += kThreads) sNodePt[i] = T.nodeFacePt[i];
 
-  // U_last of the thread's own nodes: issued now, consumed in R4, so the latency hides behind the whole stage
-  double ulast[ITERS][NV];
+  // U_last is consumed at the very end (R4): pull its lines into L2 now
   if (A.mode == 0 && A.aLast != 0.0) {
-#pragma unroll
-    for (int it = 0; it < ITERS; it++) {
-      const int nd = tid + it * kThreads;
-      if (nd < nNodes) {
-        const int el = FIXQ ? el0 + it * EL_STEP : nd / NN, q = FIXQ ? q0 : nd - el * NN;
-        const double* g = A.Ulast + ((size_t)(e0 + el) * NV) * NN + q;
-#pragma unroll
-        for (int v = 0; v < NV; v++) ulast[it][v] = g[(size_t)v * NN];
-      }
-    }
+    const char* p = reinterpret_cast<const char*>(A.Ulast + (size_t)e0 * NV * NN);
+    const int bytes = ne * NV * NN * (int)sizeof(double);
+    for (int o = tid * 128; o < bytes; o += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
   }
   __syncthreads();
   mbarWait(&mbar, 0);
@@ -289,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
         const int dn = faceDirOf<D>(lfL), side = faceSideOf<D>(lfL);
         const int base = sFaceBase[lfL * NQF + j], stride = strideOf<N, D>(dn);
         if (inL) lineTraceRot<N, NV, NN>(sU + locL * NV * NN, base, stride, sLend + side * N, rl, consL);
-        else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, sLend + side * N, rl, consL);
+        else lineTraceGlobal<N, NV, NN>(A.Uin + (size_t)eL * NV * NN, base, stride, sLend + side * N, consL);
       }
       const double irL = compFromCons<D>(ph, consL, compL);
       int jr = j;
@@ -298,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
         const int dn = faceDirOf<D>(lfR), side = faceSideOf<D>(lfR);
         const int base = sFaceBase[lfR * NQF + jr], stride = strideOf<N, D>(dn);
         if (inR) lineTraceRot<N, NV, NN>(sU + locR * NV * NN, base, stride, sLend + side * N, rl, consR);
-        else lineTraceRot<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, sLend + side * N, rl, consR);
+        else lineTraceGlobal<N, NV, NN>(A.Uin + (size_t)eR * NV * NN, base, stride, sLend + side * N, consR);
         const double irR = compFromCons<D>(ph, consR, compR);
         convFlux<D>(ph, n, consL, compL, irL, consR, compR, irR, Fn);
       } else {
@@ -423,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
 #pragma unroll
         for (int v = 0; v < NV; v++) {
           double u = A.aCur * cons[v] + A.bdt * (R[it][v] * ijw);
-          if (A.aLast != 0.0) u += A.aLast * ulast[it][v];
+          if (A.aLast != 0.0) u += A.aLast * __ldg(A.Ulast + g + (size_t)v * NN);
           A.Uout[g + (size_t)v * NN] = u;
         }
       } else {

@@ -440,3 +440,20 @@ def cubed_sphere_shell(n, nr, r0=0.5, r1=5.0, geom_order=3, stretch=2.0, phys_bc
         return np.where(r < 0.5 * (r0 + r1), 2, 1).astype(np.int32)
 
     return mesh_from_blocks(3, {HEXAHEDRON: hexes}, geom_order, phys_bc, tagger, None, info=dict(kind="cubed_sphere_shell", r0=r0, r1=r1))
+
+
+def write_flat(mesh: Mesh, path) -> None:
+    """Flat little-endian mesh file for the C++ host side (`SubrosaDG::MeshData::readFlat`,
+    include/SubrosaDG_b200/SubrosaDG.hpp): magic "SDGM", dim, nblocks, per block {type, geom_order, n, nn, coords[n][nn][dim]},
+    n_int, n_bnd, then le, lt, lf, re, rt, rf, rot, bc, phys as int32."""
+    with open(path, "wb") as f:
+        f.write(b"SDGM")
+        f.write(np.array([mesh.dim, len(mesh.blocks)], dtype="<i4").tobytes())
+        for t in sorted(mesh.blocks):
+            c = np.ascontiguousarray(mesh.blocks[t]["coords"], dtype="<f8")
+            f.write(np.array([t, mesh.blocks[t]["geom_order"], c.shape[0], c.shape[1]], dtype="<i4").tobytes())
+            f.write(c.tobytes())
+        fc = mesh.faces
+        f.write(np.array([fc["n_int"], fc["n_bnd"]], dtype="<i4").tobytes())
+        for k in ("le", "lt", "lf", "re", "rt", "rf", "rot", "bc", "phys"):
+            f.write(np.ascontiguousarray(fc[k], dtype="<i4").tobytes())
