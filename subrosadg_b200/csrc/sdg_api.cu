@@ -6,11 +6,13 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 
 #include "../../include/subrosadg_b200.h"
 #include "host_plan.hpp"
+#include "line_kernels.cuh"
 #include "ns_kernels.cuh"
 #include "tensor_kernels.cuh"
 
@@ -46,6 +48,17 @@ void launchEuler(const StageArgs& a, int nBlocks, cudaStream_t s) {
     configured = true;
   }
   eulerStageKernel<D, N, K, AFFINE, PH><<<nBlocks, kThreads, L::bytes, s>>>(a);
+}
+
+template <int N, int K, bool AFFINE, int PH>
+void launchEulerLine(const StageArgs& a, int nBlocks, cudaStream_t s) {
+  using L = LineLayout<N, K>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(eulerLineKernel<N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+    configured = true;
+  }
+  eulerLineKernel<N, K, AFFINE, PH><<<nBlocks, L::THREADS, L::bytes, s>>>(a);
 }
 
 template <int D, int N, int K, bool AFFINE>
@@ -107,7 +120,13 @@ StageFn pickEulerFn(int D, int N, bool affine, int ph, int& K) {
   if (D == 2 && N == 4) { K = ChunkOf<2, 4>::K; return pickEuler<2, 4>(affine, ph); }
   if (D == 3 && N == 2) { K = ChunkOf<3, 2>::K; return pickEuler<3, 2>(affine, ph); }
   if (D == 3 && N == 3) { K = ChunkOf<3, 3>::K; return pickEuler<3, 3>(affine, ph); }
-  if (D == 3 && N == 4) { K = ChunkOf<3, 4>::K; return pickEuler<3, 4>(affine, ph); }
+  if (D == 3 && N == 4) {
+    K = ChunkOf<3, 4>::K;
+    if (getenv("SDG_NODE_KERNEL")) return pickEuler<3, 4>(affine, ph);   // A/B switch: node-per-thread kernel of tensor_kernels.cuh
+    constexpr int KK = ChunkOf<3, 4>::K;
+    if (affine) return ph ? launchEulerLine<4, KK, true, 1> : launchEulerLine<4, KK, true, 0>;
+    return ph ? launchEulerLine<4, KK, false, 1> : launchEulerLine<4, KK, false, 0>;
+  }
   throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..3");
 }
 
@@ -153,6 +172,9 @@ void fillArgs(sdg_ctx* c, StageArgs& a) {
   a.faceRec = reinterpret_cast<const int4*>(c->faceRec.p); a.chunkFaceOff = c->chunkOff.p; a.chunkList = nullptr;
   a.dummy = c->dummy.p; a.tab = c->tab.p; a.normPartial = nullptr;
   a.nOwned = B.nOwned; a.nInt = c->plan.F.nInt; a.mode = 0; a.phys = c->phys;
+  const int N = B.T.N;
+  for (int i = 0; i < N * N; i++) { a.dm[i] = B.T.Dm[i]; a.k1[i] = B.T.K1[i]; }
+  for (int i = 0; i < 2 * N; i++) a.lend[i] = B.T.Lend[i];
 }
 
 // one pass of one stage over a subset of the chunks

@@ -63,6 +63,7 @@ struct StageArgs {
   const TensorDev* tab;
   double* normPartial;    // [nChunks][NV] (last stage) or nullptr
   double aLast, aCur, bdt;
+  double dm[kMaxN * kMaxN], lend[2 * kMaxN], k1[kMaxN * kMaxN];   // 1-D operators in the parameter (constant) bank: Dm[a*N+b], Lend[side*N+a], K1
   int nOwned, nInt;
   int mode;               // 0 RK update, 1 write dU/dt, 2 write R (nodal, un-inverted)
   PhysParams phys;
