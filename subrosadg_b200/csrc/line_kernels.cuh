@@ -32,15 +32,16 @@ struct LineLayout {
   static constexpr int NNP = N * PQ;            // padded nodes per variable
   static constexpr int REC = (D * D + 2) & ~1;
   static constexpr int MAXF = K * NF;
-  static constexpr int oU = 0;                                  // [K][NV][NNP]  states, later the flux tile of one direction
-  static constexpr int oT = oU + K * NV * NNP;                  // [K][NF][NV][NL] traces, later face fluxes
+  static constexpr int oU = 0;                                  // [K][NNP]  exchange tile of ONE variable (state for the traces, then fluxes)
+  static constexpr int oT = oU + K * NNP;                       // [K][NF][NV][NL] traces, later face fluxes
   static constexpr int oW = oT + K * NF * NV * NL;              // wq[NN], invWq[NN], wf[NL]
   static constexpr int oGeoE = oW + 2 * NN + NL;                // affine: [K][REC]
   static constexpr int oInvDet = oGeoE + K * REC;               // [K]
   static constexpr int oCf = oInvDet + ((K + 1) & ~1);          // affine: [MAXF][kCF]
   static constexpr int oRec = oCf + MAXF * kCF;                 // [MAXF] int4
   static constexpr int oRed = oRec + MAXF * 2;                  // [32][NV] block reduction scratch
-  static constexpr int nDoubles = oRed + 32 * NV;
+  static constexpr int oL = oRed + 32 * NV;                     // [K][NV][NN]  U_last of the chunk, landed by TMA while the stage is computed
+  static constexpr int nDoubles = oL + K * NV * NN;
   static constexpr int nBytes = 2 * NF * NL + 8 * NL + NF * NL + 2 * K * NF;   // nat2jf, jf2nat, seq, invseq, faceBase, sEF (int16)
   static constexpr size_t bytes = sizeof(double) * nDoubles + ((nBytes + 15) / 16) * 16;
   static constexpr int THREADS = K * NL;
@@ -48,14 +49,18 @@ struct LineLayout {
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
+#ifndef SDG_LINE_MINB
+#define SDG_LINE_MINB 3
+#endif
 template <int N, int K, bool AFFINE, int PH>
-__global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLineKernel(const __grid_constant__ StageArgs A) {
+__global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? SDG_LINE_MINB : 1) eulerLineKernel(const __grid_constant__ StageArgs A) {
   static_assert(N % 2 == 0, "16-byte accesses along the line need an even number of nodes");
   using L = LineLayout<N, K>;
   constexpr int D = 3, NV = 5, NL = L::NL, NN = L::NN, NF = 6, PQ = L::PQ, NNP = L::NNP, THREADS = L::THREADS;
   extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long mbar, mbarLast;
   double* sU = smem + L::oU;
+  double* sL = smem + L::oL;
   double* sT = smem + L::oT;
   double* sWq = smem + L::oW;
   double* sInvWq = sWq + NN;
@@ -83,14 +88,15 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
   const TensorDev& T = *A.tab;
   const int f0 = A.chunkFaceOff[chunk], nfc = A.chunkFaceOff[chunk + 1] - f0;
 
-  if (A.mode == 0 && A.aLast != 0.0) {   // U_last is consumed at the very end: pull its lines into L2 now
-    const char* p = reinterpret_cast<const char*>(A.Ulast + (size_t)e0 * NV * NN);
-    const int bytes = ne * NV * NN * (int)sizeof(double);
-    for (int o = tid * 128; o < bytes; o += THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-  }
-  if (tid == 0) mbarInit(&mbar, 1);
+  const bool needLast = A.mode == 0 && A.aLast != 0.0;
+  if (tid == 0) { mbarInit(&mbar, 1); mbarInit(&mbarLast, 1); }
   __syncthreads();
   if (tid == 0) {
+    if (needLast) {   // U_last is consumed at the very end: its TMA copy overlaps the whole stage
+      const unsigned bytes = (unsigned)(ne * NV * NN * sizeof(double));
+      mbarExpectTx(&mbarLast, bytes);
+      bulkLoad(sL, A.Ulast + (size_t)e0 * NV * NN, bytes, &mbarLast);
+    }
     unsigned total = (unsigned)(nfc * sizeof(int4));
     if constexpr (AFFINE) total += (unsigned)(ne * L::REC * sizeof(double)) + (unsigned)(nfc * kCF * sizeof(double));
     mbarExpectTx(&mbar, total);
@@ -101,18 +107,17 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
     }
   }
 
-  // ---- own line -> registers (16-byte loads) and into the padded state tile ------------------------------------------------
+  // ---- own line -> registers (16-byte loads); the copy into the padded state tile follows the table set-up so that the
+  //      two groups of global loads overlap ------------------------------------------------------------------------------------
   double u[NV][N];
   {
     const double* gU = A.Uin + ((size_t)(e0 + (active ? el : 0)) * NV) * NN + t * N;
-    double* sUe = sU + (el * NV) * NNP + i * PQ + j * N;
 #pragma unroll
     for (int v = 0; v < NV; v++) {
 #pragma unroll
       for (int k = 0; k < N; k += 2) {
         const double2 x = ldg2(gU + v * NN + k);
         u[v][k] = x.x; u[v][k + 1] = x.y;
-        *reinterpret_cast<double2*>(sUe + v * NNP + k) = x;
       }
     }
   }
@@ -159,21 +164,25 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
     if (inR) sEF[locR * NF + ((rec.w >> 4) & 15)] = (short)(x | 0x100 | (inL ? 0 : 0x200));
   }
   if constexpr (AFFINE) { if (tid < ne) sInvDet[tid] = 1.0 / sGeoE[tid * L::REC + D * D]; }
-  __syncwarp();   // the state tile of an element is written and read by the N^2 lines of that element only (one half warp)
 
-  // ---- xi / eta face traces from the state tile (both sides of an axis share the loads) ---------------------------------------
+  // ---- xi / eta face traces, one variable at a time through the exchange tile (both sides of an axis share the loads).  The
+  //      tile of an element is written and read by the N^2 lines of that element only (half a warp): __syncwarp suffices. ------
   {
-    const double* sUel = sU + (el * NV) * NNP;
+    double* sXe = sU + el * NNP;
 #pragma unroll
-    for (int d = 0; d < 2; d++) {
-      const int base = d == 0 ? t : i * PQ + j;          // nat = t: d = 0 -> (j',k') = t; d = 1 -> (i',k') = (i, j)
-      const int stride = d == 0 ? PQ : N;
+    for (int v = 0; v < NV; v++) {
+      if (v > 0) __syncwarp();
 #pragma unroll
-      for (int v = 0; v < NV; v++) {
+      for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sXe + i * PQ + j * N + k) = make_double2(u[v][k], u[v][k + 1]);
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < 2; d++) {
+        const int base = d == 0 ? t : i * PQ + j;          // nat = t: d = 0 -> (j',k') = t; d = 1 -> (i',k') = (i, j)
+        const int stride = d == 0 ? PQ : N;
         double xm = 0.0, xp = 0.0;
 #pragma unroll
         for (int a = 0; a < N; a++) {
-          const double x = sUel[v * NNP + base + a * stride];
+          const double x = sXe[base + a * stride];
           xm += A.lend[a] * x; xp += A.lend[N + a] * x;
         }
         sT[((el * NF + hexFaceOfAxis(d, 0)) * NV + v) * NL + t] = xm;
@@ -255,12 +264,6 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
   for (int v = 0; v < NV; v++)
 #pragma unroll
     for (int k = 0; k < N; k++) R[v][k] = 0.0;
-  double ijw[N];
-#pragma unroll
-  for (int k = 0; k < N; k++) {
-    if constexpr (AFFINE) ijw[k] = sInvDet[el] * sInvWq[t * N + k];
-    else ijw[k] = active ? __ldg(A.invjw + (size_t)(e0 + el) * NN + t * N + k) : 1.0;
-  }
   // contravariant flux of reference direction dd at the own nodes
   auto fluxDir = [&](int dd, double (&F)[NV][N]) {
 #pragma unroll
@@ -300,37 +303,57 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
     }
   }
 #pragma unroll
-  for (int d = 0; d < 2; d++) {   // xi (d = 0), eta (d = 1): one flux tile through shared memory
+  for (int d = 0; d < 2; d++) {   // xi (d = 0), eta (d = 1): the flux of one variable at a time through the exchange tile
     const int id = d == 0 ? i : j;                      // own index along the axis
     double dmi[N];
 #pragma unroll
     for (int a = 0; a < N; a++) dmi[a] = A.dm[a * N + id];
     const double lm = A.lend[id], lp = A.lend[N + id];
-    {
-      double F[NV][N];
-      fluxDir(d, F);
-      if (d == 1) __syncwarp();                         // the xi tile has been consumed by every line of the element
-      double* sFe = sU + (el * NV) * NNP + i * PQ + j * N;
+    // metric row d of (J^T)^-1 detJ w at the own nodes: affine = (element constant) x (node weight); curved = read per use (L1 / L2)
+    double gd[D], wk[N], um[N];
+    if constexpr (AFFINE) {
 #pragma unroll
-      for (int v = 0; v < NV; v++)
+      for (int c = 0; c < D; c++) gd[c] = sGeoE[el * L::REC + d * D + c];
 #pragma unroll
-        for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sFe + v * NNP + k) = make_double2(F[v][k], F[v][k + 1]);
+      for (int k = 0; k < N; k++) wk[k] = sWq[t * N + k];
     }
-    __syncwarp();
-    const double* sFl = sU + (el * NV) * NNP + (d == 0 ? j * N : i * PQ);   // line start: (0, j, :) or (i, 0, :)
+    auto metric = [&](int c, int k) -> double {
+      if constexpr (AFFINE) return gd[c] * wk[k];
+      else return active ? __ldg(A.geoE + ((size_t)(e0 + el) * (D * D) + d * D + c) * NN + t * N + k) : 0.0;
+    };
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      double x = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; c++) x += u[1 + c][k] * metric(c, k);
+      um[k] = x * ir[k];
+    }
+    double* sXe = sU + el * NNP;
+    const double* sFl = sXe + (d == 0 ? j * N : i * PQ);   // line start: (0, j, :) or (i, 0, :)
     const int stride = d == 0 ? PQ : N;
     const int natRow = d == 0 ? j * N : i * N;            // face point of the own nodes: (j, k) or (i, k)
     const double* fm = sT + ((el * NF + hexFaceOfAxis(d, 0)) * NV) * NL + natRow;
     const double* fp = sT + ((el * NF + hexFaceOfAxis(d, 1)) * NV) * NL + natRow;
 #pragma unroll
     for (int v = 0; v < NV; v++) {
+      double F[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        if (v == 0) F[k] = u[0][k] * um[k];
+        else if (v <= D) F[k] = u[v][k] * um[k] + pr[k] * metric(v - 1, k);
+        else F[k] = ph.comp() ? (u[D + 1][k] + pr[k]) * um[k] : u[D + 1][k] * um[k];
+      }
+      __syncwarp();                                     // the previous tile has been consumed by every line of the element
+#pragma unroll
+      for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sXe + i * PQ + j * N + k) = make_double2(F[k], F[k + 1]);
+      __syncwarp();
 #pragma unroll
       for (int k = 0; k < N; k += 2) {
         const double2 a0 = *reinterpret_cast<const double2*>(fm + v * NL + k), a1 = *reinterpret_cast<const double2*>(fp + v * NL + k);
         double r0 = -(lm * a0.x + lp * a1.x), r1 = -(lm * a0.y + lp * a1.y);
 #pragma unroll
         for (int a = 0; a < N; a++) {
-          const double2 x = *reinterpret_cast<const double2*>(sFl + v * NNP + a * stride + k);
+          const double2 x = *reinterpret_cast<const double2*>(sFl + a * stride + k);
           r0 += dmi[a] * x.x; r1 += dmi[a] * x.y;
         }
         R[v][k] += r0; R[v][k + 1] += r1;
@@ -339,6 +362,12 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
   }
 
   // ---- R4: mass inverse, RK update (16-byte stores) -------------------------------------------------------------------------------
+  double ijw[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    if constexpr (AFFINE) ijw[k] = sInvDet[el] * sInvWq[t * N + k];
+    else ijw[k] = active ? __ldg(A.invjw + (size_t)(e0 + el) * NN + t * N + k) : 1.0;
+  }
   if (A.phys.source == kBoussinesq) {  // SpatialDiscrete.cpp:254-262 + :1016-1032 (source·detJ w, times Φ)
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -349,8 +378,10 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
       R[D][k] += boussinesqSource<D>(ph, comp) / ijw[k];
     }
   }
+  if (needLast) mbarWait(&mbarLast, 0);
   if (active) {
     const size_t g = ((size_t)(e0 + el) * NV) * NN + t * N;
+    const double* sLe = sL + (el * NV) * NN + t * N;
 #pragma unroll
     for (int v = 0; v < NV; v++) {
 #pragma unroll
@@ -359,7 +390,7 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
         if (A.mode == 0) {
           o.x = A.aCur * u[v][k] + A.bdt * (R[v][k] * ijw[k]);
           o.y = A.aCur * u[v][k + 1] + A.bdt * (R[v][k + 1] * ijw[k + 1]);
-          if (A.aLast != 0.0) { const double2 l = ldg2(A.Ulast + g + (size_t)v * NN + k); o.x += A.aLast * l.x; o.y += A.aLast * l.y; }
+          if (A.aLast != 0.0) { const double2 l = *reinterpret_cast<const double2*>(sLe + v * NN + k); o.x += A.aLast * l.x; o.y += A.aLast * l.y; }
         } else if (A.mode == 1) { o.x = R[v][k] * ijw[k]; o.y = R[v][k + 1] * ijw[k + 1]; }
         else { o.x = R[v][k]; o.y = R[v][k + 1]; }
         *reinterpret_cast<double2*>(A.Uout + g + (size_t)v * NN + k) = o;
@@ -387,24 +418,23 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? 3 : 1) eulerLi
 #pragma unroll
     for (int d = 0; d < 2; d++) {
       const int id = d == 0 ? i : j;
-      __syncwarp();
-      double* sFe = sU + (el * NV) * NNP + i * PQ + j * N;
-#pragma unroll
-      for (int v = 0; v < NV; v++)
-#pragma unroll
-        for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sFe + v * NNP + k) = make_double2(R[v][k], R[v][k + 1]);
-      __syncwarp();
-      const double* sFl = sU + (el * NV) * NNP + (d == 0 ? j * N : i * PQ);
+      double* sXe = sU + el * NNP;
+      const double* sFl = sXe + (d == 0 ? j * N : i * PQ);
       const int stride = d == 0 ? PQ : N;
 #pragma unroll
-      for (int v = 0; v < NV; v++)
+      for (int v = 0; v < NV; v++) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sXe + i * PQ + j * N + k) = make_double2(R[v][k], R[v][k + 1]);
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < N; k++) {
-          double s = 0.0;
+          double x = 0.0;
 #pragma unroll
-          for (int a = 0; a < N; a++) s += A.k1[a * N + id] * sFl[v * NNP + a * stride + k];
-          R[v][k] = s;
+          for (int a = 0; a < N; a++) x += A.k1[a * N + id] * sFl[a * stride + k];
+          R[v][k] = x;
         }
+      }
     }
 #pragma unroll
     for (int v = 0; v < NV; v++) { double s = 0.0;

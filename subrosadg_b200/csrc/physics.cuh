@@ -20,10 +20,33 @@ enum { kRiemannFarfield = 0, kVelocityInflow = 1, kPressureOutflow = 2, kIsoTher
        kAdiabaticNonSlipWall = 5, kPeriodic = 6 };
 enum { kForwardEuler = 0, kHeunRK2 = 1, kSSPRK3 = 2 };
 
+// Reciprocal / square root for the hot loops: hardware seed (MUFU.RCP64H / RSQ64H, >= 20 good bits) + two Newton steps = full
+// double precision to within an ulp, without the special-case branches of the IEEE-exact library sequences (the stage kernels
+// are bound by the FP64 pipe and by dependent-issue latency, profiles/r01_euler_line_ncu.md).  NaN and sign propagate as usual;
+// arguments here are densities, pressures and wave-speed differences (never denormal).
+__device__ __forceinline__ double frcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double fsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  double s = x * y;
+  s = fma(0.5 * y, fma(-s, s, x), s);
+  return x == 0.0 ? 0.0 : s;
+}
+
 struct PhysParams {
   int model, eos, transport, conv, visc, source;
   int compressible, ns;
-  double cp, cv, gamma, mu0, k0, c0, rho0, padd, beta, tref;
+  double cp, cv, icv, kg, gamma, mu0, k0, c0, rho0, padd, beta, tref;
 };
 
 // PH = 1: compile-time specialisation CompresibleEuler/NS + IdealGas + HLLC (the benchmark configurations);
@@ -39,9 +62,9 @@ struct Phys {
     return ideal() ? (P.gamma - 1.0) * rho * e : P.c0 * P.c0 * (rho - P.rho0) + P.padd;
   }
   __device__ __forceinline__ double sound(double rho, double p) const {  // :51-54,74-77
-    return ideal() ? sqrt(P.gamma * p / rho) : P.c0;
+    return ideal() ? fsqrt(P.gamma * p * frcp(rho)) : P.c0;
   }
-  __device__ __forceinline__ double TFromE(double e) const { return e / P.cv; }
+  __device__ __forceinline__ double TFromE(double e) const { return e * P.icv; }
   __device__ __forceinline__ double sutherland(double T) const {  // :100-122
     const double Ts = 110.4 / 273.15;
     return sqrt(T * T * T) * (1.0 + Ts) / (T + Ts);
@@ -59,7 +82,7 @@ __device__ __forceinline__ double dotn(const double* c, const double* n) { doubl
 template <int D, int PH>
 __device__ __forceinline__ double compFromCons(const Phys<PH>& ph, const double* cons, double* comp) {
   const double rho = cons[0];
-  const double ir = 1.0 / rho;
+  const double ir = frcp(rho);
   comp[0] = rho;
 #pragma unroll
   for (int d = 0; d < D; d++) comp[1 + d] = cons[1 + d] * ir;
@@ -127,13 +150,13 @@ __device__ __forceinline__ void hllcFlux(const Phys<PH>& ph, const double* n, co
   const double g = ph.P.gamma;
   const double rL = compL[0], rR = compR[0], pL = compL[D + 2], pR = compR[D + 2];
   const double unL = dotn<D>(compL, n), unR = dotn<D>(compR, n);
-  const double cL = sqrt(g * pL * irL), cR = sqrt(g * pR * irR);
+  const double cL = fsqrt(g * pL * irL), cR = fsqrt(g * pR * irR);
   const double ps = fmax(0.0, 0.5 * (pL + pR) - (unR - unL) * (0.5 * (rL + rR)) * (0.5 * (cL + cR)));
-  const double kg = 0.5 * (g + 1.0) / g;
-  const double SL = unL - sqrt(g * irL * (pL + kg * fmax(ps - pL, 0.0)));
-  const double SR = unR + sqrt(g * irR * (pR + kg * fmax(ps - pR, 0.0)));
+  const double kg = ph.P.kg;   // (gamma + 1) / (2 gamma)
+  const double SL = unL - fsqrt(g * irL * (pL + kg * fmax(ps - pL, 0.0)));
+  const double SR = unR + fsqrt(g * irR * (pR + kg * fmax(ps - pR, 0.0)));
   const double mL = rL * (SL - unL), mR = rR * (SR - unR);
-  const double Ss = (pR - pL + mL * unL - mR * unR) / (mL - mR);
+  const double Ss = (pR - pL + mL * unL - mR * unR) * frcp(mL - mR);
   const bool left = SL >= 0.0 ? true : (SR <= 0.0 ? false : Ss >= 0.0);
   const bool pure = SL >= 0.0 || SR <= 0.0;
   const double S = left ? SL : SR, un = left ? unL : unR, p = left ? pL : pR, m = left ? mL : mR;
@@ -144,7 +167,7 @@ __device__ __forceinline__ void hllcFlux(const Phys<PH>& ph, const double* n, co
   for (int v = 0; v < NV; v++) cons[v] = left ? consL[v] : consR[v];
   double FK[NV];
   convNormalFlux<D>(ph, n, comp, FK);
-  const double inv = 1.0 / (S - Ss);
+  const double inv = frcp(S - Ss);
   double Us[NV];
   Us[0] = m * inv;
 #pragma unroll
@@ -224,7 +247,7 @@ __device__ __forceinline__ void convFlux(const Phys<PH>& ph, const double* n, co
 // VariableGradient::calculatePrimitiveFromConserved, VariableConvertor.cpp:574-620 (gradient of rho, u, T)
 template <int D, int PH>
 __device__ __forceinline__ void primGradFromConsGrad(const Phys<PH>& ph, const double* cons, const double* comp, const double* gc, double* gp) {
-  const double ir = 1.0 / comp[0];
+  const double ir = frcp(comp[0]);
 #pragma unroll
   for (int d = 0; d < D; d++) gp[d] = gc[d];
 #pragma unroll
@@ -232,7 +255,7 @@ __device__ __forceinline__ void primGradFromConsGrad(const Phys<PH>& ph, const d
 #pragma unroll
     for (int r = 0; r < D; r++) gp[(1 + c) * D + r] = (gc[(1 + c) * D + r] - gc[r] * comp[1 + c]) * ir;
   const double E = cons[D + 1] * ir;
-  const double icv = 1.0 / ph.P.cv;
+  const double icv = ph.P.icv;
 #pragma unroll
   for (int r = 0; r < D; r++) {
     double ge = (gc[(D + 1) * D + r] - gc[r] * E) * ir;

@@ -253,7 +253,7 @@ int sdg_create(const sdg_config* cfg, sdg_ctx** out) {
   P.model = cfg->model; P.eos = cfg->eos; P.transport = cfg->transport; P.conv = cfg->conv_flux; P.visc = cfg->visc_flux; P.source = cfg->source;
   P.compressible = (cfg->model == kCompresibleEuler || cfg->model == kCompresibleNS) ? 1 : 0;
   P.ns = (cfg->model == kCompresibleNS || cfg->model == kIncompresibleNS) ? 1 : 0;
-  P.cp = cfg->cp; P.cv = cfg->cv; P.gamma = 1.4;  // EquationOfState<IdealGas>::kSpecificHeatRatio, PhysicalModel.cpp:45
+  P.cp = cfg->cp; P.cv = cfg->cv; P.icv = 1.0 / cfg->cv; P.kg = 0.5 * (1.4 + 1.0) / 1.4; P.gamma = 1.4;  // EquationOfState<IdealGas>::kSpecificHeatRatio, PhysicalModel.cpp:45
   P.mu0 = cfg->mu; P.k0 = cfg->cp * cfg->mu / 0.71;  // Pr = 0.71, PhysicalModel.cpp:152-156
   P.c0 = cfg->c0; P.rho0 = cfg->rho0; P.padd = 0.01 * cfg->rho0 * cfg->c0 * cfg->c0;  // :63-66
   P.beta = cfg->beta; P.tref = cfg->t_ref;
