@@ -38,7 +38,7 @@ struct NsLayout {
   static constexpr int oN = oB + K * NV * NAQ;                      // affine: [K][NF][D]; curved: [K][D][NAQ]
   static constexpr int nN = AFFINE ? ((K * NF * D + 1) & ~1) : K * D * NAQ;
   static constexpr int oTab = oN + nN;                              // Dm, K1, Lend, Wq, InvWq, Wf, LiftC
-  static constexpr int nTab = (2 * N * N + 2 * N + 2 * NN + NQF + NF * NQF + 1) & ~1;
+  static constexpr int nTab = (2 * N * N + 2 * N + 2 * NN + NQF + 1) & ~1;
   static constexpr int oGeoE = oTab + nTab;                         // affine: [K][REC]
   static constexpr int oInvDet = oGeoE + (AFFINE ? K * REC : 0);    // affine: [K]
   static constexpr int oCf = oInvDet + ((K + 1) & ~1);              // affine: [MAXF][kCF]
@@ -52,12 +52,12 @@ struct NsLayout {
 template <int D, int N, int K, bool AFFINE, bool WITHG>
 struct NsShared {
   using L = NsLayout<D, N, K, AFFINE, WITHG>;
-  double *sU, *sG, *sFlux, *sB, *sN, *sDm, *sK1, *sLend, *sWq, *sInvWq, *sWf, *sLiftC, *sGeoE, *sInvDet, *sCf;
+  double *sU, *sG, *sFlux, *sB, *sN, *sDm, *sK1, *sLend, *sWq, *sInvWq, *sWf, *sGeoE, *sInvDet, *sCf;
   const int4* sRec;
   unsigned char *sFaceBase, *sSeq, *sNodePt;
   __device__ __forceinline__ void carve(double* smem) {
     sU = smem + L::oU; sG = smem + L::oG; sFlux = smem + L::oFlux; sB = smem + L::oB; sN = smem + L::oN;
-    sDm = smem + L::oTab; sK1 = sDm + N * N; sLend = sK1 + N * N; sWq = sLend + 2 * N; sInvWq = sWq + L::NN; sWf = sInvWq + L::NN; sLiftC = sWf + L::NQF;
+    sDm = smem + L::oTab; sK1 = sDm + N * N; sLend = sK1 + N * N; sWq = sLend + 2 * N; sInvWq = sWq + L::NN; sWf = sInvWq + L::NN;
     sGeoE = smem + L::oGeoE; sInvDet = smem + L::oInvDet; sCf = smem + L::oCf;
     sRec = reinterpret_cast<const int4*>(smem + L::oRec);
     sFaceBase = reinterpret_cast<unsigned char*>(smem + L::nDoubles); sSeq = sFaceBase + L::NF * L::NQF; sNodePt = sSeq + 4 * L::NQF;
@@ -67,14 +67,7 @@ struct NsShared {
     for (int i = tid; i < 2 * N; i += kThreads) sLend[i] = T.Lend[i];
     for (int i = tid; i < L::NN; i += kThreads) { const double w = T.wq[i]; sWq[i] = w; sInvWq[i] = 1.0 / w; }
     for (int i = tid; i < L::NQF; i += kThreads) sWf[i] = T.wf[i];
-    for (int i = tid; i < L::NF * L::NQF; i += kThreads) {
-      // trace of the rank-one BR2 lift at its own face, without the 1/detJ:  Σ_a l_a(±1)^2 / w(node(a, j))
-      const int f = i / L::NQF, dn = faceDirOf<D>(f), side = faceSideOf<D>(f), base = T.faceBase[i], st = strideOf<N, D>(dn);
-      double s = 0.0;
-      for (int a = 0; a < N; a++) { const double l = T.Lend[side * N + a]; s += l * l / T.wq[base + a * st]; }
-      sLiftC[i] = s;
-      sFaceBase[i] = (unsigned char)base;
-    }
+    for (int i = tid; i < L::NF * L::NQF; i += kThreads) sFaceBase[i] = (unsigned char)T.faceBase[i];
     for (int i = tid; i < 4 * L::NQF; i += kThreads) sSeq[i] = (unsigned char)T.seq[i];
     for (int i = tid; i < L::NF * L::NN; i += kThreads) sNodePt[i] = T.nodeFacePt[i];
   }
@@ -84,6 +77,14 @@ struct NsShared {
 template <int D, int NN>
 __device__ __forceinline__ double metricCurved(const StageArgs& A, int e, int q, int dd, int c) {
   return __ldg(A.geoE + ((size_t)e * (D * D) + dd * D + c) * NN + q);
+}
+// trace of the rank-one BR2 lift at its own face point, without the 1/detJ (affine meshes):  Σ_a l_a(±1)^2 / w(node(a, j))
+template <int N>
+__device__ __forceinline__ double liftTraceFactorAffine(const double* sInvWq, int base, int stride, const double* lend) {
+  double s = 0.0;
+#pragma unroll
+  for (int a = 0; a < N; a++) s += lend[a] * lend[a] * sInvWq[base + a * stride];
+  return s;
 }
 // lifting factor of a face point on curved meshes:  Σ_a l_a(±1)^2 / (detJ w)(node(a, j))
 template <int D, int N, int NN>
@@ -127,8 +128,11 @@ __device__ __forceinline__ void nsStageIn(const StageArgs& A, SH& S, unsigned lo
 // =====================================================================================================================
 // pass G
 // =====================================================================================================================
+#ifndef SDG_NSG_MINB
+#define SDG_NSG_MINB 3
+#endif
 template <int D, int N, int K, bool AFFINE>
-__global__ void __launch_bounds__(kThreads, 2) nsGradKernel(const __grid_constant__ StageArgs A) {
+__global__ void __launch_bounds__(kThreads, SDG_NSG_MINB) nsGradKernel(const __grid_constant__ StageArgs A) {
   using L = NsLayout<D, N, K, AFFINE, false>;
   constexpr int NV = L::NV, NG = L::NG, NN = L::NN, NQF = L::NQF, NF = L::NF, NAQ = L::NAQ;
   extern __shared__ __align__(16) double smem[];
@@ -302,8 +306,11 @@ __global__ void __launch_bounds__(kThreads, 2) nsGradKernel(const __grid_constan
 // =====================================================================================================================
 // pass R
 // =====================================================================================================================
+#ifndef SDG_NSR_MINB
+#define SDG_NSR_MINB 2
+#endif
 template <int D, int N, int K, bool AFFINE, int PH>
-__global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_constant__ StageArgs A) {
+__global__ void __launch_bounds__(kThreads, SDG_NSR_MINB) nsStageKernel(const __grid_constant__ StageArgs A) {
   using L = NsLayout<D, N, K, AFFINE, true>;
   constexpr int NV = L::NV, NG = L::NG, NN = L::NN, NQF = L::NQF, NF = L::NF, NAQ = L::NAQ, ITERS = L::ITERS;
   extern __shared__ __align__(16) double smem[];
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
     const double irL = compFromCons<D>(ph, consL, compL);
     double lamL = 0.0;
     if (br2) {
-      if constexpr (AFFINE) lamL = S.sLiftC[lfL * NQF + j] * invDetL;
+      if constexpr (AFFINE) lamL = liftTraceFactorAffine<N>(S.sInvWq, baseL, strideL, S.sLend + sideL * N) * invDetL;
       else lamL = liftTraceFactorCurved<D, N, NN>(A, eL, baseL, strideL, S.sLend + sideL * N);
     }
     int jr = j;
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 2) nsStageKernel(const __grid_consta
         else lineTraceGlobal<N, NG, NN>(A.Gvol + (size_t)eR * NG * NN, baseR, strideR, S.sLend + sideR * N, g);
         if (br2) {
           double lamR;
-          if constexpr (AFFINE) lamR = S.sLiftC[lfR * NQF + jr] * invDetR;
+          if constexpr (AFFINE) lamR = liftTraceFactorAffine<N>(S.sInvWq, baseR, strideR, S.sLend + sideR * N) * invDetR;
           else lamR = liftTraceFactorCurved<D, N, NN>(A, eR, baseR, strideR, S.sLend + sideR * N);
 #pragma unroll
           for (int v = 0; v < NV; v++)
