@@ -42,6 +42,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(model, elements):
+    """DRAM bytes per launch of the dominant kernel(s) from the committed `ncu --set full` capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per element of the profiled launch), scaled to this run's element count."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    per = d.get(model, {}).get("dram_bytes_per_element")
+    return None if per is None else float(per) * elements
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -190,8 +202,8 @@ def main():
            "config": {"workload": workload, "elements": sz.n, "scalar_dof": dof, "dt": dt, "l2": f"state {dof * 8 / 1e9:.2f} GB per buffer >> 126 MB L2 (inputs larger than L2, no flush needed)",
                       "relative_error": [float(x) for x in err]},
            "gpu_launches": int(launches), "clocks": ck,
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                        "kernel": "eulerStageKernel<3,4,8,affine,HLLC>" if a.model == "euler" else "nsGradKernel<3,4,8,affine> + nsStageKernel<3,4,8,affine,HLLC> (one stage = both launches)",
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": measured_traffic(a.model, sz.n),
+                        "kernel": "eulerLineKernel<4,8,affine,HLLC>" if a.model == "euler" else "nsGradKernel<3,4,8,affine> + nsStageKernel<3,4,8,affine,HLLC> (one stage = both launches)",
                         "kernel_ms": stage_ms, "algorithmic_bytes_per_launch": bytes_per_dof * dof,
                         "peak_source": how}}
 
@@ -201,12 +213,12 @@ def main():
         Un = U.numpy()
         Un[...] = S.get_state(t)
         n_e2e = max(1, min(a.steps, 3))
-        S.set_state(t, Un); S.stepSolver(dt, 1); Un[...] = S.get_state(t)  # warm
+        S.set_state(t, Un); S.stepSolver(dt, 1); S.get_state(t, out=Un)  # warm
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            S.set_state(t, Un)
-            e = S.stepSolver(dt, 1)
-            S_out = S.get_state(t)
+            S.set_state(t, Un)                 # host (pinned) modal coefficients -> device
+            e = S.stepSolver(dt, 1)            # one time step = 3 stages; relative_error_ comes back to the host
+            S_out = S.get_state(t, out=Un)     # device -> the caller's host buffer
         torch.cuda.synchronize()
         sec_e = time.perf_counter() - t0
         out["e2e"] = {"value": dof * nst * n_e2e / sec_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(dof * 8), "d2h_bytes_per_step": int(dof * 8 + 8 * sz.Nv),

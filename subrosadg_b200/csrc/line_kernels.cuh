@@ -32,8 +32,8 @@ struct LineLayout {
   static constexpr int NNP = N * PQ;            // padded nodes per variable
   static constexpr int REC = (D * D + 2) & ~1;
   static constexpr int MAXF = K * NF;
-  static constexpr int oU = 0;                                  // [K][NNP]  exchange tile of ONE variable (state for the traces, then fluxes)
-  static constexpr int oT = oU + K * NNP;                       // [K][NF][NV][NL] traces, later face fluxes
+  static constexpr int oU = 0;                                  // [2][K][NNP]  exchange tiles of TWO variables (state for the traces, then fluxes)
+  static constexpr int oT = oU + 2 * K * NNP;                   // [K][NF][NV][NL] traces, later face fluxes
   static constexpr int oW = oT + K * NF * NV * NL;              // wq[NN], invWq[NN], wf[NL]
   static constexpr int oGeoE = oW + 2 * NN + NL;                // affine: [K][REC]
   static constexpr int oInvDet = oGeoE + K * REC;               // [K]
@@ -170,23 +170,29 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? SDG_LINE_MINB 
   {
     double* sXe = sU + el * NNP;
 #pragma unroll
-    for (int v = 0; v < NV; v++) {
-      if (v > 0) __syncwarp();
+    for (int v0 = 0; v0 < NV; v0 += 2) {   // two variables per round: twice the loads in flight, half the warp barriers
+      if (v0 > 0) __syncwarp();
 #pragma unroll
-      for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sXe + i * PQ + j * N + k) = make_double2(u[v][k], u[v][k + 1]);
+      for (int vv = v0; vv < NV && vv < v0 + 2; vv++)
+#pragma unroll
+        for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sXe + (vv - v0) * K * NNP + i * PQ + j * N + k) = make_double2(u[vv][k], u[vv][k + 1]);
       __syncwarp();
 #pragma unroll
-      for (int d = 0; d < 2; d++) {
-        const int base = d == 0 ? t : i * PQ + j;          // nat = t: d = 0 -> (j',k') = t; d = 1 -> (i',k') = (i, j)
-        const int stride = d == 0 ? PQ : N;
-        double xm = 0.0, xp = 0.0;
+      for (int vv = v0; vv < NV && vv < v0 + 2; vv++) {
+        const double* sX = sXe + (vv - v0) * K * NNP;
 #pragma unroll
-        for (int a = 0; a < N; a++) {
-          const double x = sXe[base + a * stride];
-          xm += A.lend[a] * x; xp += A.lend[N + a] * x;
+        for (int d = 0; d < 2; d++) {
+          const int base = d == 0 ? t : i * PQ + j;          // nat = t: d = 0 -> (j',k') = t; d = 1 -> (i',k') = (i, j)
+          const int stride = d == 0 ? PQ : N;
+          double xm = 0.0, xp = 0.0;
+#pragma unroll
+          for (int a = 0; a < N; a++) {
+            const double x = sX[base + a * stride];
+            xm += A.lend[a] * x; xp += A.lend[N + a] * x;
+          }
+          sT[((el * NF + hexFaceOfAxis(d, 0)) * NV + vv) * NL + t] = xm;
+          sT[((el * NF + hexFaceOfAxis(d, 1)) * NV + vv) * NL + t] = xp;
         }
-        sT[((el * NF + hexFaceOfAxis(d, 0)) * NV + v) * NL + t] = xm;
-        sT[((el * NF + hexFaceOfAxis(d, 1)) * NV + v) * NL + t] = xp;
       }
     }
   }
@@ -335,28 +341,35 @@ __global__ void __launch_bounds__(K * N * N, (N == 4 && K == 8) ? SDG_LINE_MINB 
     const double* fm = sT + ((el * NF + hexFaceOfAxis(d, 0)) * NV) * NL + natRow;
     const double* fp = sT + ((el * NF + hexFaceOfAxis(d, 1)) * NV) * NL + natRow;
 #pragma unroll
-    for (int v = 0; v < NV; v++) {
-      double F[N];
+    for (int v0 = 0; v0 < NV; v0 += 2) {   // two variables per round through the two exchange tiles
+      __syncwarp();                                     // the previous tiles have been consumed by every line of the element
 #pragma unroll
-      for (int k = 0; k < N; k++) {
-        if (v == 0) F[k] = u[0][k] * um[k];
-        else if (v <= D) F[k] = u[v][k] * um[k] + pr[k] * metric(v - 1, k);
-        else F[k] = ph.comp() ? (u[D + 1][k] + pr[k]) * um[k] : u[D + 1][k] * um[k];
+      for (int v = v0; v < NV && v < v0 + 2; v++) {
+        double F[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          if (v == 0) F[k] = u[0][k] * um[k];
+          else if (v <= D) F[k] = u[v][k] * um[k] + pr[k] * metric(v - 1, k);
+          else F[k] = ph.comp() ? (u[D + 1][k] + pr[k]) * um[k] : u[D + 1][k] * um[k];
+        }
+#pragma unroll
+        for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sXe + (v - v0) * K * NNP + i * PQ + j * N + k) = make_double2(F[k], F[k + 1]);
       }
-      __syncwarp();                                     // the previous tile has been consumed by every line of the element
-#pragma unroll
-      for (int k = 0; k < N; k += 2) *reinterpret_cast<double2*>(sXe + i * PQ + j * N + k) = make_double2(F[k], F[k + 1]);
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < N; k += 2) {
-        const double2 a0 = *reinterpret_cast<const double2*>(fm + v * NL + k), a1 = *reinterpret_cast<const double2*>(fp + v * NL + k);
-        double r0 = -(lm * a0.x + lp * a1.x), r1 = -(lm * a0.y + lp * a1.y);
+      for (int v = v0; v < NV && v < v0 + 2; v++) {
+        const double* sFv = sFl + (v - v0) * K * NNP;
 #pragma unroll
-        for (int a = 0; a < N; a++) {
-          const double2 x = *reinterpret_cast<const double2*>(sFl + a * stride + k);
-          r0 += dmi[a] * x.x; r1 += dmi[a] * x.y;
+        for (int k = 0; k < N; k += 2) {
+          const double2 a0 = *reinterpret_cast<const double2*>(fm + v * NL + k), a1 = *reinterpret_cast<const double2*>(fp + v * NL + k);
+          double r0 = -(lm * a0.x + lp * a1.x), r1 = -(lm * a0.y + lp * a1.y);
+#pragma unroll
+          for (int a = 0; a < N; a++) {
+            const double2 x = *reinterpret_cast<const double2*>(sFv + a * stride + k);
+            r0 += dmi[a] * x.x; r1 += dmi[a] * x.y;
+          }
+          R[v][k] += r0; R[v][k + 1] += r1;
         }
-        R[v][k] += r0; R[v][k + 1] += r1;
       }
     }
   }

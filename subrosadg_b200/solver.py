@@ -178,9 +178,13 @@ class Solver:
         _chk(load_library().sdg_set_boundary_primitive(self.h, _dp(prim)))
 
     # -- state access --------------------------------------------------------------------------------------------------------
-    def get_state(self, t):
+    def get_state(self, t, out=None):
+        """Modal coefficients [n][Nb][Nv]; `out` may be a caller-owned (e.g. pinned) float64 array of that shape."""
         s = self.sizes(t)
-        out = np.zeros((s.n, s.Nb, s.Nv))
+        if out is None:
+            out = np.zeros((s.n, s.Nb, s.Nv))
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size != s.n * s.Nb * s.Nv:
+            raise ValueError("out must be a C-contiguous float64 array with n*Nb*Nv entries")
         _chk(load_library().sdg_get_state(self.h, t, _dp(out)))
         return out
 
