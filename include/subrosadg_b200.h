@@ -11,7 +11,9 @@
  * There is no CPU fallback: sdg_create fails when no CUDA device is usable.
  *
  * Data order at the seam (identical to the reference):
- *   element types      ElementEnum values (src/Utils/Enum.cpp:28-36): 1 line, 2 triangle, 3 quadrangle, 6 hexahedron
+ *   element types      ElementEnum values (src/Utils/Enum.cpp:28-36): 1 line, 2 triangle, 3 quadrangle, 6 hexahedron.
+ *                      One quadrangle or hexahedron block -> collocation tensor kernels; triangle blocks or several types in
+ *                      one 2-D mesh -> dense-operator kernels in the reference's modal representation (single GPU).
  *   node coordinates   [n][nn][D], gmsh node order of Lagrange order `geom_order` (PerElementMesh::node_coordinate_,
  *                      src/Mesh/ReadControl.cpp:86-92)
  *   modal state        [n][Nb][Nv] = Eigen::Matrix<Real,Nv,Nb> column-major per element (SolveControl.cpp:45-58),
@@ -43,7 +45,7 @@ typedef struct sdg_config {
   int32_t source;     /* SourceTermEnum: 0 None 1 Boussinesq */
   int32_t rk;         /* TimeIntegrationEnum: 0 ForwardEuler 1 HeunRK2 2 SSPRK3 */
   int32_t device;     /* CUDA device ordinal */
-  int32_t chunk;      /* elements per thread block (0 = automatic) */
+  int32_t chunk;      /* elements per thread block (0 = automatic; -1 = force the dense-operator path, diagnostics) */
   int32_t reorder;    /* 1: internal space-filling-curve element order (invisible at the seam); 0: keep caller order */
   double cp, cv;      /* ThermodynamicModel<Constant>, PhysicalModel.cpp:26-38 */
   double mu;          /* TransportModel dynamic viscosity (reference value for Sutherland), PhysicalModel.cpp:83-123 */
@@ -139,7 +141,10 @@ int sdg_get_state_device(sdg_ctx* ctx, int32_t type, void* U_device);
  * what: 0 geoE  1 invjw  2 minEdge  3 geoF  4 Phi[Nq][Nb]  5 1-D differentiation matrix  6 end-point interpolation
  *       7 Gauss abscissae  8 Gauss weights (doubles);  10 perm  11 chunkFaceOff  12 faceRec  13 chunkInterior
  *       14 chunkBoundary  15 {affine, K, nChunks, nOwned}  16 face-point permutations [4][Nqf]  17 faceBase  18 nodeFacePt
- *       19 modal function index triples (int32).  Element arrays are in INTERNAL order (position perm[e]). */
+ *       19 modal function index triples (int32).  Element arrays are in INTERNAL order (position perm[e]).
+ * Meshes with triangle blocks / several element types (dense-operator path): what = 100*type + {0 Phi[Nq][Nb], 1 grad Phi[Nq][D][Nb],
+ *       2 Phi_f[Naq][Nb], 3 least-squares projection[Nb][Nq], 4 detJ w[n][Nq], 5 (J^T)^-1 detJ w[n][Nq][D*D], 6 M^-1[n][Nb][Nb],
+ *       7 minEdge[n]}; 90 face normals[nf][Nqf][D]; 91 face |J| w[nf][Nqf] (doubles, caller element order). */
 int sdg_debug_plan(sdg_ctx* ctx, int32_t what, double* out_d, int32_t* out_i, int64_t* count);
 
 /* counters: number of kernels this library launched since creation (bench.py's gpu_launches) */

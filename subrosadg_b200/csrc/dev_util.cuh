@@ -1,0 +1,30 @@
+// dev_util.cuh — small RAII helpers shared by the C ABI translation unit and the device paths.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace sdg {
+
+#define CUDA_OK(x)                                                                                              \
+  do {                                                                                                          \
+    cudaError_t e_ = (x);                                                                                       \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  void alloc(size_t count) { release(); n = count; if (count) CUDA_OK(cudaMalloc(&p, count * sizeof(T))); }
+  void upload(const std::vector<T>& v, cudaStream_t s = 0) { alloc(v.size()); if (!v.empty()) { CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s)); CUDA_OK(cudaStreamSynchronize(s)); } }
+  void zero(cudaStream_t s = 0) { if (n) CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+}  // namespace sdg

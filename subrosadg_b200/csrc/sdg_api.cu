@@ -11,8 +11,10 @@
 #include <mutex>
 
 #include "../../include/subrosadg_b200.h"
+#include "dev_util.cuh"
 #include "host_plan.hpp"
 #include "line_kernels.cuh"
+#include "mixed_path.hpp"
 #include "ns_kernels.cuh"
 #include "tensor_kernels.cuh"
 
@@ -21,21 +23,6 @@ using namespace sdg;
 namespace {
 
 thread_local std::string g_err;
-
-#define CUDA_OK(x)                                                                                              \
-  do {                                                                                                          \
-    cudaError_t e_ = (x);                                                                                       \
-    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_));           \
-  } while (0)
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr; size_t n = 0;
-  void alloc(size_t count) { release(); n = count; if (count) CUDA_OK(cudaMalloc(&p, count * sizeof(T))); }
-  void upload(const std::vector<T>& v, cudaStream_t s = 0) { alloc(v.size()); if (!v.empty()) { CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s)); CUDA_OK(cudaStreamSynchronize(s)); } }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-  ~DevBuf() { release(); }
-};
 
 using StageFn = void (*)(const StageArgs&, int nBlocks, cudaStream_t);
 
@@ -154,6 +141,7 @@ struct sdg_ctx {
   double stepDt = 0.0;
   int nSend = 0;
   std::vector<double> hostNorm;
+  std::unique_ptr<MixedSolver> mx;   // dense-operator path: meshes with triangle blocks / several element types (mixed_path.cu)
 
   size_t stateDoubles() const { return (size_t)plan.blk.n * NV * plan.blk.T.NN; }
   size_t elemDoubles() const { return (size_t)NV * plan.blk.T.NN; }
@@ -294,10 +282,22 @@ void sdg_destroy(sdg_ctx* c) {
 int sdg_add_elements(sdg_ctx* c, int32_t type, int32_t n, int32_t n_ghost, int32_t geom_order, const double* coords) {
   SDG_TRY
   if (c->finalized) throw std::runtime_error("context already finalized");
-  if (!(type == kQuadrangle || type == kHexahedron)) throw std::runtime_error("device path implements quadrangle and hexahedron blocks (triangle blocks: not yet)");
+  if (!(type == kTriangle || type == kQuadrangle || type == kHexahedron)) throw std::runtime_error("device path implements triangle, quadrangle and hexahedron blocks");
   if (elemDim(type) != c->D) throw std::runtime_error("element dimension mismatch");
-  if (c->haveBlock) throw std::runtime_error("one element block per context on the device path");
   if (n <= 0 || n_ghost < 0 || n_ghost >= n || geom_order < 1 || geom_order > 5) throw std::runtime_error("bad element block arguments");
+  // Single quadrangle / hexahedron block: collocation tensor path.  Triangles, several element types in one mesh, or
+  // cfg.chunk == -1 (diagnostics): dense-operator path in the reference's modal representation (mixed_path.cu).
+  if (type == kTriangle || c->haveBlock || c->mx || c->cfg.chunk == -1) {
+    if (c->D != 2) throw std::runtime_error("several element types in one mesh: 2-D (triangle / quadrangle) only");
+    if (!c->mx) c->mx = std::make_unique<MixedSolver>(c->cfg.p, c->phys, c->nStages, c->rkc, c->stream, c->hasDevice, c->cfg.device);
+    if (c->haveBlock) {  // a tensor block was registered first: hand it over
+      BlockPlan& B = c->plan.blk;
+      c->mx->addBlock(B.type, B.n, B.nGhost, B.g, B.X.data());
+      B = BlockPlan{}; c->haveBlock = false;
+    }
+    c->mx->addBlock(type, n, n_ghost, geom_order, coords);
+    return 0;
+  }
   BlockPlan& B = c->plan.blk;
   B.type = type; B.D = c->D; B.p = c->cfg.p; B.g = geom_order; B.n = n; B.nGhost = n_ghost; B.nOwned = n - n_ghost;
   B.T = buildTensorTables(type, c->cfg.p);
@@ -325,6 +325,11 @@ int sdg_set_faces(sdg_ctx* c, int32_t n_int, int32_t n_bnd, const int32_t* le, c
 int sdg_finalize(sdg_ctx* c) {
   SDG_TRY
   if (c->finalized) throw std::runtime_error("context already finalized");
+  if (c->mx) {
+    if (!c->haveFaces) throw std::runtime_error("elements and faces must be set before sdg_finalize");
+    c->mx->setFaces(c->plan.F); c->mx->finalize(); c->finalized = true;
+    return 0;
+  }
   if (!c->haveBlock || !c->haveFaces) throw std::runtime_error("elements and faces must be set before sdg_finalize");
   MeshPlan& M = c->plan; BlockPlan& B = M.blk; const FaceInput& F = M.F;
   const int nf = F.nInt + F.nBnd;
@@ -409,6 +414,7 @@ int sdg_finalize(sdg_ctx* c) {
 
 int sdg_sizes(sdg_ctx* c, int32_t type, int32_t* out) {
   SDG_TRY
+  if (c->mx) { c->mx->sizes(type, out); return 0; }
   needType(c, type);
   const BlockPlan& B = c->plan.blk;
   out[0] = B.n; out[1] = B.T.NN; out[2] = B.T.NN; out[3] = B.T.NF; out[4] = B.T.NF * B.T.NQF; out[5] = B.nn; out[6] = B.T.NQF; out[7] = c->NV;
@@ -417,6 +423,7 @@ int sdg_sizes(sdg_ctx* c, int32_t type, int32_t* out) {
 
 int sdg_get_quadrature_coordinates(sdg_ctx* c, int32_t type, double* xq) {
   SDG_TRY
+  if (c->mx) { c->mx->quadratureCoordinates(type, xq); return 0; }
   needType(c, type);
   c->plan.quadratureCoordinates(xq);
   SDG_CATCH
@@ -424,6 +431,7 @@ int sdg_get_quadrature_coordinates(sdg_ctx* c, int32_t type, double* xq) {
 
 int sdg_get_boundary_quadrature_coordinates(sdg_ctx* c, double* xb) {
   SDG_TRY
+  if (c->mx) { if (!c->haveFaces) throw std::runtime_error("elements and faces must be set first"); if (!c->finalized) c->mx->setFaces(c->plan.F); c->mx->boundaryQuadratureCoordinates(xb); return 0; }
   if (!c->haveBlock || !c->haveFaces) throw std::runtime_error("elements and faces must be set first");
   MeshPlan tmp = c->plan;  // coordinates only; leaves the finalized plan untouched
   tmp.buildFaces(xb, true);
@@ -432,6 +440,7 @@ int sdg_get_boundary_quadrature_coordinates(sdg_ctx* c, double* xb) {
 
 int sdg_set_state_from_primitive(sdg_ctx* c, int32_t type, const double* prim) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->setStateFromPrimitive(type, prim); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
@@ -451,6 +460,7 @@ int sdg_set_state_from_primitive(sdg_ctx* c, int32_t type, const double* prim) {
 
 int sdg_set_boundary_primitive(sdg_ctx* c, const double* prim) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->setBoundaryPrimitive(prim); return 0; }
   needFinal(c); needDevice(c);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk; const int nb = c->plan.F.nBnd;
@@ -475,6 +485,7 @@ static void transformModal(sdg_ctx* c, const double* in, double* out, const doub
 
 int sdg_set_state_device(sdg_ctx* c, int32_t type, const void* U_device) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->setStateDevice(type, U_device); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   transformModal(c, (const double*)U_device, c->U[c->cur].p, c->Phi.p, 0);
@@ -483,6 +494,7 @@ int sdg_set_state_device(sdg_ctx* c, int32_t type, const void* U_device) {
 }
 int sdg_get_state_device(sdg_ctx* c, int32_t type, void* U_device) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->getStateDevice(type, U_device); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   transformModal(c, c->U[c->cur].p, (double*)U_device, c->PhiInv.p, 1);
@@ -491,6 +503,7 @@ int sdg_get_state_device(sdg_ctx* c, int32_t type, void* U_device) {
 
 int sdg_set_state(sdg_ctx* c, int32_t type, const double* U) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->setState(type, U); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const size_t nd = c->stateDoubles();
@@ -503,6 +516,7 @@ int sdg_set_state(sdg_ctx* c, int32_t type, const double* U) {
 }
 int sdg_get_state(sdg_ctx* c, int32_t type, double* U) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->getState(type, U); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const size_t nd = c->stateDoubles();
@@ -515,6 +529,7 @@ int sdg_get_state(sdg_ctx* c, int32_t type, double* U) {
 
 int sdg_get_state_at_quadrature(sdg_ctx* c, int32_t type, double* Uq) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->stateAtQuadrature(type, Uq); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
@@ -530,6 +545,7 @@ int sdg_get_state_at_quadrature(sdg_ctx* c, int32_t type, double* Uq) {
 
 int sdg_get_gradient_at_quadrature(sdg_ctx* c, int32_t type, double* Gq) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->gradientAtQuadrature(type, Gq); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   if (!c->phys.ns) throw std::runtime_error("gradient state exists for Navier-Stokes models only");
   CUDA_OK(cudaSetDevice(c->cfg.device));
@@ -553,6 +569,7 @@ int sdg_get_gradient_at_quadrature(sdg_ctx* c, int32_t type, double* Gq) {
 
 int sdg_compute_dt(sdg_ctx* c, double cfl, double* dt) {
   SDG_TRY
+  if (c->mx) { needFinal(c); *dt = c->mx->computeDt(cfl); return 0; }
   needFinal(c); needDevice(c);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
@@ -573,7 +590,7 @@ int sdg_compute_dt(sdg_ctx* c, double cfl, double* dt) {
 int sdg_num_stages(sdg_ctx* c) { return c->nStages; }
 int sdg_num_passes(sdg_ctx* c) { return c->phys.ns ? 2 : 1; }
 void* sdg_stream(sdg_ctx* c) { return (void*)c->stream; }
-int64_t sdg_launch_count(sdg_ctx* c) { return c->launches; }
+int64_t sdg_launch_count(sdg_ctx* c) { return c->launches + (c->mx ? c->mx->launches : 0); }
 
 int sdg_synchronize(sdg_ctx* c) {
   SDG_TRY
@@ -585,6 +602,7 @@ int sdg_synchronize(sdg_ctx* c) {
 
 int sdg_step_begin(sdg_ctx* c, double dt) {
   SDG_TRY
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c);
   c->stepDt = dt;
   SDG_CATCH
@@ -592,6 +610,7 @@ int sdg_step_begin(sdg_ctx* c, double dt) {
 
 int sdg_stage_pass(sdg_ctx* c, int32_t stage, int32_t pass, int32_t part, void* stream) {
   SDG_TRY
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c);
   if (stage < 0 || stage >= c->nStages || pass < 0 || pass >= sdg_num_passes(c) || part < -1 || part > 1) throw std::runtime_error("bad stage/pass/part");
   CUDA_OK(cudaSetDevice(c->cfg.device));
@@ -601,6 +620,7 @@ int sdg_stage_pass(sdg_ctx* c, int32_t stage, int32_t pass, int32_t part, void* 
 
 int sdg_step_end(sdg_ctx* c, double* sums) {
   SDG_TRY
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   finishStep(c);
@@ -610,6 +630,7 @@ int sdg_step_end(sdg_ctx* c, double* sums) {
 
 int sdg_step(sdg_ctx* c, double dt, int32_t n_steps, double* relative_error) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->step(dt, n_steps, relative_error, nullptr); return 0; }
   needFinal(c); needDevice(c);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   c->stepDt = dt;
@@ -629,6 +650,7 @@ int sdg_step(sdg_ctx* c, double dt, int32_t n_steps, double* relative_error) {
 
 int sdg_step_timed(sdg_ctx* c, double dt, int32_t n_steps, double* relative_error, float* milliseconds) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->step(dt, n_steps, relative_error, milliseconds); return 0; }
   needFinal(c); needDevice(c);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   cudaEvent_t e0, e1;
@@ -654,6 +676,7 @@ int sdg_step_timed(sdg_ctx* c, double dt, int32_t n_steps, double* relative_erro
 
 int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
   SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->residual(type, Rmodal, rhsq); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
@@ -684,6 +707,13 @@ int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
 
 int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int64_t* count) {
   SDG_TRY
+  if (c->mx) {
+    needFinal(c);
+    const std::vector<double>& d = c->mx->debugArray(what);
+    if (count) *count = (int64_t)d.size();
+    if (out_d) std::memcpy(out_d, d.data(), d.size() * sizeof(double));
+    return 0;
+  }
   needFinal(c);
   const BlockPlan& B = c->plan.blk;
   const std::vector<double>* d = nullptr; const std::vector<int>* i = nullptr;
@@ -709,6 +739,7 @@ int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int6
 
 int sdg_set_halo_send(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* elems) {
   SDG_TRY
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
@@ -722,6 +753,7 @@ int sdg_set_halo_send(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* e
 
 int sdg_halo_pack(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
   SDG_TRY
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c); needType(c, type);
   if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
   CUDA_OK(cudaSetDevice(c->cfg.device));
@@ -737,6 +769,7 @@ int sdg_halo_pack(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
 
 int sdg_halo_buffers_device(sdg_ctx* c, int32_t type, int32_t what, void** send, int64_t* send_doubles, void** recv, int64_t* recv_doubles) {
   SDG_TRY
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c); needType(c, type);
   if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
   const BlockPlan& B = c->plan.blk;

@@ -249,7 +249,7 @@ class Solver:
         cnt = ctypes.c_int64(0)
         lib = load_library()
         _chk(lib.sdg_debug_plan(self.h, what, None, None, ctypes.byref(cnt)))
-        if what < 10:
+        if what < 10 or what >= 90:   # doubles (>= 90: dense-operator path tables, see sdg_debug_plan)
             out = np.zeros(cnt.value)
             _chk(lib.sdg_debug_plan(self.h, what, _dp(out), None, ctypes.byref(cnt)))
         else:
