@@ -26,7 +26,7 @@
 
 namespace sdg {
 
-template <int D, int N, int K, bool AFFINE, bool WITHG>
+template <int D, int N, int K, bool AFFINE, bool WITHG, int TH = kThreads>
 struct NsLayout {
   static constexpr int NV = D + 2, NG = NV * D, NN = Pow<N, D>::v, NQF = NN / N, NF = 2 * D, NAQ = NF * NQF;
   static constexpr int REC = (D * D + 2) & ~1;
@@ -46,12 +46,12 @@ struct NsLayout {
   static constexpr int nDoubles = oRec + MAXF * 2;
   static constexpr int nBytesTab = NF * NQF + 4 * NQF + NF * NN;
   static constexpr size_t bytes = sizeof(double) * nDoubles + ((nBytesTab + 15) / 16) * 16;
-  static constexpr int ITERS = (K * NN + kThreads - 1) / kThreads;
+  static constexpr int ITERS = (K * NN + TH - 1) / TH;
 };
 
-template <int D, int N, int K, bool AFFINE, bool WITHG>
+template <int D, int N, int K, bool AFFINE, bool WITHG, int TH = kThreads>
 struct NsShared {
-  using L = NsLayout<D, N, K, AFFINE, WITHG>;
+  using L = NsLayout<D, N, K, AFFINE, WITHG, TH>;
   double *sU, *sG, *sFlux, *sB, *sN, *sDm, *sK1, *sLend, *sWq, *sInvWq, *sWf, *sGeoE, *sInvDet, *sCf;
   const int4* sRec;
   unsigned char *sFaceBase, *sSeq, *sNodePt;
@@ -63,13 +63,13 @@ struct NsShared {
     sFaceBase = reinterpret_cast<unsigned char*>(smem + L::nDoubles); sSeq = sFaceBase + L::NF * L::NQF; sNodePt = sSeq + 4 * L::NQF;
   }
   __device__ __forceinline__ void loadTables(const TensorDev& T, int tid) {
-    for (int i = tid; i < N * N; i += kThreads) { sDm[i] = T.Dm[i]; sK1[i] = T.K1[i]; }
-    for (int i = tid; i < 2 * N; i += kThreads) sLend[i] = T.Lend[i];
-    for (int i = tid; i < L::NN; i += kThreads) { const double w = T.wq[i]; sWq[i] = w; sInvWq[i] = 1.0 / w; }
-    for (int i = tid; i < L::NQF; i += kThreads) sWf[i] = T.wf[i];
-    for (int i = tid; i < L::NF * L::NQF; i += kThreads) sFaceBase[i] = (unsigned char)T.faceBase[i];
-    for (int i = tid; i < 4 * L::NQF; i += kThreads) sSeq[i] = (unsigned char)T.seq[i];
-    for (int i = tid; i < L::NF * L::NN; i += kThreads) sNodePt[i] = T.nodeFacePt[i];
+    for (int i = tid; i < N * N; i += TH) { sDm[i] = T.Dm[i]; sK1[i] = T.K1[i]; }
+    for (int i = tid; i < 2 * N; i += TH) sLend[i] = T.Lend[i];
+    for (int i = tid; i < L::NN; i += TH) { const double w = T.wq[i]; sWq[i] = w; sInvWq[i] = 1.0 / w; }
+    for (int i = tid; i < L::NQF; i += TH) sWf[i] = T.wf[i];
+    for (int i = tid; i < L::NF * L::NQF; i += TH) sFaceBase[i] = (unsigned char)T.faceBase[i];
+    for (int i = tid; i < 4 * L::NQF; i += TH) sSeq[i] = (unsigned char)T.seq[i];
+    for (int i = tid; i < L::NF * L::NN; i += TH) sNodePt[i] = T.nodeFacePt[i];
   }
 };
 
@@ -96,7 +96,7 @@ __device__ __forceinline__ double liftTraceFactorCurved(const StageArgs& A, int 
 }
 
 // stages the chunk-owned contiguous ranges with TMA bulk copies; returns after the data has landed
-template <class SH, int D, int N, int K, bool AFFINE, bool WITHG>
+template <class SH, int D, int N, int K, bool AFFINE, bool WITHG, int TH = kThreads>
 __device__ __forceinline__ void nsStageIn(const StageArgs& A, SH& S, unsigned long long* mbar, int tid, int chunk, int e0, int ne, int f0, int nfc) {
   using L = NsLayout<D, N, K, AFFINE, WITHG>;
   constexpr int NV = L::NV, NG = L::NG, NN = L::NN;
@@ -117,8 +117,8 @@ __device__ __forceinline__ void nsStageIn(const StageArgs& A, SH& S, unsigned lo
       bulkLoad(S.sCf, A.cfGeo + (size_t)f0 * kCF, (unsigned)(nfc * kCF * sizeof(double)), mbar);
     }
   }
-  if (!bulkU) { const double* src = A.Uin + (size_t)e0 * NV * NN; for (int i = tid; i < ne * NV * NN; i += kThreads) S.sU[i] = src[i]; }
-  if constexpr (WITHG) { if (!bulkG) { const double* src = A.Gvol + (size_t)e0 * NG * NN; for (int i = tid; i < ne * NG * NN; i += kThreads) S.sG[i] = src[i]; } }
+  if (!bulkU) { const double* src = A.Uin + (size_t)e0 * NV * NN; for (int i = tid; i < ne * NV * NN; i += TH) S.sU[i] = src[i]; }
+  if constexpr (WITHG) { if (!bulkG) { const double* src = A.Gvol + (size_t)e0 * NG * NN; for (int i = tid; i < ne * NG * NN; i += TH) S.sG[i] = src[i]; } }
   S.loadTables(*A.tab, tid);
   mbarWait(mbar, 0);
   if constexpr (AFFINE) { if (tid < ne) S.sInvDet[tid] = 1.0 / S.sGeoE[tid * L::REC + D * D]; }
@@ -309,13 +309,13 @@ __global__ void __launch_bounds__(kThreads, SDG_NSG_MINB) nsGradKernel(const __g
 #ifndef SDG_NSR_MINB
 #define SDG_NSR_MINB 2
 #endif
-template <int D, int N, int K, bool AFFINE, int PH>
-__global__ void __launch_bounds__(kThreads, SDG_NSR_MINB) nsStageKernel(const __grid_constant__ StageArgs A) {
-  using L = NsLayout<D, N, K, AFFINE, true>;
+template <int D, int N, int K, bool AFFINE, int PH, int TH = kThreads>
+__global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_constant__ StageArgs A) {
+  using L = NsLayout<D, N, K, AFFINE, true, TH>;
   constexpr int NV = L::NV, NG = L::NG, NN = L::NN, NQF = L::NQF, NF = L::NF, NAQ = L::NAQ, ITERS = L::ITERS;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
-  NsShared<D, N, K, AFFINE, true> S; S.carve(smem);
+  NsShared<D, N, K, AFFINE, true, TH> S; S.carve(smem);
   const int tid = threadIdx.x;
   const int chunk = A.chunkList ? A.chunkList[blockIdx.x] : blockIdx.x;
   const int e0 = chunk * K;
@@ -327,12 +327,12 @@ __global__ void __launch_bounds__(kThreads, SDG_NSR_MINB) nsStageKernel(const __
   if (A.mode == 0 && A.aLast != 0.0) {   // U_last is consumed at the very end: pull its lines into L2 now
     const char* p = reinterpret_cast<const char*>(A.Ulast + (size_t)e0 * NV * NN);
     const int bytes = ne * NV * NN * (int)sizeof(double);
-    for (int o = tid * 128; o < bytes; o += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+    for (int o = tid * 128; o < bytes; o += TH * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
   }
-  nsStageIn<decltype(S), D, N, K, AFFINE, true>(A, S, &mbar, tid, chunk, e0, ne, f0, nfc);
+  nsStageIn<decltype(S), D, N, K, AFFINE, true, TH>(A, S, &mbar, tid, chunk, e0, ne, f0, nfc);
 
   // ---- R2: Riemann flux minus averaged viscous normal flux at the face points ------------------------------------------------------
-  for (int fp = tid; fp < nfc * NQF; fp += kThreads) {
+  for (int fp = tid; fp < nfc * NQF; fp += TH) {
     const int fi = fp / NQF, j = fp - fi * NQF;
     const int4 rec = S.sRec[fi];
     const int eL = rec.x, eR = rec.y, faceId = rec.z;
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, SDG_NSR_MINB) nsStageKernel(const __
   double ijwv[ITERS];
 #pragma unroll
   for (int it = 0; it < ITERS; it++) {
-    const int nd = tid + it * kThreads;
+    const int nd = tid + it * TH;
     ijwv[it] = 0.0;
     if (nd < nNodes) {
       const int el = nd / NN, q = nd - el * NN;
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, SDG_NSR_MINB) nsStageKernel(const __
   double R[ITERS][NV];
 #pragma unroll
   for (int it = 0; it < ITERS; it++) {
-    const int nd = tid + it * kThreads;
+    const int nd = tid + it * TH;
 #pragma unroll
     for (int v = 0; v < NV; v++) R[it][v] = 0.0;
     if (nd < nNodes) {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, SDG_NSR_MINB) nsStageKernel(const __
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
-      const int nd = tid + it * kThreads;
+      const int nd = tid + it * TH;
       if (nd < nNodes) {
         const int el = nd / NN, q = nd - el * NN;
 #pragma unroll
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, SDG_NSR_MINB) nsStageKernel(const __
       const double* in = (dd & 1) ? bufB : bufA;
       double* out = (dd & 1) ? bufA : bufB;
       const int st = strideOf<N, D>(dd);
-      for (int nd = tid; nd < nNodes; nd += kThreads) {
+      for (int nd = tid; nd < nNodes; nd += TH) {
         const int el = nd / NN, q = nd - el * NN;
         const int id = (q / st) % N, qb = q - id * st;
 #pragma unroll
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, SDG_NSR_MINB) nsStageKernel(const __
     __syncthreads();
     if (tid < NV) {
       double s = 0.0;
-      for (int w = 0; w < kThreads / 32; w++) s += red[w * NV + tid];
+      for (int w = 0; w < TH / 32; w++) s += red[w * NV + tid];
       A.normPartial[(size_t)chunk * NV + tid] = s / NN;
     }
   }

@@ -55,12 +55,20 @@ void launchNsGrad(const StageArgs& a, int nBlocks, cudaStream_t s) {
   if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsGradKernel<D, N, K, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
   nsGradKernel<D, N, K, AFFINE><<<nBlocks, kThreads, L::bytes, s>>>(a);
 }
+// threads per block of the NS residual pass: one face point per thread in the face phase where the register budget allows
+// (P3 hexahedra: 2x2x1 brick = 20 faces x 16 points = 320 face points, 256 nodes)
+template <int D, int N> struct NsThreadsOf { static constexpr int TH = kThreads; };
+#ifndef SDG_NSR_TH34
+#define SDG_NSR_TH34 256
+#endif
+template <> struct NsThreadsOf<3, 4> { static constexpr int TH = SDG_NSR_TH34; };
 template <int D, int N, int K, bool AFFINE, int PH>
 void launchNsStage(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  using L = NsLayout<D, N, K, AFFINE, true>;
+  constexpr int TH = NsThreadsOf<D, N>::TH;
+  using L = NsLayout<D, N, K, AFFINE, true, TH>;
   static bool configured = false;
-  if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsStageKernel<D, N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
-  nsStageKernel<D, N, K, AFFINE, PH><<<nBlocks, kThreads, L::bytes, s>>>(a);
+  if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsStageKernel<D, N, K, AFFINE, PH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
+  nsStageKernel<D, N, K, AFFINE, PH, TH><<<nBlocks, TH, L::bytes, s>>>(a);
 }
 template <int D, int N> struct NsChunkOf;
 template <> struct NsChunkOf<2, 2> { static constexpr int K = 32; };
