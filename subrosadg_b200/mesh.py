@@ -457,3 +457,25 @@ def write_flat(mesh: Mesh, path) -> None:
         f.write(np.array([fc["n_int"], fc["n_bnd"]], dtype="<i4").tobytes())
         for k in ("le", "lt", "lf", "re", "rt", "rf", "rot", "bc", "phys"):
             f.write(np.ascontiguousarray(fc[k], dtype="<i4").tobytes())
+
+
+# named meshes of the BASELINE configurations for the C++ example drivers (examples/*.cpp): `python -m subrosadg_b200.mesh NAME FILE [scale]`
+EXAMPLE_MESHES = {
+    # config 2: O-mesh of curved P3 quads around the NACA0012 (examples/naca0012_2d_ceuler.cpp:155-172 uses 4 transfinite blocks)
+    "naca0012": lambda s: naca0012(nr=max(4, int(19 * s)), nt=max(12, 2 * int(39 * s))),
+    # config 3: curved P3 quad rings at the cylinder + triangles outside (examples/karmanvortex_2d_cns.cpp: 4 ring blocks 15x11 + tris)
+    "karmanvortex": lambda s: annulus(max(4, int(22 * s)), max(12, 4 * int(15 * s)), r0=0.5, r1=20.0, geom_order=3, stretch=2.0,
+                                      tri_rings=max(2, int(11 * s)), phys_bc={1: RIEMANN_FARFIELD, 2: ADIABATIC_NONSLIP_WALL}),
+    # config 5: cubed-sphere shell of curved P3 hexahedra (examples/sphere_3d_cns.cpp:259-296: 6 sphere blocks 11x11x9 + far blocks)
+    "sphere": lambda s: cubed_sphere_shell(max(2, int(11 * s)), max(2, int(9 * s)), r0=0.5, r1=5.0, geom_order=3,
+                                           phys_bc={1: RIEMANN_FARFIELD, 2: ADIABATIC_NONSLIP_WALL}),
+}
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) < 3 or sys.argv[1] not in EXAMPLE_MESHES:
+        raise SystemExit(f"usage: python -m subrosadg_b200.mesh {{{'|'.join(EXAMPLE_MESHES)}}} out.sdgm [scale=1.0]")
+    m = EXAMPLE_MESHES[sys.argv[1]](float(sys.argv[3]) if len(sys.argv) > 3 else 1.0)
+    write_flat(m, sys.argv[2])
+    print({t: int(np.asarray(b["coords"]).shape[0]) for t, b in m.blocks.items()}, "faces", int(m.faces["n_int"]), "+", int(m.faces["n_bnd"]))
