@@ -76,7 +76,10 @@ template <> struct NsChunkOf<2, 3> { static constexpr int K = 16; };
 template <> struct NsChunkOf<2, 4> { static constexpr int K = 16; };
 template <> struct NsChunkOf<3, 2> { static constexpr int K = 16; };
 template <> struct NsChunkOf<3, 3> { static constexpr int K = 8; };
-template <> struct NsChunkOf<3, 4> { static constexpr int K = 4; };
+#ifndef SDG_NS34_K
+#define SDG_NS34_K 4
+#endif
+template <> struct NsChunkOf<3, 4> { static constexpr int K = SDG_NS34_K; };
 template <int D, int N>
 void pickNs(bool affine, int ph, StageFn& grad, StageFn& stage, int& K) {
   constexpr int KK = NsChunkOf<D, N>::K;

@@ -68,3 +68,43 @@ def test_cpp_driver_matches_ctypes_path(examples_built, tmp_path, name, dim, vel
     ref = S.state_at_quadrature(S.types[0])
     got = np.fromfile(out, dtype=np.float64).reshape(ref.shape)
     assert np.array_equal(got, ref), f"C++ driver vs ctypes path: rel-L2 {cases.rel_l2(got, ref):.3e}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,producer,scale,cfg,vel", [
+    ("naca0012_2d_ceuler", "naca0012", 0.3, dict(p=3, conv_flux=2, rk=2), [0.63 * np.cos(np.deg2rad(2.0)), 0.63 * np.sin(np.deg2rad(2.0))]),
+    ("karmanvortex_2d_cns", "karmanvortex", 0.3, dict(p=3, model=1, transport=2, mu=1.4 * 0.2 / 200.0, conv_flux=2, visc_flux=2, rk=2), [0.2, 0.0]),
+    ("sphere_3d_cns", "sphere", 0.3, dict(p=3, model=1, transport=1, mu=1.4 * 0.2 / 200.0, conv_flux=2, visc_flux=2, rk=2), [0.0, 0.2, 0.0]),
+])
+def test_cpp_config_drivers_match_ctypes_path(examples_built, tmp_path, name, producer, scale, cfg, vel):
+    """examples/{naca0012_2d_ceuler,karmanvortex_2d_cns,sphere_3d_cns}.cpp (configs 2, 3, 5 with the reference's IC / BC values)
+    over a flat mesh file: same result as the Python host mirror, bit for bit, on every element type."""
+    from subrosadg_b200.solver import Solver
+    mesh = M.EXAMPLE_MESHES[producer](scale)
+    path = tmp_path / "mesh.sdgm"
+    M.write_flat(mesh, path)
+    out = tmp_path / "state"
+    r = subprocess.run([os.path.join(EX, "_build", name), str(path), "3", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    dim = mesh.dim
+
+    def ic(x):
+        one = np.ones(x.shape[:-1])
+        return np.stack([1.4 * one] + [v * one for v in vel] + [one], axis=-1)
+
+    def bc(x, phys, time=None):
+        one = np.ones(x.shape[:-1])
+        return np.stack([1.4 * one] + [np.where(phys == 2, 0.0, v) * one for v in vel] + [one], axis=-1)
+
+    S = Solver(cfg, mesh, device=0)
+    S.initializeSolver(ic, bc)
+    dt = S.calculateDeltaTime(1.0)
+    assert abs(float(r.stdout.strip().splitlines()[-1].split()[-1]) - dt) <= 1e-5 * dt   # printed with 6 significant digits
+    S.stepSolver(dt, 3)
+    assert len(S.types) == (2 if producer == "karmanvortex" else 1)
+    for t in S.types:
+        ref = S.state_at_quadrature(t)
+        got = np.fromfile(f"{out}.{t}.bin", dtype=np.float64).reshape(ref.shape)
+        assert np.isfinite(ref).all()
+        assert np.array_equal(got, ref), f"{name} type {t}: C++ driver vs ctypes path rel-L2 {cases.rel_l2(got, ref):.3e}"
+    assert dim == len(vel)
