@@ -142,7 +142,7 @@ struct sdg_ctx {
   int64_t launches = 0;
 
   // device state
-  DevBuf<double> U[3], geoE, invjw, minEdge, geoF, dummy, Phi, PhiInv, PhiT, normPartial, normOut, dtPartial, scratch, sendBuf, cfGeo;
+  DevBuf<double> U[3], geoE, invjw, minEdge, geoF, dummy, Phi, PhiInv, PhiT, normPartial, normSlices, normOut, dtPartial, scratch, sendBuf, cfGeo;
   DevBuf<int> perm, faceRec, chunkOff, chunkInterior, chunkBoundary, sendList;
   DevBuf<TensorDev> tab;
   int cur = 0;          // index of the buffer holding the current state
@@ -219,8 +219,10 @@ void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st, int pass = -1) {
 void finishStep(sdg_ctx* c) { if (c->nStages == 1) c->cur = (c->cur + 1) % 3; c->latest = c->cur; }
 
 void reduceNorm(sdg_ctx* c, double* sums) {
-  normReduceKernel<<<c->NV, 256, 0, c->stream>>>(c->normPartial.p, c->plan.blk.nChunks, c->NV, c->normOut.p);
-  c->launches++;
+  constexpr int kSlices = 128;
+  normReduceKernel<<<dim3(c->NV, kSlices), 256, 0, c->stream>>>(c->normPartial.p, c->plan.blk.nChunks, c->NV, c->normSlices.p);
+  normReduceKernel<<<dim3(c->NV, 1), 128, 0, c->stream>>>(c->normSlices.p, kSlices, c->NV, c->normOut.p);
+  c->launches += 2;
   CUDA_OK(cudaMemcpyAsync(c->hostNorm.data(), c->normOut.p, sizeof(double) * c->NV, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   for (int v = 0; v < c->NV; v++) sums[v] = c->hostNorm[v];
@@ -400,7 +402,7 @@ int sdg_finalize(sdg_ctx* c) {
     c->Phi.upload(B.T.Phi, c->stream); c->PhiInv.upload(B.T.PhiInv, c->stream);
     { std::vector<double> PT(B.T.Phi.size()); const int NN = B.T.NN; for (int q = 0; q < NN; q++) for (int b = 0; b < NN; b++) PT[(size_t)b * NN + q] = B.T.Phi[(size_t)q * NN + b]; c->PhiT.upload(PT, c->stream); }
     if (c->phys.ns) { c->G.alloc((size_t)B.n * c->NV * c->D * B.T.NN); CUDA_OK(cudaMemsetAsync(c->G.p, 0, c->G.n * sizeof(double), c->stream)); }
-    c->normPartial.alloc((size_t)B.nChunks * c->NV); c->normOut.alloc(8); c->dtPartial.alloc(1024);
+    c->normPartial.alloc((size_t)B.nChunks * c->NV); c->normSlices.alloc(128 * 8); c->normOut.alloc(8); c->dtPartial.alloc(1024);
     CUDA_OK(cudaMemsetAsync(c->normPartial.p, 0, c->normPartial.n * sizeof(double), c->stream));
     std::vector<TensorDev> td(1);
     TensorDev& t = td[0]; std::memset(&t, 0, sizeof(t));

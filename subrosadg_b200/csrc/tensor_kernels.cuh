@@ -609,16 +609,20 @@ __global__ void deltaTimeKernel(const double* __restrict__ U, const double* __re
   }
 }
 
-// deterministic final reduction of the per-chunk norm partials: out[v] = sum_c partial[c][v]
-__global__ void normReduceKernel(const double* __restrict__ partial, int nChunks, int NV, double* __restrict__ out) {
-  __shared__ double red[8][32];
+// deterministic reduction of the per-chunk norm partials: block (v, y) sums its contiguous slice of the rows,
+// out[y][v] = sum_{c in slice y} partial[c][v]; launched twice (slices, then the slice sums) so that a 2M-element mesh is not
+// summed by NV thread blocks
+__global__ void normReduceKernel(const double* __restrict__ partial, int nRows, int NV, double* __restrict__ out) {
+  __shared__ double red[32];
   const int v = blockIdx.x;
+  const int per = (nRows + gridDim.y - 1) / gridDim.y;
+  const int lo = blockIdx.y * per, hi = min(nRows, lo + per);
   double s = 0.0;
-  for (int c = threadIdx.x; c < nChunks; c += blockDim.x) s += partial[(size_t)c * NV + v];
+  for (int c = lo + threadIdx.x; c < hi; c += blockDim.x) s += partial[(size_t)c * NV + v];
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[0][w]; out[v] = t; }
+  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w]; out[(size_t)blockIdx.y * NV + v] = t; }
 }
 
 // gather of the halo send list: out[i][:] = U[elems[i]][:]
