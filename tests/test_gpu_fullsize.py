@@ -63,7 +63,7 @@ def test_modal_roundtrip_at_scale(built):
     U = S.get_state(HEX)
     S.set_state(HEX, U)
     V = S.get_state(HEX)
-    assert cases.rel_l2(V, U) < 1e-14
+    assert cases.rel_l2(V, U) < 1e-12   # modal -> collocation -> modal through Phi / Phi^-1 (cond ~ 1e2)
     # every face of the mesh appears in the chunk lists of both of its parents: 3 faces per element, listed twice unless both
     # parents share a 2x2x2 brick (12 of a brick's 36 faces)
     off = S.debug_plan(11)
