@@ -474,8 +474,17 @@ EXAMPLE_MESHES = {
 
 if __name__ == "__main__":
     import sys
+    if len(sys.argv) >= 4 and sys.argv[1] == "convert":
+        # gmsh MSH 4.1 file -> flat mesh file; boundary types as physical:BoundaryConditionEnum pairs, e.g. 1:0,2:4
+        from . import msh
+        bc = {int(a): int(b) for a, b in (kv.split(":") for kv in (sys.argv[4] if len(sys.argv) > 4 else "1:0").split(","))}
+        m = msh.read_msh(sys.argv[2], bc)
+        write_flat(m, sys.argv[3])
+        print({t: int(np.asarray(b["coords"]).shape[0]) for t, b in m.blocks.items()}, "faces", int(m.faces["n_int"]), "+", int(m.faces["n_bnd"]))
+        raise SystemExit(0)
     if len(sys.argv) < 3 or sys.argv[1] not in EXAMPLE_MESHES:
-        raise SystemExit(f"usage: python -m subrosadg_b200.mesh {{{'|'.join(EXAMPLE_MESHES)}}} out.sdgm [scale=1.0]")
+        raise SystemExit(f"usage: python -m subrosadg_b200.mesh {{{'|'.join(EXAMPLE_MESHES)}}} out.sdgm [scale=1.0]\n"
+                         "       python -m subrosadg_b200.mesh convert in.msh out.sdgm [phys:bc,...]")
     m = EXAMPLE_MESHES[sys.argv[1]](float(sys.argv[3]) if len(sys.argv) > 3 else 1.0)
     write_flat(m, sys.argv[2])
     print({t: int(np.asarray(b["coords"]).shape[0]) for t, b in m.blocks.items()}, "faces", int(m.faces["n_int"]), "+", int(m.faces["n_bnd"]))
