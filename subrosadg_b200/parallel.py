@@ -398,7 +398,12 @@ def bench_main(a, workload, metric, unit, bytes_per_dof, peaks, ClockSampler, ic
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line (NCCL_DEBUG=VERSION/INFO print there)
+    # stdout carries exactly one JSON line: NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) on file descriptor 1 when a
+    # communicator is created, so fd 1 points at stderr until the communicators exist (end of the warm-up steps)
+    import sys
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # NCCL's internal stream: ahead of the interior thread blocks
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     mesh = M.periodic_box_fast(3, a.cells)
@@ -411,6 +416,8 @@ def bench_main(a, workload, metric, unit, bytes_per_dof, peaks, ClockSampler, ic
     dt = D.calculateDeltaTime(1.0)
     warmup = max(a.warmup, 3)
     D.stepSolver(dt, warmup)
+    D.synchronize(); sys.stdout.flush()
+    os.dup2(saved_stdout, 1); os.close(saved_stdout)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
