@@ -113,6 +113,8 @@ def run_oracle(cells, p, steps, warmup, threads=None, base=None):
     from subrosadg_b200 import mesh as M
     mesh = M.periodic_box_fast(3, cells)
     cfg = dict(base or CFG); cfg["p"] = p
+    if threads is None:   # all host cores this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     O = oracle.Oracle(cfg, mesh, threads=threads)
     O.initialize(ic_config4)
     dt = 1e-4
@@ -123,7 +125,7 @@ def run_oracle(cells, p, steps, warmup, threads=None, base=None):
     sec = time.perf_counter() - t0
     s = O.sizes(6)
     dof = s.n * s.Nb * s.Nv
-    return dof * 3 * steps / sec / 1e9, sec, oracle.max_threads()
+    return dof * 3 * steps / sec / 1e9, sec, int(threads)
 
 
 def main():
