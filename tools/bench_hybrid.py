@@ -14,13 +14,20 @@ from subrosadg_b200.solver import Solver
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 4.0
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-mesh = M.EXAMPLE_MESHES["karmanvortex"](scale)
+mesh = M.annulus(int(22 * scale), 4 * int(15 * scale), r0=0.5, r1=20.0, geom_order=3, stretch=1.3, tri_rings=int(11 * scale),
+                 phys_bc={1: M.RIEMANN_FARFIELD, 2: M.ADIABATIC_NONSLIP_WALL})
 cfg = dict(p=3, model=1, transport=2, mu=1.4 * 0.2 / 200.0, conv_flux=2, visc_flux=2, rk=2)
 S = Solver(cfg, mesh, device=0)
 one = lambda x: np.ones(x.shape[:-1])
-S.initializeSolver(lambda x: np.stack([1.4 * one(x), 0.2 * one(x), 0 * one(x), one(x)], axis=-1),
-                   lambda x, phys, time=None: np.stack([1.4 * one(x), np.where(phys == 2, 0.0, 0.2) * one(x), 0 * one(x), one(x)], axis=-1))
-dt = 0.05 * S.calculateDeltaTime(1.0)   # the convective CFL formula of the reference ignores the viscous limit (Re = 200 wall cells)
+
+
+def ic(x):   # smooth start (no-slip already satisfied at the cylinder): the impulsive start of the example is too stiff for a timing run
+    f = np.tanh((np.hypot(x[..., 0], x[..., 1]) - 0.5) / 0.5)
+    return np.stack([1.4 * one(x), 0.2 * f, 0 * one(x), one(x)], axis=-1)
+
+
+S.initializeSolver(ic, lambda x, phys, time=None: np.stack([1.4 * one(x), np.where(phys == 2, 0.0, 0.2) * one(x), 0 * one(x), one(x)], axis=-1))
+dt = 0.1 * S.calculateDeltaTime(1.0)   # the convective CFL formula of the reference ignores the viscous limit of the wall cells
 S.step_timed(dt, 3)
 l0 = S.launch_count
 err, ms = S.step_timed(dt, steps)
