@@ -91,3 +91,31 @@ def test_rk_tables(built):
             e.append(np.abs(O.get_state(3) - Oref.get_state(3)).max())
         errs[rk] = np.log2(e[0] / e[1])
         assert errs[rk] > order - 0.3, errs
+
+
+@pytest.mark.parametrize("visc", [1, 2])
+def test_oracle_shear_wave_decay(built, visc):
+    """Analytic pin of the oracle's viscous terms (BR1 / BR2): u = A sin(pi y) decays like exp(-nu pi^2 t) (compressible NS up to
+    O(A^2)); the same check runs on the CUDA path in tests/test_gpu_physics.py."""
+    mu, rho, A, k = 0.02, 1.4, 1e-4, np.pi
+    m = M.periodic_box(2, 6)
+    O = oracle.Oracle(dict(p=3, model=1, transport=1, mu=mu, conv_flux=2, visc_flux=visc, rk=2, accurate=0), m)
+
+    def ic(x):
+        one = np.ones(x.shape[:-1])
+        return np.stack([rho * one, A * np.sin(k * x[..., 1]), 0 * one, one], axis=-1)
+
+    O.initialize(ic)
+    t = O.types[0]
+    s = np.sin(k * O.quadrature_coordinates(t)[..., 1])
+
+    def amplitude():
+        q = O.state_at_quadrature(t)
+        return float(np.sum(q[..., 1] / q[..., 0] * s) / np.sum(s * s))
+
+    a0 = amplitude()
+    dt = 0.2 * O.compute_dt(1.0)
+    nsteps = int(round(0.5 / dt))
+    O.step(dt, nsteps)
+    want = np.exp(-(mu / rho) * k * k * dt * nsteps)
+    assert abs(amplitude() / a0 / want - 1.0) < 5e-4 and want < 0.95
