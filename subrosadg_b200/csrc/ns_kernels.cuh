@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
   // ---- K: relative error (same reduction as the Euler kernel) -------------------------------------------------------------------------
   if (A.normPartial != nullptr) {
     double* bufA = S.sG;      // >= [K][NV][NN]
-    double* bufB = S.sFlux;   // [K][NV][NAQ] >= [K][NV][NN]
+    double* bufB = (NAQ >= NN) ? S.sFlux : S.sU;   // [K][NV][NAQ] >= [K][NV][NN] in 3-D and for N <= 4 in 2-D; otherwise the (dead) state tile
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {

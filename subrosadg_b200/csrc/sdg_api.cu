@@ -74,6 +74,8 @@ template <int D, int N> struct NsChunkOf;
 template <> struct NsChunkOf<2, 2> { static constexpr int K = 32; };
 template <> struct NsChunkOf<2, 3> { static constexpr int K = 16; };
 template <> struct NsChunkOf<2, 4> { static constexpr int K = 16; };
+template <> struct NsChunkOf<2, 5> { static constexpr int K = 8; };
+template <> struct NsChunkOf<2, 6> { static constexpr int K = 4; };
 template <> struct NsChunkOf<3, 2> { static constexpr int K = 16; };
 template <> struct NsChunkOf<3, 3> { static constexpr int K = 8; };
 #ifndef SDG_NS34_K
@@ -87,6 +89,8 @@ void pickNs(bool affine, int ph, StageFn& grad, StageFn& stage, int& K) {
   if (affine) { grad = launchNsGrad<D, N, KK, true>; stage = ph ? launchNsStage<D, N, KK, true, 1> : launchNsStage<D, N, KK, true, 0>; }
   else { grad = launchNsGrad<D, N, KK, false>; stage = ph ? launchNsStage<D, N, KK, false, 1> : launchNsStage<D, N, KK, false, 0>; }
 }
+template <> struct NsChunkOf<3, 5> { static constexpr int K = 2; };
+template <> struct NsChunkOf<3, 6> { static constexpr int K = 1; };
 void pickNsFn(int D, int N, bool affine, int ph, StageFn& grad, StageFn& stage, int& K) {
   if (D == 2 && N == 2) return pickNs<2, 2>(affine, ph, grad, stage, K);
   if (D == 2 && N == 3) return pickNs<2, 3>(affine, ph, grad, stage, K);
@@ -94,7 +98,11 @@ void pickNsFn(int D, int N, bool affine, int ph, StageFn& grad, StageFn& stage, 
   if (D == 3 && N == 2) return pickNs<3, 2>(affine, ph, grad, stage, K);
   if (D == 3 && N == 3) return pickNs<3, 3>(affine, ph, grad, stage, K);
   if (D == 3 && N == 4) return pickNs<3, 4>(affine, ph, grad, stage, K);
-  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..3");
+  if (D == 2 && N == 5) return pickNs<2, 5>(affine, ph, grad, stage, K);
+  if (D == 2 && N == 6) return pickNs<2, 6>(affine, ph, grad, stage, K);
+  if (D == 3 && N == 5) return pickNs<3, 5>(affine, ph, grad, stage, K);
+  if (D == 3 && N == 6) return pickNs<3, 6>(affine, ph, grad, stage, K);
+  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..5");
 }
 
 // chunk sizes: bricks of 2^D .. elements, sized so that two blocks fit an SM
@@ -105,6 +113,10 @@ template <> struct ChunkOf<2, 4> { static constexpr int K = 16; };
 template <> struct ChunkOf<3, 2> { static constexpr int K = 32; };
 template <> struct ChunkOf<3, 3> { static constexpr int K = 8; };
 template <> struct ChunkOf<3, 4> { static constexpr int K = 8; };
+template <> struct ChunkOf<2, 5> { static constexpr int K = 16; };
+template <> struct ChunkOf<2, 6> { static constexpr int K = 8; };
+template <> struct ChunkOf<3, 5> { static constexpr int K = 2; };
+template <> struct ChunkOf<3, 6> { static constexpr int K = 1; };
 
 template <int D, int N>
 StageFn pickEuler(bool affine, int ph) {
@@ -125,7 +137,11 @@ StageFn pickEulerFn(int D, int N, bool affine, int ph, int& K) {
     if (affine) return ph ? launchEulerLine<4, KK, true, 1> : launchEulerLine<4, KK, true, 0>;
     return ph ? launchEulerLine<4, KK, false, 1> : launchEulerLine<4, KK, false, 0>;
   }
-  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..3");
+  if (D == 2 && N == 5) { K = ChunkOf<2, 5>::K; return pickEuler<2, 5>(affine, ph); }
+  if (D == 2 && N == 6) { K = ChunkOf<2, 6>::K; return pickEuler<2, 6>(affine, ph); }
+  if (D == 3 && N == 5) { K = ChunkOf<3, 5>::K; return pickEuler<3, 5>(affine, ph); }
+  if (D == 3 && N == 6) { K = ChunkOf<3, 6>::K; return pickEuler<3, 6>(affine, ph); }
+  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..5");
 }
 
 }  // namespace
@@ -248,7 +264,7 @@ int sdg_create(const sdg_config* cfg, sdg_ctx** out) {
   auto c = std::make_unique<sdg_ctx>();
   c->cfg = *cfg;
   if (cfg->dim < 2 || cfg->dim > 3) throw std::runtime_error("dim must be 2 or 3 on the device path");
-  if (cfg->p < 1 || cfg->p > 3) throw std::runtime_error("polynomial order must be 1..3 on the device path");
+  if (cfg->p < 1 || cfg->p > 5) throw std::runtime_error("polynomial order must be 1..5 (PolynomialOrderEnum P1..P5)");
   c->D = cfg->dim; c->NV = cfg->dim + 2;
   PhysParams& P = c->phys;
   P.model = cfg->model; P.eos = cfg->eos; P.transport = cfg->transport; P.conv = cfg->conv_flux; P.visc = cfg->visc_flux; P.source = cfg->source;

@@ -30,7 +30,7 @@
 namespace sdg {
 
 constexpr int kThreads = 256;
-constexpr int kMaxN = 4;
+constexpr int kMaxN = 6;   // PolynomialOrderEnum P1..P5 (src/Utils/Enum.cpp)
 constexpr int kCF = 6;   // chunk-face geometry record (affine meshes): {n[D], |J|, 1/detJ_left, 1/detJ_right}, padded to 6 doubles
 
 // Device image of TensorTables (host_tables.hpp); lives in global memory, staged into shared memory by every block.
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
   // ---- K: relative error = mean_q |R_modal Φᵀ| = mean_q |(K1⊗…⊗K1) R_nodal|, summed over the chunk's elements --------------
   if (A.normPartial != nullptr) {
     double* bufA = sF;      // [K][NV][NN]
-    double* bufB = sFlux;   // [K][NV][NAQ] >= [K][NV][NN]  (2D: 4N >= N^2 for N <= 4; 3D: 6N^2 >= N^3 for N <= 6)
+    double* bufB = (L::NAQ >= L::NN) ? sFlux : sU;   // [K][NV][NAQ] >= [K][NV][NN] in 3-D (6N^2 >= N^3) and for N <= 4 in 2-D; otherwise the (dead) state tile
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {

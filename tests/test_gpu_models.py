@@ -121,3 +121,32 @@ def test_time_varying_boundary(built):
     O2, S2 = cases.make_pair(dict(p=3, conv_flux=2, rk=2), mesh, cases.ic_perturbed_freestream(0.3, 0.0, 2), bc)
     S2.set_state(t, O2.get_state(t)); S2.stepSolver(dt, 4)
     assert cases.rel_l2(S2.state_at_quadrature(t), S.state_at_quadrature(t)) > 1e-6
+
+
+# ---- PolynomialOrderEnum P4 / P5 (src/Utils/Enum.cpp): tensor path, quadrangles and hexahedra ---------------------------------
+@pytest.mark.parametrize("p", [4, 5])
+def test_high_order_euler_2d(built, p):
+    mesh = M.box(2, (5, 4), 0.0, 1.0, geom_order=2, warp=lambda x: x + 0.03 * np.sin(np.pi * x[:, ::-1]),
+                 phys_bc={1: M.RIEMANN_FARFIELD, 2: M.RIEMANN_FARFIELD, 3: M.ADIABATIC_SLIP_WALL, 4: M.RIEMANN_FARFIELD})
+    ic = cases.ic_perturbed_freestream(0.5, 2.0, 2)
+    O, S = cases.make_pair(dict(p=p, conv_flux=3, rk=2), mesh, ic, cases.bc_freestream(0.5, 2.0, 2, wall_phys=(3,)))
+    dt = O.compute_dt(0.5)
+    assert abs(S.calculateDeltaTime(0.5) - dt) <= 1e-13 * dt
+    compare(O, S, dt, 4, label=f"high order euler 2d p{p}")
+
+
+@pytest.mark.parametrize("p", [4, 5])
+def test_high_order_periodic_3d(built, p):
+    mesh = M.periodic_box_fast(3, 3)
+    O, S = cases.make_pair(dict(p=p, conv_flux=2, rk=2), mesh, cases.ic_density_wave([0.5, 0.3, 0.2]))
+    # the modal <-> collocation map of 216 Lobatto products is worse conditioned than at P3: 1.7e-12 on the IC coefficients at P5
+    compare(O, S, 5e-4, 3, label=f"high order euler 3d p{p}", tol_ic=5e-12)
+
+
+@pytest.mark.parametrize("p,dim", [(4, 2), (5, 2), (4, 3), (5, 3)])
+def test_high_order_cns(built, p, dim):
+    mesh = M.periodic_box(2, 4) if dim == 2 else M.periodic_box_fast(3, 3)
+    vel = [0.7, 0.3] if dim == 2 else [0.5, 0.3, 0.2]
+    cfg = dict(p=p, model=1, transport=1, mu=0.01, conv_flux=2, visc_flux=2, rk=2)
+    O, S = cases.make_pair(cfg, mesh, cases.ic_density_wave(vel))
+    compare_ns(O, S, 2e-4, 3, f"high order cns p{p} dim{dim}")
