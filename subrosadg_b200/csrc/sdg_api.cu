@@ -13,9 +13,8 @@
 #include "../../include/subrosadg_b200.h"
 #include "dev_util.cuh"
 #include "host_plan.hpp"
-#include "line_kernels.cuh"
+#include "launchers.hpp"
 #include "mixed_path.hpp"
-#include "ns_kernels.cuh"
 #include "tensor_kernels.cuh"
 
 using namespace sdg;
@@ -23,126 +22,6 @@ using namespace sdg;
 namespace {
 
 thread_local std::string g_err;
-
-using StageFn = void (*)(const StageArgs&, int nBlocks, cudaStream_t);
-
-template <int D, int N, int K, bool AFFINE, int PH>
-void launchEuler(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  using L = Layout<D, N, K>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(eulerStageKernel<D, N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
-    configured = true;
-  }
-  eulerStageKernel<D, N, K, AFFINE, PH><<<nBlocks, kThreads, L::bytes, s>>>(a);
-}
-
-template <int N, int K, bool AFFINE, int PH>
-void launchEulerLine(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  using L = LineLayout<N, K>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(eulerLineKernel<N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
-    configured = true;
-  }
-  eulerLineKernel<N, K, AFFINE, PH><<<nBlocks, L::THREADS, L::bytes, s>>>(a);
-}
-
-template <int D, int N, int K, bool AFFINE>
-void launchNsGrad(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  using L = NsLayout<D, N, K, AFFINE, false>;
-  static bool configured = false;
-  if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsGradKernel<D, N, K, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
-  nsGradKernel<D, N, K, AFFINE><<<nBlocks, kThreads, L::bytes, s>>>(a);
-}
-// threads per block of the NS residual pass: one face point per thread in the face phase where the register budget allows
-// (P3 hexahedra: 2x2x1 brick = 20 faces x 16 points = 320 face points, 256 nodes)
-template <int D, int N> struct NsThreadsOf { static constexpr int TH = kThreads; };
-#ifndef SDG_NSR_TH34
-#define SDG_NSR_TH34 256
-#endif
-template <> struct NsThreadsOf<3, 4> { static constexpr int TH = SDG_NSR_TH34; };
-template <int D, int N, int K, bool AFFINE, int PH>
-void launchNsStage(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  constexpr int TH = NsThreadsOf<D, N>::TH;
-  using L = NsLayout<D, N, K, AFFINE, true, TH>;
-  static bool configured = false;
-  if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsStageKernel<D, N, K, AFFINE, PH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
-  nsStageKernel<D, N, K, AFFINE, PH, TH><<<nBlocks, TH, L::bytes, s>>>(a);
-}
-template <int D, int N> struct NsChunkOf;
-template <> struct NsChunkOf<2, 2> { static constexpr int K = 32; };
-template <> struct NsChunkOf<2, 3> { static constexpr int K = 16; };
-template <> struct NsChunkOf<2, 4> { static constexpr int K = 16; };
-template <> struct NsChunkOf<2, 5> { static constexpr int K = 8; };
-template <> struct NsChunkOf<2, 6> { static constexpr int K = 4; };
-template <> struct NsChunkOf<3, 2> { static constexpr int K = 16; };
-template <> struct NsChunkOf<3, 3> { static constexpr int K = 8; };
-#ifndef SDG_NS34_K
-#define SDG_NS34_K 4
-#endif
-template <> struct NsChunkOf<3, 4> { static constexpr int K = SDG_NS34_K; };
-template <int D, int N>
-void pickNs(bool affine, int ph, StageFn& grad, StageFn& stage, int& K) {
-  constexpr int KK = NsChunkOf<D, N>::K;
-  K = KK;
-  if (affine) { grad = launchNsGrad<D, N, KK, true>; stage = ph ? launchNsStage<D, N, KK, true, 1> : launchNsStage<D, N, KK, true, 0>; }
-  else { grad = launchNsGrad<D, N, KK, false>; stage = ph ? launchNsStage<D, N, KK, false, 1> : launchNsStage<D, N, KK, false, 0>; }
-}
-template <> struct NsChunkOf<3, 5> { static constexpr int K = 2; };
-template <> struct NsChunkOf<3, 6> { static constexpr int K = 1; };
-void pickNsFn(int D, int N, bool affine, int ph, StageFn& grad, StageFn& stage, int& K) {
-  if (D == 2 && N == 2) return pickNs<2, 2>(affine, ph, grad, stage, K);
-  if (D == 2 && N == 3) return pickNs<2, 3>(affine, ph, grad, stage, K);
-  if (D == 2 && N == 4) return pickNs<2, 4>(affine, ph, grad, stage, K);
-  if (D == 3 && N == 2) return pickNs<3, 2>(affine, ph, grad, stage, K);
-  if (D == 3 && N == 3) return pickNs<3, 3>(affine, ph, grad, stage, K);
-  if (D == 3 && N == 4) return pickNs<3, 4>(affine, ph, grad, stage, K);
-  if (D == 2 && N == 5) return pickNs<2, 5>(affine, ph, grad, stage, K);
-  if (D == 2 && N == 6) return pickNs<2, 6>(affine, ph, grad, stage, K);
-  if (D == 3 && N == 5) return pickNs<3, 5>(affine, ph, grad, stage, K);
-  if (D == 3 && N == 6) return pickNs<3, 6>(affine, ph, grad, stage, K);
-  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..5");
-}
-
-// chunk sizes: bricks of 2^D .. elements, sized so that two blocks fit an SM
-template <int D, int N> struct ChunkOf;
-template <> struct ChunkOf<2, 2> { static constexpr int K = 64; };
-template <> struct ChunkOf<2, 3> { static constexpr int K = 32; };
-template <> struct ChunkOf<2, 4> { static constexpr int K = 16; };
-template <> struct ChunkOf<3, 2> { static constexpr int K = 32; };
-template <> struct ChunkOf<3, 3> { static constexpr int K = 8; };
-template <> struct ChunkOf<3, 4> { static constexpr int K = 8; };
-template <> struct ChunkOf<2, 5> { static constexpr int K = 16; };
-template <> struct ChunkOf<2, 6> { static constexpr int K = 8; };
-template <> struct ChunkOf<3, 5> { static constexpr int K = 2; };
-template <> struct ChunkOf<3, 6> { static constexpr int K = 1; };
-
-template <int D, int N>
-StageFn pickEuler(bool affine, int ph) {
-  constexpr int K = ChunkOf<D, N>::K;
-  if (affine) return ph ? launchEuler<D, N, K, true, 1> : launchEuler<D, N, K, true, 0>;
-  return ph ? launchEuler<D, N, K, false, 1> : launchEuler<D, N, K, false, 0>;
-}
-StageFn pickEulerFn(int D, int N, bool affine, int ph, int& K) {
-  if (D == 2 && N == 2) { K = ChunkOf<2, 2>::K; return pickEuler<2, 2>(affine, ph); }
-  if (D == 2 && N == 3) { K = ChunkOf<2, 3>::K; return pickEuler<2, 3>(affine, ph); }
-  if (D == 2 && N == 4) { K = ChunkOf<2, 4>::K; return pickEuler<2, 4>(affine, ph); }
-  if (D == 3 && N == 2) { K = ChunkOf<3, 2>::K; return pickEuler<3, 2>(affine, ph); }
-  if (D == 3 && N == 3) { K = ChunkOf<3, 3>::K; return pickEuler<3, 3>(affine, ph); }
-  if (D == 3 && N == 4) {
-    K = ChunkOf<3, 4>::K;
-    if (getenv("SDG_NODE_KERNEL")) return pickEuler<3, 4>(affine, ph);   // A/B switch: node-per-thread kernel of tensor_kernels.cuh
-    constexpr int KK = ChunkOf<3, 4>::K;
-    if (affine) return ph ? launchEulerLine<4, KK, true, 1> : launchEulerLine<4, KK, true, 0>;
-    return ph ? launchEulerLine<4, KK, false, 1> : launchEulerLine<4, KK, false, 0>;
-  }
-  if (D == 2 && N == 5) { K = ChunkOf<2, 5>::K; return pickEuler<2, 5>(affine, ph); }
-  if (D == 2 && N == 6) { K = ChunkOf<2, 6>::K; return pickEuler<2, 6>(affine, ph); }
-  if (D == 3 && N == 5) { K = ChunkOf<3, 5>::K; return pickEuler<3, 5>(affine, ph); }
-  if (D == 3 && N == 6) { K = ChunkOf<3, 6>::K; return pickEuler<3, 6>(affine, ph); }
-  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..5");
-}
 
 }  // namespace
 

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
 // out[pos(e)][v][i] = sum_b M[i*nin+b] * in[e][b][v]      (modal -> nodal, M = Phi)        dir = 0
 // out[e][i][v]      = sum_q M[i*nin+q] * in[pos(e)][v][q] (nodal -> modal, M = Phi^-1;
 //                                                          or R_modal = Phi^T R_nodal)     dir = 1
-__global__ void seamTransformKernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ M, const int* __restrict__ perm,
+static __global__ void seamTransformKernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ M, const int* __restrict__ perm,
                                     int n, int NV, int NN, int dir) {
   extern __shared__ double sbuf[];  // one element: NV*NN
   const int e = blockIdx.x;
@@ -536,7 +536,7 @@ __global__ void seamTransformKernel(const double* __restrict__ in, double* __res
 }
 
 // [n][Nq][C] (caller order) <-> internal [pos][C][Nq]; dir 0: in -> internal, 1: internal -> out
-__global__ void seamTransposeKernel(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ perm, int n, int C, int NN, int dir) {
+static __global__ void seamTransposeKernel(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ perm, int n, int C, int NN, int dir) {
   const size_t total = (size_t)n * C * NN;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int e = (int)(i / ((size_t)C * NN));
@@ -612,7 +612,7 @@ __global__ void deltaTimeKernel(const double* __restrict__ U, const double* __re
 // deterministic reduction of the per-chunk norm partials: block (v, y) sums its contiguous slice of the rows,
 // out[y][v] = sum_{c in slice y} partial[c][v]; launched twice (slices, then the slice sums) so that a 2M-element mesh is not
 // summed by NV thread blocks
-__global__ void normReduceKernel(const double* __restrict__ partial, int nRows, int NV, double* __restrict__ out) {
+static __global__ void normReduceKernel(const double* __restrict__ partial, int nRows, int NV, double* __restrict__ out) {
   __shared__ double red[32];
   const int v = blockIdx.x;
   const int per = (nRows + gridDim.y - 1) / gridDim.y;
@@ -626,7 +626,7 @@ __global__ void normReduceKernel(const double* __restrict__ partial, int nRows, 
 }
 
 // gather of the halo send list: out[i][:] = U[elems[i]][:]
-__global__ void haloPackKernel(const double* __restrict__ U, const int* __restrict__ elems, int n, int stride, double* __restrict__ out) {
+static __global__ void haloPackKernel(const double* __restrict__ U, const int* __restrict__ elems, int n, int stride, double* __restrict__ out) {
   const size_t total = (size_t)n * stride;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i / stride);
