@@ -12,7 +12,7 @@
  *
  * Data order at the seam (identical to the reference):
  *   element types      ElementEnum values (src/Utils/Enum.cpp:28-36): 1 line, 2 triangle, 3 quadrangle, 6 hexahedron.
- *                      One quadrangle or hexahedron block -> collocation tensor kernels; triangle blocks or several types in
+ *                      One line, quadrangle or hexahedron block -> collocation tensor kernels; triangle blocks or several types in
  *                      one 2-D mesh -> dense-operator kernels in the reference's modal representation (single GPU).
  *   node coordinates   [n][nn][D], gmsh node order of Lagrange order `geom_order` (PerElementMesh::node_coordinate_,
  *                      src/Mesh/ReadControl.cpp:86-92)
@@ -35,7 +35,7 @@ typedef struct sdg_ctx sdg_ctx;
 /* POD image of SimulationControl<...> (src/Solver/SimulationControl.cpp:1197-1279); integer fields carry the enum
  * values of src/Utils/Enum.cpp. */
 typedef struct sdg_config {
-  int32_t dim;        /* DimensionEnum 1..3 (2 and 3 implemented on the device) */
+  int32_t dim;        /* DimensionEnum 1..3 */
   int32_t p;          /* PolynomialOrderEnum 1..5 */
   int32_t model;      /* EquationModelEnum: 0 CompresibleEuler 1 CompresibleNS 2 IncompresibleEuler 3 IncompresibleNS */
   int32_t eos;        /* EquationOfStateEnum: 0 IdealGas 1 WeakCompressibleFluid */

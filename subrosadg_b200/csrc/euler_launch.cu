@@ -35,6 +35,11 @@ void launchEulerLine(const StageArgs& a, int nBlocks, cudaStream_t s) {
 
 // chunk sizes: bricks of 2^D .. elements, sized so that two blocks fit an SM
 template <int D, int N> struct ChunkOf;
+template <> struct ChunkOf<1, 2> { static constexpr int K = 64; };
+template <> struct ChunkOf<1, 3> { static constexpr int K = 64; };
+template <> struct ChunkOf<1, 4> { static constexpr int K = 64; };
+template <> struct ChunkOf<1, 5> { static constexpr int K = 32; };
+template <> struct ChunkOf<1, 6> { static constexpr int K = 32; };
 template <> struct ChunkOf<2, 2> { static constexpr int K = 64; };
 template <> struct ChunkOf<2, 3> { static constexpr int K = 32; };
 template <> struct ChunkOf<2, 4> { static constexpr int K = 16; };
@@ -55,6 +60,11 @@ StageFn pickEuler(bool affine, int ph) {
 }  // namespace
 
 StageFn pickEulerFn(int D, int N, bool affine, int ph, int& K) {
+  if (D == 1 && N == 2) { K = ChunkOf<1, 2>::K; return pickEuler<1, 2>(affine, ph); }
+  if (D == 1 && N == 3) { K = ChunkOf<1, 3>::K; return pickEuler<1, 3>(affine, ph); }
+  if (D == 1 && N == 4) { K = ChunkOf<1, 4>::K; return pickEuler<1, 4>(affine, ph); }
+  if (D == 1 && N == 5) { K = ChunkOf<1, 5>::K; return pickEuler<1, 5>(affine, ph); }
+  if (D == 1 && N == 6) { K = ChunkOf<1, 6>::K; return pickEuler<1, 6>(affine, ph); }
   if (D == 2 && N == 2) { K = ChunkOf<2, 2>::K; return pickEuler<2, 2>(affine, ph); }
   if (D == 2 && N == 3) { K = ChunkOf<2, 3>::K; return pickEuler<2, 3>(affine, ph); }
   if (D == 2 && N == 4) { K = ChunkOf<2, 4>::K; return pickEuler<2, 4>(affine, ph); }
@@ -71,7 +81,7 @@ StageFn pickEulerFn(int D, int N, bool affine, int ph, int& K) {
   if (D == 2 && N == 6) { K = ChunkOf<2, 6>::K; return pickEuler<2, 6>(affine, ph); }
   if (D == 3 && N == 5) { K = ChunkOf<3, 5>::K; return pickEuler<3, 5>(affine, ph); }
   if (D == 3 && N == 6) { K = ChunkOf<3, 6>::K; return pickEuler<3, 6>(affine, ph); }
-  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..5");
+  throw std::runtime_error("device path implements line/quadrangle/hexahedron blocks with p = 1..5");
 }
 
 

@@ -98,10 +98,10 @@ struct MeshPlan {
     const int Dm = B.D, nn = B.nn, N = B.T.N, NN = B.T.NN, n = B.n;
     GeomEval G(B.type, B.g);
     B.lattice = G.lat;
-    const int nc = Dm == 2 ? 4 : 8;
+    const int nc = Dm == 1 ? 2 : Dm == 2 ? 4 : 8;
     // affine test (order-1 geometry whose corners form a parallelogram / parallelepiped)
     B.affine = B.g == 1;
-    if (B.affine) {
+    if (B.affine && Dm > 1) {
       bool ok = true;
 #pragma omp parallel for schedule(static) reduction(&& : ok)
       for (int e = 0; e < n; e++) {
@@ -188,7 +188,8 @@ struct MeshPlan {
       }
       double me = 1e300;
       auto dist = [&](int a, int b) { double s = 0; for (int l = 0; l < Dm; l++) { const double d = X[a * Dm + l] - X[b * Dm + l]; s += d * d; } return std::sqrt(s); };
-      if (Dm == 2) for (int k = 0; k < 4; k++) me = std::min(me, dist(k, (k + 1) % 4));
+      if (Dm == 1) me = dist(0, 1);
+      else if (Dm == 2) for (int k = 0; k < 4; k++) me = std::min(me, dist(k, (k + 1) % 4));
       else for (auto& ed : kHexEdge) me = std::min(me, dist(ed[0], ed[1]));
       B.minEdge[pos] = me;
     }
@@ -241,7 +242,9 @@ struct MeshPlan {
         for (int k = 0; k < Dm; k++) for (int m = 0; m < nn; m++) { const double w = d[(size_t)k * nn + m]; for (int l = 0; l < Dm; l++) Jt[k * Dm + l] += w * X[m * Dm + l]; }
         double nv[3] = {0, 0, 0}, scale;
         const double* ta = &B.T.faceTan[((size_t)f * 2 + 0) * 3];
-        if (Dm == 2) {  // Geometry.cpp:114-129: normal = (t_y, -t_x)/|t|
+        if (Dm == 1) {  // Geometry.cpp:102-112: end points of a line
+          nv[0] = f == 0 ? -1.0 : 1.0; scale = 1.0;
+        } else if (Dm == 2) {  // Geometry.cpp:114-129: normal = (t_y, -t_x)/|t|
           double t[2] = {0, 0};
           for (int k = 0; k < 2; k++) for (int l = 0; l < 2; l++) t[l] += ta[k] * Jt[k * 2 + l];
           scale = std::sqrt(t[0] * t[0] + t[1] * t[1]);

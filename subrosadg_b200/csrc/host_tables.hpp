@@ -254,6 +254,13 @@ inline TensorTables buildTensorTables(int type, int p) {
   T.faceDir.assign(T.NF, 0); T.faceSide.assign(T.NF, 0); T.faceBase.assign((size_t)T.NF * T.NQF, 0);
   T.nodeFacePt.assign((size_t)T.NF * T.NN, 0); T.faceTan.assign((size_t)T.NF * 2 * 3, 0.0);
   std::vector<int> stride(D); for (int dd = 0; dd < D; dd++) { int s = 1; for (int k = D - 1; k > dd; k--) s *= N; stride[dd] = s; }
+  if (D == 1) {  // line element: the two faces are its end points (face f = node f, SimulationControl.cpp:177-216), one face "point" each
+    for (int f = 0; f < 2; f++) {
+      T.faceDir[f] = 0; T.faceSide[f] = f; T.faceBase[f] = 0;
+      for (int a = 0; a < N; a++) T.nodeFacePt[(size_t)f * T.NN + a] = 0;
+    }
+    return T;
+  }
   for (int f = 0; f < T.NF; f++) {
     double c[4][3] = {{0}}; int nc = D == 2 ? 2 : 4;
     for (int m = 0; m < nc; m++) {

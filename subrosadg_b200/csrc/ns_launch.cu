@@ -32,6 +32,11 @@ void launchNsStage(const StageArgs& a, int nBlocks, cudaStream_t s) {
   nsStageKernel<D, N, K, AFFINE, PH, TH><<<nBlocks, TH, L::bytes, s>>>(a);
 }
 template <int D, int N> struct NsChunkOf;
+template <> struct NsChunkOf<1, 2> { static constexpr int K = 64; };
+template <> struct NsChunkOf<1, 3> { static constexpr int K = 64; };
+template <> struct NsChunkOf<1, 4> { static constexpr int K = 64; };
+template <> struct NsChunkOf<1, 5> { static constexpr int K = 32; };
+template <> struct NsChunkOf<1, 6> { static constexpr int K = 32; };
 template <> struct NsChunkOf<2, 2> { static constexpr int K = 32; };
 template <> struct NsChunkOf<2, 3> { static constexpr int K = 16; };
 template <> struct NsChunkOf<2, 4> { static constexpr int K = 16; };
@@ -55,6 +60,11 @@ template <> struct NsChunkOf<3, 6> { static constexpr int K = 1; };
 }  // namespace
 
 void pickNsFn(int D, int N, bool affine, int ph, StageFn& grad, StageFn& stage, int& K) {
+  if (D == 1 && N == 2) return pickNs<1, 2>(affine, ph, grad, stage, K);
+  if (D == 1 && N == 3) return pickNs<1, 3>(affine, ph, grad, stage, K);
+  if (D == 1 && N == 4) return pickNs<1, 4>(affine, ph, grad, stage, K);
+  if (D == 1 && N == 5) return pickNs<1, 5>(affine, ph, grad, stage, K);
+  if (D == 1 && N == 6) return pickNs<1, 6>(affine, ph, grad, stage, K);
   if (D == 2 && N == 2) return pickNs<2, 2>(affine, ph, grad, stage, K);
   if (D == 2 && N == 3) return pickNs<2, 3>(affine, ph, grad, stage, K);
   if (D == 2 && N == 4) return pickNs<2, 4>(affine, ph, grad, stage, K);
@@ -65,7 +75,7 @@ void pickNsFn(int D, int N, bool affine, int ph, StageFn& grad, StageFn& stage, 
   if (D == 2 && N == 6) return pickNs<2, 6>(affine, ph, grad, stage, K);
   if (D == 3 && N == 5) return pickNs<3, 5>(affine, ph, grad, stage, K);
   if (D == 3 && N == 6) return pickNs<3, 6>(affine, ph, grad, stage, K);
-  throw std::runtime_error("device path implements quadrangle/hexahedron blocks with p = 1..5");
+  throw std::runtime_error("device path implements line/quadrangle/hexahedron blocks with p = 1..5");
 }
 
 

@@ -142,7 +142,7 @@ int sdg_create(const sdg_config* cfg, sdg_ctx** out) {
   if (!cfg || !out) throw std::runtime_error("null argument");
   auto c = std::make_unique<sdg_ctx>();
   c->cfg = *cfg;
-  if (cfg->dim < 2 || cfg->dim > 3) throw std::runtime_error("dim must be 2 or 3 on the device path");
+  if (cfg->dim < 1 || cfg->dim > 3) throw std::runtime_error("dim must be 1, 2 or 3");
   if (cfg->p < 1 || cfg->p > 5) throw std::runtime_error("polynomial order must be 1..5 (PolynomialOrderEnum P1..P5)");
   c->D = cfg->dim; c->NV = cfg->dim + 2;
   PhysParams& P = c->phys;
@@ -190,7 +190,7 @@ void sdg_destroy(sdg_ctx* c) {
 int sdg_add_elements(sdg_ctx* c, int32_t type, int32_t n, int32_t n_ghost, int32_t geom_order, const double* coords) {
   SDG_TRY
   if (c->finalized) throw std::runtime_error("context already finalized");
-  if (!(type == kTriangle || type == kQuadrangle || type == kHexahedron)) throw std::runtime_error("device path implements triangle, quadrangle and hexahedron blocks");
+  if (!(type == kLine || type == kTriangle || type == kQuadrangle || type == kHexahedron)) throw std::runtime_error("device path implements line, triangle, quadrangle and hexahedron blocks");
   if (elemDim(type) != c->D) throw std::runtime_error("element dimension mismatch");
   if (n <= 0 || n_ghost < 0 || n_ghost >= n || geom_order < 1 || geom_order > 5) throw std::runtime_error("bad element block arguments");
   // Single quadrangle / hexahedron block: collocation tensor path.  Triangles, several element types in one mesh, or
@@ -260,8 +260,8 @@ int sdg_finalize(sdg_ctx* c) {
   M.buildChunkFaces();
   // the compile-time face direction / side tables of the kernels must agree with the numerically derived ones
   for (int f = 0; f < B.T.NF; f++) {
-    const int dirRef = c->D == 2 ? ((0x1 | 0x0 << 2 | 0x1 << 4 | 0x0 << 6) >> (2 * f)) & 3 : ((0x2 | 0x1 << 2 | 0x0 << 4 | 0x0 << 6 | 0x1 << 8 | 0x2 << 10) >> (2 * f)) & 3;
-    const int sideRef = c->D == 2 ? ((0x6 >> f) & 1) : (f >= 3);
+    const int dirRef = c->D == 1 ? 0 : c->D == 2 ? ((0x1 | 0x0 << 2 | 0x1 << 4 | 0x0 << 6) >> (2 * f)) & 3 : ((0x2 | 0x1 << 2 | 0x0 << 4 | 0x0 << 6 | 0x1 << 8 | 0x2 << 10) >> (2 * f)) & 3;
+    const int sideRef = c->D == 1 ? f : c->D == 2 ? ((0x6 >> f) & 1) : (f >= 3);
     if (dirRef != B.T.faceDir[f] || sideRef != B.T.faceSide[f]) throw std::runtime_error("internal: face direction table mismatch");
   }
   if (c->hasDevice) {
@@ -356,7 +356,8 @@ int sdg_set_state_from_primitive(sdg_ctx* c, int32_t type, const double* prim) {
   c->scratch.alloc(nd);
   CUDA_OK(cudaMemcpyAsync(c->scratch.p, prim, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   const int blocks = (int)std::min<size_t>(((size_t)B.n * B.T.NN + 255) / 256, 148 * 16);
-  if (c->D == 2) primitiveToStateKernel<2><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
+  if (c->D == 1) primitiveToStateKernel<1><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
+  else if (c->D == 2) primitiveToStateKernel<2><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
   else primitiveToStateKernel<3><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
   c->launches++;
   CUDA_OK(cudaGetLastError());
@@ -376,7 +377,8 @@ int sdg_set_boundary_primitive(sdg_ctx* c, const double* prim) {
   DevBuf<double> tmp; tmp.alloc((size_t)nb * B.T.NQF * c->NV);
   CUDA_OK(cudaMemcpyAsync(tmp.p, prim, tmp.n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   const int blocks = (nb * B.T.NQF + 255) / 256;
-  if (c->D == 2) boundaryPrimitiveKernel<2><<<blocks, 256, 0, c->stream>>>(tmp.p, c->dummy.p, nb, B.T.NQF, c->phys);
+  if (c->D == 1) boundaryPrimitiveKernel<1><<<blocks, 256, 0, c->stream>>>(tmp.p, c->dummy.p, nb, B.T.NQF, c->phys);
+  else if (c->D == 2) boundaryPrimitiveKernel<2><<<blocks, 256, 0, c->stream>>>(tmp.p, c->dummy.p, nb, B.T.NQF, c->phys);
   else boundaryPrimitiveKernel<3><<<blocks, 256, 0, c->stream>>>(tmp.p, c->dummy.p, nb, B.T.NQF, c->phys);
   c->launches++;
   CUDA_OK(cudaGetLastError());
@@ -482,7 +484,8 @@ int sdg_compute_dt(sdg_ctx* c, double cfl, double* dt) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
   const int blocks = (int)std::min<size_t>(((size_t)B.nOwned * B.T.NN + 255) / 256, 1024);
-  if (c->D == 2) deltaTimeKernel<2><<<blocks, 256, 0, c->stream>>>(c->U[c->cur].p, c->minEdge.p, B.nOwned, B.T.NN, c->cfg.p, cfl, c->phys, c->dtPartial.p);
+  if (c->D == 1) deltaTimeKernel<1><<<blocks, 256, 0, c->stream>>>(c->U[c->cur].p, c->minEdge.p, B.nOwned, B.T.NN, c->cfg.p, cfl, c->phys, c->dtPartial.p);
+  else if (c->D == 2) deltaTimeKernel<2><<<blocks, 256, 0, c->stream>>>(c->U[c->cur].p, c->minEdge.p, B.nOwned, B.T.NN, c->cfg.p, cfl, c->phys, c->dtPartial.p);
   else deltaTimeKernel<3><<<blocks, 256, 0, c->stream>>>(c->U[c->cur].p, c->minEdge.p, B.nOwned, B.T.NN, c->cfg.p, cfl, c->phys, c->dtPartial.p);
   c->launches++;
   CUDA_OK(cudaGetLastError());

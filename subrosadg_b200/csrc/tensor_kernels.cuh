@@ -127,10 +127,10 @@ __device__ __forceinline__ constexpr int strideOf(int d) { int s = 1; for (int k
 // sdg_finalize checks these against the numerically derived tables of host_tables.hpp.
 template <int D>
 __device__ __forceinline__ constexpr int faceDirOf(int f) {
-  return D == 2 ? ((0x1 | 0x0 << 2 | 0x1 << 4 | 0x0 << 6) >> (2 * f)) & 3 : ((0x2 | 0x1 << 2 | 0x0 << 4 | 0x0 << 6 | 0x1 << 8 | 0x2 << 10) >> (2 * f)) & 3;
+  return D == 1 ? 0 : D == 2 ? ((0x1 | 0x0 << 2 | 0x1 << 4 | 0x0 << 6) >> (2 * f)) & 3 : ((0x2 | 0x1 << 2 | 0x0 << 4 | 0x0 << 6 | 0x1 << 8 | 0x2 << 10) >> (2 * f)) & 3;
 }
 template <int D>
-__device__ __forceinline__ constexpr int faceSideOf(int f) { return D == 2 ? (0x6 >> f) & 1 : (f >= 3 ? 1 : 0); }
+__device__ __forceinline__ constexpr int faceSideOf(int f) { return D == 1 ? f : D == 2 ? (0x6 >> f) & 1 : (f >= 3 ? 1 : 0); }
 
 // Trace of the conserved variables of one element at one face point: U·Φ_f[face]ᵀ (AdjacencyElementVariable::get,
 // VariableConvertor.cpp:432-485) = end-point interpolation along the face-normal line.

@@ -150,3 +150,43 @@ def test_high_order_cns(built, p, dim):
     cfg = dict(p=p, model=1, transport=1, mu=0.01, conv_flux=2, visc_flux=2, rk=2)
     O, S = cases.make_pair(cfg, mesh, cases.ic_density_wave(vel))
     compare_ns(O, S, 2e-4, 3, f"high order cns p{p} dim{dim}")
+
+
+# ---- DimensionEnum::D1: line elements (LineTrait), point faces ---------------------------------------------------------------------
+def ic_wave_1d(x):
+    rho = 1.0 + 0.2 * np.sin(np.pi * x[..., 0])
+    return np.stack([rho, 0.5 + 0 * rho, 1.4 / rho], axis=-1)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5])
+def test_periodic_1d_ceuler(built, p):
+    mesh = M.box(1, (12,), 0.0, 2.0, periodic_axes=(0,))
+    O, S = cases.make_pair(dict(p=p, conv_flux=2, rk=2), mesh, ic_wave_1d)
+    dt = O.compute_dt(0.5)
+    assert abs(S.calculateDeltaTime(0.5) - dt) <= 1e-13 * dt
+    compare(O, S, dt, 6, label=f"periodic_1d p{p}", tol_ic=5e-12)
+
+
+@pytest.mark.parametrize("flux", [0, 1, 3])
+def test_fluxes_1d_curved(built, flux):
+    mesh = M.box(1, (9,), 0.0, 2.0, periodic_axes=(0,), geom_order=3, warp=lambda x: x + 0.05 * np.sin(np.pi * x))
+    O, S = cases.make_pair(dict(p=3, conv_flux=flux, rk=1), mesh, ic_wave_1d)
+    compare(O, S, 1e-3, 4, label=f"1d curved flux {flux}")
+
+
+@pytest.mark.parametrize("visc", [1, 2])
+def test_shock_tube_like_1d_cns(built, visc):
+    """1-D Navier-Stokes with far-field ends (sod_1d-style domain without the artificial viscosity the shipped example adds)"""
+    mesh = M.box(1, (10,), 0.0, 1.0)
+
+    def ic(x):
+        s = np.tanh((x[..., 0] - 0.5) / 0.1)
+        return np.stack([1.0 - 0.3 * s, 0.1 + 0 * s, 1.0 - 0.1 * s], axis=-1)
+
+    def bc(x, phys, time=None):
+        left = x[..., 0] < 0.5
+        return np.stack([np.where(left, 1.3, 0.7), 0.1 + 0 * x[..., 0], np.where(left, 1.1, 0.9)], axis=-1)
+
+    cfg = dict(p=3, model=1, transport=1, mu=0.01, conv_flux=2, visc_flux=visc, rk=2)
+    O, S = cases.make_pair(cfg, mesh, ic, bc)
+    compare_ns(O, S, 0.2 * O.compute_dt(1.0), 4, f"1d cns visc{visc}")

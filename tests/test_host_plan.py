@@ -53,6 +53,8 @@ def test_rejects_bad_input(built):
 
 
 MESHES = {
+    "line1d": (lambda: M.box(1, (9,), 0.0, 2.0), 3),
+    "line1d_periodic_curved": (lambda: M.box(1, (7,), 0.0, 2.0, periodic_axes=(0,), geom_order=3, warp=lambda x: x + 0.05 * np.sin(np.pi * x)), 4),
     "periodic2d": (lambda: M.periodic_box(2, 10), 3),
     "periodic3d": (lambda: M.periodic_box(3, 4), 3),
     "periodic3d_fast": (lambda: M.periodic_box_fast(3, 5), 2),
