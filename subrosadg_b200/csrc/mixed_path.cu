@@ -145,73 +145,83 @@ __global__ void __launch_bounds__(128) mxFaceKernel(const __grid_constant__ Args
   }
 }
 
-// G1 + G3 + G4 of one element per thread block (blockDim = 128 >= Nb * 8)
+// G1 + G3 + G4: one WARP per element, kElemThreads / 32 elements per thread block (the per-element tiles are a few hundred
+// doubles: a whole thread block per element left most of its threads idle)
 __global__ void __launch_bounds__(kElemThreads) mxGradElemKernel(const __grid_constant__ Args A, int slot) {
   const MxType& T = A.t[slot];
-  const int e = blockIdx.x, Nb = T.Nb, Nq = T.Nq, Naq = T.Naq, tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * (kElemThreads / 32) + wib, Nb = T.Nb, Nq = T.Nq, Naq = T.Naq;
+  if (e >= T.n) return;   // whole warp
   extern __shared__ double sm[];
-  double* sU = sm; double* sUq = sU + Nb * kNV; double* sRg = sUq + Nq * kNV;
-  for (int k = tid; k < Nb * kNV; k += blockDim.x) sU[k] = T.U[(size_t)e * Nb * kNV + k];
-  __syncthreads();
-  for (int k = tid; k < Nq * kNV; k += blockDim.x) {
+  double* sU = sm + (size_t)wib * (Nb * kNV + Nq * kNV + Nb * kG); double* sUq = sU + Nb * kNV; double* sRg = sUq + Nq * kNV;
+  for (int k = lane; k < Nb * kNV; k += 32) sU[k] = T.U[(size_t)e * Nb * kNV + k];
+  __syncwarp();
+  for (int k = lane; k < Nq * kNV; k += 32) {
     const int q = k / kNV, v = k - q * kNV;
     double s = 0.0;
     for (int b = 0; b < Nb; b++) s = fma(sU[b * kNV + v], T.Phi[q * Nb + b], s);
     sUq[k] = s;
   }
-  __syncthreads();
-  const int b0 = tid / kG, r = tid - b0 * kG, v = r / kD, c = r - v * kD;
-  const bool act = tid < Nb * kG;
+  __syncwarp();
+  const int nOut = Nb * kG;   // <= 128: at most 4 outputs per lane
   const double* Mi = T.Minv + (size_t)e * Nb * Nb;
+  const double* av = T.AGv + (size_t)e * Naq * kG;
+  const double* mt = T.mt + (size_t)e * Nq * 4;
   // Rg_vol = A_vol Phi_f - Q_vol grad Phi, SpatialDiscrete.cpp:1034-1068
-  if (act) {
+  for (int k = lane; k < nOut; k += 32) {
+    const int b0 = k / kG, r = k - b0 * kG, v = r / kD, c = r - v * kD;
     double s = 0.0;
-    const double* av = T.AGv + (size_t)e * Naq * kG;
     for (int aq = 0; aq < Naq; aq++) s = fma(av[aq * kG + r], T.PhiF[aq * Nb + b0], s);
-    const double* mt = T.mt + (size_t)e * Nq * 4;
     for (int q = 0; q < Nq; q++) for (int dd = 0; dd < kD; dd++) s = fma(-sUq[q * kNV + v] * mt[q * 4 + dd * kD + c], T.dPhi[(q * 2 + dd) * Nb + b0], s);
-    sRg[b0 * kG + r] = s;
+    sRg[k] = s;
   }
-  __syncthreads();
-  double tot = 0.0;
-  if (act) {  // G_vol = Rg_vol M^-1, TimeIntegration.cpp:200-228
+  __syncwarp();
+  double tot[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k = lane, m = 0; k < nOut; k += 32, m++) {  // G_vol = Rg_vol M^-1, TimeIntegration.cpp:200-228
+    const int b0 = k / kG, r = k - b0 * kG;
     double s = 0.0;
     for (int b = 0; b < Nb; b++) s = fma(sRg[b * kG + r], Mi[b * Nb + b0], s);
-    T.Gvol[((size_t)e * Nb + b0) * kG + r] = s; tot = s;
+    T.Gvol[(size_t)e * Nb * kG + k] = s; tot[m] = s;
   }
-  const int nl = A.phys.visc == kBR2 ? T.Nf : 1;
+  const bool br2 = A.phys.visc == kBR2;
+  const int nl = br2 ? T.Nf : 1;
+  const double* ai = T.AGi + (size_t)e * Naq * kG;
   for (int f = 0; f < nl; f++) {
-    __syncthreads();
-    if (act) {  // BR1: A_int Phi_f; BR2: per face A_int[:, f] Phi_f[f, :]
-      const int lo = A.phys.visc == kBR2 ? f * T.Nqf : 0, hi = A.phys.visc == kBR2 ? lo + T.Nqf : Naq;
+    __syncwarp();
+    const int lo = br2 ? f * T.Nqf : 0, hi = br2 ? lo + T.Nqf : Naq;   // BR1: A_int Phi_f; BR2: per face A_int[:, f] Phi_f[f, :]
+    for (int k = lane; k < nOut; k += 32) {
+      const int b0 = k / kG, r = k - b0 * kG;
       double s = 0.0;
-      const double* ai = T.AGi + (size_t)e * Naq * kG;
       for (int aq = lo; aq < hi; aq++) s = fma(ai[aq * kG + r], T.PhiF[aq * Nb + b0], s);
-      sRg[b0 * kG + r] = s;
+      sRg[k] = s;
     }
-    __syncthreads();
-    if (act) {
+    __syncwarp();
+    for (int k = lane, m = 0; k < nOut; k += 32, m++) {
+      const int b0 = k / kG, r = k - b0 * kG;
       double s = 0.0;
       for (int b = 0; b < Nb; b++) s = fma(sRg[b * kG + r], Mi[b * Nb + b0], s);
-      if (A.phys.visc == kBR2) T.Gf[(((size_t)e * T.Nf + f) * Nb + b0) * kG + r] = s;
-      tot += s;
+      if (br2) T.Gf[((size_t)e * T.Nf + f) * Nb * kG + k] = s;
+      tot[m] += s;
     }
   }
-  if (act) T.Gtot[((size_t)e * Nb + b0) * kG + r] = tot;
+  for (int k = lane, m = 0; k < nOut; k += 32, m++) T.Gtot[(size_t)e * Nb * kG + k] = tot[m];
 }
 
-// R1 + R3 + R4 + K of one element per thread block
+// R1 + R3 + R4 + K: one warp per element, kElemThreads / 32 elements per thread block
 __global__ void __launch_bounds__(kElemThreads) mxElemKernel(const __grid_constant__ Args A, int slot) {
   const MxType& T = A.t[slot];
   const Phys<0> ph(A.phys);
-  const int e = blockIdx.x, Nb = T.Nb, Nq = T.Nq, Naq = T.Naq, tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * (kElemThreads / 32) + wib, Nb = T.Nb, Nq = T.Nq, Naq = T.Naq;
+  if (e >= T.n) return;   // whole warp
   const bool ns = A.phys.ns != 0, src = A.phys.source != kSourceNone;
   extern __shared__ double sm[];
-  double* sU = sm; double* sG = sU + Nb * kNV; double* sQ = sG + Nb * kG; double* sS = sQ + Nq * kD * kNV; double* sR = sS + Nq * kNV;
-  for (int k = tid; k < Nb * kNV; k += blockDim.x) sU[k] = T.U[(size_t)e * Nb * kNV + k];
-  if (ns) for (int k = tid; k < Nb * kG; k += blockDim.x) sG[k] = T.Gtot[(size_t)e * Nb * kG + k];
-  __syncthreads();
-  for (int q = tid; q < Nq; q += blockDim.x) {  // calculateElementQuadrature, SpatialDiscrete.cpp:194-266
+  const int per = Nb * kNV + Nb * kG + Nq * kD * kNV + Nq * kNV + Nb * kNV;
+  double* sU = sm + (size_t)wib * per; double* sG = sU + Nb * kNV; double* sQ = sG + Nb * kG; double* sS = sQ + Nq * kD * kNV; double* sR = sS + Nq * kNV;
+  for (int k = lane; k < Nb * kNV; k += 32) sU[k] = T.U[(size_t)e * Nb * kNV + k];
+  if (ns) for (int k = lane; k < Nb * kG; k += 32) sG[k] = T.Gtot[(size_t)e * Nb * kG + k];
+  __syncwarp();
+  for (int q = lane; q < Nq; q += 32) {  // calculateElementQuadrature, SpatialDiscrete.cpp:194-266
     double cons[kNV] = {0, 0, 0, 0}, comp[kD + 3], Fc[kD * kNV];
     for (int b = 0; b < Nb; b++) { const double f = T.Phi[q * Nb + b]; for (int v = 0; v < kNV; v++) cons[v] = fma(sU[b * kNV + v], f, cons[v]); }
     compFromCons<kD>(ph, cons, comp);
@@ -236,20 +246,20 @@ __global__ void __launch_bounds__(kElemThreads) mxElemKernel(const __grid_consta
       sS[q * kNV + kD] = boussinesqSource<kD>(ph, comp) * jw;   // SourceTerm.cpp:29-58, SpatialDiscrete.cpp:254-262
     }
   }
-  __syncthreads();
-  for (int k = tid; k < Nb * kNV; k += blockDim.x) {  // calculateElementResidual, SpatialDiscrete.cpp:1016-1032
+  __syncwarp();
+  const double* a = T.A + (size_t)e * Naq * kNV;
+  for (int k = lane; k < Nb * kNV; k += 32) {  // calculateElementResidual, SpatialDiscrete.cpp:1016-1032
     const int b = k / kNV, v = k - b * kNV;
     double s = 0.0;
     for (int qd = 0; qd < Nq * kD; qd++) s = fma(sQ[qd * kNV + v], T.dPhi[qd * Nb + b], s);
-    const double* a = T.A + (size_t)e * Naq * kNV;
     for (int aq = 0; aq < Naq; aq++) s = fma(-a[aq * kNV + v], T.PhiF[aq * Nb + b], s);
     if (src) for (int q = 0; q < Nq; q++) s = fma(sS[q * kNV + v], T.Phi[q * Nb + b], s);
     sR[k] = s;
     if (A.mode == 1) T.R[(size_t)e * Nb * kNV + k] = s;
   }
-  __syncthreads();
+  __syncwarp();
   const double* Mi = T.Minv + (size_t)e * Nb * Nb;
-  for (int k = tid; k < Nb * kNV; k += blockDim.x) {  // updateElementBasisFunctionCoefficient, TimeIntegration.cpp:181-198
+  for (int k = lane; k < Nb * kNV; k += 32) {  // updateElementBasisFunctionCoefficient, TimeIntegration.cpp:181-198
     const int b0 = k / kNV, v = k - b0 * kNV;
     double s = 0.0;
     for (int b = 0; b < Nb; b++) s = fma(sR[b * kNV + v], Mi[b * Nb + b0], s);
@@ -258,17 +268,17 @@ __global__ void __launch_bounds__(kElemThreads) mxElemKernel(const __grid_consta
     else T.U[at] = A.aCur * sU[k] + A.aLast * T.Ulast[at] + A.bdt * s;
   }
   if (A.normPartial) {  // calculateElementRelativeError, TimeIntegration.cpp:279-298: mean_q |R Phi^T|
-    for (int k = tid; k < Nq * kNV; k += blockDim.x) {
+    for (int k = lane; k < Nq * kNV; k += 32) {
       const int q = k / kNV, v = k - q * kNV;
       double s = 0.0;
       for (int b = 0; b < Nb; b++) s = fma(sR[b * kNV + v], T.Phi[q * Nb + b], s);
       sQ[k] = fabs(s);
     }
-    __syncthreads();
-    if (tid < kNV) {
+    __syncwarp();
+    if (lane < kNV) {
       double s = 0.0;
-      for (int q = 0; q < Nq; q++) s += sQ[q * kNV + tid];
-      A.normPartial[(size_t)(T.normOff + e) * kNV + tid] = s / Nq;
+      for (int q = 0; q < Nq; q++) s += sQ[q * kNV + lane];
+      A.normPartial[(size_t)(T.normOff + e) * kNV + lane] = s / Nq;
     }
   }
 }
@@ -346,8 +356,9 @@ __global__ void mxNormReduceKernel(const double* __restrict__ partial, int n, do
   if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w]; out[v] = t; }
 }
 
-size_t elemSmemBytes(const MixedTable& T) { return sizeof(double) * ((size_t)T.Nb * kNV + (size_t)T.Nb * kG + (size_t)T.Nq * kD * kNV + (size_t)T.Nq * kNV + (size_t)T.Nb * kNV); }
-size_t gradSmemBytes(const MixedTable& T) { return sizeof(double) * ((size_t)T.Nb * kNV + (size_t)T.Nq * kNV + (size_t)T.Nb * kG); }
+int elemBlocks(int n) { return (n + kElemThreads / 32 - 1) / (kElemThreads / 32); }
+size_t elemSmemBytes(const MixedTable& T) { return (kElemThreads / 32) * sizeof(double) * ((size_t)T.Nb * kNV + (size_t)T.Nb * kG + (size_t)T.Nq * kD * kNV + (size_t)T.Nq * kNV + (size_t)T.Nb * kNV); }
+size_t gradSmemBytes(const MixedTable& T) { return (kElemThreads / 32) * sizeof(double) * ((size_t)T.Nb * kNV + (size_t)T.Nq * kNV + (size_t)T.Nb * kG); }
 
 }  // namespace
 
@@ -527,12 +538,12 @@ void MixedSolver::evalResidual(Args& a, int mode, bool wantNorm) {
   if (phys_.ns) {
     mxFaceKernel<0><<<fb, 128, 0, stream_>>>(a); launches++;
     for (int type : {(int)kTriangle, (int)kQuadrangle}) if (blk_[type]) {
-      mxGradElemKernel<<<blk_[type]->n, kElemThreads, gradSmemBytes(blk_[type]->T), stream_>>>(a, type == kTriangle ? 0 : 1); launches++;
+      mxGradElemKernel<<<elemBlocks(blk_[type]->n), kElemThreads, gradSmemBytes(blk_[type]->T), stream_>>>(a, type == kTriangle ? 0 : 1); launches++;
     }
   }
   mxFaceKernel<1><<<fb, 128, 0, stream_>>>(a); launches++;
   for (int type : {(int)kTriangle, (int)kQuadrangle}) if (blk_[type]) {
-    mxElemKernel<<<blk_[type]->n, kElemThreads, elemSmemBytes(blk_[type]->T), stream_>>>(a, type == kTriangle ? 0 : 1); launches++;
+    mxElemKernel<<<elemBlocks(blk_[type]->n), kElemThreads, elemSmemBytes(blk_[type]->T), stream_>>>(a, type == kTriangle ? 0 : 1); launches++;
   }
   CUDA_OK(cudaGetLastError());
 }
@@ -643,7 +654,7 @@ void MixedSolver::gradientAtQuadrature(int type, double* Gq) {
   Args a; fill(a);
   const int nfp = (F_.nInt + F_.nBnd) * (p_ + 1);
   mxFaceKernel<0><<<std::max(1, (nfp + 127) / 128), 128, 0, stream_>>>(a); launches++;
-  for (int t : {(int)kTriangle, (int)kQuadrangle}) if (blk_[t]) { mxGradElemKernel<<<blk_[t]->n, kElemThreads, gradSmemBytes(blk_[t]->T), stream_>>>(a, t == kTriangle ? 0 : 1); launches++; }
+  for (int t : {(int)kTriangle, (int)kQuadrangle}) if (blk_[t]) { mxGradElemKernel<<<elemBlocks(blk_[t]->n), kElemThreads, gradSmemBytes(blk_[t]->T), stream_>>>(a, t == kTriangle ? 0 : 1); launches++; }
   DevBuf<double> tmp; tmp.alloc((size_t)B.n * T.Nq * kG);
   mxToQuadratureKernel<<<148 * 4, 256, 0, stream_>>>(B.Gtot.p, B.dPhi_.p, B.n, T.Nb, T.Nq, kG, tmp.p); launches++;
   CUDA_OK(cudaGetLastError());
