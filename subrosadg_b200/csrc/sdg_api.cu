@@ -47,6 +47,9 @@ struct sdg_ctx {
   double stepDt = 0.0;
   int nSend = 0;
   std::vector<double> hostNorm;
+  // one time step (nStages x passes launches) captured as a CUDA graph: launch-bound meshes (the reference's shipped configs have
+  // 1e2-3e4 elements) replay it instead of issuing every launch from the host
+  cudaGraphExec_t stepGraph = nullptr; double graphDt = 0.0; int graphCur = -1; bool graphWarm = false;
   std::unique_ptr<MixedSolver> mx;   // dense-operator path: meshes with triangle blocks / several element types (mixed_path.cu)
 
   size_t stateDoubles() const { return (size_t)plan.blk.n * NV * plan.blk.T.NN; }
@@ -182,6 +185,7 @@ int sdg_create(const sdg_config* cfg, sdg_ctx** out) {
 void sdg_destroy(sdg_ctx* c) {
   if (!c) return;
   if (c->hasDevice) { cudaSetDevice(c->cfg.device); cudaDeviceSynchronize(); }
+  if (c->stepGraph) cudaGraphExecDestroy(c->stepGraph);
   cudaStream_t s = c->stream; const bool dev = c->hasDevice;
   delete c;
   if (dev && s) cudaStreamDestroy(s);
@@ -539,16 +543,47 @@ int sdg_step_end(sdg_ctx* c, double* sums) {
   SDG_CATCH
 }
 
+namespace {
+constexpr int kGraphMaxChunks = 1 << 15;   // above this a stage kernel runs for >= 100 us and launch overhead is irrelevant
+
+void launchOneStep(sdg_ctx* c) {
+  for (int s = 0; s < c->nStages; s++) stageLaunch(c, s, -1, c->stream);
+  finishStep(c);
+}
+
+// n_steps time steps on the context's stream
+void runSteps(sdg_ctx* c, double dt, int n_steps) {
+  c->stepDt = dt;
+  const bool useGraph = c->plan.blk.nChunks <= kGraphMaxChunks && c->nStages > 1 && n_steps >= 4 && !getenv("SDG_NO_GRAPH");
+  int it = 0;
+  if (useGraph) {
+    if (!c->graphWarm) { launchOneStep(c); it++; c->graphWarm = true; }   // first launches set the kernels' function attributes
+    if (c->stepGraph == nullptr || c->graphDt != dt || c->graphCur != c->cur) {
+      if (c->stepGraph) { cudaGraphExecDestroy(c->stepGraph); c->stepGraph = nullptr; }
+      cudaGraph_t g = nullptr;
+      const int64_t l0 = c->launches;
+      CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      launchOneStep(c);                                   // nStages > 1: the buffer rotation returns to `cur`, every step is identical
+      CUDA_OK(cudaStreamEndCapture(c->stream, &g));
+      c->launches = l0;                                   // captured, not launched
+      CUDA_OK(cudaGraphInstantiate(&c->stepGraph, g, 0));
+      cudaGraphDestroy(g);
+      c->graphDt = dt; c->graphCur = c->cur;
+    }
+    const int perStep = c->nStages * (c->phys.ns ? 2 : 1);
+    for (; it < n_steps; it++) { CUDA_OK(cudaGraphLaunch(c->stepGraph, c->stream)); c->launches += perStep; }
+    return;
+  }
+  for (; it < n_steps; it++) launchOneStep(c);
+}
+}  // namespace
+
 int sdg_step(sdg_ctx* c, double dt, int32_t n_steps, double* relative_error) {
   SDG_TRY
   if (c->mx) { needFinal(c); c->mx->step(dt, n_steps, relative_error, nullptr); return 0; }
   needFinal(c); needDevice(c);
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  c->stepDt = dt;
-  for (int it = 0; it < n_steps; it++) {
-    for (int s = 0; s < c->nStages; s++) stageLaunch(c, s, -1, c->stream);
-    finishStep(c);
-  }
+  runSteps(c, dt, n_steps);
   if (relative_error) {
     double sums[8];
     reduceNorm(c, sums);
@@ -569,10 +604,7 @@ int sdg_step_timed(sdg_ctx* c, double dt, int32_t n_steps, double* relative_erro
   c->stepDt = dt;
   CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaEventRecord(e0, c->stream));
-  for (int it = 0; it < n_steps; it++) {
-    for (int s = 0; s < c->nStages; s++) stageLaunch(c, s, -1, c->stream);
-    finishStep(c);
-  }
+  runSteps(c, dt, n_steps);
   CUDA_OK(cudaEventRecord(e1, c->stream));
   CUDA_OK(cudaEventSynchronize(e1));
   if (milliseconds) CUDA_OK(cudaEventElapsedTime(milliseconds, e0, e1));
