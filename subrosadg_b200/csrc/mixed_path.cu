@@ -12,6 +12,7 @@
 #include "mixed_path.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace sdg {
@@ -554,13 +555,32 @@ void MixedSolver::step(double dt, int nSteps, double* relErr, float* ms) {
   Args a; fill(a);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ms) { CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1)); CUDA_OK(cudaStreamSynchronize(stream_)); CUDA_OK(cudaEventRecord(e0, stream_)); }
-  for (int it = 0; it < nSteps; it++) {
+  auto oneStep = [&]() {
     if (nStages_ > 1) for (auto& b : blk_) if (b) CUDA_OK(cudaMemcpyAsync(b->Ulast.p, b->U.p, b->U.n * sizeof(double), cudaMemcpyDeviceToDevice, stream_));  // copyElementBasisFunctionCoefficient, TimeIntegration.cpp:70-78
     for (int s = 0; s < nStages_; s++) {
       a.aLast = s == 0 ? 0.0 : rkc_[s][0]; a.aCur = s == 0 ? 1.0 : rkc_[s][1]; a.bdt = rkc_[s][2] * dt;
       evalResidual(a, 0, s == nStages_ - 1);
     }
+  };
+  // these meshes are launch bound (6 launches per stage): one step is captured as a CUDA graph and replayed
+  int it = 0;
+  if (nSteps >= 4 && !getenv("SDG_NO_GRAPH")) {
+    if (!graphWarm_) { oneStep(); it++; graphWarm_ = true; }
+    if (stepGraph_ == nullptr || graphDt_ != dt) {
+      if (stepGraph_) { cudaGraphExecDestroy(stepGraph_); stepGraph_ = nullptr; }
+      cudaGraph_t g = nullptr;
+      const int64_t l0 = launches;
+      CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      oneStep();
+      CUDA_OK(cudaStreamEndCapture(stream_, &g));
+      launchesPerStep_ = launches - l0; launches = l0;
+      CUDA_OK(cudaGraphInstantiate(&stepGraph_, g, 0));
+      cudaGraphDestroy(g);
+      graphDt_ = dt;
+    }
+    for (; it < nSteps; it++) { CUDA_OK(cudaGraphLaunch(stepGraph_, stream_)); launches += launchesPerStep_; }
   }
+  for (; it < nSteps; it++) oneStep();
   if (ms) { CUDA_OK(cudaEventRecord(e1, stream_)); CUDA_OK(cudaEventSynchronize(e1)); CUDA_OK(cudaEventElapsedTime(ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
   if (relErr) {
     const int ne = totalElements();

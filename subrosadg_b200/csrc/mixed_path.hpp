@@ -32,6 +32,7 @@ class MixedSolver {
  public:
   MixedSolver(int p, const PhysParams& phys, int nStages, const double (*rkc)[3], cudaStream_t stream, bool hasDevice, int device);
   void addBlock(int type, int n, int nGhost, int g, const double* coords);
+  ~MixedSolver() { if (stepGraph_) cudaGraphExecDestroy(stepGraph_); }
   void setFaces(const FaceInput& F) { F_ = F; }
   void finalize();
   bool hasType(int type) const { return type >= 0 && type < 7 && blk_[type] != nullptr; }
@@ -85,6 +86,7 @@ class MixedSolver {
   std::vector<double> xf_, nrm_, fjw_;
   DevBuf<int> dLe, dLt, dLf, dRe, dRt, dRf, dBc;
   DevBuf<double> dNrm, dFjw, dDummy, normPartial, normOut, dtPartial;
+  cudaGraphExec_t stepGraph_ = nullptr; double graphDt_ = 0.0; bool graphWarm_ = false; int64_t launchesPerStep_ = 0;
 };
 
 }  // namespace sdg
