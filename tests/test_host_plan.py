@@ -56,6 +56,8 @@ MESHES = {
     "line1d": (lambda: M.box(1, (9,), 0.0, 2.0), 3),
     "line1d_periodic_curved": (lambda: M.box(1, (7,), 0.0, 2.0, periodic_axes=(0,), geom_order=3, warp=lambda x: x + 0.05 * np.sin(np.pi * x)), 4),
     "periodic2d": (lambda: M.periodic_box(2, 10), 3),
+    "box2d_p5_curved": (lambda: M.box(2, (3, 3), 0, 1, geom_order=2, warp=lambda x: x + 0.03 * np.sin(np.pi * x[:, ::-1])), 5),
+    "box3d_p4": (lambda: M.box(3, (2, 2, 2), 0, 1), 4),
     "periodic3d": (lambda: M.periodic_box(3, 4), 3),
     "periodic3d_fast": (lambda: M.periodic_box_fast(3, 5), 2),
     "box2d": (lambda: M.box(2, (5, 4), 0, 1), 3),
