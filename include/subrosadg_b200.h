@@ -132,6 +132,19 @@ int sdg_num_stages(sdg_ctx* ctx);
 void* sdg_stream(sdg_ctx* ctx);       /* the context's cudaStream_t */
 int sdg_synchronize(sdg_ctx* ctx);
 
+/* Peer-memory halo exchange (one process per GPU on one NVLink / NVSwitch box): instead of staging + send/recv, sdg_halo_push
+ * gathers the send elements and stores them straight into the peers' ghost ranges, then raises this rank's arrival flag at every
+ * peer; sdg_halo_wait makes `stream` wait for the matching pushes of all peers.  Set-up: every rank exports the CUDA IPC handles of
+ * its U[0..2], G and flag allocations (sdg_ipc_export, 5 x 64 bytes), the driver exchanges them, and sdg_ipc_connect opens the
+ * peers' handles: per peer the element index of the first ghost element this rank feeds in the PEER's arrays (its n_owned + the
+ * start of its receive range for this rank), this rank's range in its own send list, and this rank's flag slot at the peer
+ * (its position in the peer's ascending peer list).  Ranks must issue the same sequence of pushes. */
+int sdg_ipc_export(sdg_ctx* ctx, unsigned char* handles /* 5 x 64 bytes */);
+int sdg_ipc_connect(sdg_ctx* ctx, int32_t n_peers, const unsigned char* handles /* n_peers x 5 x 64 */, const int64_t* ghost_first,
+                    const int32_t* send_first, const int32_t* send_count, const int32_t* slot_at_peer);
+int sdg_halo_push(sdg_ctx* ctx, int32_t type, int32_t what, void* stream);
+int sdg_halo_wait(sdg_ctx* ctx, void* stream);
+
 /* Device-resident access for callers that already hold the state in HBM (bench.py's `value` leg):
  * modal state buffer [n][Nb][Nv] <-> internal representation, both on the device. */
 int sdg_set_state_device(sdg_ctx* ctx, int32_t type, const void* U_device);

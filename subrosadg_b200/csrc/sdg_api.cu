@@ -50,6 +50,10 @@ struct sdg_ctx {
   // one time step (nStages x passes launches) captured as a CUDA graph: launch-bound meshes (the reference's shipped configs have
   // 1e2-3e4 elements) replay it instead of issuing every launch from the host
   cudaGraphExec_t stepGraph = nullptr; double graphDt = 0.0; int graphCur = -1; bool graphWarm = false;
+  // peer-memory halo exchange (CUDA IPC): the peers' arrays opened in this process, arrival flags, exchange counter
+  std::vector<PeerDev> peerLinks; std::vector<void*> ipcOpened;
+  DevBuf<PeerDev> peerDev; DevBuf<long long> ipcFlags; DevBuf<unsigned int> pushCounter; DevBuf<int> haloErr;
+  long long pushEpoch = 0;
   std::unique_ptr<MixedSolver> mx;   // dense-operator path: meshes with triangle blocks / several element types (mixed_path.cu)
 
   size_t stateDoubles() const { return (size_t)plan.blk.n * NV * plan.blk.T.NN; }
@@ -186,6 +190,7 @@ void sdg_destroy(sdg_ctx* c) {
   if (!c) return;
   if (c->hasDevice) { cudaSetDevice(c->cfg.device); cudaDeviceSynchronize(); }
   if (c->stepGraph) cudaGraphExecDestroy(c->stepGraph);
+  for (void* q : c->ipcOpened) cudaIpcCloseMemHandle(q);
   cudaStream_t s = c->stream; const bool dev = c->hasDevice;
   delete c;
   if (dev && s) cudaStreamDestroy(s);
@@ -540,6 +545,12 @@ int sdg_step_end(sdg_ctx* c, double* sums) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   finishStep(c);
   if (sums) reduceNorm(c, sums);
+  if (sums && c->haloErr.p) {   // a wait on the peers' pushes timed out (ranks out of step): fail loudly instead of computing on stale ghosts
+    int h = 0;
+    CUDA_OK(cudaMemcpyAsync(&h, c->haloErr.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (h != 0) throw std::runtime_error("peer-memory halo exchange: a rank waited in vain for a peer's push");
+  }
   SDG_CATCH
 }
 
@@ -720,6 +731,72 @@ int sdg_halo_buffers_device(sdg_ctx* c, int32_t type, int32_t what, void** send,
   double* base = what == 1 ? c->G.p : c->U[c->latest].p;
   *send = c->sendBuf.p; *send_doubles = (int64_t)c->nSend * per;
   *recv = base + (size_t)B.nOwned * per; *recv_doubles = (int64_t)B.nGhost * per;
+  SDG_CATCH
+}
+
+// ---- peer-memory halo exchange ------------------------------------------------------------------------------------------------------
+int sdg_ipc_export(sdg_ctx* c, unsigned char* handles) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (!c->ipcFlags.p) { c->ipcFlags.alloc(64); c->ipcFlags.zero(c->stream); c->pushCounter.alloc(1); c->pushCounter.zero(c->stream); c->haloErr.alloc(1); c->haloErr.zero(c->stream); CUDA_OK(cudaStreamSynchronize(c->stream)); }
+  void* ptrs[5] = {c->U[0].p, c->U[1].p, c->U[2].p, c->G.p, c->ipcFlags.p};
+  std::memset(handles, 0, 5 * sizeof(cudaIpcMemHandle_t));
+  for (int i = 0; i < 5; i++) if (ptrs[i]) { cudaIpcMemHandle_t h; CUDA_OK(cudaIpcGetMemHandle(&h, ptrs[i])); std::memcpy(handles + i * sizeof(h), &h, sizeof(h)); }
+  SDG_CATCH
+}
+
+int sdg_ipc_connect(sdg_ctx* c, int32_t n_peers, const unsigned char* handles, const int64_t* ghost_first, const int32_t* send_first,
+                    const int32_t* send_count, const int32_t* slot_at_peer) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  if (n_peers < 0 || n_peers > 32) throw std::runtime_error("bad peer count");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  c->peerLinks.assign(n_peers, PeerDev{});
+  for (int p = 0; p < n_peers; p++) {
+    PeerDev& L = c->peerLinks[p];
+    for (int i = 0; i < 5; i++) {
+      cudaIpcMemHandle_t h; std::memcpy(&h, handles + ((size_t)p * 5 + i) * sizeof(h), sizeof(h));
+      bool zero = true; for (size_t b = 0; b < sizeof(h); b++) zero = zero && reinterpret_cast<const unsigned char*>(&h)[b] == 0;
+      void* q = nullptr;
+      if (!zero) { CUDA_OK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess)); c->ipcOpened.push_back(q); }
+      if (i < 4) L.dst[i] = static_cast<double*>(q); else L.flags = static_cast<long long*>(q);
+    }
+    L.ghostFirst = ghost_first[p]; L.sendFirst = send_first[p]; L.sendCount = send_count[p]; L.slot = slot_at_peer[p];
+    if (L.slot < 0 || L.slot >= 64) throw std::runtime_error("bad flag slot");
+  }
+  c->peerDev.upload(c->peerLinks, c->stream);
+  SDG_CATCH
+}
+
+int sdg_halo_push(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
+  if (c->peerLinks.empty() && c->nSend > 0) throw std::runtime_error("sdg_ipc_connect has not been called");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  c->pushEpoch++;
+  if (c->peerLinks.empty()) return 0;
+  const int stride = (int)c->elemDoubles() * (what == 1 ? c->D : 1);
+  const double* src = what == 1 ? c->G.p : c->U[c->latest].p;
+  const int which = what == 1 ? 3 : c->latest;
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((size_t)c->nSend * stride + 255) / 256, 148 * 4));
+  haloPushKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(src, c->sendList.p, c->nSend, stride, c->peerDev.p, (int)c->peerLinks.size(), which,
+                                                                                 c->pushCounter.p, c->pushEpoch);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  SDG_CATCH
+}
+
+int sdg_halo_wait(sdg_ctx* c, void* stream) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (c->peerLinks.empty()) return 0;
+  haloWaitKernel<<<1, 32, 0, stream ? (cudaStream_t)stream : c->stream>>>(c->ipcFlags.p, (int)c->peerLinks.size(), c->pushEpoch, c->haloErr.p);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
   SDG_CATCH
 }
 

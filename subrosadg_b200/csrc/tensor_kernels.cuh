@@ -625,6 +625,51 @@ static __global__ void normReduceKernel(const double* __restrict__ partial, int 
   if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w]; out[(size_t)blockIdx.y * NV + v] = t; }
 }
 
+// ---- peer-memory halo exchange (one process per GPU, CUDA IPC over NVLink / NVSwitch) -----------------------------------------------
+// A peer's arrays as seen from this rank (cudaIpcOpenMemHandle) and where this rank's send elements land in them.
+struct PeerDev {
+  double* dst[4];        // the peer's U[0], U[1], U[2], G allocations
+  long long* flags;      // the peer's arrival flags; this rank owns entry `slot`
+  long long ghostFirst;  // element index, in the peer's arrays, of the first ghost element fed by this rank
+  int sendFirst, sendCount, slot;
+};
+// Gather the send elements of field `which` and store them STRAIGHT into the peers' ghost ranges (no staging buffer, no
+// send/recv pair); the last thread block to finish publishes this exchange's epoch in every peer's flag entry.
+static __global__ void haloPushKernel(const double* __restrict__ src, const int* __restrict__ elems, int nSend, int stride, const PeerDev* __restrict__ peers,
+                                      int nPeers, int which, unsigned int* counter, long long epoch) {
+  const size_t total = (size_t)nSend * stride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / stride), r = (int)(i - (size_t)k * stride);
+    int p = 0;
+    while (p + 1 < nPeers && k >= peers[p].sendFirst + peers[p].sendCount) p++;
+    peers[p].dst[which][(size_t)(peers[p].ghostFirst + (k - peers[p].sendFirst)) * stride + r] = src[(size_t)elems[k] * stride + r];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) {   // every block's stores are fenced: the data is visible at the peers before the flag
+      *counter = 0u;
+      __threadfence_system();
+      for (int p = 0; p < nPeers; p++) *reinterpret_cast<volatile long long*>(peers[p].flags + peers[p].slot) = epoch;
+      __threadfence_system();
+    }
+  }
+}
+// Stream-side wait for the peers' pushes of exchange `epoch` (one lane per peer); gives up after ~10 s and raises errFlag.
+static __global__ void haloWaitKernel(const long long* __restrict__ flags, int nPeers, long long epoch, int* errFlag) {
+  const int p = threadIdx.x;
+  if (p < nPeers) {
+    const volatile long long* f = flags + p;
+    unsigned spins = 0;
+    while (*f < epoch) {
+      __nanosleep(200);
+      if (++spins > (1u << 25)) { atomicExch(errFlag, 1); break; }
+    }
+  }
+  __threadfence_system();
+}
+
 // gather of the halo send list: out[i][:] = U[elems[i]][:]
 static __global__ void haloPackKernel(const double* __restrict__ U, const int* __restrict__ elems, int n, int stride, double* __restrict__ out) {
   const size_t total = (size_t)n * stride;

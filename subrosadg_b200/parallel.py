@@ -209,6 +209,10 @@ class DistributedSolver:
         self.ev_ready = torch.cuda.Event()
         self.ev_halo = torch.cuda.Event()
         self._views = {}
+        # halo transport: "ipc" = peer-memory stores over NVLink (CUDA IPC, no staging, no send/recv), "nccl" = pack + ncclSend/Recv
+        self.transport = os.environ.get("SDG_HALO", "ipc" if (self.world > 1 and dist.get_backend(group) == "nccl") else "nccl")
+        if self.transport == "ipc":
+            self._connect_peers()
         self.relative_error_ = np.zeros(self.Nv)
         self.delta_time_ = 0.0
         self.launches_extra = 0
@@ -232,12 +236,48 @@ class DistributedSolver:
         self._chk(self.lib.sdg_halo_buffers_device(self.S.h, self.etype, what, ctypes.byref(sp), ctypes.byref(sn), ctypes.byref(rp), ctypes.byref(rn)))
         return self._view(sp.value or 0, sn.value), self._view(rp.value or 0, rn.value)
 
+    def _connect_peers(self):
+        """CUDA IPC set-up of the peer-memory exchange: every rank publishes the handles of its state / gradient / flag
+        allocations and where it expects each peer's elements; the library opens the peers' handles (sdg_ipc_connect)."""
+        lib, part = self.lib, self.part
+        mine = np.zeros(5 * 64, dtype=np.uint8)
+        self._chk(lib.sdg_ipc_export(self.S.h, mine.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte))))
+        info = dict(handles=mine.tobytes(), n_owned=int(part.n_owned), peers=[int(q) for q in part.peers],
+                    recv={int(q): (int(part.recv_range[q][0]), int(part.recv_range[q][1])) for q in part.peers})
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, info, group=self.group)
+        peers = [int(q) for q in part.peers]
+        n = len(peers)
+        handles = np.zeros(max(n, 1) * 5 * 64, dtype=np.uint8)
+        ghost_first = np.zeros(max(n, 1), dtype=np.int64)
+        send_first = np.zeros(max(n, 1), dtype=np.int32); send_count = np.zeros(max(n, 1), dtype=np.int32); slot = np.zeros(max(n, 1), dtype=np.int32)
+        for k, q in enumerate(peers):
+            other = everyone[q]
+            handles[k * 320:(k + 1) * 320] = np.frombuffer(other["handles"], dtype=np.uint8)
+            r0, nr = other["recv"].get(self.rank, (0, 0))
+            ns = int(part.send_local[q].size)
+            if nr != ns:
+                raise RuntimeError(f"halo mismatch: rank {self.rank} sends {ns} elements to {q}, which expects {nr}")
+            ghost_first[k] = other["n_owned"] + r0
+            send_first[k] = self.halo.send_off[q]; send_count[k] = ns
+            slot[k] = other["peers"].index(self.rank)
+        self._chk(lib.sdg_ipc_connect(self.S.h, n, handles.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+                                      ghost_first.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), send_first.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                      send_count.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), slot.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        self.dist.barrier(group=self.group)
+
     def _exchange(self, what):
         """Refresh the ghost copies of field `what` (0 state, 1 volume gradient); returns after ENQUEUEING the work on the
         communication stream and recording ev_halo there."""
         torch = self.torch
         self.ev_ready.record(self.main)
         self.comm.wait_event(self.ev_ready)
+        if self.transport == "ipc":
+            cs = ctypes.c_void_p(self.comm.cuda_stream)
+            self._chk(self.lib.sdg_halo_push(self.S.h, self.etype, what, cs))   # stores into the peers' ghost ranges + arrival flags
+            self._chk(self.lib.sdg_halo_wait(self.S.h, cs))                     # the peers' pushes into OUR ghost ranges
+            self.ev_halo.record(self.comm)
+            return
         with torch.cuda.stream(self.comm):
             self._chk(self.lib.sdg_halo_pack(self.S.h, self.etype, what, ctypes.c_void_p(self.comm.cuda_stream)))
             send, recv = self._buffers(what)
