@@ -781,7 +781,8 @@ int sdg_halo_push(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
   const int stride = (int)c->elemDoubles() * (what == 1 ? c->D : 1);
   const double* src = what == 1 ? c->G.p : c->U[c->latest].p;
   const int which = what == 1 ? 3 : c->latest;
-  const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((size_t)c->nSend * stride + 255) / 256, 148 * 4));
+  static const int maxBlocks = getenv("SDG_PUSH_BLOCKS") ? std::max(1, atoi(getenv("SDG_PUSH_BLOCKS"))) : 148 * 2;   // 2 CTAs per SM measured best at 4 GPUs (96: 280, 296: 285, 592: 282 GDOF/s): more blocks steal SM slots from the interior launch
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((size_t)c->nSend * stride + 255) / 256, (size_t)maxBlocks));
   haloPushKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(src, c->sendList.p, c->nSend, stride, c->peerDev.p, (int)c->peerLinks.size(), which,
                                                                                  c->pushCounter.p, c->pushEpoch);
   c->launches++;
