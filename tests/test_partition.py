@@ -118,3 +118,21 @@ def test_gloo_world2_matches_single_process(built, tmp_path, dim, n, p, model):
     got = np.concatenate([np.load(tmp_path / f"rank{r}.npy") for r in range(world)])
     assert got.shape == ref.shape
     assert cases.rel_l2(got, ref) < 1e-12
+
+
+@pytest.mark.parametrize("dim,n,world", [(3, 6, 4), (2, 9, 3), (3, 4, 8)])
+def test_push_targets_match_ghost_ranges(dim, n, world):
+    """The peer-memory exchange (sdg_halo_push) stores element k of rank r's send list for peer q at ghost element
+    n_owned_q + recv_range_q[r].first + k of q's arrays: those must be the same global elements, in the same order."""
+    from subrosadg_b200.parallel import partition
+    mesh = M.periodic_box_fast(dim, n)
+    parts = [partition(mesh, r, world) for r in range(world)]
+    for r, pr in enumerate(parts):
+        for q in pr.peers:
+            pq = parts[q]
+            assert r in pq.peers                                   # adjacency is symmetric: every peer has a flag slot for r
+            r0, nr = pq.recv_range[r]
+            sent_global = pr.lo + np.asarray(pr.send_local[q])
+            assert nr == sent_global.size
+            assert np.array_equal(pq.ghost_global[r0:r0 + nr], sent_global)
+            assert sorted(pq.peers).index(r) < 64                  # flag slot bound of the library
