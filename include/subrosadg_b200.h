@@ -3,7 +3,7 @@
  * The reference (SubrosaDG) has no FFI: its seam is the C++ class SubrosaDG::Solver<SimulationControl>
  * (src/Solver/SolveControl.cpp:327-436) driven by System<SC>::solve() (src/Utils/SystemControl.cpp:159-195).
  * Every entry point below replaces one member of that class (cited per function); the header-only shim
- * include/SubrosaDG_b200/Solver.hpp maps the reference's template configuration surface onto this ABI.
+ * include/SubrosaDG_b200/SubrosaDG.hpp maps the reference's template configuration surface onto this ABI.
  *
  * Conventions: plain pointers and sizes, caller-owned HOST buffers unless the name says `_device`; every function
  * returns 0 on success and non-zero on failure with the message available from sdg_last_error().  NaNs in the state
