@@ -443,8 +443,8 @@ struct System {
     solver_.initializeSolver(mesh_, physical_model_, source_term_, boundary_condition_, initial_condition_, device_);
     if (time_integration_.delta_time_ == 0.0) solver_.calculateDeltaTime(time_integration_);
     for (int i = time_integration_.iteration_start_ + 1; i <= time_integration_.iteration_end_; i++) {
-      time_integration_.iteration_ = i;
       solver_.stepSolver(boundary_condition_, time_integration_);
+      time_integration_.iteration_ = i;   // after the step, as SystemControl.cpp:175-177: step i sees t = (i - 1) dt
       bool all_nan = true;
       for (Real e : solver_.relative_error_) all_nan = all_nan && std::isnan(e);
       if (print_ && (i == time_integration_.iteration_end_ || i % std::max(1, io_interval_ > 0 ? io_interval_ : time_integration_.iteration_end_) == 0)) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -13,6 +14,17 @@ namespace sdg {
     cudaError_t e_ = (x);                                                                                       \
     if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_));           \
   } while (0)
+
+// cudaFuncSetAttribute is per DEVICE: remember, per kernel instantiation, on which devices the attribute has been set (one process
+// may hold contexts on several devices, sdg_config.device).  Setting it twice from two threads is harmless.
+inline bool firstUseOnThisDevice(std::atomic<unsigned long long>& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  if (mask.load(std::memory_order_acquire) & bit) return false;
+  mask.fetch_or(bit, std::memory_order_acq_rel);
+  return true;
+}
 
 template <typename T>
 struct DevBuf {

@@ -14,22 +14,16 @@ namespace {
 template <int D, int N, int K, bool AFFINE, int PH>
 void launchEuler(const StageArgs& a, int nBlocks, cudaStream_t s) {
   using L = Layout<D, N, K>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(eulerStageKernel<D, N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (firstUseOnThisDevice(configured)) CUDA_OK(cudaFuncSetAttribute(eulerStageKernel<D, N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
   eulerStageKernel<D, N, K, AFFINE, PH><<<nBlocks, kThreads, L::bytes, s>>>(a);
 }
 
 template <int N, int K, bool AFFINE, int PH>
 void launchEulerLine(const StageArgs& a, int nBlocks, cudaStream_t s) {
   using L = LineLayout<N, K>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(eulerLineKernel<N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (firstUseOnThisDevice(configured)) CUDA_OK(cudaFuncSetAttribute(eulerLineKernel<N, K, AFFINE, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
   eulerLineKernel<N, K, AFFINE, PH><<<nBlocks, L::THREADS, L::bytes, s>>>(a);
 }
 

@@ -12,8 +12,8 @@ namespace {
 template <int D, int N, int K, bool AFFINE>
 void launchNsGrad(const StageArgs& a, int nBlocks, cudaStream_t s) {
   using L = NsLayout<D, N, K, AFFINE, false>;
-  static bool configured = false;
-  if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsGradKernel<D, N, K, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
+  static std::atomic<unsigned long long> configured{0};
+  if (firstUseOnThisDevice(configured)) CUDA_OK(cudaFuncSetAttribute(nsGradKernel<D, N, K, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
   nsGradKernel<D, N, K, AFFINE><<<nBlocks, kThreads, L::bytes, s>>>(a);
 }
 // threads per block of the NS residual pass: one face point per thread in the face phase where the register budget allows
@@ -27,8 +27,8 @@ template <int D, int N, int K, bool AFFINE, int PH>
 void launchNsStage(const StageArgs& a, int nBlocks, cudaStream_t s) {
   constexpr int TH = NsThreadsOf<D, N>::TH;
   using L = NsLayout<D, N, K, AFFINE, true, TH>;
-  static bool configured = false;
-  if (!configured) { CUDA_OK(cudaFuncSetAttribute(nsStageKernel<D, N, K, AFFINE, PH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes)); configured = true; }
+  static std::atomic<unsigned long long> configured{0};
+  if (firstUseOnThisDevice(configured)) CUDA_OK(cudaFuncSetAttribute(nsStageKernel<D, N, K, AFFINE, PH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
   nsStageKernel<D, N, K, AFFINE, PH, TH><<<nBlocks, TH, L::bytes, s>>>(a);
 }
 template <int D, int N> struct NsChunkOf;

@@ -364,10 +364,11 @@ int sdg_set_state_from_primitive(sdg_ctx* c, int32_t type, const double* prim) {
   const size_t nd = c->stateDoubles();
   c->scratch.alloc(nd);
   CUDA_OK(cudaMemcpyAsync(c->scratch.p, prim, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  const int blocks = (int)std::min<size_t>(((size_t)B.n * B.T.NN + 255) / 256, 148 * 16);
-  if (c->D == 1) primitiveToStateKernel<1><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
-  else if (c->D == 2) primitiveToStateKernel<2><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
-  else primitiveToStateKernel<3><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, B.n, B.T.NN, c->phys);
+  const int nSet = B.nOwned;   // ghosts are fed by the halo exchange only (see transformModal)
+  const int blocks = (int)std::min<size_t>(((size_t)nSet * B.T.NN + 255) / 256, 148 * 16);
+  if (c->D == 1) primitiveToStateKernel<1><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, nSet, B.T.NN, c->phys);
+  else if (c->D == 2) primitiveToStateKernel<2><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, nSet, B.T.NN, c->phys);
+  else primitiveToStateKernel<3><<<blocks, 256, 0, c->stream>>>(c->scratch.p, c->U[c->cur].p, c->perm.p, nSet, B.T.NN, c->phys);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -395,9 +396,12 @@ int sdg_set_boundary_primitive(sdg_ctx* c, const double* prim) {
   SDG_CATCH
 }
 
-static void transformModal(sdg_ctx* c, const double* in, double* out, const double* M, int dir) {
+// nElems < B.n: the state setters of a partitioned block touch the OWNED elements only — the trailing ghost range of U[cur]
+// belongs to the peers' halo pushes, which may land before or after this rank's setter (no receiver-ready handshake)
+static void transformModal(sdg_ctx* c, const double* in, double* out, const double* M, int dir, int nElems = -1) {
   const BlockPlan& B = c->plan.blk;
-  seamTransformKernel<<<B.n, 128, sizeof(double) * c->NV * B.T.NN, c->stream>>>(in, out, M, c->perm.p, B.n, c->NV, B.T.NN, dir);
+  const int n = nElems < 0 ? B.n : nElems;
+  seamTransformKernel<<<n, 128, sizeof(double) * c->NV * B.T.NN, c->stream>>>(in, out, M, c->perm.p, n, c->NV, B.T.NN, dir);
   c->launches++;
   CUDA_OK(cudaGetLastError());
 }
@@ -407,7 +411,7 @@ int sdg_set_state_device(sdg_ctx* c, int32_t type, const void* U_device) {
   if (c->mx) { needFinal(c); c->mx->setStateDevice(type, U_device); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  transformModal(c, (const double*)U_device, c->U[c->cur].p, c->Phi.p, 0);
+  transformModal(c, (const double*)U_device, c->U[c->cur].p, c->Phi.p, 0, c->plan.blk.nOwned);
   c->latest = c->cur;
   SDG_CATCH
 }
@@ -428,7 +432,7 @@ int sdg_set_state(sdg_ctx* c, int32_t type, const double* U) {
   const size_t nd = c->stateDoubles();
   const int s = (c->cur + 1) % 3;  // scratch: a stage buffer that holds no live data between steps
   CUDA_OK(cudaMemcpyAsync(c->U[s].p, U, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  transformModal(c, c->U[s].p, c->U[c->cur].p, c->Phi.p, 0);
+  transformModal(c, c->U[s].p, c->U[c->cur].p, c->Phi.p, 0, c->plan.blk.nOwned);
   CUDA_OK(cudaStreamSynchronize(c->stream));
   c->latest = c->cur;
   SDG_CATCH
@@ -545,11 +549,11 @@ int sdg_step_end(sdg_ctx* c, double* sums) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   finishStep(c);
   if (sums) reduceNorm(c, sums);
-  if (sums && c->haloErr.p) {   // a wait on the peers' pushes timed out (ranks out of step): fail loudly instead of computing on stale ghosts
-    int h = 0;
-    CUDA_OK(cudaMemcpyAsync(&h, c->haloErr.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    if (h != 0) throw std::runtime_error("peer-memory halo exchange: a rank waited in vain for a peer's push");
+  // a wait on the peers' pushes that timed out has trapped (haloWaitKernel): the sticky error surfaces here on every step,
+  // with or without `sums`, without adding a synchronisation to the healthy path
+  if (c->haloErr.p) {
+    const cudaError_t q = cudaStreamQuery(c->stream);
+    if (q != cudaSuccess && q != cudaErrorNotReady) throw std::runtime_error(std::string("peer-memory halo exchange: a rank waited in vain for a peer's push (") + cudaGetErrorString(q) + ")");
   }
   SDG_CATCH
 }
@@ -795,7 +799,10 @@ int sdg_halo_wait(sdg_ctx* c, void* stream) {
   needFinal(c); needDevice(c);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   if (c->peerLinks.empty()) return 0;
-  haloWaitKernel<<<1, 32, 0, stream ? (cudaStream_t)stream : c->stream>>>(c->ipcFlags.p, (int)c->peerLinks.size(), c->pushEpoch, c->haloErr.p);
+  // a rank may legitimately lag by a multi-GB host copy or a first-launch module load: generous default, SDG_HALO_TIMEOUT_S overrides
+  static const double timeoutS = getenv("SDG_HALO_TIMEOUT_S") ? std::max(1.0, atof(getenv("SDG_HALO_TIMEOUT_S"))) : 120.0;
+  haloWaitKernel<<<1, 32, 0, stream ? (cudaStream_t)stream : c->stream>>>(c->ipcFlags.p, (int)c->peerLinks.size(), c->pushEpoch, c->haloErr.p,
+                                                                          (unsigned long long)(timeoutS * 1e9));
   c->launches++;
   CUDA_OK(cudaGetLastError());
   SDG_CATCH

@@ -656,15 +656,20 @@ static __global__ void haloPushKernel(const double* __restrict__ src, const int*
     }
   }
 }
-// Stream-side wait for the peers' pushes of exchange `epoch` (one lane per peer); gives up after ~10 s and raises errFlag.
-static __global__ void haloWaitKernel(const long long* __restrict__ flags, int nPeers, long long epoch, int* errFlag) {
+// Stream-side wait for the peers' pushes of exchange `epoch` (one lane per peer).  A wait that outlasts `timeoutNs` (ranks out
+// of step for good) is FATAL: the flag is raised and the kernel traps, so every later call on this context fails loudly
+// instead of computing a stage on stale ghost data.
+static __global__ void haloWaitKernel(const long long* __restrict__ flags, int nPeers, long long epoch, int* errFlag, unsigned long long timeoutNs) {
   const int p = threadIdx.x;
   if (p < nPeers) {
     const volatile long long* f = flags + p;
-    unsigned spins = 0;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*f < epoch) {
       __nanosleep(200);
-      if (++spins > (1u << 25)) { atomicExch(errFlag, 1); break; }
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeoutNs) { atomicExch(errFlag, 1); __threadfence_system(); __trap(); }
     }
   }
   __threadfence_system();

@@ -442,6 +442,74 @@ def cubed_sphere_shell(n, nr, r0=0.5, r1=5.0, geom_order=3, stretch=2.0, phys_bc
     return mesh_from_blocks(3, {HEXAHEDRON: hexes}, geom_order, phys_bc, tagger, None, info=dict(kind="cubed_sphere_shell", r0=r0, r1=r1))
 
 
+def _progression(n, ratio):
+    """gmsh transfinite "Progression": n cells whose lengths grow by `ratio` from the start; returns the n+1 points in [0, 1]."""
+    h = ratio ** np.arange(n, dtype=float)
+    return np.concatenate([[0.0], np.cumsum(h)]) / h.sum()
+
+
+def sphere_in_box(n_mid=11, n_out=9, n_rad=9, half=5.0, r_sphere=0.5, geom_order=3, phys_bc=None) -> Mesh:
+    """Block topology of examples/sphere_3d_cns.cpp:72-296 (config 5): a 3x3x3 arrangement of transfinite blocks on [-half, half]^3
+    whose centre block is replaced by SIX blocks between the sphere (wall, physical 2) and the faces of the centre cube, 26 + 6 blocks in
+    total.  Cells per axis: n_out (progression 1.3 away from the centre, :259-274), n_mid, n_out; sphere blocks n_mid x n_mid x n_rad
+    (radial progression 1.2, :286-292).  Defaults = the shipped mesh: 29^3 - 11^3 + 6 * 11 * 11 * 9 = 29,592 hexahedra.  The corners of the
+    centre cube lie on the sphere of radius 1 (x = sqrt(3)/6, :73-78) and its edges are circle arcs (:108-113); gmsh's surface filling is
+    not available here, so the curved faces are those of a transfinite blend of each block's edges (arcs on the centre cube, straight elsewhere).
+    Far field = physical 1."""
+    phys_bc = phys_bc or {1: RIEMANN_FARFIELD, 2: ADIABATIC_NONSLIP_WALL}
+    a0 = 2.0 * np.sqrt(3.0) / 6.0          # half width of the centre cube; a0 * sqrt(3) = 1
+    # 1-D point distributions of the three segments of an axis, as functions of the logical coordinate in [0, 1]
+    seg_pts = [-half + (half - a0) * (1.0 - _progression(n_out, 1.3)[::-1]), np.linspace(-a0, a0, n_mid + 1), a0 + (half - a0) * _progression(n_out, 1.3)]
+    seg_n = [n_out, n_mid, n_out]
+
+    def axis_coord(seg, s):   # piecewise-linear in the cell index, so that element nodes of order g are equispaced inside a cell
+        return np.interp(s * seg_n[seg], np.arange(seg_n[seg] + 1), seg_pts[seg])
+
+    def morph(p):
+        # transfinite blend per block: q = closest point of the centre cube; its displacement onto the unit sphere fades out linearly
+        # along every axis that leaves the cube.  Face blocks: (1 - w) sphere patch + w flat far face; edge blocks: bilinear blend whose
+        # inner edge is the circle arc; corner blocks: identity (the cube corners already lie on the sphere) — smooth inside each block.
+        q = np.clip(p, -a0, a0)
+        w = np.clip((np.abs(p) - a0) / (half - a0), 0.0, 1.0)
+        fade = np.prod(1.0 - w, axis=1)
+        sph = q / np.linalg.norm(q, axis=1, keepdims=True)
+        return p + fade[:, None] * (sph - q)
+
+    blocks = []
+    for bk in range(3):
+        for bj in range(3):
+            for bi in range(3):
+                if bi == 1 and bj == 1 and bk == 1:
+                    continue
+
+                def mapping(s, bi=bi, bj=bj, bk=bk):
+                    p = np.stack([axis_coord(bi, s[:, 0]), axis_coord(bj, s[:, 1]), axis_coord(bk, s[:, 2])], axis=1)
+                    return morph(p)
+
+                blocks.append(_structured_elements(3, (seg_n[bi], seg_n[bj], seg_n[bk]), mapping, geom_order))
+    frames = [((0, 1, 0), (0, 0, 1), (1, 0, 0)), ((0, 0, 1), (0, 1, 0), (-1, 0, 0)), ((0, 0, 1), (1, 0, 0), (0, 1, 0)),
+              ((1, 0, 0), (0, 0, 1), (0, -1, 0)), ((1, 0, 0), (0, 1, 0), (0, 0, 1)), ((0, 1, 0), (1, 0, 0), (0, 0, -1))]
+    rad_pts = r_sphere + (1.0 - r_sphere) * _progression(n_rad, 1.2)
+    for ea, eb, en in frames:
+        ea, eb, en = np.array(ea, float), np.array(eb, float), np.array(en, float)
+
+        def mapping(s, ea=ea, eb=eb, en=en):
+            a = a0 * (2.0 * s[:, 0] - 1.0); b = a0 * (2.0 * s[:, 1] - 1.0)
+            q = a[:, None] * ea + b[:, None] * eb + a0 * en
+            q /= np.linalg.norm(q, axis=1, keepdims=True)
+            r = np.interp(s[:, 2] * n_rad, np.arange(n_rad + 1), rad_pts)
+            return q * r[:, None]
+
+        blocks.append(_structured_elements(3, (n_mid, n_mid, n_rad), mapping, geom_order))
+    hexes = np.concatenate(blocks)
+
+    def tagger(c):
+        return np.where(np.linalg.norm(c, axis=1) < 0.5 * (r_sphere + half), 2, 1).astype(np.int32)
+
+    return mesh_from_blocks(3, {HEXAHEDRON: hexes}, geom_order, phys_bc, tagger, None,
+                            info=dict(kind="sphere_in_box", blocks=32, n_mid=n_mid, n_out=n_out, n_rad=n_rad))
+
+
 def write_flat(mesh: Mesh, path) -> None:
     """Flat little-endian mesh file for the C++ host side (`SubrosaDG::MeshData::readFlat`,
     include/SubrosaDG_b200/SubrosaDG.hpp): magic "SDGM", dim, nblocks, per block {type, geom_order, n, nn, coords[n][nn][dim]},

@@ -1,0 +1,147 @@
+"""GPU parity tests against the CPU oracle AT BASELINE.json's sizes: the scaled-down cases of
+test_gpu_parity.py never reach the code paths that only exist at scale (more than 32 K thread-block chunks = no CUDA graph, full Morton
+bricks, long chunk-face lists), and two instantiations of the benchmarked kernel (curved P3 hexahedra, run-time physics switches on P3
+hexahedra) had no oracle comparison at all.
+
+Tolerances are BASELINE.json's: per-stage residual rel-L2 <= 1e-12, conserved fields after N steps <= 1e-10 (fp64)."""
+import numpy as np
+import pytest
+
+import cases
+from subrosadg_b200 import mesh as M
+from test_gpu_mixed import compare as compare_mixed
+from test_gpu_mixed import pair as pair_mixed
+from test_gpu_parity import NS, compare, compare_ns
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- config 2: naca0012_2d_ceuler at the shipped size (4 transfinite blocks 39x19, 39x19, 19x19, 19x19 = 2,204 P3 quads) ----------
+def test_config2_naca0012_full_size(built):
+    mesh = M.naca0012(nr=19, nt=116)
+    assert mesh.n_elements == 2204
+    ic = cases.ic_perturbed_freestream(0.63, 2.0, 2, amp=1e-3)
+    O, S = cases.make_pair(dict(p=3, conv_flux=2, rk=2), mesh, ic, cases.bc_freestream(0.63, 2.0, 2))
+    dt = O.compute_dt(1.0)
+    assert abs(S.calculateDeltaTime(1.0) - dt) <= 1e-13 * dt
+    compare(O, S, dt, 5, label="config 2 full size")
+
+
+def test_config2_hybrid_roe_full_size(built):
+    """BASELINE's wording of config 2: hybrid tri/quad mesh, Roe flux, Riemann far field — at the same element count"""
+    mesh = M.annulus(19, 80, r0=0.5, r1=20.0, geom_order=3, stretch=2.0, tri_rings=8)
+    assert sorted(mesh.blocks) == [M.TRIANGLE, M.QUADRANGLE] and 2000 <= mesh.n_elements <= 2400
+    ic = cases.ic_perturbed_freestream(0.3, 2.0, 2, amp=1e-3)   # impulsive start around a cylinder: M = 0.3 and CFL 0.2 keep the transient tame
+    O, S = pair_mixed(dict(p=3, conv_flux=3, rk=2), mesh, ic, cases.bc_freestream(0.3, 2.0, 2))
+    dt = O.compute_dt(0.2)
+    assert abs(S.calculateDeltaTime(0.2) - dt) <= 1e-13 * dt
+    compare_mixed(O, S, dt, 4, "config 2 hybrid Roe full size")
+
+
+# ---- config 3: karmanvortex_2d_cns, 1,280 P3 quads at the cylinder + 3,840 triangles = 5,120 elements --------------------------------
+def test_config3_karmanvortex_5k(built):
+    mesh = M.annulus(40, 80, r0=0.5, r1=20.0, geom_order=3, stretch=1.5, tri_rings=24, phys_bc={1: M.RIEMANN_FARFIELD, 2: M.ADIABATIC_NONSLIP_WALL})
+    assert mesh.n_elements >= 5000
+    cfg = dict(NS, p=3, visc_flux=2, transport=2)
+    ic = cases.ic_perturbed_freestream(0.2, 0.0, 2, amp=1e-3)
+    O, S = pair_mixed(cfg, mesh, ic, cases.bc_freestream(0.2, 0.0, 2, wall_phys=(2,)))
+    dt = 0.3 * O.compute_dt(1.0)
+    compare_mixed(O, S, dt, 3, "config 3 at 5k elements", ns=True)
+
+
+# ---- config 4: periodic_3d_ceuler, 32^3 P3 hexahedra (4,096 full 2x2x2 bricks) -----------------------------------------------------------
+def test_config4_32cube(built):
+    mesh = M.periodic_box_fast(3, 32)
+    O, S = cases.make_pair(dict(p=3, conv_flux=2, rk=2), mesh, cases.ic_density_wave([0.5, 0.3, 0.2]))
+    dt = O.compute_dt(1.0)
+    assert abs(S.calculateDeltaTime(1.0) - dt) <= 1e-13 * dt
+    compare(O, S, dt, 2, label="config 4 at 32^3")
+
+
+def test_ns_target_24cube(built):
+    """north_star's NS target family (periodic cube, BR2, constant viscosity) on 13,824 P3 hexahedra"""
+    mesh = M.periodic_box_fast(3, 24)
+    cfg = dict(NS, p=3, visc_flux=2, conv_flux=2, rk=2)
+    O, S = cases.make_pair(cfg, mesh, cases.ic_density_wave([0.5, 0.3, 0.2]))
+    compare_ns(O, S, O.compute_dt(1.0), 2, "NS target at 24^3")
+
+
+# ---- more than 32 K chunks: sdg_step issues every launch from the host, no CUDA graph (sdg_api.cu: kGraphMaxChunks) ------------------------
+def test_no_graph_path_above_32k_chunks(built):
+    n = 728                                   # 529,984 P3 quads / 16 per chunk = 33,124 chunks
+    mesh = M.periodic_box_fast(2, n)
+    O, S = cases.make_pair(dict(p=3, conv_flux=2, rk=2), mesh, cases.ic_density_wave([0.7, 0.3]))
+    misc = S.debug_plan(15)
+    assert misc[2] > (1 << 15), misc
+    compare(O, S, O.compute_dt(1.0), 4, label="728^2 quads, no graph")
+
+
+# ---- config 5: sphere_3d_cns with the shipped block topology (26 far blocks + 6 sphere blocks = 29,592 curved P3 hexahedra) -----------
+def test_config5_sphere_full_size(built):
+    mesh = M.sphere_in_box()
+    assert mesh.n_elements == 29 ** 3 - 11 ** 3 + 6 * 11 * 11 * 9 == 29592
+    cfg = dict(NS, p=3, visc_flux=2)
+    ic = cases.ic_perturbed_freestream(0.2, 0.0, 3, amp=1e-3)
+    O, S = cases.make_pair(cfg, mesh, ic, cases.bc_freestream(0.2, 0.0, 3, wall_phys=(2,)))
+    dt = 0.3 * O.compute_dt(1.0)
+    compare_ns(O, S, dt, 2, "config 5 full size")
+
+
+# ---- instantiations of the benchmarked Euler kernel that had no oracle comparison: curved P3 hexahedra, run-time physics (PH = 0) ----
+@pytest.mark.parametrize("flux", [2, 3, 1, 0])   # HLLC (PH = 1), Roe, Lax-Friedrichs, Central (PH = 0)
+def test_curved_p3_hexahedra_euler(built, flux):
+    """eulerLineKernel<4, 8, AFFINE = false, PH>: warped order-2 geometry, far-field boundary"""
+    warp = lambda x: x + 0.03 * np.sin(np.pi * np.roll(x, 1, axis=1))
+    mesh = M.box(3, (4, 5, 4), 0.0, 1.0, geom_order=2, warp=warp)
+    ic = cases.ic_perturbed_freestream(0.5, 3.0, 3)
+    O, S = cases.make_pair(dict(p=3, conv_flux=flux, rk=2), mesh, ic, cases.bc_freestream(0.5, 3.0, 3, wall_phys=()))
+    assert S.debug_plan(15)[0] == 0           # not affine
+    compare(O, S, 5e-4, 4, label=f"curved P3 hex flux {flux}")
+
+
+@pytest.mark.parametrize("flux", [3, 1, 0])
+def test_affine_p3_hexahedra_runtime_physics(built, flux):
+    """eulerLineKernel<4, 8, AFFINE = true, PH = 0>: periodic P3 hexahedra with Roe / Lax-Friedrichs / Central"""
+    mesh = M.periodic_box_fast(3, 6)
+    O, S = cases.make_pair(dict(p=3, conv_flux=flux, rk=2), mesh, cases.ic_density_wave([0.5, 0.3, 0.2]))
+    compare(O, S, 5e-4, 4, label=f"affine P3 hex flux {flux}")
+
+
+@pytest.mark.parametrize("curved", [False, True])
+def test_p3_hexahedra_weak_eos_exact_flux(built, curved):
+    """IncompresibleEuler + WeakCompressibleFluid + Exact flux on P3 hexahedra (PH = 0), affine and curved"""
+    warp = (lambda x: x + 0.03 * np.sin(np.pi * np.roll(x, 1, axis=1))) if curved else None
+    mesh = M.box(3, (4, 4, 3), 0.0, 1.0, geom_order=2 if curved else 1, warp=warp)
+    cfg = dict(p=3, model=2, eos=1, conv_flux=4, rk=2, c0=10.0, rho0=1.0)
+
+    def ic(x):
+        s = 1e-2 * np.sin(np.pi * x[..., 0]) * np.cos(np.pi * x[..., 1]) * np.cos(np.pi * x[..., 2])
+        return np.stack([1.0 + 0.1 * s, 0.1 + s, 0.05 - s, 0.02 + 0.5 * s, 1.0 + s], axis=-1)
+
+    def bc(x, phys, time=None):
+        one = np.ones(x.shape[:-1])
+        return np.stack([one, 0.1 * one, 0.05 * one, 0.02 * one, one], axis=-1)
+
+    O, S = cases.make_pair(cfg, mesh, ic, bc)
+    dt = 0.3 * O.compute_dt(1.0)
+    compare(O, S, dt, 4, label=f"weak EOS exact flux curved={curved}")
+
+
+# ---- a state setter must not touch the ghost range of a partitioned block (race against the peers' halo pushes) -------------
+def test_state_setters_leave_ghosts_alone(built):
+    from subrosadg_b200.parallel import InProcessCluster
+    mesh = M.periodic_box_fast(3, 4)
+    C = InProcessCluster(dict(p=2, conv_flux=2, rk=2), mesh, 2, device=0)
+    C.initializeSolver(cases.ic_density_wave([0.5, 0.3, 0.2]))
+    C._exchange(0)                                         # ghosts now hold the neighbours' states
+    S, part, t = C.S[0], C.parts[0], C.etype
+    before = S.state_at_quadrature(t)
+    assert np.abs(before[part.n_owned:]).min() > 0
+    U = S.get_state(t)
+    poisoned = U.copy(); poisoned[part.n_owned:] = 7.0     # what a stale host copy of the ghost rows would look like
+    S.set_state(t, poisoned)
+    after = S.state_at_quadrature(t)
+    assert np.array_equal(after[part.n_owned:], before[part.n_owned:])
+    assert cases.rel_l2(after[:part.n_owned], before[:part.n_owned]) < 1e-13
+    S.initializeSolver(lambda x: 2.0 + 0.0 * cases.ic_density_wave([0.5, 0.3, 0.2])(x))
+    assert np.array_equal(S.state_at_quadrature(t)[part.n_owned:], before[part.n_owned:])
