@@ -113,6 +113,7 @@ def run_oracle(cells, p, steps, warmup, threads=None, base=None):
     from subrosadg_b200 import mesh as M
     mesh = M.periodic_box_fast(3, cells)
     cfg = dict(base or CFG); cfg["p"] = p
+    cfg["accurate"] = 0   # the timed baseline runs the reference's arithmetic (plain double M^-1 apply), not the checker's extended-precision mode
     if threads is None:   # all host cores this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
         threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     O = oracle.Oracle(cfg, mesh, threads=threads)
@@ -156,8 +157,8 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        import __graft_entry__ as g
-        g.build()
+        import oracle   # the reference arm loads the CPU oracle only: the product library is neither built nor dlopened here
+        oracle.build()
         # bounded sample of the same workload: a cpu_cells^3 cube of the same family; per-DOF rate is size independent
         val, sec, cores = run_oracle(a.cpu_cells, a.p, max(1, a.steps), a.warmup, base=base_cfg)
         sample = f"{a.cpu_cells}^3 hexes p={a.p}, {max(1, a.steps)} steps x 3 stages, {sec:.1f} s (CPU restatement of the reference algorithm incl. its dense M^-1 and gradient sweeps; the reference itself cannot be built here)"

@@ -16,8 +16,11 @@ TOL_STATE = 1e-10   # conserved fields after N steps, BASELINE.json
 TOL_RHS = 2e-11
 
 
-def compare(O, S, dt, nsteps, tol_res=TOL_RES, tol_state=TOL_STATE, label="", tol_ic=1e-12):
+def compare(O, S, dt, nsteps, tol_res=TOL_RES, tol_state=TOL_STATE, label="", tol_ic=1e-12, cond=1.0):
+    """cond >= 1 loosens the residual tolerances for ill-conditioned set-ups: cases.conditioning() measures how far the ORACLE's own
+    residual moves when its inputs move by one unit round-off; no two fp64 implementations can agree better than a few times that."""
     t = S.types[0]
+    tol_res = tol_res * cond
     # Solver::initializeSolver parity: modal coefficients of the IC projection (same H1Legendre convention on both sides)
     assert cases.rel_l2(S.get_state(t), O.get_state(t)) < tol_ic, label
     # identical inputs from here on: hand the oracle's modal coefficients to the CUDA path through the seam
@@ -26,7 +29,7 @@ def compare(O, S, dt, nsteps, tol_res=TOL_RES, tol_state=TOL_STATE, label="", to
     Rs, qs = S.residual()[t]
     e_q, e_R = cases.rel_l2(qs, qo), cases.rel_l2(Rs, Ro)
     assert e_R < tol_res, f"{label}: modal residual rel-L2 {e_R:.3e}"
-    assert e_q < TOL_RHS, f"{label}: dU/dt at quadrature points rel-L2 {e_q:.3e}"
+    assert e_q < TOL_RHS * cond, f"{label}: dU/dt at quadrature points rel-L2 {e_q:.3e}"
     err_o = O.step(dt, nsteps)
     err_s = S.stepSolver(dt, nsteps)
     e_u = cases.rel_l2(S.state_at_quadrature(t), O.state_at_quadrature(t))
@@ -100,7 +103,7 @@ def test_modal_state_roundtrip(built):
 NS = dict(model=1, transport=1, mu=1.4 * 0.2 / 200.0)   # examples/sphere_3d_cns.cpp:57-60 (Re = 200)
 
 
-def compare_ns(O, S, dt, nsteps, label):
+def compare_ns(O, S, dt, nsteps, label, cond=1.0):
     t = S.types[0]
     S.set_state(t, O.get_state(t))
     Ro, qo = O.residual()[t]
@@ -108,10 +111,10 @@ def compare_ns(O, S, dt, nsteps, label):
     gs = S.gradient_at_quadrature(t)
     Rs, qs = S.residual()[t]
     e_g = cases.rel_l2(gs, go)
-    assert e_g < 1e-11, f"{label}: total gradient at quadrature points rel-L2 {e_g:.3e}"
+    assert e_g < 1e-11 * cond, f"{label}: total gradient at quadrature points rel-L2 {e_g:.3e}"
     e_R, e_q = cases.rel_l2(Rs, Ro), cases.rel_l2(qs, qo)
-    assert e_R < TOL_RES, f"{label}: modal residual rel-L2 {e_R:.3e}"
-    assert e_q < TOL_RHS, f"{label}: dU/dt rel-L2 {e_q:.3e}"
+    assert e_R < TOL_RES * cond, f"{label}: modal residual rel-L2 {e_R:.3e}"
+    assert e_q < TOL_RHS * cond, f"{label}: dU/dt rel-L2 {e_q:.3e}"
     err_o = O.step(dt, nsteps)
     err_s = S.stepSolver(dt, nsteps)
     e_u = cases.rel_l2(S.state_at_quadrature(t), O.state_at_quadrature(t))
