@@ -122,6 +122,9 @@ int sdg_set_halo_send(sdg_ctx* ctx, int32_t type, int32_t n_send, const int32_t*
 int sdg_halo_pack(sdg_ctx* ctx, int32_t type, int32_t what, void* stream);
 int sdg_halo_buffers_device(sdg_ctx* ctx, int32_t type, int32_t what, void** send, int64_t* send_doubles, void** recv,
                             int64_t* recv_doubles);
+/* Doubles exchanged per halo element for field `what`: the element's state / volume-gradient coefficients, or — P3 hexahedra with
+ * Navier-Stokes, whose kernels read published face traces — its six face-trace rows (0: conserved variables, 1: viscous normal flux). */
+int sdg_halo_doubles_per_element(sdg_ctx* ctx, int32_t what);
 /* Split stepping used by the multi-GPU driver: stage `s` of the current step, restricted to thread blocks that do not
  * (part 0) / do (part 1) touch ghost elements; part -1 = all.  sdg_step_begin / sdg_step_end bracket one step. */
 int sdg_step_begin(sdg_ctx* ctx, double dt);

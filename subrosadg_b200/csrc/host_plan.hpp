@@ -33,6 +33,16 @@ struct BlockPlan {
   std::vector<int> chunkInterior, chunkBoundary;  // chunks without / with a ghost parent on one of their faces
 };
 
+// Host image of what the trace-based line kernels (nsl_kernels.cuh) read besides the states: per-(element, local face) link
+// records and affine face geometry, boundary-face records, the face-point correspondence tables in natural point order.
+struct LinePlan {
+  std::vector<int> links;       // [nOwned][6] x {other parent | -1, face id, lfo | rot<<3 | bc<<5 | amRight<<8 | handles<<9 | inChunk<<10, 0}
+  std::vector<double> lfGeo;    // affine: [nOwned][6][4] = normal of the face (outward from its LEFT parent), |J| scale
+  std::vector<int> bndRec;      // [nBnd] x {left parent, its local face, boundary condition, face id}
+  std::vector<unsigned char> partner, jLeft;
+  double cLift = 0.0;
+};
+
 struct GeomEval {  // Lagrange geometry map of one tensor element type
   int D, g, nn;
   std::vector<Lat> lat;
@@ -261,6 +271,55 @@ struct MeshPlan {
         else { double* g = &geoF[(size_t)i * (Dm + 1) * NQF]; for (int l = 0; l < Dm; l++) g[(size_t)l * NQF + j] = nv[l]; g[(size_t)Dm * NQF + j] = scale * B.T.wf[j]; }
       }
     }
+  }
+
+  // ---- trace-based line kernels: every owned (element, local face) names its other parent -----------------------------------------
+  LinePlan buildLinePlan() const {
+    const BlockPlan& B = blk;
+    if (B.D != 3 || B.T.N != 4) throw std::runtime_error("line plan: P3 hexahedra only");
+    LinePlan P;
+    const int nf = F.nInt + F.nBnd, NF = 6, NL = 16;
+    P.links.assign((size_t)B.nOwned * NF * 4, -2);
+    if (B.affine) P.lfGeo.assign((size_t)B.nOwned * NF * 4, 0.0);
+    P.bndRec.assign((size_t)std::max(F.nBnd, 1) * 4, 0);
+    auto sameChunk = [&](int a, int b) { return a < B.nOwned && b < B.nOwned && a / B.K == b / B.K; };
+    for (int i = 0; i < nf; i++) {
+      const bool interior = i < F.nInt;
+      const int pL = B.perm[F.le[i]], pR = interior ? B.perm[F.re[i]] : -1;
+      const int lfL = F.lf[i], lfR = interior ? F.rf[i] : 0, rot = interior ? F.rot[i] : 0, bc = interior ? 0 : (F.bc[i] & 7);
+      const bool in = interior && sameChunk(pL, pR);
+      auto put = [&](int pos, int lf, int other, int z) {
+        int* r = &P.links[((size_t)pos * NF + lf) * 4];
+        if (r[0] != -2) throw std::runtime_error("line plan: an element face appears in two face records");
+        r[0] = other; r[1] = i; r[2] = z; r[3] = 0;
+        if (B.affine) { double* g = &P.lfGeo[((size_t)pos * NF + lf) * 4]; for (int l = 0; l < 4; l++) g[l] = geoF[(size_t)i * 4 + l]; }
+      };
+      if (pL < B.nOwned) put(pL, lfL, pR, lfR | (rot << 3) | (bc << 5) | (1 << 9) | ((in ? 1 : 0) << 10));
+      if (interior && pR < B.nOwned) put(pR, lfR, pL, lfL | (rot << 3) | (1 << 8) | ((in ? 0 : 1) << 9) | ((in ? 1 : 0) << 10));
+      if (!interior) { int* r = &P.bndRec[(size_t)(i - F.nInt) * 4]; r[0] = pL; r[1] = lfL; r[2] = bc; r[3] = i; }
+    }
+    for (size_t k = 0; k < P.links.size(); k += 4) if (P.links[k] == -2) throw std::runtime_error("line plan: an element face without a face record");
+    // natural point index of face point jf of face f: its two tangential lattice indices, lower axis first
+    const TensorTables& T = B.T;
+    std::vector<int> nat2jf(NF * NL), jf2nat(NF * NL);
+    for (int f = 0; f < NF; f++) for (int jf = 0; jf < NL; jf++) {
+      const int base = T.faceBase[(size_t)f * NL + jf], i = (base / 16) % 4, j = (base / 4) % 4, k = base % 4, dn = T.faceDir[f];
+      const int nat = dn == 0 ? j * 4 + k : dn == 1 ? i * 4 + k : i * 4 + j;
+      nat2jf[f * NL + nat] = jf; jf2nat[f * NL + jf] = nat;
+    }
+    P.partner.assign(6 * 6 * 4 * 2 * 16, 0); P.jLeft.assign(6 * 4 * 2 * 16, 0);
+    for (int rot = 0; rot < 4; rot++) {
+      const std::vector<int> seq = faceSequence(kQuadrangle, 4, rot);   // right parent's point of the left parent's point j
+      std::vector<int> inv(NL); for (int jl = 0; jl < NL; jl++) inv[seq[jl]] = jl;
+      for (int f = 0; f < NF; f++) for (int amR = 0; amR < 2; amR++) for (int t = 0; t < NL; t++) {
+        const int jfMine = nat2jf[f * NL + t];
+        const int jL = amR ? inv[jfMine] : jfMine, jO = amR ? jL : seq[jfMine];
+        P.jLeft[((f * 4 + rot) * 2 + amR) * 16 + t] = (unsigned char)jL;
+        for (int lfo = 0; lfo < NF; lfo++) P.partner[(((f * 6 + lfo) * 4 + rot) * 2 + amR) * 16 + t] = (unsigned char)jf2nat[lfo * NL + jO];
+      }
+    }
+    for (int a = 0; a < 4; a++) P.cLift += T.Lend[a] * T.Lend[a] / T.w[a];
+    return P;
   }
 
   // ---- per-chunk face lists ------------------------------------------------------------------------------------------------------

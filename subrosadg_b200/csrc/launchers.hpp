@@ -14,4 +14,10 @@ StageFn pickEulerFn(int D, int N, bool affine, int ph, int& K);
 // NS gradient pass + residual pass
 void pickNsFn(int D, int N, bool affine, int ph, StageFn& grad, StageFn& stage, int& K);
 
+// trace-based line kernels for P3 hexahedra (nsl_kernels.cuh): U -> TU, boundary virtual traces, pass G, pass R (visc = false: the
+// same residual pass without viscous terms, i.e. an Euler stage through published traces)
+using BoundaryFn = void (*)(const StageArgs&, const int4* bndRec, int nBnd, cudaStream_t);
+struct LineFns { StageFn trace = nullptr, grad = nullptr, stage = nullptr; BoundaryFn boundary = nullptr; };
+void pickNslFns(bool affine, int ph, bool visc, LineFns& out, int& K);
+
 }  // namespace sdg

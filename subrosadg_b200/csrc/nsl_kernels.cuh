@@ -1,0 +1,763 @@
+// nsl_kernels.cuh — trace-based, thread-per-line Navier–Stokes (BR1 / BR2) stage kernels for P3 hexahedra (sm_100a, fp64).
+//
+// Same two passes per RK stage as ns_kernels.cuh (pass G = G1–G4, pass R = R1–R4 + K of Solver::stepSolver,
+// src/Solver/TimeIntegration.cpp:326-350), restructured after the round-1 profiles (profiles/r01_ns_s4_ncu.md: the face phase was
+// 65 % of the residual pass — two 20-field line traces per face point, evaluated 5.0 times per element, neighbour lines gathered
+// from L2 — at 16 warps per SM):
+//
+//   * every element PUBLISHES the traces of its own six faces once, like the reference's variable_adjacency_quadrature_ slots
+//     (SolveControl.cpp:45-58) but per element side:  TU[e][f][v][pt]  = trace of the conserved variables (written by the residual pass
+//     for the state it has just produced, read by both passes of the next stage) and  TV[e][f][v][pt] = this side's viscous normal
+//     flux  F_v(U_own, trace_f(G_vol + G_f)) · n  (ViscousFlux.cpp:116-153; written by pass G, which knows the jump and therefore the
+//     BR2 lift of that face, read by pass R).  A face point of the residual pass is then 20 coalesced loads, one Riemann solve and an
+//     average — no line traces, no gathers of whole neighbour elements, no redundant own-side work;
+//   * pass G stores the TOTAL gradient  G_vol + Σ_f G_f  at the nodes (what the volume term of pass R needs, TimeIntegration.cpp:208-223),
+//     so pass R needs neither the jumps nor the lifting coefficients;
+//   * a thread owns one zeta-line of one element (as eulerLineKernel): zeta operators in registers, xi / eta through a swizzled
+//     shared-memory tile synchronised with __syncwarp (an element = half a warp);
+//   * boundary faces look like interior faces to pass G: a small kernel writes the virtual neighbour trace  R = 2 U_vol − L  of every
+//     boundary face point (BoundaryConditionImpl::calculateBoundaryGradientVariable, BoundaryCondition.cpp:287-297,426-441,...), for
+//     which  ½(L+R) = U_vol  and  ½(R−L) = U_vol − L  are exactly the volume- and interface-gradient states of the reference.
+//
+// Point order inside a TU / TV row: the face point's position in the element's own node lattice ("natural" order: the two tangential
+// lattice indices, lower axis first); LineTabDev maps a point to the partner's natural index for every (face, face, rotation, side).
+#pragma once
+#include "line_kernels.cuh"
+
+namespace sdg {
+
+constexpr int kLK = 8;                 // elements per thread block (a 2x2x2 brick of the internal Morton order)
+constexpr int kRow = 5 * 16;           // doubles per (element, face) row of TU / TV
+constexpr int kLG = 4;                 // affine per-(element, face) geometry record: face normal n[3] (left-outward), |J| scale
+
+// link record of (element, local face): .x = other parent (internal position, -1 = boundary face), .y = face id,
+// .z = lfo | rot << 3 | bc << 5 | amRight << 8 | handles << 9 | otherInChunk << 10, .w = unused
+__device__ __forceinline__ int linkLfo(int z) { return z & 7; }
+__device__ __forceinline__ int linkRot(int z) { return (z >> 3) & 3; }
+__device__ __forceinline__ int linkBc(int z) { return (z >> 5) & 7; }
+__device__ __forceinline__ bool linkAmRight(int z) { return (z >> 8) & 1; }
+__device__ __forceinline__ bool linkHandles(int z) { return (z >> 9) & 1; }
+__device__ __forceinline__ bool linkInChunk(int z) { return (z >> 10) & 1; }
+
+struct LineTabDev {
+  unsigned char partner[6 * 6 * 4 * 2 * 16];   // [(((f*6+lfo)*4+rot)*2+amRight)*16 + t]: natural point index at the other parent
+  unsigned char jLeft[6 * 4 * 2 * 16];         // [((f*4+rot)*2+amRight)*16 + t]: point index (reference order) at the LEFT parent = column of geoF / dummy
+};
+
+// swizzled tile of one field of one element: node (i, j, k) at i*16 + ((j+i)&3)*4 + k — lines along xi, eta and zeta are all
+// read without bank conflicts, no padding
+__device__ __forceinline__ int swz(int i, int j) { return i * 16 + (((j + i) & 3) << 2); }
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+// Traces of the conserved variables of one element at its own 6 x 16 face points (AdjacencyElementVariable::get,
+// VariableConvertor.cpp:432-485), from the line registers; sXe = the element's exchange tile [5][64].
+__device__ __forceinline__ void lineTracesOut(const StageArgs& A, const double (&u)[5][4], double* sXe, int i, int j, int t, unsigned wm, double* gT) {
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int f = hexFaceOfAxis(2, s);
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+      double x = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) x += A.lend[s * 4 + k] * u[v][k];
+      gT[(f * 5 + v) * 16 + t] = x;
+    }
+  }
+  const int sw = swz(i, j);
+#pragma unroll
+  for (int v = 0; v < 5; v++) { sts2(sXe + v * 64 + sw, u[v][0], u[v][1]); sts2(sXe + v * 64 + sw + 2, u[v][2], u[v][3]); }
+  __syncwarp(wm);
+#pragma unroll
+  for (int v = 0; v < 5; v++) {
+    double xm = 0.0, xp = 0.0, ym = 0.0, yp = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double x = sXe[v * 64 + a * 16 + (((i + a) & 3) << 2) + j];   // xi-normal faces: point (j', k') = (i, j), nodes (a, i, j)
+      const double y = sXe[v * 64 + i * 16 + (((a + i) & 3) << 2) + j];   // eta-normal faces: point (i', k') = (i, j), nodes (i, a, j)
+      xm += A.lend[a] * x; xp += A.lend[4 + a] * x;
+      ym += A.lend[a] * y; yp += A.lend[4 + a] * y;
+    }
+    gT[(2 * 5 + v) * 16 + t] = xm; gT[(3 * 5 + v) * 16 + t] = xp;
+    gT[(1 * 5 + v) * 16 + t] = ym; gT[(4 * 5 + v) * 16 + t] = yp;
+  }
+}
+
+// ---- U -> TU for a state that did not come out of the residual pass (initial condition, sdg_set_state) ------------------------------
+static __global__ void __launch_bounds__(128) nslTraceKernel(const __grid_constant__ StageArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, chunk = A.chunkList ? A.chunkList[blockIdx.x] : blockIdx.x;
+  const int e0 = chunk * kLK, ne = min(kLK, A.nOwned - e0);
+  const int el = tid >> 4, t = tid & 15, i = t >> 2, j = t & 3;
+  const bool active = el < ne;
+  const unsigned wm = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const int e = e0 + el;
+  double u[5][4];
+#pragma unroll
+  for (int v = 0; v < 5; v++)
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) { const double2 x = ldg2(A.Uin + ((size_t)e * 5 + v) * 64 + t * 4 + k); u[v][k] = x.x; u[v][k + 1] = x.y; }
+  lineTracesOut(A, u, smem + el * 5 * 64, i, j, t, wm, A.TUout + (size_t)e * 6 * kRow);
+}
+
+// ---- virtual neighbour traces of the boundary faces (see the header) ------------------------------------------------------------------
+template <bool AFFINE>
+__global__ void __launch_bounds__(128) nslBoundaryKernel(const __grid_constant__ StageArgs A, const int4* __restrict__ bndRec, int nBnd) {
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  const int fb = idx >> 4, t = idx & 15;
+  if (fb >= nBnd) return;
+  const Phys<0> ph(A.phys);
+  const int4 r = bndRec[fb];   // left parent (internal position), its local face, boundary condition, face id
+  const int jL = A.ltab->jLeft[((r.y * 4 + 0) * 2 + 0) * 16 + t];
+  double n[3];
+  if constexpr (AFFINE) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) n[c] = A.lfGeo[((size_t)r.x * 6 + r.y) * kLG + c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; c++) n[c] = __ldg(A.geoF + ((size_t)r.w * 4 + c) * 16 + jL);
+  }
+  double consL[5], compL[6], compR[6], vol[5], itf[5];
+#pragma unroll
+  for (int v = 0; v < 5; v++) consL[v] = A.TUin[((size_t)r.x * 6 + r.y) * kRow + v * 16 + t];
+  compFromCons<3>(ph, consL, compL);
+#pragma unroll
+  for (int k = 0; k < 6; k++) compR[k] = A.dummy[((size_t)fb * 6 + k) * 16 + jL];
+  bcBoundaryGradientVariable<3>(ph, r.z, n, consL, compL, compR, vol, itf);
+#pragma unroll
+  for (int v = 0; v < 5; v++) A.TUb[(size_t)fb * kRow + v * 16 + t] = 2.0 * vol[v] - consL[v];
+}
+
+// =====================================================================================================================
+// pass G: total gradient at the nodes + this side's viscous normal flux at the face points
+// =====================================================================================================================
+template <bool AFFINE>
+struct NslGradLayout {
+  static constexpr int SLC = AFFINE ? 1 : 3;                      // slot components: a (affine, the normal is a face constant) or a*n[c]
+  static constexpr int oGv = 0;                                   // [K][15][64]  swizzled tiles of G_vol (BR2) / G (BR1)
+  static constexpr int oSl = oGv + kLK * 15 * 64;                 // [K][4][2*SLC][16]  xi / eta face slots of the current variable
+  static constexpr int oX = oSl + kLK * 4 * 2 * SLC * 16;         // curved: [K][6][64] exchange of metric x state products
+  static constexpr int oGeoE = oX + (AFFINE ? 0 : kLK * 6 * 64);  // affine: [K][10]
+  static constexpr int oLg = oGeoE + (AFFINE ? kLK * 10 : 0);     // affine: [K][6][kLG]
+  static constexpr int oLink = oLg + (AFFINE ? kLK * 6 * kLG : 0);   // [K][6] int4
+  static constexpr int nDoubles = oLink + kLK * 6 * 2;
+  static constexpr size_t bytes = sizeof(double) * nDoubles;
+};
+
+// viscous normal flux of one side at one face point from the (lifted) trace of the conserved-variable gradient
+template <int PH>
+__device__ __forceinline__ void ownViscousNormalFlux(const Phys<PH>& ph, const double* n, const double* cons, const double* comp, const double* g, double* va) {
+  double gp[15];
+  primGradFromConsGrad<3>(ph, cons, comp, g, gp);
+  viscNormalFlux<3>(ph, n, comp, gp, va);
+}
+
+template <bool AFFINE>
+__global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __grid_constant__ StageArgs A) {
+  using L = NslGradLayout<AFFINE>;
+  constexpr int K = kLK, SLC = L::SLC;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  double* sGv = smem + L::oGv;
+  double* sSl = smem + L::oSl;
+  double* sGeoE = smem + L::oGeoE;
+  double* sLg = smem + L::oLg;
+  const int4* sLink = reinterpret_cast<const int4*>(smem + L::oLink);
+  const int tid = threadIdx.x, chunk = A.chunkList ? A.chunkList[blockIdx.x] : blockIdx.x;
+  const int e0 = chunk * K, ne = min(K, A.nOwned - e0);
+  const int el = tid >> 4, t = tid & 15, i = t >> 2, j = t & 3;
+  const bool active = el < ne;
+  const Phys<0> ph(A.phys);
+  const bool br1 = A.phys.visc == kBR1;
+  if (tid == 0) mbarInit(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned total = (unsigned)(ne * 6 * sizeof(int4));
+    if constexpr (AFFINE) total += (unsigned)(ne * 10 * sizeof(double)) + (unsigned)(ne * 6 * kLG * sizeof(double));
+    mbarExpectTx(&mbar, total);
+    bulkLoad(smem + L::oLink, A.links + (size_t)e0 * 6, (unsigned)(ne * 6 * sizeof(int4)), &mbar);
+    if constexpr (AFFINE) {
+      bulkLoad(sGeoE, A.geoE + (size_t)e0 * 10, (unsigned)(ne * 10 * sizeof(double)), &mbar);
+      bulkLoad(sLg, A.lfGeo + (size_t)e0 * 6 * kLG, (unsigned)(ne * 6 * kLG * sizeof(double)), &mbar);
+    }
+  }
+  const unsigned wm = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const int e = e0 + el;
+  const int sw = swz(i, j);
+  double u[5][4];
+#pragma unroll
+  for (int v = 0; v < 5; v++)
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) { const double2 x = ldg2(A.Uin + ((size_t)e * 5 + v) * 64 + t * 4 + k); u[v][k] = x.x; u[v][k + 1] = x.y; }
+  mbarWait(&mbar, 0);
+
+  // ---- per-face set-up of this thread's face point (natural index t on each of the six faces) ---------------------------------------
+  int nbr[6];          // >= 0: offset of the partner's value of variable 0 inside TU; < 0: -(1 + offset inside TUb) for a boundary face
+  double jw[6];        // |J| w at the point
+  unsigned amRightBits = 0;
+  const double wij = A.w1[i] * A.w1[j];   // weight of the face point (t = two lattice indices) and of the line's nodes without w1[k]
+#pragma unroll
+  for (int f = 0; f < 6; f++) {
+    const int4 lk = sLink[el * 6 + f];
+    const int z = lk.z, lfo = linkLfo(z), rot = linkRot(z), amR = linkAmRight(z) ? 1 : 0;
+    amRightBits |= (unsigned)amR << f;
+    if (lk.x >= 0) nbr[f] = (lk.x * 6 + lfo) * kRow + A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + amR) * 16 + t];
+    else nbr[f] = -1 - ((lk.y - A.nInt) * kRow + t);
+    if constexpr (AFFINE) jw[f] = sLg[(el * 6 + f) * kLG + 3] * wij;
+    else jw[f] = __ldg(A.geoF + ((size_t)lk.y * 4 + 3) * 16 + A.ltab->jLeft[((f * 4 + rot) * 2 + amR) * 16 + t]);
+  }
+  double invDet = 0.0, ijw[4];
+  if constexpr (AFFINE) {
+    invDet = 1.0 / sGeoE[el * 10 + 9];
+#pragma unroll
+    for (int k = 0; k < 4; k++) ijw[k] = invDet / (wij * A.w1[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) ijw[k] = __ldg(A.invjw + (size_t)e * 64 + t * 4 + k);
+  }
+  auto normalAt = [&](int f, int jL, double* n) {   // face normal at this thread's point of face f
+    if constexpr (AFFINE) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) n[c] = sLg[(el * 6 + f) * kLG + c];
+    } else {
+      const int4 lk = sLink[el * 6 + f];
+#pragma unroll
+      for (int c = 0; c < 3; c++) n[c] = __ldg(A.geoF + ((size_t)lk.y * 4 + c) * 16 + jL);
+    }
+  };
+  const double* gTU = A.TUin + (size_t)e * 6 * kRow + t;
+
+  // ---- G1-G4, one conserved variable at a time --------------------------------------------------------------------------------------
+#pragma unroll
+  for (int v = 0; v < 5; v++) {
+    double aZ[2][2][3];   // zeta faces (this thread's own line): [side][vol / tot][c] = a n[c]
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+      const bool amR = (amRightBits >> f) & 1;
+      const double mine = gTU[(f * 5 + v) * 16];
+      const double other = nbr[f] >= 0 ? A.TUin[(size_t)nbr[f] + v * 16] : A.TUb[(size_t)(-1 - nbr[f]) + v * 16];
+      const double avg = 0.5 * (mine + other), jmp = 0.5 * (amR ? mine - other : other - mine);   // ViscousFlux.cpp:33-56
+      const double aV = (amR ? -avg : avg) * jw[f], aT = aV + jmp * jw[f];                        // SpatialDiscrete.cpp:885-906
+      constexpr int dnTab[6] = {2, 1, 0, 0, 1, 2};
+      const int dn = dnTab[f], side = f >= 3 ? 1 : 0;
+      if (dn == 2 || !AFFINE) {
+        double n[3];
+        int jL = 0;
+        if constexpr (!AFFINE) { const int z = sLink[el * 6 + f].z; jL = A.ltab->jLeft[((f * 4 + linkRot(z)) * 2 + (amR ? 1 : 0)) * 16 + t]; }
+        normalAt(f, jL, n);
+        if (dn == 2) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) { aZ[side][0][c] = aV * n[c]; aZ[side][1][c] = aT * n[c]; }
+        } else {
+          const int fs = dn == 0 ? side : 2 + side;
+#pragma unroll
+          for (int c = 0; c < 3; c++) { sSl[((el * 4 + fs) * 2 * SLC + c) * 16 + t] = aV * n[c]; sSl[((el * 4 + fs) * 2 * SLC + SLC + c) * 16 + t] = aT * n[c]; }
+        }
+      } else {
+        const int fs = dn == 0 ? side : 2 + side;
+        sSl[((el * 4 + fs) * 2 + 0) * 16 + t] = aV; sSl[((el * 4 + fs) * 2 + 1) * 16 + t] = aT;
+      }
+    }
+    // volume term  − (U ⊗ (J^T)^-1 detJ w) ∇Φ  (SpatialDiscrete.cpp:294-322,1034-1068)
+    double Gv[3][4], Gt[3][4];
+    if constexpr (AFFINE) {
+      double* sX = sGv + (el * 15 + 3 * v) * 64;   // tile of a field that has not been written yet
+      double uw[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) uw[k] = u[v][k] * (wij * A.w1[k]);
+      sts2(sX + sw, uw[0], uw[1]); sts2(sX + sw + 2, uw[2], uw[3]);
+      __syncwarp(wm);
+      double tx[4] = {0, 0, 0, 0}, ty[4] = {0, 0, 0, 0}, tz[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const double dx = A.dm[a * 4 + i], dy = A.dm[a * 4 + j];
+        const double2 x0 = lds2(sX + a * 16 + (((j + a) & 3) << 2)), x1 = lds2(sX + a * 16 + (((j + a) & 3) << 2) + 2);
+        const double2 y0 = lds2(sX + i * 16 + (((a + i) & 3) << 2)), y1 = lds2(sX + i * 16 + (((a + i) & 3) << 2) + 2);
+        tx[0] += dx * x0.x; tx[1] += dx * x0.y; tx[2] += dx * x1.x; tx[3] += dx * x1.y;
+        ty[0] += dy * y0.x; ty[1] += dy * y0.y; ty[2] += dy * y1.x; ty[3] += dy * y1.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) s += A.dm[a * 4 + k] * uw[a];
+        tz[k] = s; }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const double g0 = sGeoE[el * 10 + c], g1 = sGeoE[el * 10 + 3 + c], g2 = sGeoE[el * 10 + 6 + c];
+#pragma unroll
+        for (int k = 0; k < 4; k++) Gv[c][k] = -(g0 * tx[k] + g1 * ty[k] + g2 * tz[k]);
+      }
+    } else {
+      // curved: the metric sits inside the line sums, so the products  metric[dd][c] * U  travel through the tile (3 fields per direction)
+      double* sX = smem + L::oX + el * 6 * 64;
+      double mz[3][4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double* ge = A.geoE + (size_t)e * 9 * 64 + t * 4 + k;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          sX[(0 + c) * 64 + sw + k] = __ldg(ge + (0 + c) * 64) * u[v][k];
+          sX[(3 + c) * 64 + sw + k] = __ldg(ge + (3 + c) * 64) * u[v][k];
+          mz[c][k] = __ldg(ge + (6 + c) * 64) * u[v][k];
+        }
+      }
+      __syncwarp(wm);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+            s += A.dm[a * 4 + i] * sX[(0 + c) * 64 + a * 16 + (((j + a) & 3) << 2) + k] + A.dm[a * 4 + j] * sX[(3 + c) * 64 + i * 16 + (((a + i) & 3) << 2) + k] +
+                 A.dm[a * 4 + k] * mz[c][a];
+          Gv[c][k] = -s;
+        }
+      }
+    }
+    // lifting of the face terms  A Φ_f  (ViscousFlux.cpp:26-56): volume-gradient states into G_vol, volume + interface into the total
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        Gt[c][k] = Gv[c][k] + A.lend[k] * aZ[0][1][c] + A.lend[4 + k] * aZ[1][1][c];
+        Gv[c][k] += A.lend[k] * aZ[0][0][c] + A.lend[4 + k] * aZ[1][0][c];
+      }
+#pragma unroll
+    for (int fs = 0; fs < 4; fs++) {   // 0, 1: xi- (face 2), xi+ (face 3): points (j, k);  2, 3: eta- (face 1), eta+ (face 4): points (i, k)
+      const int side = fs & 1, f = fs == 0 ? 2 : fs == 1 ? 3 : fs == 2 ? 1 : 4;
+      const double cf = A.lend[side * 4 + (fs < 2 ? i : j)];
+      const int row = (fs < 2 ? j : i) * 4;
+      if constexpr (AFFINE) {
+        const double* s0 = sSl + ((el * 4 + fs) * 2 + 0) * 16 + row;
+        const double2 v0 = lds2(s0), v1 = lds2(s0 + 2), t0 = lds2(s0 + 16), t1 = lds2(s0 + 18);
+        const double av[4] = {v0.x, v0.y, v1.x, v1.y}, at[4] = {t0.x, t0.y, t1.x, t1.y};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const double nc = sLg[(el * 6 + f) * kLG + c] * cf;
+#pragma unroll
+          for (int k = 0; k < 4; k++) { Gv[c][k] += nc * av[k]; Gt[c][k] += nc * at[k]; }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const double* s0 = sSl + ((el * 4 + fs) * 6 + c) * 16 + row;
+          const double2 v0 = lds2(s0), v1 = lds2(s0 + 2), t0 = lds2(s0 + 48), t1 = lds2(s0 + 50);
+          Gv[c][0] += cf * v0.x; Gv[c][1] += cf * v0.y; Gv[c][2] += cf * v1.x; Gv[c][3] += cf * v1.y;
+          Gt[c][0] += cf * t0.x; Gt[c][1] += cf * t0.y; Gt[c][2] += cf * t1.x; Gt[c][3] += cf * t1.y;
+        }
+      }
+    }
+    // G4: mass inverse (diagonal in the collocation basis, TimeIntegration.cpp:200-228).  The total goes to HBM with zeta as the SLOWEST
+    // node index (thread t reads / writes entry k*16 + t: coalesced 8-byte accesses for a thread per line); G_vol stays in the tile.
+    __syncwarp(wm);   // every lane of the element has finished reading the exchange tile and the slots of this variable
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double* out = A.Gout + ((size_t)e * 15 + v * 3 + c) * 64 + t;
+#pragma unroll
+      for (int k = 0; k < 4; k++) out[k * 16] = Gt[c][k] * ijw[k];
+      double* tile = sGv + (el * 15 + v * 3 + c) * 64 + sw;
+      if (br1) { sts2(tile, Gt[c][0] * ijw[0], Gt[c][1] * ijw[1]); sts2(tile + 2, Gt[c][2] * ijw[2], Gt[c][3] * ijw[3]); }
+      else { sts2(tile, Gv[c][0] * ijw[0], Gv[c][1] * ijw[1]); sts2(tile + 2, Gv[c][2] * ijw[2], Gv[c][3] * ijw[3]); }
+    }
+  }
+  __syncwarp(wm);
+
+  // ---- this side's viscous normal flux at the own face points: trace_f(G_vol) + BR2 lift of face f (VariableConvertor.cpp:674-688) ----
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double gm[15], gp[15];
+#pragma unroll
+    for (int fld = 0; fld < 15; fld++) {
+      const double* tile = sGv + (el * 15 + fld) * 64;
+      double x[4];
+      if (d == 2) { const double2 a = lds2(tile + sw), b = lds2(tile + sw + 2); x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; }
+      else {
+#pragma unroll
+        for (int a = 0; a < 4; a++) x[a] = d == 0 ? tile[a * 16 + (((i + a) & 3) << 2) + j] : tile[i * 16 + (((a + i) & 3) << 2) + j];
+      }
+      gm[fld] = A.lend[0] * x[0] + A.lend[1] * x[1] + A.lend[2] * x[2] + A.lend[3] * x[3];
+      gp[fld] = A.lend[4] * x[0] + A.lend[5] * x[1] + A.lend[6] * x[2] + A.lend[7] * x[3];
+    }
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int f = hexFaceOfAxis(d, side);
+      double* g = side ? gp : gm;
+      const int4 lk = sLink[el * 6 + f];
+      const int z = lk.z;
+      const bool amR = (amRightBits >> f) & 1;
+      const int jL = A.ltab->jLeft[((f * 4 + linkRot(z)) * 2 + (amR ? 1 : 0)) * 16 + t];
+      double n[3];
+      normalAt(f, jL, n);
+      double lam = 0.0;   // trace at the own point of the rank-one lift of this face:  Σ_a l_a(±1)^2 / (detJ w)(node a of the normal line)
+      if (!br1) {
+        if constexpr (AFFINE) lam = A.cLift * invDet / wij;
+        else {
+#pragma unroll
+          for (int a = 0; a < 4; a++) {
+            const int node = d == 2 ? t * 4 + a : d == 0 ? a * 16 + i * 4 + j : i * 16 + a * 4 + j;
+            lam += A.lend[side * 4 + a] * A.lend[side * 4 + a] * __ldg(A.invjw + (size_t)e * 64 + node);
+          }
+        }
+      }
+      double cm[5], comp[6], va[5];
+#pragma unroll
+      for (int v = 0; v < 5; v++) cm[v] = gTU[(f * 5 + v) * 16];
+      compFromCons<3>(ph, cm, comp);
+      if (lk.x >= 0) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+          const double other = A.TUin[(size_t)nbr[f] + v * 16];
+          const double jl = 0.5 * (amR ? cm[v] - other : other - cm[v]) * jw[f] * lam;
+#pragma unroll
+          for (int c = 0; c < 3; c++) g[v * 3 + c] += jl * n[c];
+        }
+        ownViscousNormalFlux(ph, n, cm, comp, g, va);
+      } else {
+        // boundary face (SpatialDiscrete.cpp:750-842): the complete averaged viscous flux of the face is this side's entry
+        const int bc = linkBc(z);
+        double compR[6], b[6], volCons[5], intCons[5], pL[15], gb[15], vb[5];
+#pragma unroll
+        for (int k = 0; k < 6; k++) compR[k] = A.dummy[((size_t)(lk.y - A.nInt) * 6 + k) * 16 + jL];
+        bcBoundaryGradientVariable<3>(ph, bc, n, cm, comp, compR, volCons, intCons);
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+          const double jl = intCons[v] * jw[f] * lam;
+#pragma unroll
+          for (int c = 0; c < 3; c++) g[v * 3 + c] += jl * n[c];
+        }
+        primGradFromConsGrad<3>(ph, cm, comp, g, pL);             // from the UNMODIFIED interior trace (:792-796)
+        bcBoundaryVariable<3>(ph, bc, n, comp, compR, b);
+        if (bcIsWall(bc)) {                                       // modifyBoundaryVariable, BoundaryCondition.cpp:443-452,490-501,535-546
+#pragma unroll
+          for (int k = 0; k < 6; k++) comp[k] = b[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 15; k++) gb[k] = pL[k];
+        if (bc == kAdiabaticSlipWall || bc == kAdiabaticNonSlipWall) { gb[12] = 0.0; gb[13] = 0.0; gb[14] = 0.0; }
+        viscNormalFlux<3>(ph, n, comp, pL, va);
+        viscNormalFlux<3>(ph, n, b, gb, vb);
+#pragma unroll
+        for (int v = 0; v < 5; v++) va[v] = 0.5 * (va[v] + vb[v]);
+      }
+      double* out = A.TVout + ((size_t)e * 6 + f) * kRow + t;
+#pragma unroll
+      for (int v = 0; v < 5; v++) out[v * 16] = va[v];
+    }
+  }
+}
+
+// =====================================================================================================================
+// pass R: residual, RK update, traces of the new state, relative error
+// =====================================================================================================================
+struct NslStageLayout {
+  static constexpr int oFl = 0;                              // [K][6][5][16] face-flux slots (natural point order)
+  static constexpr int oX = oFl + kLK * 6 * 5 * 16;          // [K][320]: 10 half tiles [2 directions][5][32] of xi / eta fluxes, later [5][64] of the new state
+  static constexpr int oGeoE = oX + kLK * 320;               // affine: [K][10]
+  static constexpr int oLg = oGeoE + kLK * 10;               // affine: [K][6][kLG]
+  static constexpr int oLink = oLg + kLK * 6 * kLG;          // [K][6] int4
+  static constexpr int oRed = oLink + kLK * 6 * 2;           // [4][5]
+  static constexpr int nDoubles = oRed + 4 * 5 + 4;
+  static constexpr size_t bytes = sizeof(double) * nDoubles;
+};
+
+#ifndef SDG_NSL_MINB
+#define SDG_NSL_MINB 3
+#endif
+template <bool AFFINE, int PH, bool VISC>
+__global__ void __launch_bounds__(128, SDG_NSL_MINB) nslStageKernel(const __grid_constant__ StageArgs A) {
+  using L = NslStageLayout;
+  constexpr int K = kLK;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  double* sFl = smem + L::oFl;
+  double* sX = smem + L::oX;
+  double* sGeoE = smem + L::oGeoE;
+  double* sLg = smem + L::oLg;
+  const int4* sLink = reinterpret_cast<const int4*>(smem + L::oLink);
+  double* sRed = smem + L::oRed;
+  const int tid = threadIdx.x, chunk = A.chunkList ? A.chunkList[blockIdx.x] : blockIdx.x;
+  const int e0 = chunk * K, ne = min(K, A.nOwned - e0);
+  const int el = tid >> 4, t = tid & 15, i = t >> 2, j = t & 3;
+  const bool active = el < ne;
+  const Phys<PH> ph(A.phys);
+  const bool needLast = A.mode == 0 && A.aLast != 0.0;
+  if (tid == 0) mbarInit(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned total = (unsigned)(ne * 6 * sizeof(int4));
+    if constexpr (AFFINE) total += (unsigned)(ne * 10 * sizeof(double)) + (unsigned)(ne * 6 * kLG * sizeof(double));
+    mbarExpectTx(&mbar, total);
+    bulkLoad(smem + L::oLink, A.links + (size_t)e0 * 6, (unsigned)(ne * 6 * sizeof(int4)), &mbar);
+    if constexpr (AFFINE) {
+      bulkLoad(sGeoE, A.geoE + (size_t)e0 * 10, (unsigned)(ne * 10 * sizeof(double)), &mbar);
+      bulkLoad(sLg, A.lfGeo + (size_t)e0 * 6 * kLG, (unsigned)(ne * 6 * kLG * sizeof(double)), &mbar);
+    }
+  }
+  if (needLast) {   // U_last is consumed at the very end: pull its lines into L2 now
+    const char* p = reinterpret_cast<const char*>(A.Ulast + (size_t)e0 * 5 * 64);
+    const int bytes = ne * 5 * 64 * (int)sizeof(double);
+    for (int o = tid * 128; o < bytes; o += 128 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+  }
+  const unsigned wm = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const int e = e0 + el;
+  const double wij = A.w1[i] * A.w1[j];
+  mbarWait(&mbar, 0);
+
+  // ---- R2: Riemann flux minus the average of the two sides' viscous normal fluxes, at this thread's point of every face it handles ----
+  const double* gTU = A.TUin + (size_t)e * 6 * kRow + t;
+  const double* gTV = A.TVin + (size_t)e * 6 * kRow + t;
+#pragma unroll 1
+  for (int f = 0; f < 6; f++) {
+    const int4 lk = sLink[el * 6 + f];
+    const int z = lk.z;
+    if (!linkHandles(z)) continue;
+    const int lfo = linkLfo(z), rot = linkRot(z);
+    const bool amR = linkAmRight(z);
+    const int jL = A.ltab->jLeft[((f * 4 + rot) * 2 + (amR ? 1 : 0)) * 16 + t];
+    double n[3], jw;
+    if constexpr (AFFINE) {
+      const double* g = sLg + (el * 6 + f) * kLG;
+      n[0] = g[0]; n[1] = g[1]; n[2] = g[2]; jw = g[3] * wij;
+    } else {
+      const double* g = A.geoF + (size_t)lk.y * 4 * 16 + jL;
+      n[0] = __ldg(g); n[1] = __ldg(g + 16); n[2] = __ldg(g + 32); jw = __ldg(g + 48);
+    }
+    double cm[5], tm[5], Fn[5];
+#pragma unroll
+    for (int v = 0; v < 5; v++) cm[v] = gTU[(f * 5 + v) * 16];
+    if constexpr (VISC) {
+#pragma unroll
+      for (int v = 0; v < 5; v++) tm[v] = gTV[(f * 5 + v) * 16];
+    }
+    double* mine = sFl + ((el * 6 + f) * 5) * 16 + t;
+    if (lk.x < 0) {
+      // boundary face: normal flux of the BC-constructed state, no Riemann solve (SpatialDiscrete.cpp:797-803)
+      double compL[6], compR[6], b[6];
+      compFromCons<3>(ph, cm, compL);
+#pragma unroll
+      for (int k = 0; k < 6; k++) compR[k] = A.dummy[((size_t)(lk.y - A.nInt) * 6 + k) * 16 + jL];
+      bcBoundaryVariable<3>(ph, linkBc(z), n, compL, compR, b);
+      convNormalFlux<3>(ph, n, b, Fn);
+#pragma unroll
+      for (int v = 0; v < 5; v++) mine[v * 16] = (VISC ? Fn[v] - tm[v] : Fn[v]) * jw;
+    } else {
+      const int natO = A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + (amR ? 1 : 0)) * 16 + t];
+      const size_t rowO = ((size_t)lk.x * 6 + lfo) * kRow + natO;
+      double co[5], to[5];
+#pragma unroll
+      for (int v = 0; v < 5; v++) co[v] = A.TUin[rowO + v * 16];
+      if constexpr (VISC) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) to[v] = A.TVin[rowO + v * 16];
+      }
+      double consL[5], consR[5], compL[6], compR[6];
+#pragma unroll
+      for (int v = 0; v < 5; v++) { consL[v] = amR ? co[v] : cm[v]; consR[v] = amR ? cm[v] : co[v]; }
+      const double irL = compFromCons<3>(ph, consL, compL), irR = compFromCons<3>(ph, consR, compR);
+      convFlux<3>(ph, n, consL, compL, irL, consR, compR, irR, Fn);
+      if constexpr (VISC) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) Fn[v] -= 0.5 * (tm[v] + to[v]);   // calculateViscousFlux, ViscousFlux.cpp:139-153
+      }
+      const double sg = amR ? -jw : jw;
+#pragma unroll
+      for (int v = 0; v < 5; v++) mine[v * 16] = Fn[v] * sg;
+      if (linkInChunk(z)) {   // both parents in this block: the left one evaluates, the right one's slot gets the negative (SpatialDiscrete.cpp:738-744)
+        double* other = sFl + (((lk.x - e0) * 6 + lfo) * 5) * 16 + natO;
+#pragma unroll
+        for (int v = 0; v < 5; v++) other[v * 16] = -Fn[v] * jw;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- R1 + R3 volume part: fluxes at the own nodes, two nodes per round; zeta contraction in registers, xi / eta through half tiles ----
+  double u[5][4];
+#pragma unroll
+  for (int v = 0; v < 5; v++)
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) { const double2 x = ldg2(A.Uin + ((size_t)e * 5 + v) * 64 + t * 4 + k); u[v][k] = x.x; u[v][k + 1] = x.y; }
+  double R[5][4];
+#pragma unroll
+  for (int v = 0; v < 5; v++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) R[v][k] = 0.0;
+  double* sXe = sX + el * 320;
+  const int sw2 = i * 8 + (((j + i) & 3) << 1);
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    double Fx[5][2], Fy[5][2];
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+      const int k = 2 * r + kk;
+      double cons[5], comp[6], Fv[15];
+#pragma unroll
+      for (int v = 0; v < 5; v++) cons[v] = u[v][k];
+      compFromCons<3>(ph, cons, comp);
+      if constexpr (VISC) {
+        double g[15], gp[15];
+        const double* gG = A.Gvol + (size_t)e * 15 * 64 + k * 16 + t;
+#pragma unroll
+        for (int fld = 0; fld < 15; fld++) g[fld] = __ldg(gG + fld * 64);
+        primGradFromConsGrad<3>(ph, cons, comp, g, gp);
+        viscRawFlux<3>(ph, comp, gp, Fv);
+      }
+#pragma unroll
+      for (int dd = 0; dd < 3; dd++) {
+        double m[3], Ft[5];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          if constexpr (AFFINE) m[c] = sGeoE[el * 10 + dd * 3 + c] * (wij * A.w1[k]);
+          else m[c] = __ldg(A.geoE + ((size_t)e * 9 + dd * 3 + c) * 64 + t * 4 + k);
+        }
+        contravariantFlux<3>(ph, cons, comp, m, Ft);
+        if constexpr (VISC) {
+#pragma unroll
+          for (int v = 0; v < 5; v++) Ft[v] -= Fv[v * 3] * m[0] + Fv[v * 3 + 1] * m[1] + Fv[v * 3 + 2] * m[2];   // SpatialDiscrete.cpp:216-232
+        }
+        if (dd == 2) {
+#pragma unroll
+          for (int v = 0; v < 5; v++)
+#pragma unroll
+            for (int k2 = 0; k2 < 4; k2++) R[v][k2] += A.dm[k * 4 + k2] * Ft[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < 5; v++) { if (dd == 0) Fx[v][kk] = Ft[v]; else Fy[v][kk] = Ft[v]; }
+        }
+      }
+    }
+    if (r > 0) __syncwarp(wm);   // the previous round's half tiles have been consumed by every line of the element
+#pragma unroll
+    for (int v = 0; v < 5; v++) { sts2(sXe + v * 32 + sw2, Fx[v][0], Fx[v][1]); sts2(sXe + (5 + v) * 32 + sw2, Fy[v][0], Fy[v][1]); }
+    __syncwarp(wm);
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+      double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const double2 x = lds2(sXe + v * 32 + a * 8 + (((j + a) & 3) << 1));
+        const double2 y = lds2(sXe + (5 + v) * 32 + i * 8 + (((a + i) & 3) << 1));
+        r0 += A.dm[a * 4 + i] * x.x + A.dm[a * 4 + j] * y.x;
+        r1 += A.dm[a * 4 + i] * x.y + A.dm[a * 4 + j] * y.y;
+      }
+      R[v][2 * r] += r0; R[v][2 * r + 1] += r1;
+    }
+  }
+  // ---- R3 face part: lifting of the face fluxes along the own line (zeta) and from the rows (j, :) / (i, :) of the xi / eta faces ----------
+#pragma unroll
+  for (int v = 0; v < 5; v++) {
+    const double fm = sFl[((el * 6 + 0) * 5 + v) * 16 + t], fp = sFl[((el * 6 + 5) * 5 + v) * 16 + t];
+    const double* x2 = sFl + ((el * 6 + 2) * 5 + v) * 16 + j * 4;
+    const double* x3 = sFl + ((el * 6 + 3) * 5 + v) * 16 + j * 4;
+    const double* y1 = sFl + ((el * 6 + 1) * 5 + v) * 16 + i * 4;
+    const double* y4 = sFl + ((el * 6 + 4) * 5 + v) * 16 + i * 4;
+    const double lxm = A.lend[i], lxp = A.lend[4 + i], lym = A.lend[j], lyp = A.lend[4 + j];
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+      const double2 a2 = lds2(x2 + k), a3 = lds2(x3 + k), b1 = lds2(y1 + k), b4 = lds2(y4 + k);
+      R[v][k] -= A.lend[k] * fm + A.lend[4 + k] * fp + lxm * a2.x + lxp * a3.x + lym * b1.x + lyp * b4.x;
+      R[v][k + 1] -= A.lend[k + 1] * fm + A.lend[4 + k + 1] * fp + lxm * a2.y + lxp * a3.y + lym * b1.y + lyp * b4.y;
+    }
+  }
+
+  // ---- R4: mass inverse, RK update -------------------------------------------------------------------------------------------------------
+  double ijw[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if constexpr (AFFINE) ijw[k] = 1.0 / (sGeoE[el * 10 + 9] * wij * A.w1[k]);
+    else ijw[k] = __ldg(A.invjw + (size_t)e * 64 + t * 4 + k);
+  }
+  if (A.phys.source == kBoussinesq) {  // SpatialDiscrete.cpp:254-262 + :1016-1032 (source·detJ w, times Φ)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      double cons[5], comp[6];
+#pragma unroll
+      for (int v = 0; v < 5; v++) cons[v] = u[v][k];
+      compFromCons<3>(ph, cons, comp);
+      R[3][k] += boussinesqSource<3>(ph, comp) / ijw[k];
+    }
+  }
+  {
+    const size_t g = ((size_t)e * 5) * 64 + t * 4;
+    if (A.mode == 0) {
+#pragma unroll
+      for (int v = 0; v < 5; v++) {
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+          double ox = A.aCur * u[v][k] + A.bdt * (R[v][k] * ijw[k]), oy = A.aCur * u[v][k + 1] + A.bdt * (R[v][k + 1] * ijw[k + 1]);
+          if (needLast) { const double2 l = ldg2(A.Ulast + g + (size_t)v * 64 + k); ox += A.aLast * l.x; oy += A.aLast * l.y; }
+          u[v][k] = ox; u[v][k + 1] = oy;
+          *reinterpret_cast<double2*>(A.Uout + g + (size_t)v * 64 + k) = make_double2(ox, oy);
+        }
+      }
+      // traces of the state just produced: what both passes of the next stage (and the neighbours) read
+      __syncwarp(wm);
+      lineTracesOut(A, u, sXe, i, j, t, wm, A.TUout + (size_t)e * 6 * kRow);
+    } else {
+#pragma unroll
+      for (int v = 0; v < 5; v++)
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+          const double ox = A.mode == 1 ? R[v][k] * ijw[k] : R[v][k], oy = A.mode == 1 ? R[v][k + 1] * ijw[k + 1] : R[v][k + 1];
+          *reinterpret_cast<double2*>(A.Uout + g + (size_t)v * 64 + k) = make_double2(ox, oy);
+        }
+    }
+  }
+
+  // ---- K: relative error = mean_q |(K1⊗K1⊗K1) R|, summed over the chunk's elements (TimeIntegration.cpp:279-324) ------------------------
+  if (A.normPartial != nullptr) {
+    {  // zeta in registers
+      double S[5][4];
+#pragma unroll
+      for (int v = 0; v < 5; v++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < 4; a++) s += A.k1[a * 4 + k] * R[v][a];
+          S[v][k] = s; }
+#pragma unroll
+      for (int v = 0; v < 5; v++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) R[v][k] = S[v][k];
+    }
+    const int sw = swz(i, j);
+#pragma unroll
+    for (int d = 0; d < 2; d++) {   // xi, then eta: all five variables through the element's [5][64] tile
+      __syncwarp(wm);
+#pragma unroll
+      for (int v = 0; v < 5; v++) { sts2(sXe + v * 64 + sw, R[v][0], R[v][1]); sts2(sXe + v * 64 + sw + 2, R[v][2], R[v][3]); }
+      __syncwarp(wm);
+#pragma unroll
+      for (int v = 0; v < 5; v++) {
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const double* p = d == 0 ? sXe + v * 64 + a * 16 + (((j + a) & 3) << 2) : sXe + v * 64 + i * 16 + (((a + i) & 3) << 2);
+          const double kk = A.k1[a * 4 + (d == 0 ? i : j)];
+          const double2 lo = lds2(p), hi = lds2(p + 2);
+          x0 += kk * lo.x; x1 += kk * lo.y; x2 += kk * hi.x; x3 += kk * hi.y;
+        }
+        R[v][0] = x0; R[v][1] = x1; R[v][2] = x2; R[v][3] = x3;
+      }
+    }
+    // deterministic block reduction: warp shuffle (inactive lanes contribute zero), then one thread sums the warp partials in order
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+      double s = fabs(R[v][0]) + fabs(R[v][1]) + fabs(R[v][2]) + fabs(R[v][3]);
+      for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_down_sync(wm, s, o); if (((tid & 31) + o < 32) && ((wm >> ((tid & 31) + o)) & 1)) s += y; }
+      if ((tid & 31) == 0) sRed[(tid >> 5) * 5 + v] = s;
+    }
+    __syncthreads();
+    if (tid < 5) {
+      double s = 0.0;
+      for (int w = 0; w < (ne * 16 + 31) / 32; w++) s += sRed[w * 5 + tid];
+      A.normPartial[(size_t)chunk * 5 + tid] = s / 64;
+    }
+  }
+}
+
+}  // namespace sdg

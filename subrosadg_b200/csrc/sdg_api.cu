@@ -15,6 +15,7 @@
 #include "host_plan.hpp"
 #include "launchers.hpp"
 #include "mixed_path.hpp"
+#include "nsl_kernels.cuh"
 #include "tensor_kernels.cuh"
 
 using namespace sdg;
@@ -49,12 +50,23 @@ struct sdg_ctx {
   std::vector<double> hostNorm;
   // one time step (nStages x passes launches) captured as a CUDA graph: launch-bound meshes (the reference's shipped configs have
   // 1e2-3e4 elements) replay it instead of issuing every launch from the host
-  cudaGraphExec_t stepGraph = nullptr; double graphDt = 0.0; int graphCur = -1; bool graphWarm = false;
+  cudaGraphExec_t stepGraph = nullptr; double graphDt = 0.0; int graphCur = -1; bool graphWarm = false; int64_t graphLaunches = 0;
   // peer-memory halo exchange (CUDA IPC): the peers' arrays opened in this process, arrival flags, exchange counter
   std::vector<PeerDev> peerLinks; std::vector<void*> ipcOpened;
   DevBuf<PeerDev> peerDev; DevBuf<long long> ipcFlags; DevBuf<unsigned int> pushCounter; DevBuf<int> haloErr;
   long long pushEpoch = 0;
   std::unique_ptr<MixedSolver> mx;   // dense-operator path: meshes with triangle blocks / several element types (mixed_path.cu)
+  // trace-based line kernels for P3 hexahedra (nsl_kernels.cuh): published face traces TU (one per stage buffer) and TV, virtual
+  // neighbour traces of the boundary faces, link records; traceValid[b] = TU[b] holds the traces of U[b]
+  bool lineTrace = false;
+  LineFns lineFns;
+  DevBuf<double> TU[3], TV, TUb, lfGeo;
+  DevBuf<int> links, bndRec;
+  DevBuf<LineTabDev> ltab;
+  double w1[kMaxN]{}, cLift = 0.0;
+  LinePlan linePlan;   // host image (diagnostics: sdg_debug_plan 20-23)
+  bool traceValid[3] = {false, false, false};
+  int64_t stepCount = 0, bndKey = -1;
 
   size_t stateDoubles() const { return (size_t)plan.blk.n * NV * plan.blk.T.NN; }
   size_t elemDoubles() const { return (size_t)NV * plan.blk.T.NN; }
@@ -76,6 +88,22 @@ void fillArgs(sdg_ctx* c, StageArgs& a) {
   const int N = B.T.N;
   for (int i = 0; i < N * N; i++) { a.dm[i] = B.T.Dm[i]; a.k1[i] = B.T.K1[i]; }
   for (int i = 0; i < 2 * N; i++) a.lend[i] = B.T.Lend[i];
+  for (int i = 0; i < N; i++) a.w1[i] = B.T.w[i];
+  if (c->lineTrace) {
+    a.TVin = c->TV.p; a.TVout = c->TV.p; a.TUb = c->TUb.p;
+    a.links = reinterpret_cast<const int4*>(c->links.p); a.lfGeo = c->lfGeo.p; a.ltab = c->ltab.p; a.cLift = c->cLift;
+  }
+}
+
+// traces of a state that did not come out of the residual pass (initial condition, state setters)
+void ensureTraces(sdg_ctx* c, int buf, cudaStream_t s) {
+  if (!c->lineTrace || c->traceValid[buf]) return;
+  StageArgs a; fillArgs(c, a);
+  a.Uin = c->U[buf].p; a.TUout = c->TU[buf].p;
+  c->lineFns.trace(a, c->plan.blk.nChunks, s);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  c->traceValid[buf] = true;
 }
 
 // one pass of one stage over a subset of the chunks
@@ -86,11 +114,23 @@ void runStage(sdg_ctx* c, const StageArgs& base, int part, cudaStream_t s, int p
   if (part == 0) { a.chunkList = c->chunkInterior.p; nBlocks = (int)B.chunkInterior.size(); }
   else if (part == 1) { a.chunkList = c->chunkBoundary.p; nBlocks = (int)B.chunkBoundary.size(); }
   if (nBlocks == 0) return;
-  if (!c->phys.ns) c->eulerFn(a, nBlocks, s);
+  if (c->lineTrace) {
+    if (pass == 0) c->lineFns.grad(a, nBlocks, s); else c->lineFns.stage(a, nBlocks, s);
+  }
+  else if (!c->phys.ns) c->eulerFn(a, nBlocks, s);
   else if (pass == 0) c->nsGradFn(a, nBlocks, s);
   else c->nsStageFn(a, nBlocks, s);
   c->launches++;
   CUDA_OK(cudaGetLastError());
+}
+
+// virtual neighbour traces of the boundary faces for the gradient pass reading TU[in]: once per (step, stage), before the first part
+void lineBoundary(sdg_ctx* c, const StageArgs& a, int64_t key, cudaStream_t s) {
+  if (c->plan.F.nBnd == 0 || (key >= 0 && c->bndKey == key)) return;
+  c->lineFns.boundary(a, reinterpret_cast<const int4*>(c->bndRec.p), c->plan.F.nBnd, s);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  c->bndKey = key;
 }
 
 // buffers of stage s: in / out indices (SSP-RK tables TimeIntegration.cpp:45-65 realised with three rotating buffers)
@@ -108,6 +148,11 @@ void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st, int pass = -1) {
   StageArgs a; fillArgs(c, a);
   a.Uin = c->U[in].p; a.Ulast = c->U[c->cur].p; a.Uout = c->U[out].p;
   a.Gvol = c->G.p; a.Gout = c->G.p;
+  if (c->lineTrace) {
+    ensureTraces(c, in, st);
+    a.TUin = c->TU[in].p; a.TUout = c->TU[out].p;
+    if (c->phys.ns && (pass == -1 || pass == 0)) lineBoundary(c, a, c->stepCount * 4 + s, st);
+  }
   if (c->phys.ns && (pass == -1 || pass == 0)) { runStage(c, a, part, st, 0); if (pass == 0) return; }
   if (!c->phys.ns && pass == 0) return;
   a.aLast = s == 0 ? 0.0 : c->rkc[s][0];
@@ -116,9 +161,10 @@ void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st, int pass = -1) {
   a.normPartial = s == c->nStages - 1 ? c->normPartial.p : nullptr;
   runStage(c, a, part, st, 1);
   c->latest = out;
+  if (c->lineTrace) c->traceValid[out] = true;   // the residual pass publishes the traces of the state it writes
 }
 
-void finishStep(sdg_ctx* c) { if (c->nStages == 1) c->cur = (c->cur + 1) % 3; c->latest = c->cur; }
+void finishStep(sdg_ctx* c) { if (c->nStages == 1) c->cur = (c->cur + 1) % 3; c->latest = c->cur; c->stepCount++; }
 
 void reduceNorm(sdg_ctx* c, double* sums) {
   constexpr int kSlices = 128;
@@ -261,7 +307,11 @@ int sdg_finalize(sdg_ctx* c) {
   const int ph = (c->phys.compressible && c->phys.eos == kIdealGas && c->phys.conv == kHLLC) ? 1 : 0;
   // decide the affine flag first (needs geometry), then the kernel
   M.buildBlock(c->cfg.reorder, 1);  // provisional chunk size; chunking is redone below once K is known
-  if (c->phys.ns) pickNsFn(c->D, N, B.affine, ph, c->nsGradFn, c->nsStageFn, K);
+  // P3 hexahedra: Navier-Stokes runs on the trace-based line kernels (SDG_NS_NODE_KERNEL = A/B switch back to the node-per-thread
+  // kernels of ns_kernels.cuh); SDG_EULER_TRACE routes Euler through the same residual pass for comparison with eulerLineKernel
+  c->lineTrace = c->D == 3 && N == 4 && (c->phys.ns ? getenv("SDG_NS_NODE_KERNEL") == nullptr : getenv("SDG_EULER_TRACE") != nullptr);
+  if (c->lineTrace) pickNslFns(B.affine, ph, c->phys.ns != 0, c->lineFns, K);
+  else if (c->phys.ns) pickNsFn(c->D, N, B.affine, ph, c->nsGradFn, c->nsStageFn, K);
   else c->eulerFn = pickEulerFn(c->D, N, B.affine, ph, K);
   if (c->cfg.chunk > 0 && c->cfg.chunk != K) throw std::runtime_error("chunk override not available: kernels are compiled for K = " + std::to_string(K));
   B.K = K; B.nChunks = (B.nOwned + K - 1) / K;
@@ -273,6 +323,7 @@ int sdg_finalize(sdg_ctx* c) {
     const int sideRef = c->D == 1 ? f : c->D == 2 ? ((0x6 >> f) & 1) : (f >= 3);
     if (dirRef != B.T.faceDir[f] || sideRef != B.T.faceSide[f]) throw std::runtime_error("internal: face direction table mismatch");
   }
+  if (c->lineTrace) c->linePlan = M.buildLinePlan();
   if (c->hasDevice) {
     CUDA_OK(cudaSetDevice(c->cfg.device));
     const size_t nd = c->stateDoubles();
@@ -323,6 +374,19 @@ int sdg_finalize(sdg_ctx* c) {
       for (int j = 0; j < B.T.NQF; j++) t.seq[r * B.T.NQF + j] = s[j];
     }
     c->tab.upload(td, c->stream);
+    if (c->lineTrace) {
+      const LinePlan& LP = c->linePlan;
+      c->links.upload(LP.links, c->stream); c->bndRec.upload(LP.bndRec, c->stream);
+      if (B.affine) c->lfGeo.upload(LP.lfGeo, c->stream);
+      std::vector<LineTabDev> lt(1);
+      std::memcpy(lt[0].partner, LP.partner.data(), sizeof(lt[0].partner)); std::memcpy(lt[0].jLeft, LP.jLeft.data(), sizeof(lt[0].jLeft));
+      c->ltab.upload(lt, c->stream);
+      c->cLift = LP.cLift;
+      const size_t nt = (size_t)B.n * 6 * kRow;
+      for (int i = 0; i < 3; i++) { c->TU[i].alloc(nt); c->TU[i].zero(c->stream); }
+      if (c->phys.ns) { c->TV.alloc(nt); c->TV.zero(c->stream); }
+      c->TUb.alloc((size_t)std::max(F.nBnd, 1) * kRow); c->TUb.zero(c->stream);
+    }
     CUDA_OK(cudaStreamSynchronize(c->stream));
   }
   c->finalized = true;
@@ -373,7 +437,7 @@ int sdg_set_state_from_primitive(sdg_ctx* c, int32_t type, const double* prim) {
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(c->stream));
   c->scratch.release();
-  c->latest = c->cur;
+  c->latest = c->cur; c->traceValid[c->cur] = false;
   SDG_CATCH
 }
 
@@ -412,7 +476,7 @@ int sdg_set_state_device(sdg_ctx* c, int32_t type, const void* U_device) {
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   transformModal(c, (const double*)U_device, c->U[c->cur].p, c->Phi.p, 0, c->plan.blk.nOwned);
-  c->latest = c->cur;
+  c->latest = c->cur; c->traceValid[c->cur] = false;
   SDG_CATCH
 }
 int sdg_get_state_device(sdg_ctx* c, int32_t type, void* U_device) {
@@ -431,10 +495,11 @@ int sdg_set_state(sdg_ctx* c, int32_t type, const double* U) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const size_t nd = c->stateDoubles();
   const int s = (c->cur + 1) % 3;  // scratch: a stage buffer that holds no live data between steps
+  c->traceValid[s] = false;
   CUDA_OK(cudaMemcpyAsync(c->U[s].p, U, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   transformModal(c, c->U[s].p, c->U[c->cur].p, c->Phi.p, 0, c->plan.blk.nOwned);
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  c->latest = c->cur;
+  c->latest = c->cur; c->traceValid[c->cur] = false;
   SDG_CATCH
 }
 int sdg_get_state(sdg_ctx* c, int32_t type, double* U) {
@@ -444,6 +509,7 @@ int sdg_get_state(sdg_ctx* c, int32_t type, double* U) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const size_t nd = c->stateDoubles();
   const int s = (c->cur + 1) % 3;
+  c->traceValid[s] = false;
   transformModal(c, c->U[c->cur].p, c->U[s].p, c->PhiInv.p, 1);
   CUDA_OK(cudaMemcpyAsync(U, c->U[s].p, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -458,6 +524,7 @@ int sdg_get_state_at_quadrature(sdg_ctx* c, int32_t type, double* Uq) {
   const BlockPlan& B = c->plan.blk;
   const size_t nd = c->stateDoubles();
   const int s = (c->cur + 1) % 3;
+  c->traceValid[s] = false;
   seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->U[c->cur].p, c->U[s].p, c->perm.p, B.n, c->NV, B.T.NN, 1);
   c->launches++;
   CUDA_OK(cudaGetLastError());
@@ -479,9 +546,14 @@ int sdg_get_gradient_at_quadrature(sdg_ctx* c, int32_t type, double* Gq) {
   StageArgs args; fillArgs(c, args);
   args.Uin = c->U[c->cur].p; args.Ulast = c->U[c->cur].p; args.Uout = c->U[(c->cur + 1) % 3].p;
   args.Gvol = c->G.p; args.Gout = c->G.p;
+  if (c->lineTrace) {   // pass G of the line kernels leaves the TOTAL gradient in G (zeta-slowest node order)
+    ensureTraces(c, c->cur, c->stream);
+    args.TUin = c->TU[c->cur].p; args.TUout = c->TU[(c->cur + 1) % 3].p;
+    lineBoundary(c, args, -1, c->stream);
+  }
   runStage(c, args, -1, c->stream, 0);
-  if (c->phys.visc == kBR2) { args.Gout = c->G2.p; args.mode = 3; runStage(c, args, -1, c->stream, 1); }
-  seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->phys.visc == kBR2 ? c->G2.p : c->G.p, tmp.p, c->perm.p, B.n, NG, B.T.NN, 1);
+  if (!c->lineTrace && c->phys.visc == kBR2) { args.Gout = c->G2.p; args.mode = 3; runStage(c, args, -1, c->stream, 1); }
+  seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>((!c->lineTrace && c->phys.visc == kBR2) ? c->G2.p : c->G.p, tmp.p, c->perm.p, B.n, NG, B.T.NN, c->lineTrace ? 3 : 1);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(Gq, tmp.p, c->G.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -569,6 +641,7 @@ void launchOneStep(sdg_ctx* c) {
 // n_steps time steps on the context's stream
 void runSteps(sdg_ctx* c, double dt, int n_steps) {
   c->stepDt = dt;
+  ensureTraces(c, c->cur, c->stream);   // outside any graph capture
   const bool useGraph = c->plan.blk.nChunks <= kGraphMaxChunks && c->nStages > 1 && n_steps >= 4 && !getenv("SDG_NO_GRAPH");
   int it = 0;
   if (useGraph) {
@@ -580,13 +653,13 @@ void runSteps(sdg_ctx* c, double dt, int n_steps) {
       CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
       launchOneStep(c);                                   // nStages > 1: the buffer rotation returns to `cur`, every step is identical
       CUDA_OK(cudaStreamEndCapture(c->stream, &g));
+      c->graphLaunches = c->launches - l0;                // kernels per replay
       c->launches = l0;                                   // captured, not launched
       CUDA_OK(cudaGraphInstantiate(&c->stepGraph, g, 0));
       cudaGraphDestroy(g);
       c->graphDt = dt; c->graphCur = c->cur;
     }
-    const int perStep = c->nStages * (c->phys.ns ? 2 : 1);
-    for (; it < n_steps; it++) { CUDA_OK(cudaGraphLaunch(c->stepGraph, c->stream)); c->launches += perStep; }
+    for (; it < n_steps; it++) { CUDA_OK(cudaGraphLaunch(c->stepGraph, c->stream)); c->launches += c->graphLaunches; }
     return;
   }
   for (; it < n_steps; it++) launchOneStep(c);
@@ -640,6 +713,7 @@ int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
   const BlockPlan& B = c->plan.blk;
   const size_t nd = c->stateDoubles();
   const int a = (c->cur + 1) % 3, b = (c->cur + 2) % 3;
+  c->traceValid[a] = c->traceValid[b] = false;   // both scratch buffers are overwritten below
   for (int mode = 1; mode <= 2; mode++) {
     double* host = mode == 1 ? rhsq : Rmodal;
     if (!host) continue;
@@ -648,6 +722,11 @@ int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
     args.aLast = 0.0; args.aCur = 0.0; args.bdt = 1.0;
     CUDA_OK(cudaMemsetAsync(c->U[a].p, 0, nd * sizeof(double), c->stream));
     args.Gvol = c->G.p; args.Gout = c->G.p;
+    if (c->lineTrace) {
+      ensureTraces(c, c->cur, c->stream);
+      args.TUin = c->TU[c->cur].p; args.TUout = c->TU[a].p;
+      if (c->phys.ns) lineBoundary(c, args, -1, c->stream);
+    }
     if (c->phys.ns) runStage(c, args, -1, c->stream, 0);
     runStage(c, args, -1, c->stream, 1);
     if (mode == 1) {
@@ -676,7 +755,9 @@ int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int6
   const BlockPlan& B = c->plan.blk;
   const std::vector<double>* d = nullptr; const std::vector<int>* i = nullptr;
   std::vector<int> misc = {B.affine ? 1 : 0, B.K, B.nChunks, B.nOwned};
-  std::vector<int> seqs, midx;
+  std::vector<int> seqs, midx, lpart, ljl;
+  for (unsigned char x : c->linePlan.partner) lpart.push_back(x);
+  for (unsigned char x : c->linePlan.jLeft) ljl.push_back(x);
   {  // right-side face-point permutations for rotations 0..3 (the table the kernels stage), modal function index triples
     const int ft = faceType(B.type);
     for (int r = 0; r < 4; r++) { std::vector<int> q = faceSequence(ft, B.T.N, ft == kLine ? 0 : r); seqs.insert(seqs.end(), q.begin(), q.end()); }
@@ -687,6 +768,7 @@ int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int6
     case 10: i = &B.perm; break; case 11: i = &B.chunkFaceOff; break; case 12: i = &B.faceRec; break;
     case 13: i = &B.chunkInterior; break; case 14: i = &B.chunkBoundary; break; case 15: i = &misc; break;
     case 16: i = &seqs; break; case 17: i = &B.T.faceBase; break; case 18: i = &B.T.nodeFacePt; break; case 19: i = &midx; break;
+    case 20: i = &c->linePlan.links; break; case 21: i = &lpart; break; case 22: i = &ljl; break; case 23: i = &c->linePlan.bndRec; break;
     case 4: d = &B.T.Phi; break; case 5: d = &B.T.Dm; break; case 6: d = &B.T.Lend; break; case 7: d = &B.T.x; break; case 8: d = &B.T.w; break;
     default: throw std::runtime_error("bad diagnostics id");
   }
@@ -694,6 +776,13 @@ int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int6
   if (i) { if (count) *count = (int64_t)i->size(); if (out_i) std::memcpy(out_i, i->data(), i->size() * sizeof(int)); }
   SDG_CATCH
 }
+
+// what travels between ranks: whole elements of the state / volume gradient, or — trace-based line kernels — the elements' face-trace rows
+// TU (what = 0) and TV (what = 1)
+static int haloStride(sdg_ctx* c, int what) { return c->lineTrace ? 6 * kRow : (int)c->elemDoubles() * (what == 1 ? c->D : 1); }
+static double* haloField(sdg_ctx* c, int what) { return c->lineTrace ? (what == 1 ? c->TV.p : c->TU[c->latest].p) : (what == 1 ? c->G.p : c->U[c->latest].p); }
+
+int sdg_halo_doubles_per_element(sdg_ctx* c, int32_t what) { return haloStride(c, what); }
 
 int sdg_set_halo_send(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* elems) {
   SDG_TRY
@@ -705,7 +794,7 @@ int sdg_set_halo_send(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* e
   for (int i = 0; i < n_send; i++) { if (elems[i] < 0 || elems[i] >= B.nOwned) throw std::runtime_error("halo send element out of range"); pos[i] = B.perm[elems[i]]; }
   c->sendList.upload(pos, c->stream);
   c->nSend = n_send;
-  c->sendBuf.alloc((size_t)std::max(n_send, 1) * c->elemDoubles() * (c->phys.ns ? c->D : 1));
+  c->sendBuf.alloc((size_t)std::max(n_send, 1) * std::max(haloStride(c, 0), c->phys.ns ? haloStride(c, 1) : 0));
   SDG_CATCH
 }
 
@@ -715,9 +804,10 @@ int sdg_halo_pack(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
   needFinal(c); needDevice(c); needType(c, type);
   if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
   CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (what == 0) ensureTraces(c, c->latest, stream ? (cudaStream_t)stream : c->stream);
   if (c->nSend == 0) return 0;
-  const int stride = (int)c->elemDoubles() * (what == 1 ? c->D : 1);
-  const double* src = what == 1 ? c->G.p : c->U[c->latest].p;
+  const int stride = haloStride(c, what);
+  const double* src = haloField(c, what);
   const int blocks = (int)std::min<size_t>(((size_t)c->nSend * stride + 255) / 256, 148 * 8);
   haloPackKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(src, c->sendList.p, c->nSend, stride, c->sendBuf.p);
   c->launches++;
@@ -731,8 +821,8 @@ int sdg_halo_buffers_device(sdg_ctx* c, int32_t type, int32_t what, void** send,
   needFinal(c); needDevice(c); needType(c, type);
   if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
   const BlockPlan& B = c->plan.blk;
-  const int64_t per = (int64_t)c->elemDoubles() * (what == 1 ? c->D : 1);
-  double* base = what == 1 ? c->G.p : c->U[c->latest].p;
+  const int64_t per = haloStride(c, what);
+  double* base = haloField(c, what);
   *send = c->sendBuf.p; *send_doubles = (int64_t)c->nSend * per;
   *recv = base + (size_t)B.nOwned * per; *recv_doubles = (int64_t)B.nGhost * per;
   SDG_CATCH
@@ -746,6 +836,7 @@ int sdg_ipc_export(sdg_ctx* c, unsigned char* handles) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   if (!c->ipcFlags.p) { c->ipcFlags.alloc(64); c->ipcFlags.zero(c->stream); c->pushCounter.alloc(1); c->pushCounter.zero(c->stream); c->haloErr.alloc(1); c->haloErr.zero(c->stream); CUDA_OK(cudaStreamSynchronize(c->stream)); }
   void* ptrs[5] = {c->U[0].p, c->U[1].p, c->U[2].p, c->G.p, c->ipcFlags.p};
+  if (c->lineTrace) { ptrs[0] = c->TU[0].p; ptrs[1] = c->TU[1].p; ptrs[2] = c->TU[2].p; ptrs[3] = c->TV.p; }
   std::memset(handles, 0, 5 * sizeof(cudaIpcMemHandle_t));
   for (int i = 0; i < 5; i++) if (ptrs[i]) { cudaIpcMemHandle_t h; CUDA_OK(cudaIpcGetMemHandle(&h, ptrs[i])); std::memcpy(handles + i * sizeof(h), &h, sizeof(h)); }
   SDG_CATCH
@@ -780,10 +871,11 @@ int sdg_halo_push(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
   if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
   if (c->peerLinks.empty() && c->nSend > 0) throw std::runtime_error("sdg_ipc_connect has not been called");
   CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (what == 0) ensureTraces(c, c->latest, stream ? (cudaStream_t)stream : c->stream);
   c->pushEpoch++;
   if (c->peerLinks.empty()) return 0;
-  const int stride = (int)c->elemDoubles() * (what == 1 ? c->D : 1);
-  const double* src = what == 1 ? c->G.p : c->U[c->latest].p;
+  const int stride = haloStride(c, what);
+  const double* src = haloField(c, what);
   const int which = what == 1 ? 3 : c->latest;
   static const int maxBlocks = getenv("SDG_PUSH_BLOCKS") ? std::max(1, atoi(getenv("SDG_PUSH_BLOCKS"))) : 148 * 2;   // 2 CTAs per SM measured best at 4 GPUs (96: 280, 296: 285, 592: 282 GDOF/s): more blocks steal SM slots from the interior launch
   const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((size_t)c->nSend * stride + 255) / 256, (size_t)maxBlocks));

@@ -46,6 +46,8 @@ struct TensorDev {
   unsigned char nodeFacePt[6 * kMaxN * kMaxN * kMaxN];
 };
 
+struct LineTabDev;   // nsl_kernels.cuh
+
 struct StageArgs {
   const double* Uin;      // [nTotal][NV][NN] state read by this stage (owned + ghost elements)
   const double* Ulast;    // state at the beginning of the step (read when aLast != 0)
@@ -67,6 +69,15 @@ struct StageArgs {
   int nOwned, nInt;
   int mode;               // 0 RK update, 1 write dU/dt, 2 write R (nodal, un-inverted)
   PhysParams phys;
+  // trace-based line kernels (nsl_kernels.cuh): published face traces [nTotal][6][5][16], per-(element, face) link / geometry records
+  const double* TUin; double* TUout;   // traces of the state read / written by this stage
+  const double* TVin; double* TVout;   // this side's viscous normal flux (pass G writes, pass R reads)
+  double* TUb;                         // virtual neighbour traces of the boundary faces [nBnd][5][16]
+  const int4* links;                   // [nOwned][6]
+  const double* lfGeo;                 // affine: [nOwned][6][4] = face normal, |J| scale
+  const LineTabDev* ltab;
+  double w1[kMaxN];                    // 1-D Gauss weights
+  double cLift;                        // sum_a l_a(-1)^2 / w_a: BR2 lift trace factor of a face point, without 1 / (detJ w_face)
 };
 
 template <int N, int D> struct Pow { static constexpr int v = N * Pow<N, D - 1>::v; };
@@ -535,7 +546,7 @@ static __global__ void seamTransformKernel(const double* __restrict__ in, double
   }
 }
 
-// [n][Nq][C] (caller order) <-> internal [pos][C][Nq]; dir 0: in -> internal, 1: internal -> out
+// [n][Nq][C] (caller order) <-> internal [pos][C][Nq]; dir 0: in -> internal, 1: internal -> out, 3: as 1 with internal node index (q % 4) * 16 + q / 4
 static __global__ void seamTransposeKernel(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ perm, int n, int C, int NN, int dir) {
   const size_t total = (size_t)n * C * NN;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -543,6 +554,7 @@ static __global__ void seamTransposeKernel(const double* __restrict__ in, double
     const int r = (int)(i - (size_t)e * C * NN);
     const int pos = perm ? perm[e] : e;
     if (dir == 0) { const int q = r / C, c = r - q * C; out[((size_t)pos * C + c) * NN + q] = in[i]; }
+    else if (dir == 3) { const int q = r / C, c = r - q * C; out[i] = in[((size_t)pos * C + c) * NN + (q & 3) * 16 + (q >> 2)]; }   // P3 hexahedra, zeta-slowest internal node order
     else { const int q = r / C, c = r - q * C; out[i] = in[((size_t)pos * C + c) * NN + q]; }
   }
 }

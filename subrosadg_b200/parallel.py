@@ -290,7 +290,7 @@ class DistributedSolver:
         with torch.cuda.stream(self.comm):
             self._chk(self.lib.sdg_halo_pack(self.S.h, self.etype, what, ctypes.c_void_p(self.comm.cuda_stream)))
             send, recv = self._buffers(what)
-            per_elem = self.elem_doubles * (self.S.dim if what == 1 else 1)
+            per_elem = int(self.lib.sdg_halo_doubles_per_element(self.S.h, what))
             reqs = self.halo.start(send, recv, per_elem)
             self.halo.finish(reqs)      # stream-ordered for NCCL: the communication stream waits, the host does not
             self.ev_halo.record(self.comm)
@@ -400,7 +400,7 @@ class InProcessCluster:
         return mk(sp.value or 0, sn.value), mk(rp.value or 0, rn.value)
 
     def _exchange(self, what):
-        per = self.elem_doubles * (self.dim if what == 1 else 1)
+        per = int(self.lib.sdg_halo_doubles_per_element(self.S[0].h, what))
         for S in self.S:
             self._chk(self.lib.sdg_halo_pack(S.h, self.etype, what, None))
             S.synchronize()

@@ -171,7 +171,8 @@ def test_sphere_3d_cns(built):
 
 
 # ---- element-block partitions (multi-rank path on one device) -----------------------------------------------------------------
-@pytest.mark.parametrize("dim,n,world,model", [(2, 8, 2, {}), (3, 6, 3, {}), (3, 4, 2, dict(NS, visc_flux=2, mu=0.01)), (2, 8, 4, dict(NS, visc_flux=1, mu=0.01))])
+@pytest.mark.parametrize("dim,n,world,model", [(2, 8, 2, {}), (3, 6, 3, {}), (3, 4, 2, dict(NS, visc_flux=2, mu=0.01)), (2, 8, 4, dict(NS, visc_flux=1, mu=0.01)),
+                                               (3, 4, 2, dict(NS, visc_flux=2, mu=0.01, p=3)), (3, 6, 3, dict(NS, visc_flux=1, mu=0.01, p=3)), (3, 4, 2, dict(p=3))])
 def test_two_contexts_match_single_context(built, dim, n, world, model):
     """`world` contexts with ghost elements, pack kernel and part-0 / part-1 launches (the N>1 path of bench.py, with
     device copies in place of NCCL) must reproduce the single-context run element for element."""
@@ -179,7 +180,7 @@ def test_two_contexts_match_single_context(built, dim, n, world, model):
     from subrosadg_b200.solver import Solver
     mesh = M.periodic_box_fast(dim, n)
     cfg = dict(p=3 if dim == 2 else 2, conv_flux=2, rk=2)
-    cfg.update(model)
+    cfg.update(model)   # p = 3 in 3-D: eulerLineKernel / the trace-based NS line kernels (halo = face-trace rows)
     vel = [0.7, 0.3] if dim == 2 else [0.5, 0.3, 0.2]
     ic = cases.ic_density_wave(vel)
     S = Solver(dict(cfg), mesh, device=0)
