@@ -47,6 +47,11 @@ struct LineTabDev {
 // swizzled tile of one field of one element: node (i, j, k) at i*16 + ((j+i)&3)*4 + k — lines along xi, eta and zeta are all
 // read without bank conflicts, no padding
 __device__ __forceinline__ int swz(int i, int j) { return i * 16 + (((j + i) & 3) << 2); }
+// DRAM -> L2 ahead of use: the ranges a block owns are contiguous (bulk prefetch by one thread), the partners' rows are 128-byte lines
+__device__ __forceinline__ void bulkPrefetchL2(const void* p, unsigned bytes) {
+  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
@@ -129,6 +134,66 @@ __global__ void __launch_bounds__(128) nslBoundaryKernel(const __grid_constant__
   for (int v = 0; v < 5; v++) A.TUb[(size_t)fb * kRow + v * 16 + t] = 2.0 * vol[v] - consL[v];
 }
 
+// ---- boundary faces, out of line: they are rare, and inlining the six boundary-condition bodies at every face of both passes pushes
+//      the hot loops out of the 32 KB instruction cache (measured: stall_no_instruction 4.4 warps per issue) -------------------------------
+struct Vals5 { double v[5]; };
+struct Vals15 { double v[15]; };
+
+// pass R (SpatialDiscrete.cpp:797-812): normal flux of the BC-constructed state minus the face's averaged viscous flux (published by pass G)
+template <int PH, bool VISC>
+__device__ __noinline__ Vals5 nslBoundaryFaceFlux(const PhysParams& P, int bc, double n0, double n1, double n2, Vals5 cm, Vals5 tm, const double* __restrict__ dummyCol) {
+  const Phys<PH> ph(P);
+  const double n[3] = {n0, n1, n2};
+  double compL[6], compR[6], b[6], Fn[5];
+  compFromCons<3>(ph, cm.v, compL);
+#pragma unroll
+  for (int k = 0; k < 6; k++) compR[k] = dummyCol[k * 16];
+  bcBoundaryVariable<3>(ph, bc, n, compL, compR, b);
+  convNormalFlux<3>(ph, n, b, Fn);
+  Vals5 out;
+#pragma unroll
+  for (int v = 0; v < 5; v++) out.v[v] = VISC ? Fn[v] - tm.v[v] : Fn[v];
+  return out;
+}
+
+// pass G (SpatialDiscrete.cpp:750-842): the complete averaged viscous flux of a boundary face from the (un-lifted) gradient trace g
+static __device__ __noinline__ Vals5 nslBoundaryViscousFlux(const PhysParams& P, int bc, double n0, double n1, double n2, double jwLam, Vals5 cmv, Vals15 gv,
+                                                            const double* __restrict__ dummyCol) {
+  const Phys<0> ph(P);
+  const double n[3] = {n0, n1, n2};
+  double comp[6], compR[6], b[6], volCons[5], intCons[5], pL[15], gb[15], va[5], vb[5];
+  double* g = gv.v;
+  const double* cm = cmv.v;
+  compFromCons<3>(ph, cm, comp);
+#pragma unroll
+  for (int k = 0; k < 6; k++) compR[k] = dummyCol[k * 16];
+  bcBoundaryGradientVariable<3>(ph, bc, n, cm, comp, compR, volCons, intCons);
+#pragma unroll
+  for (int v = 0; v < 5; v++) {
+    const double jl = intCons[v] * jwLam;
+#pragma unroll
+    for (int c = 0; c < 3; c++) g[v * 3 + c] += jl * n[c];
+  }
+  primGradFromConsGrad<3>(ph, cm, comp, g, pL);             // from the UNMODIFIED interior trace (:792-796)
+  bcBoundaryVariable<3>(ph, bc, n, comp, compR, b);
+  if (bcIsWall(bc)) {                                       // modifyBoundaryVariable, BoundaryCondition.cpp:443-452,490-501,535-546
+#pragma unroll
+    for (int k = 0; k < 6; k++) comp[k] = b[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 15; k++) gb[k] = pL[k];
+  if (bc == kAdiabaticSlipWall || bc == kAdiabaticNonSlipWall) { gb[12] = 0.0; gb[13] = 0.0; gb[14] = 0.0; }
+  viscNormalFlux<3>(ph, n, comp, pL, va);
+  viscNormalFlux<3>(ph, n, b, gb, vb);
+  Vals5 out;
+#pragma unroll
+  for (int v = 0; v < 5; v++) out.v[v] = 0.5 * (va[v] + vb[v]);
+  return out;
+}
+
+// local faces of axis d: (xi-, xi+) = (2, 3), (eta-, eta+) = (1, 4), (zeta-, zeta+) = (0, 5)
+__device__ __forceinline__ int hexFaceRt(int d, int side) { return side ? 3 + d : 2 - d; }
+
 // =====================================================================================================================
 // pass G: total gradient at the nodes + this side's viscous normal flux at the face points
 // =====================================================================================================================
@@ -182,16 +247,29 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
       bulkLoad(sLg, A.lfGeo + (size_t)e0 * 6 * kLG, (unsigned)(ne * 6 * kLG * sizeof(double)), &mbar);
     }
   }
+  if (tid == 32) {
+    // DRAM -> L2 one wave of thread blocks AHEAD: the block that will run on this SM slot next finds its contiguous ranges in L2, and
+    // the DRAM transfer overlaps this block's arithmetic (the first wave fetches its own)
+    for (int b = (int)blockIdx.x < A.ahead ? (int)blockIdx.x : (int)blockIdx.x + A.ahead; b < (int)gridDim.x && b <= (int)blockIdx.x + A.ahead; b += A.ahead) {
+      const int c2 = A.chunkList ? A.chunkList[b] : b;
+      const int f0 = c2 * K, n2 = min(K, A.nOwned - f0);
+      bulkPrefetchL2(A.TUin + (size_t)f0 * 6 * kRow, (unsigned)(n2 * 6 * kRow * sizeof(double)));
+      bulkPrefetchL2(A.Uin + (size_t)f0 * 5 * 64, (unsigned)(n2 * 5 * 64 * sizeof(double)));
+    }
+  }
   const unsigned wm = __ballot_sync(0xffffffffu, active);
   if (!active) return;
   const int e = e0 + el;
   const int sw = swz(i, j);
-  double u[5][4];
-#pragma unroll
-  for (int v = 0; v < 5; v++)
-#pragma unroll
-    for (int k = 0; k < 4; k += 2) { const double2 x = ldg2(A.Uin + ((size_t)e * 5 + v) * 64 + t * 4 + k); u[v][k] = x.x; u[v][k + 1] = x.y; }
+  const double* gU = A.Uin + (size_t)e * 5 * 64 + t * 4;
+  double un[4];   // the line of the NEXT variable (requested one iteration ahead)
+  { const double2 a = ldg2(gU), b = ldg2(gU + 2); un[0] = a.x; un[1] = a.y; un[2] = b.x; un[3] = b.y; }
   mbarWait(&mbar, 0);
+  for (int c = t; c < 30; c += 16) {   // the partners' rows of the six faces, one 128-byte line per (face, variable)
+    const int f = c / 5, v = c - f * 5;
+    const int4 lk = sLink[el * 6 + f];
+    if (lk.x >= 0) prefetchL2(A.TUin + ((size_t)lk.x * 6 + linkLfo(lk.z)) * kRow + v * 16);
+  }
 
   // ---- per-face set-up of this thread's face point (natural index t on each of the six faces) ---------------------------------------
   int nbr[6];          // >= 0: offset of the partner's value of variable 0 inside TU; < 0: -(1 + offset inside TUb) for a boundary face
@@ -229,15 +307,35 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
   };
   const double* gTU = A.TUin + (size_t)e * 6 * kRow + t;
 
-  // ---- G1-G4, one conserved variable at a time --------------------------------------------------------------------------------------
+  // ---- G1-G4, one conserved variable at a time (a rolled loop: the body is ~600 instructions); the line and the face values of the
+  //      NEXT variable are requested before this one is worked on ---------------------------------------------------------------------
+  double fmine[6], fother[6];
+  auto loadFaceValues = [&](int v) {
 #pragma unroll
+    for (int f = 0; f < 6; f++) {
+      fmine[f] = __ldg(gTU + (f * 5 + v) * 16);
+      fother[f] = nbr[f] >= 0 ? __ldg(A.TUin + (size_t)nbr[f] + v * 16) : A.TUb[(size_t)(-1 - nbr[f]) + v * 16];
+    }
+  };
+  loadFaceValues(0);
+#pragma unroll 1
   for (int v = 0; v < 5; v++) {
     double aZ[2][2][3];   // zeta faces (this thread's own line): [side][vol / tot][c] = a n[c]
+    double cmine[6], cother[6], uv[4];
+#pragma unroll
+    for (int f = 0; f < 6; f++) { cmine[f] = fmine[f]; cother[f] = fother[f]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) uv[k] = un[k];
+    if (v + 1 < 5) {
+      loadFaceValues(v + 1);
+      const double2 a = ldg2(gU + (v + 1) * 64), b2 = ldg2(gU + (v + 1) * 64 + 2);
+      un[0] = a.x; un[1] = a.y; un[2] = b2.x; un[3] = b2.y;
+    }
 #pragma unroll
     for (int f = 0; f < 6; f++) {
       const bool amR = (amRightBits >> f) & 1;
-      const double mine = gTU[(f * 5 + v) * 16];
-      const double other = nbr[f] >= 0 ? A.TUin[(size_t)nbr[f] + v * 16] : A.TUb[(size_t)(-1 - nbr[f]) + v * 16];
+      const double mine = cmine[f];
+      const double other = cother[f];
       const double avg = 0.5 * (mine + other), jmp = 0.5 * (amR ? mine - other : other - mine);   // ViscousFlux.cpp:33-56
       const double aV = (amR ? -avg : avg) * jw[f], aT = aV + jmp * jw[f];                        // SpatialDiscrete.cpp:885-906
       constexpr int dnTab[6] = {2, 1, 0, 0, 1, 2};
@@ -266,7 +364,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
       double* sX = sGv + (el * 15 + 3 * v) * 64;   // tile of a field that has not been written yet
       double uw[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) uw[k] = u[v][k] * (wij * A.w1[k]);
+      for (int k = 0; k < 4; k++) uw[k] = uv[k] * (wij * A.w1[k]);
       sts2(sX + sw, uw[0], uw[1]); sts2(sX + sw + 2, uw[2], uw[3]);
       __syncwarp(wm);
       double tx[4] = {0, 0, 0, 0}, ty[4] = {0, 0, 0, 0}, tz[4];
@@ -298,9 +396,9 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
         const double* ge = A.geoE + (size_t)e * 9 * 64 + t * 4 + k;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          sX[(0 + c) * 64 + sw + k] = __ldg(ge + (0 + c) * 64) * u[v][k];
-          sX[(3 + c) * 64 + sw + k] = __ldg(ge + (3 + c) * 64) * u[v][k];
-          mz[c][k] = __ldg(ge + (6 + c) * 64) * u[v][k];
+          sX[(0 + c) * 64 + sw + k] = __ldg(ge + (0 + c) * 64) * uv[k];
+          sX[(3 + c) * 64 + sw + k] = __ldg(ge + (3 + c) * 64) * uv[k];
+          mz[c][k] = __ldg(ge + (6 + c) * 64) * uv[k];
         }
       }
       __syncwarp(wm);
@@ -366,31 +464,37 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
   __syncwarp(wm);
 
   // ---- this side's viscous normal flux at the own face points: trace_f(G_vol) + BR2 lift of face f (VariableConvertor.cpp:674-688) ----
-#pragma unroll
+#pragma unroll 1
   for (int d = 0; d < 3; d++) {
+    int off[4];   // tile offsets of the four nodes of the normal line through this thread's point (natural index t) of the direction's faces
+#pragma unroll
+    for (int a = 0; a < 4; a++) off[a] = d == 2 ? sw + a : d == 0 ? a * 16 + (((i + a) & 3) << 2) + j : i * 16 + (((a + i) & 3) << 2) + j;
     double gm[15], gp[15];
 #pragma unroll
     for (int fld = 0; fld < 15; fld++) {
       const double* tile = sGv + (el * 15 + fld) * 64;
-      double x[4];
-      if (d == 2) { const double2 a = lds2(tile + sw), b = lds2(tile + sw + 2); x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; }
-      else {
-#pragma unroll
-        for (int a = 0; a < 4; a++) x[a] = d == 0 ? tile[a * 16 + (((i + a) & 3) << 2) + j] : tile[i * 16 + (((a + i) & 3) << 2) + j];
-      }
-      gm[fld] = A.lend[0] * x[0] + A.lend[1] * x[1] + A.lend[2] * x[2] + A.lend[3] * x[3];
-      gp[fld] = A.lend[4] * x[0] + A.lend[5] * x[1] + A.lend[6] * x[2] + A.lend[7] * x[3];
+      double x0, x1, x2, x3;
+      if (d == 2) { const double2 a = lds2(tile + sw), b = lds2(tile + sw + 2); x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y; }   // own line: 16-byte accesses (8-byte ones are 8-way bank conflicted)
+      else { x0 = tile[off[0]]; x1 = tile[off[1]]; x2 = tile[off[2]]; x3 = tile[off[3]]; }
+      gm[fld] = A.lend[0] * x0 + A.lend[1] * x1 + A.lend[2] * x2 + A.lend[3] * x3;
+      gp[fld] = A.lend[4] * x0 + A.lend[5] * x1 + A.lend[6] * x2 + A.lend[7] * x3;
     }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
-      const int f = hexFaceOfAxis(d, side);
+      const int f = hexFaceRt(d, side);
       double* g = side ? gp : gm;
       const int4 lk = sLink[el * 6 + f];
       const int z = lk.z;
-      const bool amR = (amRightBits >> f) & 1;
+      const bool amR = linkAmRight(z);
       const int jL = A.ltab->jLeft[((f * 4 + linkRot(z)) * 2 + (amR ? 1 : 0)) * 16 + t];
-      double n[3];
-      normalAt(f, jL, n);
+      double n[3], jwf;
+      if constexpr (AFFINE) {
+        const double* lg = sLg + (el * 6 + f) * kLG;
+        n[0] = lg[0]; n[1] = lg[1]; n[2] = lg[2]; jwf = lg[3] * wij;
+      } else {
+        const double* gf = A.geoF + (size_t)lk.y * 4 * 16 + jL;
+        n[0] = __ldg(gf); n[1] = __ldg(gf + 16); n[2] = __ldg(gf + 32); jwf = __ldg(gf + 48);
+      }
       double lam = 0.0;   // trace at the own point of the rank-one lift of this face:  Σ_a l_a(±1)^2 / (detJ w)(node a of the normal line)
       if (!br1) {
         if constexpr (AFFINE) lam = A.cLift * invDet / wij;
@@ -402,45 +506,30 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
           }
         }
       }
-      double cm[5], comp[6], va[5];
+      double cm[5], va[5];
 #pragma unroll
-      for (int v = 0; v < 5; v++) cm[v] = gTU[(f * 5 + v) * 16];
-      compFromCons<3>(ph, cm, comp);
+      for (int v = 0; v < 5; v++) cm[v] = __ldg(gTU + (f * 5 + v) * 16);
       if (lk.x >= 0) {
+        const size_t rowO = ((size_t)lk.x * 6 + linkLfo(z)) * kRow + A.ltab->partner[(((f * 6 + linkLfo(z)) * 4 + linkRot(z)) * 2 + (amR ? 1 : 0)) * 16 + t];
+        double comp[6];
+        compFromCons<3>(ph, cm, comp);
 #pragma unroll
         for (int v = 0; v < 5; v++) {
-          const double other = A.TUin[(size_t)nbr[f] + v * 16];
-          const double jl = 0.5 * (amR ? cm[v] - other : other - cm[v]) * jw[f] * lam;
+          const double other = __ldg(A.TUin + rowO + v * 16);
+          const double jl = 0.5 * (amR ? cm[v] - other : other - cm[v]) * jwf * lam;
 #pragma unroll
           for (int c = 0; c < 3; c++) g[v * 3 + c] += jl * n[c];
         }
         ownViscousNormalFlux(ph, n, cm, comp, g, va);
       } else {
-        // boundary face (SpatialDiscrete.cpp:750-842): the complete averaged viscous flux of the face is this side's entry
-        const int bc = linkBc(z);
-        double compR[6], b[6], volCons[5], intCons[5], pL[15], gb[15], vb[5];
+        Vals5 c5; Vals15 g15;
 #pragma unroll
-        for (int k = 0; k < 6; k++) compR[k] = A.dummy[((size_t)(lk.y - A.nInt) * 6 + k) * 16 + jL];
-        bcBoundaryGradientVariable<3>(ph, bc, n, cm, comp, compR, volCons, intCons);
+        for (int v = 0; v < 5; v++) c5.v[v] = cm[v];
 #pragma unroll
-        for (int v = 0; v < 5; v++) {
-          const double jl = intCons[v] * jw[f] * lam;
+        for (int k = 0; k < 15; k++) g15.v[k] = g[k];
+        const Vals5 r = nslBoundaryViscousFlux(A.phys, linkBc(z), n[0], n[1], n[2], jwf * lam, c5, g15, A.dummy + (size_t)(lk.y - A.nInt) * 6 * 16 + jL);
 #pragma unroll
-          for (int c = 0; c < 3; c++) g[v * 3 + c] += jl * n[c];
-        }
-        primGradFromConsGrad<3>(ph, cm, comp, g, pL);             // from the UNMODIFIED interior trace (:792-796)
-        bcBoundaryVariable<3>(ph, bc, n, comp, compR, b);
-        if (bcIsWall(bc)) {                                       // modifyBoundaryVariable, BoundaryCondition.cpp:443-452,490-501,535-546
-#pragma unroll
-          for (int k = 0; k < 6; k++) comp[k] = b[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 15; k++) gb[k] = pL[k];
-        if (bc == kAdiabaticSlipWall || bc == kAdiabaticNonSlipWall) { gb[12] = 0.0; gb[13] = 0.0; gb[14] = 0.0; }
-        viscNormalFlux<3>(ph, n, comp, pL, va);
-        viscNormalFlux<3>(ph, n, b, gb, vb);
-#pragma unroll
-        for (int v = 0; v < 5; v++) va[v] = 0.5 * (va[v] + vb[v]);
+        for (int v = 0; v < 5; v++) va[v] = r.v[v];
       }
       double* out = A.TVout + ((size_t)e * 6 + f) * kRow + t;
 #pragma unroll
@@ -466,8 +555,11 @@ struct NslStageLayout {
 #ifndef SDG_NSL_MINB
 #define SDG_NSL_MINB 3
 #endif
+#ifndef SDG_NSL_MINB_EULER
+#define SDG_NSL_MINB_EULER 3
+#endif
 template <bool AFFINE, int PH, bool VISC>
-__global__ void __launch_bounds__(128, SDG_NSL_MINB) nslStageKernel(const __grid_constant__ StageArgs A) {
+__global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER) nslStageKernel(const __grid_constant__ StageArgs A) {
   using L = NslStageLayout;
   constexpr int K = kLK;
   extern __shared__ __align__(16) double smem[];
@@ -496,84 +588,102 @@ __global__ void __launch_bounds__(128, SDG_NSL_MINB) nslStageKernel(const __grid
       bulkLoad(sLg, A.lfGeo + (size_t)e0 * 6 * kLG, (unsigned)(ne * 6 * kLG * sizeof(double)), &mbar);
     }
   }
-  if (needLast) {   // U_last is consumed at the very end: pull its lines into L2 now
-    const char* p = reinterpret_cast<const char*>(A.Ulast + (size_t)e0 * 5 * 64);
-    const int bytes = ne * 5 * 64 * (int)sizeof(double);
-    for (int o = tid * 128; o < bytes; o += 128 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+  if (tid == 32) {
+    // DRAM -> L2 one wave of thread blocks AHEAD (see nslGradKernel): everything a block reads from its own contiguous ranges
+    for (int b = (int)blockIdx.x < A.ahead ? (int)blockIdx.x : (int)blockIdx.x + A.ahead; b < (int)gridDim.x && b <= (int)blockIdx.x + A.ahead; b += A.ahead) {
+      const int c2 = A.chunkList ? A.chunkList[b] : b;
+      const int f0 = c2 * K, n2 = min(K, A.nOwned - f0);
+      bulkPrefetchL2(A.TUin + (size_t)f0 * 6 * kRow, (unsigned)(n2 * 6 * kRow * sizeof(double)));
+      if constexpr (VISC) bulkPrefetchL2(A.TVin + (size_t)f0 * 6 * kRow, (unsigned)(n2 * 6 * kRow * sizeof(double)));
+      bulkPrefetchL2(A.Uin + (size_t)f0 * 5 * 64, (unsigned)(n2 * 5 * 64 * sizeof(double)));
+      if constexpr (VISC) bulkPrefetchL2(A.Gvol + (size_t)f0 * 15 * 64, (unsigned)(n2 * 15 * 64 * sizeof(double)));
+      if (needLast) bulkPrefetchL2(A.Ulast + (size_t)f0 * 5 * 64, (unsigned)(n2 * 5 * 64 * sizeof(double)));
+    }
   }
   const unsigned wm = __ballot_sync(0xffffffffu, active);
   if (!active) return;
   const int e = e0 + el;
   const double wij = A.w1[i] * A.w1[j];
   mbarWait(&mbar, 0);
+  for (int c = t; c < (VISC ? 60 : 30); c += 16) {   // the partners' rows: one 128-byte line per (face, field)
+    const int f = c / (VISC ? 10 : 5), r = c - f * (VISC ? 10 : 5);
+    const int4 lk = sLink[el * 6 + f];
+    if (lk.x >= 0) {
+      const size_t row = ((size_t)lk.x * 6 + linkLfo(lk.z)) * kRow;
+      prefetchL2(r < 5 ? A.TUin + row + r * 16 : A.TVin + row + (r - 5) * 16);
+    }
+  }
 
-  // ---- R2: Riemann flux minus the average of the two sides' viscous normal fluxes, at this thread's point of every face it handles ----
+  // ---- R2: Riemann flux minus the average of the two sides' viscous normal fluxes, at this thread's point of ALL six faces of its element.
+  //      A face inside the block is evaluated by both of its parents (same inputs in the same left / right roles, hence bit-identical
+  //      values): no slot of another element is ever written, so the phases of an element only need __syncwarp, and the loads of the two
+  //      faces of a direction are requested together before either Riemann solve starts. ------------------------------------------------
   const double* gTU = A.TUin + (size_t)e * 6 * kRow + t;
   const double* gTV = A.TVin + (size_t)e * 6 * kRow + t;
 #pragma unroll 1
-  for (int f = 0; f < 6; f++) {
-    const int4 lk = sLink[el * 6 + f];
-    const int z = lk.z;
-    if (!linkHandles(z)) continue;
-    const int lfo = linkLfo(z), rot = linkRot(z);
-    const bool amR = linkAmRight(z);
-    const int jL = A.ltab->jLeft[((f * 4 + rot) * 2 + (amR ? 1 : 0)) * 16 + t];
-    double n[3], jw;
-    if constexpr (AFFINE) {
-      const double* g = sLg + (el * 6 + f) * kLG;
-      n[0] = g[0]; n[1] = g[1]; n[2] = g[2]; jw = g[3] * wij;
-    } else {
-      const double* g = A.geoF + (size_t)lk.y * 4 * 16 + jL;
-      n[0] = __ldg(g); n[1] = __ldg(g + 16); n[2] = __ldg(g + 32); jw = __ldg(g + 48);
+  for (int d = 0; d < 3; d++) {
+    int4 lk[2];
+    int jL[2];
+    size_t rowO[2];
+    double cm[2][5], tm[2][5], co[2][5], to[2][5];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int f = hexFaceRt(d, side);
+      lk[side] = sLink[el * 6 + f];
+      const int z = lk[side].z, lfo = linkLfo(z), rot = linkRot(z), amR = linkAmRight(z) ? 1 : 0;
+      jL[side] = A.ltab->jLeft[((f * 4 + rot) * 2 + amR) * 16 + t];
+      // boundary face: the partner loads fall back on the own row (valid memory, values unused) so that no load sits behind a branch
+      rowO[side] = lk[side].x >= 0 ? ((size_t)lk[side].x * 6 + lfo) * kRow + A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + amR) * 16 + t]
+                                   : ((size_t)e * 6 + f) * kRow + t;
     }
-    double cm[5], tm[5], Fn[5];
 #pragma unroll
-    for (int v = 0; v < 5; v++) cm[v] = gTU[(f * 5 + v) * 16];
-    if constexpr (VISC) {
+    for (int side = 0; side < 2; side++) {
+      const int f = hexFaceRt(d, side);
 #pragma unroll
-      for (int v = 0; v < 5; v++) tm[v] = gTV[(f * 5 + v) * 16];
-    }
-    double* mine = sFl + ((el * 6 + f) * 5) * 16 + t;
-    if (lk.x < 0) {
-      // boundary face: normal flux of the BC-constructed state, no Riemann solve (SpatialDiscrete.cpp:797-803)
-      double compL[6], compR[6], b[6];
-      compFromCons<3>(ph, cm, compL);
-#pragma unroll
-      for (int k = 0; k < 6; k++) compR[k] = A.dummy[((size_t)(lk.y - A.nInt) * 6 + k) * 16 + jL];
-      bcBoundaryVariable<3>(ph, linkBc(z), n, compL, compR, b);
-      convNormalFlux<3>(ph, n, b, Fn);
-#pragma unroll
-      for (int v = 0; v < 5; v++) mine[v * 16] = (VISC ? Fn[v] - tm[v] : Fn[v]) * jw;
-    } else {
-      const int natO = A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + (amR ? 1 : 0)) * 16 + t];
-      const size_t rowO = ((size_t)lk.x * 6 + lfo) * kRow + natO;
-      double co[5], to[5];
-#pragma unroll
-      for (int v = 0; v < 5; v++) co[v] = A.TUin[rowO + v * 16];
+      for (int v = 0; v < 5; v++) { cm[side][v] = __ldg(gTU + (f * 5 + v) * 16); co[side][v] = __ldg(A.TUin + rowO[side] + v * 16); }
       if constexpr (VISC) {
 #pragma unroll
-        for (int v = 0; v < 5; v++) to[v] = A.TVin[rowO + v * 16];
+        for (int v = 0; v < 5; v++) { tm[side][v] = __ldg(gTV + (f * 5 + v) * 16); to[side][v] = __ldg(A.TVin + rowO[side] + v * 16); }
       }
-      double consL[5], consR[5], compL[6], compR[6];
+    }
 #pragma unroll
-      for (int v = 0; v < 5; v++) { consL[v] = amR ? co[v] : cm[v]; consR[v] = amR ? cm[v] : co[v]; }
-      const double irL = compFromCons<3>(ph, consL, compL), irR = compFromCons<3>(ph, consR, compR);
-      convFlux<3>(ph, n, consL, compL, irL, consR, compR, irR, Fn);
-      if constexpr (VISC) {
-#pragma unroll
-        for (int v = 0; v < 5; v++) Fn[v] -= 0.5 * (tm[v] + to[v]);   // calculateViscousFlux, ViscousFlux.cpp:139-153
+    for (int side = 0; side < 2; side++) {
+      const int f = hexFaceRt(d, side);
+      const int z = lk[side].z;
+      const bool amR = linkAmRight(z);
+      double n[3], jw, Fn[5];
+      if constexpr (AFFINE) {
+        const double* g = sLg + (el * 6 + f) * kLG;
+        n[0] = g[0]; n[1] = g[1]; n[2] = g[2]; jw = g[3] * wij;
+      } else {
+        const double* g = A.geoF + (size_t)lk[side].y * 4 * 16 + jL[side];
+        n[0] = __ldg(g); n[1] = __ldg(g + 16); n[2] = __ldg(g + 32); jw = __ldg(g + 48);
       }
-      const double sg = amR ? -jw : jw;
+      double* mine = sFl + ((el * 6 + f) * 5) * 16 + t;
+      if (lk[side].x < 0) {
+        Vals5 c5, t5;
 #pragma unroll
-      for (int v = 0; v < 5; v++) mine[v * 16] = Fn[v] * sg;
-      if (linkInChunk(z)) {   // both parents in this block: the left one evaluates, the right one's slot gets the negative (SpatialDiscrete.cpp:738-744)
-        double* other = sFl + (((lk.x - e0) * 6 + lfo) * 5) * 16 + natO;
+        for (int v = 0; v < 5; v++) { c5.v[v] = cm[side][v]; t5.v[v] = VISC ? tm[side][v] : 0.0; }
+        const Vals5 r = nslBoundaryFaceFlux<PH, VISC>(A.phys, linkBc(z), n[0], n[1], n[2], c5, t5, A.dummy + (size_t)(lk[side].y - A.nInt) * 6 * 16 + jL[side]);
 #pragma unroll
-        for (int v = 0; v < 5; v++) other[v * 16] = -Fn[v] * jw;
+        for (int v = 0; v < 5; v++) mine[v * 16] = r.v[v] * jw;
+      } else {
+        double consL[5], consR[5], compL[6], compR[6];
+#pragma unroll
+        for (int v = 0; v < 5; v++) { consL[v] = amR ? co[side][v] : cm[side][v]; consR[v] = amR ? cm[side][v] : co[side][v]; }
+        const double irL = compFromCons<3>(ph, consL, compL), irR = compFromCons<3>(ph, consR, compR);
+        convFlux<3>(ph, n, consL, compL, irL, consR, compR, irR, Fn);
+        if constexpr (VISC) {
+#pragma unroll
+          for (int v = 0; v < 5; v++) Fn[v] -= 0.5 * (tm[side][v] + to[side][v]);   // calculateViscousFlux, ViscousFlux.cpp:139-153
+        }
+        const double sg = amR ? -jw : jw;   // left parent +, right parent - (SpatialDiscrete.cpp:738-744)
+#pragma unroll
+        for (int v = 0; v < 5; v++) mine[v * 16] = Fn[v] * sg;
       }
     }
   }
-  __syncthreads();
+  __syncwarp(wm);
 
   // ---- R1 + R3 volume part: fluxes at the own nodes, two nodes per round; zeta contraction in registers, xi / eta through half tiles ----
   double u[5][4];

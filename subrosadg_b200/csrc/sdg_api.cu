@@ -92,6 +92,8 @@ void fillArgs(sdg_ctx* c, StageArgs& a) {
   if (c->lineTrace) {
     a.TVin = c->TV.p; a.TVout = c->TV.p; a.TUb = c->TUb.p;
     a.links = reinterpret_cast<const int4*>(c->links.p); a.lfGeo = c->lfGeo.p; a.ltab = c->ltab.p; a.cLift = c->cLift;
+    static const int ahead = std::max(1, getenv("SDG_AHEAD") ? atoi(getenv("SDG_AHEAD")) : 1 << 30);   // default: every block fetches its OWN ranges; fetching one wave ahead (444, 148) measured slower: 1.90 / 1.66 vs 1.42 ms per residual pass at 64^3 (L2 churn)
+    a.ahead = ahead;
   }
 }
 

@@ -77,6 +77,7 @@ struct StageArgs {
   const double* lfGeo;                 // affine: [nOwned][6][4] = face normal, |J| scale
   const LineTabDev* ltab;
   double w1[kMaxN];                    // 1-D Gauss weights
+  int ahead;                           // thread blocks per wave: how far ahead a block prefetches the contiguous ranges of a later block into L2
   double cLift;                        // sum_a l_a(-1)^2 / w_a: BR2 lift trace factor of a face point, without 1 / (detJ w_face)
 };
 
