@@ -166,6 +166,14 @@ int sdg_debug_plan(sdg_ctx* ctx, int32_t what, double* out_d, int32_t* out_i, in
 /* counters: number of kernels this library launched since creation (bench.py's gpu_launches) */
 int64_t sdg_launch_count(sdg_ctx* ctx);
 
+/* Parity hook: the pointwise device functions (conserved -> computational variables, the five Riemann fluxes of
+ * src/Solver/ConvectiveFlux.cpp, the six BoundaryConditionImpl of BoundaryCondition.cpp:79-547 with their gradient states and
+ * modifyBoundaryVariable, VariableGradient::calculatePrimitiveFromConserved, ViscousFlux.cpp:59-124, SourceTerm.cpp:29-58) evaluated on
+ * caller-supplied points.  cfg = {dim, model, eos, transport, conv_flux, source} (Enum.cpp values), params = {cp, cv, mu, c0, rho0, beta,
+ * t_ref}; `what` and the row layouts are those of tests/golden/reference_physics.json, which was generated from the reference's own
+ * sources (oracle/ref_physics.cpp).  Needs a CUDA device. */
+int sdg_debug_physics(const int32_t* cfg, const double* params, int32_t what, int32_t bc, int32_t n, const double* in, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,10 +6,16 @@
 // (four gradient sweeps that also run for Euler, TimeIntegration.cpp:339-348), face -> element scatter.  OpenMP
 // `parallel for` replaces tbb::parallel_for over the same ranges.  It doubles as the timed CPU baseline of bench.py.
 //
-// PARITY UNPINNED w.r.t. the reference binary: the reference cannot be built here (icpx/SYCL, oneTBB, Eigen, Gmsh
-// 4.13.1 SDK, magic_enum, dbg-macro, zstd are absent; g++ rejects VariableConvertor.cpp:228) and ships no tests or
-// golden vectors.  What pins this file: the reference's embedded integer tables (tests/golden/), exactness
-// properties of the tables, free-stream preservation, and the exact travelling-wave solution of the periodic cases.
+// PARITY, what is pinned and what is not.  The whole reference cannot be built here (icpx/SYCL, oneTBB, Eigen, Gmsh 4.13.1 SDK,
+// magic_enum, dbg-macro, zstd are absent) and it ships no tests or golden vectors.  PINNED AGAINST THE REFERENCE'S OWN CODE: the
+// pointwise physics (physics.hpp: variable conversions, the five Riemann fluxes, the six boundary conditions with their gradient states
+// and modifyBoundaryVariable, primitive gradients, viscous fluxes, Sutherland, Boussinesq) — `make ref` compiles the reference's
+// src/Solver/{VariableConvertor,ConvectiveFlux,ViscousFlux,BoundaryCondition,PhysicalModel,SourceTerm}.cpp where they lie (ref_physics.cpp
+// + the stand-in headers of ref_shim/), tests/golden/reference_physics.json holds their outputs and tests/test_reference_physics.py checks
+// orc_physics against every vector to 1e-13; and the integer tables embedded in the reference (tests/golden/reference_tables.json).
+// STILL UNPINNED w.r.t. a reference binary: the assembly around the physics (sweeps, face scatter, RK update) and the Gmsh-provided
+// tables (quadrature, H1Legendre basis, Jacobians) — pinned only by exactness properties, free-stream preservation, the exact
+// travelling-wave solution and the analytic viscous decay (tests/test_oracle_*.py).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
 #include <omp.h>
@@ -924,6 +930,75 @@ int orc_get_gradient_at_quadrature(void* h, int type, double* out) {
     gemmNT(s.G, s.Nq, s.Nb, 1.0, &C[(size_t)e * s.G * s.Nb], s.G, B.tab.Phi.data(), s.Nq, 0.0, &out[(size_t)e * s.Nq * s.G], s.G);
   ORC_CATCH
 }
+// Pointwise physics of the oracle behind the SAME entry point as oracle/ref_physics.cpp (the reference's own functions): what = 0 Riemann
+// flux, 1 boundary face point, 2 viscous terms, 3 conversions / raw flux / source.  cfg = {dim, model, eos, transport, conv_flux, source},
+// params = {cp, cv, mu, c0, rho0, beta, t_ref}; input / output layouts as documented there.  Pins the restatement against
+// tests/golden/reference_physics.json.
+int orc_physics(const int32_t* cfg, const double* params, int what, int bc, int n, const double* in, double* out) {
+  ORC_TRY
+  Phys P;
+  P.D = cfg[0]; P.Nv = cfg[0] + 2; P.model = cfg[1]; P.eos = cfg[2]; P.transport = cfg[3]; P.conv = cfg[4]; P.source = cfg[5];
+  P.visc = P.ns() ? kBR2 : kViscNone;
+  P.cp = params[0]; P.cv = params[1]; P.mu0 = params[2]; P.k0 = params[0] * params[2] / 0.71;
+  P.c0 = params[3]; P.rho0 = params[4]; P.padd = 0.01 * params[4] * params[3] * params[3]; P.beta = params[5]; P.Tref = params[6];
+  const int D = P.D, Nv = P.Nv, NC = D + 3, G = Nv * D;
+  for (int i = 0; i < n; i++) {
+    if (what == 0) {
+      const double* a = in + (size_t)i * (D + 2 * Nv);
+      Var L, R;
+      for (int k = 0; k < Nv; k++) { L.cons[k] = a[D + k]; R.cons[k] = a[D + Nv + k]; }
+      compFromCons(P, L); compFromCons(P, R);
+      convFlux(P, a, L, R, out + (size_t)i * Nv);
+    } else if (what == 1) {
+      const int ni = D + 2 * Nv + G, no = NC + 3 * Nv + (P.ns() ? NC + Nv : 0);
+      const double* a = in + (size_t)i * ni; double* o = out + (size_t)i * no;
+      Var L, dummy, b;
+      for (int k = 0; k < Nv; k++) { L.cons[k] = a[D + k]; dummy.prim[k] = a[D + Nv + k]; }
+      compFromCons(P, L);
+      consFromPrim(P, dummy); compFromPrim(P, dummy);
+      bcBoundaryVariable(P, bc, a, L, dummy, b.comp);
+      bcBoundaryGradientVariable(P, bc, a, L, dummy, o + NC, o + NC + Nv);
+      for (int k = 0; k < NC; k++) o[k] = b.comp[k];
+      convNormalFlux(P, a, b.comp, o + NC + 2 * Nv);
+      if (P.ns()) {
+        double pL[kMaxD * kMaxV], gb[kMaxD * kMaxV], va[kMaxV], vb[kMaxV];
+        primGradFromConsGrad(P, L, a + D + 2 * Nv, pL);
+        if (bcIsWall(bc)) for (int k = 0; k < NC; k++) L.comp[k] = b.comp[k];
+        for (int k = 0; k < G; k++) gb[k] = pL[k];
+        if (bc == kAdiabaticSlipWall || bc == kAdiabaticNonSlipWall) for (int d = 0; d < D; d++) gb[(D + 1) * D + d] = 0.0;
+        viscNormalFlux(P, a, L.comp, pL, va);
+        viscNormalFlux(P, a, b.comp, gb, vb);
+        for (int k = 0; k < NC; k++) o[NC + 3 * Nv + k] = L.comp[k];
+        for (int k = 0; k < Nv; k++) o[2 * NC + 3 * Nv + k] = (va[k] + vb[k]) / 2.0;
+      }
+    } else if (what == 2) {
+      if (!P.ns()) throw std::runtime_error("viscous terms need a Navier-Stokes model");
+      const int ni = D + Nv + G, no = 2 * G + Nv;
+      const double* a = in + (size_t)i * ni; double* o = out + (size_t)i * no;
+      Var V;
+      for (int k = 0; k < Nv; k++) V.cons[k] = a[D + k];
+      compFromCons(P, V);
+      primGradFromConsGrad(P, V, a + D + Nv, o);
+      viscRawFlux(P, V.comp, o, o + G);
+      viscNormalFlux(P, a, V.comp, o, o + 2 * G);
+    } else if (what == 3) {
+      const int no = NC + Nv + G + Nv;
+      double* o = out + (size_t)i * no;
+      Var V;
+      for (int k = 0; k < Nv; k++) V.cons[k] = in[(size_t)i * Nv + k];
+      compFromCons(P, V);
+      for (int k = 0; k < NC; k++) o[k] = V.comp[k];
+      o[NC] = V.comp[0]; for (int d = 0; d < D; d++) o[NC + 1 + d] = V.comp[1 + d]; o[NC + D + 1] = P.TFromE(V.comp[D + 1]);   // VariableConvertor.cpp:383-421
+      convRawFlux(P, V.comp, o + NC + Nv);
+      for (int k = 0; k < Nv; k++) o[NC + Nv + G + k] = 0.0;
+      if (P.source != kSourceNone) sourceTerm(P, V.comp, o + NC + Nv + G);
+    } else {
+      throw std::runtime_error("orc_physics: bad selector");
+    }
+  }
+  ORC_CATCH
+}
+
 int orc_set_threads(int n) { omp_set_num_threads(n); return 0; }
 int orc_max_threads() { return omp_get_max_threads(); }
 

@@ -1,7 +1,9 @@
 // stand-in for oneTBB: the declarations the reference's headers name; the golden-vector driver never runs a parallel loop.
 // TEST INFRASTRUCTURE ONLY.
 #pragma once
+#include <algorithm>
 #include <functional>
+#include <ranges>
 namespace tbb {
 template <typename T> struct blocked_range {
   T b_, e_;

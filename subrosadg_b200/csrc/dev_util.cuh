@@ -26,6 +26,8 @@ inline bool firstUseOnThisDevice(std::atomic<unsigned long long>& mask) {
   return true;
 }
 
+void setLastError(const char* msg);   // sdg_api.cu: message returned by sdg_last_error()
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr; size_t n = 0;

@@ -26,6 +26,8 @@ thread_local std::string g_err;
 
 }  // namespace
 
+namespace sdg { void setLastError(const char* msg) { g_err = msg; } }   // for the other translation units behind sdg_last_error()
+
 struct sdg_ctx {
   sdg_config cfg{};
   PhysParams phys{};
