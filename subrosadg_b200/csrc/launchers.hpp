@@ -18,6 +18,6 @@ void pickNsFn(int D, int N, bool affine, int ph, StageFn& grad, StageFn& stage, 
 // same residual pass without viscous terms, i.e. an Euler stage through published traces)
 using BoundaryFn = void (*)(const StageArgs&, const int4* bndRec, int nBnd, cudaStream_t);
 struct LineFns { StageFn trace = nullptr, grad = nullptr, stage = nullptr; BoundaryFn boundary = nullptr; };
-void pickNslFns(bool affine, int ph, bool visc, LineFns& out, int& K);
+void pickNslFns(bool affine, int ph, bool visc, bool gather, LineFns& out, int& K);   // gather (inviscid): no published traces, partners interpolated from their nodal states
 
 }  // namespace sdg

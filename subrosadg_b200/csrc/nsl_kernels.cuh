@@ -44,9 +44,11 @@ struct LineTabDev {
   unsigned char jLeft[6 * 4 * 2 * 16];         // [((f*4+rot)*2+amRight)*16 + t]: point index (reference order) at the LEFT parent = column of geoF / dummy
 };
 
-// swizzled tile of one field of one element: node (i, j, k) at i*16 + ((j+i)&3)*4 + k — lines along xi, eta and zeta are all
-// read without bank conflicts, no padding
-__device__ __forceinline__ int swz(int i, int j) { return i * 16 + (((j + i) & 3) << 2); }
+// swizzled tile of one field of one element: node (i, j, k) at i*16 + ((j+i)&3)*4 + (k ^ 2(i&1)) — lines along xi and eta are read
+// with 8-byte accesses, the own zeta line is written / read as two 16-byte pairs, all without bank conflicts and without padding
+// (the pair swap by the parity of i separates the lines (0, j) and (1, j), which a quarter warp of 16-byte accesses covers together)
+__device__ __forceinline__ int tIdx(int i, int j, int k) { return i * 16 + (((j + i) & 3) << 2) + (k ^ ((i & 1) << 1)); }
+__device__ __forceinline__ int tPair(int i, int j, int p) { return i * 16 + (((j + i) & 3) << 2) + ((p ^ (i & 1)) << 1); }
 // DRAM -> L2 ahead of use: the ranges a block owns are contiguous (bulk prefetch by one thread), the partners' rows are 128-byte lines
 __device__ __forceinline__ void bulkPrefetchL2(const void* p, unsigned bytes) {
   if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -69,17 +71,17 @@ __device__ __forceinline__ void lineTracesOut(const StageArgs& A, const double (
       gT[(f * 5 + v) * 16 + t] = x;
     }
   }
-  const int sw = swz(i, j);
+  const int p0 = tPair(i, j, 0), p1 = tPair(i, j, 1);
 #pragma unroll
-  for (int v = 0; v < 5; v++) { sts2(sXe + v * 64 + sw, u[v][0], u[v][1]); sts2(sXe + v * 64 + sw + 2, u[v][2], u[v][3]); }
+  for (int v = 0; v < 5; v++) { sts2(sXe + v * 64 + p0, u[v][0], u[v][1]); sts2(sXe + v * 64 + p1, u[v][2], u[v][3]); }
   __syncwarp(wm);
 #pragma unroll
   for (int v = 0; v < 5; v++) {
     double xm = 0.0, xp = 0.0, ym = 0.0, yp = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; a++) {
-      const double x = sXe[v * 64 + a * 16 + (((i + a) & 3) << 2) + j];   // xi-normal faces: point (j', k') = (i, j), nodes (a, i, j)
-      const double y = sXe[v * 64 + i * 16 + (((a + i) & 3) << 2) + j];   // eta-normal faces: point (i', k') = (i, j), nodes (i, a, j)
+      const double x = sXe[v * 64 + tIdx(a, i, j)];   // xi-normal faces: point (j', k') = (i, j), nodes (a, i, j)
+      const double y = sXe[v * 64 + tIdx(i, a, j)];   // eta-normal faces: point (i', k') = (i, j), nodes (i, a, j)
       xm += A.lend[a] * x; xp += A.lend[4 + a] * x;
       ym += A.lend[a] * y; yp += A.lend[4 + a] * y;
     }
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
   const unsigned wm = __ballot_sync(0xffffffffu, active);
   if (!active) return;
   const int e = e0 + el;
-  const int sw = swz(i, j);
+  const int p0 = tPair(i, j, 0), p1 = tPair(i, j, 1);
   const double* gU = A.Uin + (size_t)e * 5 * 64 + t * 4;
   double un[4];   // the line of the NEXT variable (requested one iteration ahead)
   { const double2 a = ldg2(gU), b = ldg2(gU + 2); un[0] = a.x; un[1] = a.y; un[2] = b.x; un[3] = b.y; }
@@ -365,14 +367,14 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
       double uw[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) uw[k] = uv[k] * (wij * A.w1[k]);
-      sts2(sX + sw, uw[0], uw[1]); sts2(sX + sw + 2, uw[2], uw[3]);
+      sts2(sX + p0, uw[0], uw[1]); sts2(sX + p1, uw[2], uw[3]);
       __syncwarp(wm);
       double tx[4] = {0, 0, 0, 0}, ty[4] = {0, 0, 0, 0}, tz[4];
 #pragma unroll
       for (int a = 0; a < 4; a++) {
         const double dx = A.dm[a * 4 + i], dy = A.dm[a * 4 + j];
-        const double2 x0 = lds2(sX + a * 16 + (((j + a) & 3) << 2)), x1 = lds2(sX + a * 16 + (((j + a) & 3) << 2) + 2);
-        const double2 y0 = lds2(sX + i * 16 + (((a + i) & 3) << 2)), y1 = lds2(sX + i * 16 + (((a + i) & 3) << 2) + 2);
+        const double2 x0 = lds2(sX + tPair(a, j, 0)), x1 = lds2(sX + tPair(a, j, 1));
+        const double2 y0 = lds2(sX + tPair(i, a, 0)), y1 = lds2(sX + tPair(i, a, 1));
         tx[0] += dx * x0.x; tx[1] += dx * x0.y; tx[2] += dx * x1.x; tx[3] += dx * x1.y;
         ty[0] += dy * y0.x; ty[1] += dy * y0.y; ty[2] += dy * y1.x; ty[3] += dy * y1.y;
       }
@@ -396,8 +398,8 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
         const double* ge = A.geoE + (size_t)e * 9 * 64 + t * 4 + k;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          sX[(0 + c) * 64 + sw + k] = __ldg(ge + (0 + c) * 64) * uv[k];
-          sX[(3 + c) * 64 + sw + k] = __ldg(ge + (3 + c) * 64) * uv[k];
+          sX[(0 + c) * 64 + tIdx(i, j, k)] = __ldg(ge + (0 + c) * 64) * uv[k];
+          sX[(3 + c) * 64 + tIdx(i, j, k)] = __ldg(ge + (3 + c) * 64) * uv[k];
           mz[c][k] = __ldg(ge + (6 + c) * 64) * uv[k];
         }
       }
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
           double s = 0.0;
 #pragma unroll
           for (int a = 0; a < 4; a++)
-            s += A.dm[a * 4 + i] * sX[(0 + c) * 64 + a * 16 + (((j + a) & 3) << 2) + k] + A.dm[a * 4 + j] * sX[(3 + c) * 64 + i * 16 + (((a + i) & 3) << 2) + k] +
+            s += A.dm[a * 4 + i] * sX[(0 + c) * 64 + tIdx(a, j, k)] + A.dm[a * 4 + j] * sX[(3 + c) * 64 + tIdx(i, a, k)] +
                  A.dm[a * 4 + k] * mz[c][a];
           Gv[c][k] = -s;
         }
@@ -456,9 +458,9 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
       double* out = A.Gout + ((size_t)e * 15 + v * 3 + c) * 64 + t;
 #pragma unroll
       for (int k = 0; k < 4; k++) out[k * 16] = Gt[c][k] * ijw[k];
-      double* tile = sGv + (el * 15 + v * 3 + c) * 64 + sw;
-      if (br1) { sts2(tile, Gt[c][0] * ijw[0], Gt[c][1] * ijw[1]); sts2(tile + 2, Gt[c][2] * ijw[2], Gt[c][3] * ijw[3]); }
-      else { sts2(tile, Gv[c][0] * ijw[0], Gv[c][1] * ijw[1]); sts2(tile + 2, Gv[c][2] * ijw[2], Gv[c][3] * ijw[3]); }
+      double* tile = sGv + (el * 15 + v * 3 + c) * 64;
+      if (br1) { sts2(tile + p0, Gt[c][0] * ijw[0], Gt[c][1] * ijw[1]); sts2(tile + p1, Gt[c][2] * ijw[2], Gt[c][3] * ijw[3]); }
+      else { sts2(tile + p0, Gv[c][0] * ijw[0], Gv[c][1] * ijw[1]); sts2(tile + p1, Gv[c][2] * ijw[2], Gv[c][3] * ijw[3]); }
     }
   }
   __syncwarp(wm);
@@ -468,13 +470,13 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
   for (int d = 0; d < 3; d++) {
     int off[4];   // tile offsets of the four nodes of the normal line through this thread's point (natural index t) of the direction's faces
 #pragma unroll
-    for (int a = 0; a < 4; a++) off[a] = d == 2 ? sw + a : d == 0 ? a * 16 + (((i + a) & 3) << 2) + j : i * 16 + (((a + i) & 3) << 2) + j;
+    for (int a = 0; a < 4; a++) off[a] = d == 0 ? tIdx(a, i, j) : tIdx(i, a, j);   // (d == 2: the own line, read as two pairs below)
     double gm[15], gp[15];
 #pragma unroll
     for (int fld = 0; fld < 15; fld++) {
       const double* tile = sGv + (el * 15 + fld) * 64;
       double x0, x1, x2, x3;
-      if (d == 2) { const double2 a = lds2(tile + sw), b = lds2(tile + sw + 2); x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y; }   // own line: 16-byte accesses (8-byte ones are 8-way bank conflicted)
+      if (d == 2) { const double2 a = lds2(tile + p0), b = lds2(tile + p1); x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y; }   // own line: 16-byte accesses (8-byte ones are 8-way bank conflicted)
       else { x0 = tile[off[0]]; x1 = tile[off[1]]; x2 = tile[off[2]]; x3 = tile[off[3]]; }
       gm[fld] = A.lend[0] * x0 + A.lend[1] * x1 + A.lend[2] * x2 + A.lend[3] * x3;
       gp[fld] = A.lend[4] * x0 + A.lend[5] * x1 + A.lend[6] * x2 + A.lend[7] * x3;
@@ -541,10 +543,13 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
 // =====================================================================================================================
 // pass R: residual, RK update, traces of the new state, relative error
 // =====================================================================================================================
+template <bool GATHER>
 struct NslStageLayout {
+  static constexpr int XE = GATHER ? 480 : 320;              // doubles per element of the exchange region
   static constexpr int oFl = 0;                              // [K][6][5][16] face-flux slots (natural point order)
-  static constexpr int oX = oFl + kLK * 6 * 5 * 16;          // [K][320]: 10 half tiles [2 directions][5][32] of xi / eta fluxes, later [5][64] of the new state
-  static constexpr int oGeoE = oX + kLK * 320;               // affine: [K][10]
+  static constexpr int oX = oFl + kLK * 6 * 5 * 16;          // [K][320]: 10 half tiles [2 directions][5][32] of xi / eta fluxes, later [5][64] of the new state;
+                                                             // GATHER: [K][6][5][16] own face traces first (dead after the face phase)
+  static constexpr int oGeoE = oX + kLK * XE;                // affine: [K][10]
   static constexpr int oLg = oGeoE + kLK * 10;               // affine: [K][6][kLG]
   static constexpr int oLink = oLg + kLK * 6 * kLG;          // [K][6] int4
   static constexpr int oRed = oLink + kLK * 6 * 2;           // [4][5]
@@ -558,10 +563,19 @@ struct NslStageLayout {
 #ifndef SDG_NSL_MINB_EULER
 #define SDG_NSL_MINB_EULER 3
 #endif
-template <bool AFFINE, int PH, bool VISC>
+// 1: the node phase reads the state two nodes at a time and the update reads it again (L1 / L2 hits) instead of holding all 20 values of
+// the line in registers next to the 20 residual accumulators
+#ifndef SDG_NSL_RELOAD_U
+#define SDG_NSL_RELOAD_U 1
+#endif
+// GATHER (inviscid only): no published traces — the own traces are computed into shared memory, partners inside the block are read from
+// there, partners outside are interpolated from their nodal states in global memory (L2), as eulerLineKernel does; HBM traffic stays at
+// the state itself (read U, read U_last, write U).
+template <bool AFFINE, int PH, bool VISC, bool GATHER = false>
 __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER) nslStageKernel(const __grid_constant__ StageArgs A) {
-  using L = NslStageLayout;
-  constexpr int K = kLK;
+  static_assert(!(GATHER && VISC), "the gathering variant is inviscid");
+  using L = NslStageLayout<GATHER>;
+  constexpr int K = kLK, XE = L::XE;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
   double* sFl = smem + L::oFl;
@@ -593,7 +607,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
     for (int b = (int)blockIdx.x < A.ahead ? (int)blockIdx.x : (int)blockIdx.x + A.ahead; b < (int)gridDim.x && b <= (int)blockIdx.x + A.ahead; b += A.ahead) {
       const int c2 = A.chunkList ? A.chunkList[b] : b;
       const int f0 = c2 * K, n2 = min(K, A.nOwned - f0);
-      bulkPrefetchL2(A.TUin + (size_t)f0 * 6 * kRow, (unsigned)(n2 * 6 * kRow * sizeof(double)));
+      if constexpr (!GATHER) bulkPrefetchL2(A.TUin + (size_t)f0 * 6 * kRow, (unsigned)(n2 * 6 * kRow * sizeof(double)));
       if constexpr (VISC) bulkPrefetchL2(A.TVin + (size_t)f0 * 6 * kRow, (unsigned)(n2 * 6 * kRow * sizeof(double)));
       bulkPrefetchL2(A.Uin + (size_t)f0 * 5 * 64, (unsigned)(n2 * 5 * 64 * sizeof(double)));
       if constexpr (VISC) bulkPrefetchL2(A.Gvol + (size_t)f0 * 15 * 64, (unsigned)(n2 * 15 * 64 * sizeof(double)));
@@ -605,7 +619,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
   const int e = e0 + el;
   const double wij = A.w1[i] * A.w1[j];
   mbarWait(&mbar, 0);
-  for (int c = t; c < (VISC ? 60 : 30); c += 16) {   // the partners' rows: one 128-byte line per (face, field)
+  for (int c = t; c < (GATHER ? 0 : VISC ? 60 : 30); c += 16) {   // the partners' rows: one 128-byte line per (face, field)
     const int f = c / (VISC ? 10 : 5), r = c - f * (VISC ? 10 : 5);
     const int4 lk = sLink[el * 6 + f];
     if (lk.x >= 0) {
@@ -620,6 +634,16 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
   //      faces of a direction are requested together before either Riemann solve starts. ------------------------------------------------
   const double* gTU = A.TUin + (size_t)e * 6 * kRow + t;
   const double* gTV = A.TVin + (size_t)e * 6 * kRow + t;
+  double u[5][4];
+  double* sTr = sX;   // GATHER: [K][6][5][16] own face traces, in the exchange region (which the node phase reuses after a block barrier)
+  if constexpr (GATHER) {
+#pragma unroll
+    for (int v = 0; v < 5; v++)
+#pragma unroll
+      for (int k = 0; k < 4; k += 2) { const double2 x = ldg2(A.Uin + ((size_t)e * 5 + v) * 64 + t * 4 + k); u[v][k] = x.x; u[v][k + 1] = x.y; }
+    lineTracesOut(A, u, sFl + el * 480, i, j, t, wm, sTr + el * 480);   // tile = the (not yet used) flux slots of the element
+    __syncthreads();                                                     // partners inside the block live in other warps
+  }
 #pragma unroll 1
   for (int d = 0; d < 3; d++) {
     int4 lk[2];
@@ -639,11 +663,38 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
 #pragma unroll
     for (int side = 0; side < 2; side++) {
       const int f = hexFaceRt(d, side);
+      if constexpr (GATHER) {
+        const int z = lk[side].z, lfo = linkLfo(z);
+        const int natO = (int)(rowO[side] % kRow);   // partner's natural point index (own point for a boundary face)
 #pragma unroll
-      for (int v = 0; v < 5; v++) { cm[side][v] = __ldg(gTU + (f * 5 + v) * 16); co[side][v] = __ldg(A.TUin + rowO[side] + v * 16); }
-      if constexpr (VISC) {
+        for (int v = 0; v < 5; v++) cm[side][v] = sTr[((el * 6 + f) * 5 + v) * 16 + t];
+        if (lk[side].x >= 0 && linkInChunk(z)) {
 #pragma unroll
-        for (int v = 0; v < 5; v++) { tm[side][v] = __ldg(gTV + (f * 5 + v) * 16); to[side][v] = __ldg(A.TVin + rowO[side] + v * 16); }
+          for (int v = 0; v < 5; v++) co[side][v] = sTr[(((lk[side].x - e0) * 6 + lfo) * 5 + v) * 16 + natO];
+        } else if (lk[side].x >= 0) {
+          // partner outside the block: end-point interpolation along its face-normal line, nodal values from global memory (L2)
+          const int p = natO >> 2, q = natO & 3, dn = lfo == 0 || lfo == 5 ? 2 : lfo == 1 || lfo == 4 ? 1 : 0;
+          const int base = dn == 0 ? p * 4 + q : dn == 1 ? p * 16 + q : p * 16 + q * 4, stride = dn == 0 ? 16 : dn == 1 ? 4 : 1;
+          const double* src = A.Uin + (size_t)lk[side].x * 5 * 64 + base;
+          const double* le = A.lend + (lfo >= 3 ? 4 : 0);
+          double x[5][4];
+#pragma unroll
+          for (int v = 0; v < 5; v++)
+#pragma unroll
+            for (int a = 0; a < 4; a++) x[v][a] = __ldg(src + v * 64 + a * stride);
+#pragma unroll
+          for (int v = 0; v < 5; v++) co[side][v] = le[0] * x[v][0] + le[1] * x[v][1] + le[2] * x[v][2] + le[3] * x[v][3];
+        } else {
+#pragma unroll
+          for (int v = 0; v < 5; v++) co[side][v] = cm[side][v];
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 5; v++) { cm[side][v] = __ldg(gTU + (f * 5 + v) * 16); co[side][v] = __ldg(A.TUin + rowO[side] + v * 16); }
+        if constexpr (VISC) {
+#pragma unroll
+          for (int v = 0; v < 5; v++) { tm[side][v] = __ldg(gTV + (f * 5 + v) * 16); to[side][v] = __ldg(A.TVin + rowO[side] + v * 16); }
+        }
       }
     }
 #pragma unroll
@@ -683,30 +734,44 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
       }
     }
   }
-  __syncwarp(wm);
+  if constexpr (GATHER) __syncthreads();   // every warp has finished reading the trace tiles: the exchange region is free
+  else __syncwarp(wm);
 
   // ---- R1 + R3 volume part: fluxes at the own nodes, two nodes per round; zeta contraction in registers, xi / eta through half tiles ----
-  double u[5][4];
+  constexpr bool RELOAD = SDG_NSL_RELOAD_U != 0;
+  const double* gUl = A.Uin + (size_t)e * 5 * 64 + t * 4;
+  if constexpr (!GATHER && !RELOAD) {
 #pragma unroll
-  for (int v = 0; v < 5; v++)
+    for (int v = 0; v < 5; v++)
 #pragma unroll
-    for (int k = 0; k < 4; k += 2) { const double2 x = ldg2(A.Uin + ((size_t)e * 5 + v) * 64 + t * 4 + k); u[v][k] = x.x; u[v][k + 1] = x.y; }
+      for (int k = 0; k < 4; k += 2) { const double2 x = ldg2(gUl + v * 64 + k); u[v][k] = x.x; u[v][k + 1] = x.y; }
+  }
   double R[5][4];
 #pragma unroll
   for (int v = 0; v < 5; v++)
 #pragma unroll
     for (int k = 0; k < 4; k++) R[v][k] = 0.0;
-  double* sXe = sX + el * 320;
+  double* sXe = sX + el * XE;
   const int sw2 = i * 8 + (((j + i) & 3) << 1);
+  double ge[9];   // affine: (J^T)^-1 detJ rows of the element, once (36 shared-memory reads per thread otherwise)
+  if constexpr (AFFINE) {
+#pragma unroll
+    for (int q = 0; q < 9; q++) ge[q] = sGeoE[el * 10 + q];
+  }
 #pragma unroll
   for (int r = 0; r < 2; r++) {
     double Fx[5][2], Fy[5][2];
+    double ur[5][2];
+    if constexpr (RELOAD) {
+#pragma unroll
+      for (int v = 0; v < 5; v++) { const double2 x = ldg2(gUl + v * 64 + 2 * r); ur[v][0] = x.x; ur[v][1] = x.y; }
+    }
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {
       const int k = 2 * r + kk;
       double cons[5], comp[6], Fv[15];
 #pragma unroll
-      for (int v = 0; v < 5; v++) cons[v] = u[v][k];
+      for (int v = 0; v < 5; v++) cons[v] = RELOAD ? ur[v][kk] : u[v][k];
       compFromCons<3>(ph, cons, comp);
       if constexpr (VISC) {
         double g[15], gp[15];
@@ -721,7 +786,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
         double m[3], Ft[5];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          if constexpr (AFFINE) m[c] = sGeoE[el * 10 + dd * 3 + c] * (wij * A.w1[k]);
+          if constexpr (AFFINE) m[c] = ge[dd * 3 + c] * (wij * A.w1[k]);
           else m[c] = __ldg(A.geoE + ((size_t)e * 9 + dd * 3 + c) * 64 + t * 4 + k);
         }
         contravariantFlux<3>(ph, cons, comp, m, Ft);
@@ -786,7 +851,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
     for (int k = 0; k < 4; k++) {
       double cons[5], comp[6];
 #pragma unroll
-      for (int v = 0; v < 5; v++) cons[v] = u[v][k];
+      for (int v = 0; v < 5; v++) cons[v] = RELOAD ? __ldg(gUl + v * 64 + k) : u[v][k];
       compFromCons<3>(ph, cons, comp);
       R[3][k] += boussinesqSource<3>(ph, comp) / ijw[k];
     }
@@ -798,15 +863,19 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
       for (int v = 0; v < 5; v++) {
 #pragma unroll
         for (int k = 0; k < 4; k += 2) {
-          double ox = A.aCur * u[v][k] + A.bdt * (R[v][k] * ijw[k]), oy = A.aCur * u[v][k + 1] + A.bdt * (R[v][k + 1] * ijw[k + 1]);
+          double uk = u[v][k], uk1 = u[v][k + 1];
+          if constexpr (RELOAD) { const double2 x = ldg2(gUl + v * 64 + k); uk = x.x; uk1 = x.y; }
+          double ox = A.aCur * uk + A.bdt * (R[v][k] * ijw[k]), oy = A.aCur * uk1 + A.bdt * (R[v][k + 1] * ijw[k + 1]);
           if (needLast) { const double2 l = ldg2(A.Ulast + g + (size_t)v * 64 + k); ox += A.aLast * l.x; oy += A.aLast * l.y; }
           u[v][k] = ox; u[v][k + 1] = oy;
           *reinterpret_cast<double2*>(A.Uout + g + (size_t)v * 64 + k) = make_double2(ox, oy);
         }
       }
       // traces of the state just produced: what both passes of the next stage (and the neighbours) read
-      __syncwarp(wm);
-      lineTracesOut(A, u, sXe, i, j, t, wm, A.TUout + (size_t)e * 6 * kRow);
+      if constexpr (!GATHER) {
+        __syncwarp(wm);
+        lineTracesOut(A, u, sXe, i, j, t, wm, A.TUout + (size_t)e * 6 * kRow);
+      }
     } else {
 #pragma unroll
       for (int v = 0; v < 5; v++)
@@ -834,21 +903,21 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
 #pragma unroll
         for (int k = 0; k < 4; k++) R[v][k] = S[v][k];
     }
-    const int sw = swz(i, j);
+    const int p0 = tPair(i, j, 0), p1 = tPair(i, j, 1);
 #pragma unroll
     for (int d = 0; d < 2; d++) {   // xi, then eta: all five variables through the element's [5][64] tile
       __syncwarp(wm);
 #pragma unroll
-      for (int v = 0; v < 5; v++) { sts2(sXe + v * 64 + sw, R[v][0], R[v][1]); sts2(sXe + v * 64 + sw + 2, R[v][2], R[v][3]); }
+      for (int v = 0; v < 5; v++) { sts2(sXe + v * 64 + p0, R[v][0], R[v][1]); sts2(sXe + v * 64 + p1, R[v][2], R[v][3]); }
       __syncwarp(wm);
 #pragma unroll
       for (int v = 0; v < 5; v++) {
         double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-          const double* p = d == 0 ? sXe + v * 64 + a * 16 + (((j + a) & 3) << 2) : sXe + v * 64 + i * 16 + (((a + i) & 3) << 2);
+          const double* p = sXe + v * 64;
           const double kk = A.k1[a * 4 + (d == 0 ? i : j)];
-          const double2 lo = lds2(p), hi = lds2(p + 2);
+          const double2 lo = lds2(p + (d == 0 ? tPair(a, j, 0) : tPair(i, a, 0))), hi = lds2(p + (d == 0 ? tPair(a, j, 1) : tPair(i, a, 1)));
           x0 += kk * lo.x; x1 += kk * lo.y; x2 += kk * hi.x; x3 += kk * hi.y;
         }
         R[v][0] = x0; R[v][1] = x1; R[v][2] = x2; R[v][3] = x3;

@@ -24,26 +24,27 @@ void launchNslGrad(const StageArgs& a, int nBlocks, cudaStream_t s) {
   nslGradKernel<AFFINE><<<nBlocks, 128, L::bytes, s>>>(a);
 }
 
-template <bool AFFINE, int PH, bool VISC>
+template <bool AFFINE, int PH, bool VISC, bool GATHER>
 void launchNslStage(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  using L = NslStageLayout;
+  using L = NslStageLayout<GATHER>;
   static std::atomic<unsigned long long> configured{0};
-  if (firstUseOnThisDevice(configured)) CUDA_OK(cudaFuncSetAttribute(nslStageKernel<AFFINE, PH, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
-  nslStageKernel<AFFINE, PH, VISC><<<nBlocks, 128, L::bytes, s>>>(a);
+  if (firstUseOnThisDevice(configured)) CUDA_OK(cudaFuncSetAttribute(nslStageKernel<AFFINE, PH, VISC, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+  nslStageKernel<AFFINE, PH, VISC, GATHER><<<nBlocks, 128, L::bytes, s>>>(a);
 }
 
-template <bool AFFINE, bool VISC>
-StageFn pickStage(int ph) { return ph ? launchNslStage<AFFINE, 1, VISC> : launchNslStage<AFFINE, 0, VISC>; }
+template <bool AFFINE, bool VISC, bool GATHER>
+StageFn pickStage(int ph) { return ph ? launchNslStage<AFFINE, 1, VISC, GATHER> : launchNslStage<AFFINE, 0, VISC, GATHER>; }
 
 }  // namespace
 
-void pickNslFns(bool affine, int ph, bool visc, LineFns& out, int& K) {
+void pickNslFns(bool affine, int ph, bool visc, bool gather, LineFns& out, int& K) {
   K = kLK;
   out.trace = launchNslTrace;
   out.boundary = affine ? launchNslBoundary<true> : launchNslBoundary<false>;
   out.grad = affine ? launchNslGrad<true> : launchNslGrad<false>;
-  if (affine) out.stage = visc ? pickStage<true, true>(ph) : pickStage<true, false>(ph);
-  else out.stage = visc ? pickStage<false, true>(ph) : pickStage<false, false>(ph);
+  if (visc && gather) throw std::runtime_error("the gathering residual pass is inviscid");
+  if (affine) out.stage = visc ? pickStage<true, true, false>(ph) : gather ? pickStage<true, false, true>(ph) : pickStage<true, false, false>(ph);
+  else out.stage = visc ? pickStage<false, true, false>(ph) : gather ? pickStage<false, false, true>(ph) : pickStage<false, false, false>(ph);
 }
 
 }  // namespace sdg

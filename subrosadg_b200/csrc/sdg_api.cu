@@ -60,7 +60,8 @@ struct sdg_ctx {
   std::unique_ptr<MixedSolver> mx;   // dense-operator path: meshes with triangle blocks / several element types (mixed_path.cu)
   // trace-based line kernels for P3 hexahedra (nsl_kernels.cuh): published face traces TU (one per stage buffer) and TV, virtual
   // neighbour traces of the boundary faces, link records; traceValid[b] = TU[b] holds the traces of U[b]
-  bool lineTrace = false;
+  bool lineTrace = false;   // link plan + nsl kernels
+  bool traceTU = false;     // ... with published face traces (TU / TV arrays, trace rows in the halo)
   LineFns lineFns;
   DevBuf<double> TU[3], TV, TUb, lfGeo;
   DevBuf<int> links, bndRec;
@@ -101,7 +102,7 @@ void fillArgs(sdg_ctx* c, StageArgs& a) {
 
 // traces of a state that did not come out of the residual pass (initial condition, state setters)
 void ensureTraces(sdg_ctx* c, int buf, cudaStream_t s) {
-  if (!c->lineTrace || c->traceValid[buf]) return;
+  if (!c->traceTU || c->traceValid[buf]) return;
   StageArgs a; fillArgs(c, a);
   a.Uin = c->U[buf].p; a.TUout = c->TU[buf].p;
   c->lineFns.trace(a, c->plan.blk.nChunks, s);
@@ -165,7 +166,7 @@ void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st, int pass = -1) {
   a.normPartial = s == c->nStages - 1 ? c->normPartial.p : nullptr;
   runStage(c, a, part, st, 1);
   c->latest = out;
-  if (c->lineTrace) c->traceValid[out] = true;   // the residual pass publishes the traces of the state it writes
+  if (c->traceTU) c->traceValid[out] = true;   // the residual pass publishes the traces of the state it writes
 }
 
 void finishStep(sdg_ctx* c) { if (c->nStages == 1) c->cur = (c->cur + 1) % 3; c->latest = c->cur; c->stepCount++; }
@@ -313,8 +314,13 @@ int sdg_finalize(sdg_ctx* c) {
   M.buildBlock(c->cfg.reorder, 1);  // provisional chunk size; chunking is redone below once K is known
   // P3 hexahedra: Navier-Stokes runs on the trace-based line kernels (SDG_NS_NODE_KERNEL = A/B switch back to the node-per-thread
   // kernels of ns_kernels.cuh); SDG_EULER_TRACE routes Euler through the same residual pass for comparison with eulerLineKernel
-  c->lineTrace = c->D == 3 && N == 4 && (c->phys.ns ? getenv("SDG_NS_NODE_KERNEL") == nullptr : getenv("SDG_EULER_TRACE") != nullptr);
-  if (c->lineTrace) pickNslFns(B.affine, ph, c->phys.ns != 0, c->lineFns, K);
+  // Euler on P3 hexahedra: SDG_EULER_KERNEL = line (eulerLineKernel, chunk face lists) | link (the residual pass of the line NS kernels
+  // without viscous terms, partners gathered from their nodal states) | trace (the same with published traces: twice the HBM traffic)
+  const char* ek = getenv("SDG_EULER_KERNEL");
+  const std::string eulerKernel = ek ? ek : (getenv("SDG_EULER_TRACE") ? "trace" : "line");
+  c->lineTrace = c->D == 3 && N == 4 && (c->phys.ns ? getenv("SDG_NS_NODE_KERNEL") == nullptr : eulerKernel != "line");
+  c->traceTU = c->lineTrace && (c->phys.ns || eulerKernel == "trace");
+  if (c->lineTrace) pickNslFns(B.affine, ph, c->phys.ns != 0, !c->traceTU, c->lineFns, K);
   else if (c->phys.ns) pickNsFn(c->D, N, B.affine, ph, c->nsGradFn, c->nsStageFn, K);
   else c->eulerFn = pickEulerFn(c->D, N, B.affine, ph, K);
   if (c->cfg.chunk > 0 && c->cfg.chunk != K) throw std::runtime_error("chunk override not available: kernels are compiled for K = " + std::to_string(K));
@@ -386,10 +392,12 @@ int sdg_finalize(sdg_ctx* c) {
       std::memcpy(lt[0].partner, LP.partner.data(), sizeof(lt[0].partner)); std::memcpy(lt[0].jLeft, LP.jLeft.data(), sizeof(lt[0].jLeft));
       c->ltab.upload(lt, c->stream);
       c->cLift = LP.cLift;
-      const size_t nt = (size_t)B.n * 6 * kRow;
-      for (int i = 0; i < 3; i++) { c->TU[i].alloc(nt); c->TU[i].zero(c->stream); }
-      if (c->phys.ns) { c->TV.alloc(nt); c->TV.zero(c->stream); }
-      c->TUb.alloc((size_t)std::max(F.nBnd, 1) * kRow); c->TUb.zero(c->stream);
+      if (c->traceTU) {
+        const size_t nt = (size_t)B.n * 6 * kRow;
+        for (int i = 0; i < 3; i++) { c->TU[i].alloc(nt); c->TU[i].zero(c->stream); }
+        if (c->phys.ns) { c->TV.alloc(nt); c->TV.zero(c->stream); }
+        c->TUb.alloc((size_t)std::max(F.nBnd, 1) * kRow); c->TUb.zero(c->stream);
+      }
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
   }
@@ -783,8 +791,8 @@ int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int6
 
 // what travels between ranks: whole elements of the state / volume gradient, or — trace-based line kernels — the elements' face-trace rows
 // TU (what = 0) and TV (what = 1)
-static int haloStride(sdg_ctx* c, int what) { return c->lineTrace ? 6 * kRow : (int)c->elemDoubles() * (what == 1 ? c->D : 1); }
-static double* haloField(sdg_ctx* c, int what) { return c->lineTrace ? (what == 1 ? c->TV.p : c->TU[c->latest].p) : (what == 1 ? c->G.p : c->U[c->latest].p); }
+static int haloStride(sdg_ctx* c, int what) { return c->traceTU ? 6 * kRow : (int)c->elemDoubles() * (what == 1 ? c->D : 1); }
+static double* haloField(sdg_ctx* c, int what) { return c->traceTU ? (what == 1 ? c->TV.p : c->TU[c->latest].p) : (what == 1 ? c->G.p : c->U[c->latest].p); }
 
 int sdg_halo_doubles_per_element(sdg_ctx* c, int32_t what) { return haloStride(c, what); }
 
@@ -840,7 +848,7 @@ int sdg_ipc_export(sdg_ctx* c, unsigned char* handles) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   if (!c->ipcFlags.p) { c->ipcFlags.alloc(64); c->ipcFlags.zero(c->stream); c->pushCounter.alloc(1); c->pushCounter.zero(c->stream); c->haloErr.alloc(1); c->haloErr.zero(c->stream); CUDA_OK(cudaStreamSynchronize(c->stream)); }
   void* ptrs[5] = {c->U[0].p, c->U[1].p, c->U[2].p, c->G.p, c->ipcFlags.p};
-  if (c->lineTrace) { ptrs[0] = c->TU[0].p; ptrs[1] = c->TU[1].p; ptrs[2] = c->TU[2].p; ptrs[3] = c->TV.p; }
+  if (c->traceTU) { ptrs[0] = c->TU[0].p; ptrs[1] = c->TU[1].p; ptrs[2] = c->TU[2].p; ptrs[3] = c->TV.p; }
   std::memset(handles, 0, 5 * sizeof(cudaIpcMemHandle_t));
   for (int i = 0; i < 5; i++) if (ptrs[i]) { cudaIpcMemHandle_t h; CUDA_OK(cudaIpcGetMemHandle(&h, ptrs[i])); std::memcpy(handles + i * sizeof(h), &h, sizeof(h)); }
   SDG_CATCH
