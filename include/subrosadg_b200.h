@@ -125,6 +125,17 @@ int sdg_halo_buffers_device(sdg_ctx* ctx, int32_t type, int32_t what, void** sen
 /* Doubles exchanged per halo element for field `what`: the element's state / volume-gradient coefficients, or — P3 hexahedra with
  * Navier-Stokes, whose kernels read published face traces — its six face-trace rows (0: conserved variables, 1: viscous normal flux). */
 int sdg_halo_doubles_per_element(sdg_ctx* ctx, int32_t what);
+/* Trace-row halo (contexts whose kernels read published face traces, sdg_uses_trace_rows() == 1): a cut face needs ONE row of its
+ * remote parent — 5 variables x 16 points = 640 bytes — instead of the whole element (640 B per face per direction).
+ * sdg_set_halo_rows lists the (owned element, local face) rows to send and the (ghost element, local face) rows to receive, both in the
+ * order the peers agree on; sdg_halo_pack / sdg_halo_buffers_device then work on rows (the receive buffer is a staging area) and
+ * sdg_halo_unpack scatters received rows to their places.  sdg_halo_doubles_per_element returns the row size (80) in this mode. */
+int sdg_uses_trace_rows(sdg_ctx* ctx);
+int sdg_set_halo_rows(sdg_ctx* ctx, int32_t type, int32_t n_send, const int32_t* send_elem, const int32_t* send_face, int32_t n_recv,
+                      const int32_t* recv_elem, const int32_t* recv_face);
+int sdg_halo_unpack(sdg_ctx* ctx, int32_t type, int32_t what, void* stream);
+/* peer-memory transport of the trace-row halo: row index, in the peer's arrays, of every send row (same order as the send list) */
+int sdg_ipc_set_destination_units(sdg_ctx* ctx, int32_t n, const int64_t* dst_units);
 /* Split stepping used by the multi-GPU driver: stage `s` of the current step, restricted to thread blocks that do not
  * (part 0) / do (part 1) touch ghost elements; part -1 = all.  sdg_step_begin / sdg_step_end bracket one step. */
 int sdg_step_begin(sdg_ctx* ctx, double dt);

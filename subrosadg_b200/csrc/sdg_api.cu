@@ -55,6 +55,8 @@ struct sdg_ctx {
   cudaGraphExec_t stepGraph = nullptr; double graphDt = 0.0; int graphCur = -1; bool graphWarm = false; int64_t graphLaunches = 0;
   // peer-memory halo exchange (CUDA IPC): the peers' arrays opened in this process, arrival flags, exchange counter
   std::vector<PeerDev> peerLinks; std::vector<void*> ipcOpened;
+  bool rowHalo = false; int nRecvRows = 0;   // trace-row halo (sdg_set_halo_rows): units = (element, face) rows of TU / TV
+  DevBuf<int> recvList; DevBuf<double> recvBuf; DevBuf<long long> dstUnit;
   DevBuf<PeerDev> peerDev; DevBuf<long long> ipcFlags; DevBuf<unsigned int> pushCounter; DevBuf<int> haloErr;
   long long pushEpoch = 0;
   std::unique_ptr<MixedSolver> mx;   // dense-operator path: meshes with triangle blocks / several element types (mixed_path.cu)
@@ -317,7 +319,7 @@ int sdg_finalize(sdg_ctx* c) {
   // Euler on P3 hexahedra: SDG_EULER_KERNEL = line (eulerLineKernel, chunk face lists) | link (the residual pass of the line NS kernels
   // without viscous terms, partners gathered from their nodal states) | trace (the same with published traces: twice the HBM traffic)
   const char* ek = getenv("SDG_EULER_KERNEL");
-  const std::string eulerKernel = ek ? ek : (getenv("SDG_EULER_TRACE") ? "trace" : "line");
+  const std::string eulerKernel = ek ? ek : "trace";   // measured at 128^3 (ms per stage): trace 8.12, line 8.80, link 8.83; 2 GPUs: 6.14 vs 6.85
   c->lineTrace = c->D == 3 && N == 4 && (c->phys.ns ? getenv("SDG_NS_NODE_KERNEL") == nullptr : eulerKernel != "line");
   c->traceTU = c->lineTrace && (c->phys.ns || eulerKernel == "trace");
   if (c->lineTrace) pickNslFns(B.affine, ph, c->phys.ns != 0, !c->traceTU, c->lineFns, K);
@@ -791,7 +793,7 @@ int sdg_debug_plan(sdg_ctx* c, int32_t what, double* out_d, int32_t* out_i, int6
 
 // what travels between ranks: whole elements of the state / volume gradient, or — trace-based line kernels — the elements' face-trace rows
 // TU (what = 0) and TV (what = 1)
-static int haloStride(sdg_ctx* c, int what) { return c->traceTU ? 6 * kRow : (int)c->elemDoubles() * (what == 1 ? c->D : 1); }
+static int haloStride(sdg_ctx* c, int what) { return c->rowHalo ? kRow : c->traceTU ? 6 * kRow : (int)c->elemDoubles() * (what == 1 ? c->D : 1); }
 static double* haloField(sdg_ctx* c, int what) { return c->traceTU ? (what == 1 ? c->TV.p : c->TU[c->latest].p) : (what == 1 ? c->G.p : c->U[c->latest].p); }
 
 int sdg_halo_doubles_per_element(sdg_ctx* c, int32_t what) { return haloStride(c, what); }
@@ -807,6 +809,53 @@ int sdg_set_halo_send(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* e
   c->sendList.upload(pos, c->stream);
   c->nSend = n_send;
   c->sendBuf.alloc((size_t)std::max(n_send, 1) * std::max(haloStride(c, 0), c->phys.ns ? haloStride(c, 1) : 0));
+  SDG_CATCH
+}
+
+int sdg_uses_trace_rows(sdg_ctx* c) { return c->traceTU ? 1 : 0; }
+
+int sdg_set_halo_rows(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* send_elem, const int32_t* send_face, int32_t n_recv,
+                      const int32_t* recv_elem, const int32_t* recv_face) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  if (!c->traceTU) throw std::runtime_error("trace-row halo: this context does not publish face traces (sdg_uses_trace_rows)");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  std::vector<int> srow(n_send), rrow(n_recv);
+  for (int i = 0; i < n_send; i++) {
+    if (send_elem[i] < 0 || send_elem[i] >= B.nOwned || send_face[i] < 0 || send_face[i] >= 6) throw std::runtime_error("halo send row out of range");
+    srow[i] = B.perm[send_elem[i]] * 6 + send_face[i];
+  }
+  for (int i = 0; i < n_recv; i++) {
+    if (recv_elem[i] < B.nOwned || recv_elem[i] >= B.n || recv_face[i] < 0 || recv_face[i] >= 6) throw std::runtime_error("halo receive row is not a ghost row");
+    rrow[i] = B.perm[recv_elem[i]] * 6 + recv_face[i];
+  }
+  c->sendList.upload(srow, c->stream); c->recvList.upload(rrow, c->stream);
+  c->nSend = n_send; c->nRecvRows = n_recv; c->rowHalo = true;
+  c->sendBuf.alloc((size_t)std::max(n_send, 1) * kRow); c->recvBuf.alloc((size_t)std::max(n_recv, 1) * kRow);
+  SDG_CATCH
+}
+
+int sdg_halo_unpack(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
+  SDG_TRY
+  needFinal(c); needDevice(c); needType(c, type);
+  if (!c->rowHalo) return 0;   // element halo: the ghost range received the data directly
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (c->nRecvRows == 0) return 0;
+  const int blocks = (int)std::min<size_t>(((size_t)c->nRecvRows * kRow + 255) / 256, 148 * 8);
+  haloUnpackKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(c->recvBuf.p, c->recvList.p, c->nRecvRows, kRow, haloField(c, what));
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  SDG_CATCH
+}
+
+int sdg_ipc_set_destination_units(sdg_ctx* c, int32_t n, const int64_t* dst_units) {
+  SDG_TRY
+  needFinal(c); needDevice(c);
+  if (n != c->nSend) throw std::runtime_error("destination units: one per send unit");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  std::vector<long long> d(dst_units, dst_units + n);
+  c->dstUnit.upload(d, c->stream);
   SDG_CATCH
 }
 
@@ -836,7 +885,8 @@ int sdg_halo_buffers_device(sdg_ctx* c, int32_t type, int32_t what, void** send,
   const int64_t per = haloStride(c, what);
   double* base = haloField(c, what);
   *send = c->sendBuf.p; *send_doubles = (int64_t)c->nSend * per;
-  *recv = base + (size_t)B.nOwned * per; *recv_doubles = (int64_t)B.nGhost * per;
+  if (c->rowHalo) { *recv = c->recvBuf.p; *recv_doubles = (int64_t)c->nRecvRows * per; }   // staging: sdg_halo_unpack scatters the rows
+  else { *recv = base + (size_t)B.nOwned * per; *recv_doubles = (int64_t)B.nGhost * per; }
   SDG_CATCH
 }
 
@@ -890,9 +940,10 @@ int sdg_halo_push(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
   const double* src = haloField(c, what);
   const int which = what == 1 ? 3 : c->latest;
   static const int maxBlocks = getenv("SDG_PUSH_BLOCKS") ? std::max(1, atoi(getenv("SDG_PUSH_BLOCKS"))) : 148 * 2;   // 2 CTAs per SM measured best at 4 GPUs (96: 280, 296: 285, 592: 282 GDOF/s): more blocks steal SM slots from the interior launch
-  const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((size_t)c->nSend * stride + 255) / 256, (size_t)maxBlocks));
+  if (c->rowHalo && !c->dstUnit.p && c->nSend > 0) throw std::runtime_error("trace-row halo: sdg_ipc_set_destination_units has not been called");
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((size_t)c->nSend + 7) / 8, (size_t)maxBlocks));   // 8 warps per block, one unit per warp
   haloPushKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(src, c->sendList.p, c->nSend, stride, c->peerDev.p, (int)c->peerLinks.size(), which,
-                                                                                 c->pushCounter.p, c->pushEpoch);
+                                                                                 c->pushCounter.p, c->pushEpoch, c->rowHalo ? c->dstUnit.p : nullptr);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   SDG_CATCH

@@ -646,16 +646,27 @@ struct PeerDev {
   long long ghostFirst;  // element index, in the peer's arrays, of the first ghost element fed by this rank
   int sendFirst, sendCount, slot;
 };
-// Gather the send elements of field `which` and store them STRAIGHT into the peers' ghost ranges (no staging buffer, no
-// send/recv pair); the last thread block to finish publishes this exchange's epoch in every peer's flag entry.
-static __global__ void haloPushKernel(const double* __restrict__ src, const int* __restrict__ elems, int nSend, int stride, const PeerDev* __restrict__ peers,
-                                      int nPeers, int which, unsigned int* counter, long long epoch) {
-  const size_t total = (size_t)nSend * stride;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i / stride), r = (int)(i - (size_t)k * stride);
+// Gather the send units (elements, or (element, face) trace rows) of field `which` and store them STRAIGHT into the peers' arrays (no
+// staging buffer, no send/recv pair): one warp per unit, 16-byte loads and stores, the peer looked up once per unit.  Destination of
+// unit k: dstUnit[k] if given (trace rows: the peer's row index), else the peer's contiguous ghost range.  The last thread block to
+// finish publishes this exchange's epoch in every peer's flag entry.
+static __global__ void haloPushKernel(const double* __restrict__ src, const int* __restrict__ units, int nSend, int stride, const PeerDev* __restrict__ peers,
+                                      int nPeers, int which, unsigned int* counter, long long epoch, const long long* __restrict__ dstUnit) {
+  const int lane = threadIdx.x & 31, warpsPerBlock = blockDim.x >> 5;
+  const int half = stride >> 1;
+  for (int k = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); k < nSend; k += gridDim.x * warpsPerBlock) {
     int p = 0;
     while (p + 1 < nPeers && k >= peers[p].sendFirst + peers[p].sendCount) p++;
-    peers[p].dst[which][(size_t)(peers[p].ghostFirst + (k - peers[p].sendFirst)) * stride + r] = src[(size_t)elems[k] * stride + r];
+    const long long d = dstUnit ? dstUnit[k] : peers[p].ghostFirst + (k - peers[p].sendFirst);
+    const double* s1 = src + (size_t)units[k] * stride;
+    double* d1 = peers[p].dst[which] + (size_t)d * stride;
+    if (stride & 1) {   // odd unit size (e.g. 27-node hexahedra x 5 variables): units are not 16-byte aligned
+      for (int r = lane; r < stride; r += 32) d1[r] = s1[r];
+    } else {
+      const double2* s2 = reinterpret_cast<const double2*>(s1);
+      double2* d2 = reinterpret_cast<double2*>(d1);
+      for (int r = lane; r < half; r += 32) d2[r] = s2[r];
+    }
   }
   __threadfence_system();
   __syncthreads();
@@ -686,6 +697,15 @@ static __global__ void haloWaitKernel(const long long* __restrict__ flags, int n
     }
   }
   __threadfence_system();
+}
+
+// scatter of received units: dst[units[i]][:] = in[i][:]  (trace rows land at their (ghost element, face) rows)
+static __global__ void haloUnpackKernel(const double* __restrict__ in, const int* __restrict__ units, int n, int stride, double* __restrict__ dst) {
+  const size_t total = (size_t)n * stride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / stride);
+    dst[(size_t)units[k] * stride + (i - (size_t)k * stride)] = in[i];
+  }
 }
 
 // gather of the halo send list: out[i][:] = U[elems[i]][:]

@@ -51,6 +51,10 @@ class Partition:
     recv_range: dict = field(default_factory=dict)  # peer -> (first ghost index relative to n_owned, count)
     face_global: np.ndarray | None = None           # global face ids of the local faces (interior first, then boundary)
     n_elements_global: int = 0
+    # trace-row halo: per peer, the (local owned element, local face) rows to send and the (local ghost element, local face) rows to
+    # receive, both ordered by global face id — the two ranks of a cut face enumerate the same faces in the same order
+    send_rows: dict = field(default_factory=dict)
+    recv_rows: dict = field(default_factory=dict)
 
 
 def block_bounds(n: int, world: int) -> np.ndarray:
@@ -126,6 +130,18 @@ def partition(mesh: M.Mesh, rank: int, world: int) -> Partition:
     for q in part.peers:
         part.send_local.setdefault(q, np.zeros(0, dtype=np.int64))
         part.recv_range.setdefault(q, (0, 0))
+    # cut faces in ascending global face id: the owned parent's row goes out, the remote parent's row comes in
+    lf_g, rf_g = np.asarray(f["lf"], dtype=np.int64)[sel], np.asarray(f["rf"], dtype=np.int64)[sel]
+    cut_l = own_l[sel] & isel & ~own_r[sel]          # I own the left parent, the right one is remote
+    cut_r = own_r[sel] & ~own_l[sel]                 # I own the right parent
+    mine_e = np.where(cut_l, le[sel], re[sel]); mine_f = np.where(cut_l, lf_g, rf_g)
+    theirs_e = np.where(cut_l, re[sel], le[sel]); theirs_f = np.where(cut_l, rf_g, lf_g)
+    cut = np.flatnonzero(cut_l | cut_r)
+    cut_owner = np.searchsorted(b, theirs_e[cut], side="right") - 1
+    for q in part.peers:
+        k = cut[cut_owner == q]
+        part.send_rows[q] = np.stack([mine_e[k] - lo, mine_f[k]], axis=1).astype(np.int64) if k.size else np.zeros((0, 2), dtype=np.int64)
+        part.recv_rows[q] = np.stack([to_local(theirs_e[k]), theirs_f[k]], axis=1).astype(np.int64) if k.size else np.zeros((0, 2), dtype=np.int64)
     return part
 
 
@@ -134,23 +150,35 @@ class HaloExchange:
     """One message per peer and direction.  `send` holds the packed states of send_local[peer] for all peers back to
     back (ascending peer rank), `recv` is the ghost range; both are 1-D float64 torch tensors (CPU or CUDA)."""
 
-    def __init__(self, part: Partition, group=None):
+    def __init__(self, part: Partition, group=None, rows: bool = False):
+        """rows = False: units are whole elements (received straight into the ghost range); rows = True: units are (element, face)
+        trace rows (received into a staging buffer, scattered by sdg_halo_unpack)."""
         self.part = part
         self.group = group
-        off = 0
-        self.send_off = {}
+        self.rows = rows
+        off, roff = 0, 0
+        self.send_off, self.send_count, self.recv_off, self.recv_count = {}, {}, {}, {}
         for q in part.peers:
             self.send_off[q] = off
-            off += int(part.send_local[q].size)
+            self.send_count[q] = int(part.send_rows[q].shape[0]) if rows else int(part.send_local[q].size)
+            off += self.send_count[q]
+            if rows:
+                self.recv_off[q], self.recv_count[q] = roff, int(part.recv_rows[q].shape[0])
+                roff += self.recv_count[q]
+            else:
+                self.recv_off[q], self.recv_count[q] = part.recv_range[q]
         self.n_send = off
+        self.n_recv = roff if rows else int(part.n_ghost)
         self.send_elems = (np.concatenate([part.send_local[q] for q in part.peers]) if part.peers else np.zeros(0, dtype=np.int64)).astype(np.int32)
+        cat = lambda d: (np.concatenate([d[q] for q in part.peers]) if part.peers else np.zeros((0, 2), dtype=np.int64)).astype(np.int32)
+        self.send_rows, self.recv_rows = cat(part.send_rows), cat(part.recv_rows)
 
     def start(self, send, recv, elem_doubles: int):
         import torch.distributed as dist
         ops = []
         for q in self.part.peers:
-            ns = int(self.part.send_local[q].size)
-            r0, nr = self.part.recv_range[q]
+            ns = self.send_count[q]
+            r0, nr = self.recv_off[q], self.recv_count[q]
             if nr:
                 ops.append(dist.P2POp(dist.irecv, recv[r0 * elem_doubles:(r0 + nr) * elem_doubles], q, group=self.group))
             if ns:
@@ -162,6 +190,18 @@ class HaloExchange:
     def finish(reqs):
         for r in reqs:
             r.wait()
+
+
+def _set_halo(lib, S, etype, halo):
+    """Registers the halo send (and, for trace rows, receive) units of one context with the library."""
+    ip = lambda a: np.ascontiguousarray(a, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    if halo.rows:
+        sr, rr = halo.send_rows, halo.recv_rows
+        rc = lib.sdg_set_halo_rows(S.h, etype, int(sr.shape[0]), ip(sr[:, 0]), ip(sr[:, 1]), int(rr.shape[0]), ip(rr[:, 0]), ip(rr[:, 1]))
+    else:
+        rc = lib.sdg_set_halo_send(S.h, etype, int(halo.n_send), ip(halo.send_elems))
+    if rc != 0:
+        raise RuntimeError(lib.sdg_last_error().decode())
 
 
 # ---- the multi-GPU solver ----------------------------------------------------------------------------------------------------
@@ -192,7 +232,9 @@ class DistributedSolver:
         self.etype = self.part.etype
         self.S = Solver(cfg, self.part.mesh, device=self.device, n_ghost={self.etype: self.part.n_ghost}, reorder=reorder)
         self.lib = load_library()
-        self.halo = HaloExchange(self.part, group)
+        # kernels that read published face traces (P3 hexahedra: Navier-Stokes, Euler through traces) exchange 640-byte trace rows
+        self.rows = bool(self.lib.sdg_uses_trace_rows(self.S.h)) and os.environ.get("SDG_HALO_ROWS", "1") != "0"
+        self.halo = HaloExchange(self.part, group, rows=self.rows)
         self.Nv = self.S.Nv
         self.n_global = self.part.n_elements_global
         sz = self.S.sizes(self.etype)
@@ -200,10 +242,7 @@ class DistributedSolver:
         self.elem_doubles = sz.Nv * sz.Nb
         self.n_pass = int(self.lib.sdg_num_passes(self.S.h))
         self.n_stage = int(self.lib.sdg_num_stages(self.S.h))
-        rc = self.lib.sdg_set_halo_send(self.S.h, self.etype, int(self.halo.n_send),
-                                        self.halo.send_elems.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
-        if rc != 0:
-            raise RuntimeError(self.lib.sdg_last_error().decode())
+        _set_halo(self.lib, self.S, self.etype, self.halo)
         self.main = torch.cuda.ExternalStream(int(self.lib.sdg_stream(self.S.h)), device=self.device)
         self.comm = torch.cuda.Stream(device=self.device, priority=-1)   # pack + NCCL get SM slots ahead of the queued interior blocks
         self.ev_ready = torch.cuda.Event()
@@ -253,7 +292,8 @@ class DistributedSolver:
         mine = np.zeros(5 * 64, dtype=np.uint8)
         self._chk(lib.sdg_ipc_export(self.S.h, mine.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte))))
         info = dict(handles=mine.tobytes(), n_owned=int(part.n_owned), peers=[int(q) for q in part.peers],
-                    recv={int(q): (int(part.recv_range[q][0]), int(part.recv_range[q][1])) for q in part.peers})
+                    recv={int(q): (int(part.recv_range[q][0]), int(part.recv_range[q][1])) for q in part.peers},
+                    recv_rows={int(q): part.recv_rows[q].tolist() for q in part.peers} if self.rows else {})
         everyone = [None] * self.world
         self.dist.all_gather_object(everyone, info, group=self.group)
         peers = [int(q) for q in part.peers]
@@ -261,19 +301,28 @@ class DistributedSolver:
         handles = np.zeros(max(n, 1) * 5 * 64, dtype=np.uint8)
         ghost_first = np.zeros(max(n, 1), dtype=np.int64)
         send_first = np.zeros(max(n, 1), dtype=np.int32); send_count = np.zeros(max(n, 1), dtype=np.int32); slot = np.zeros(max(n, 1), dtype=np.int32)
+        dst_units = np.zeros(max(int(self.halo.n_send), 1), dtype=np.int64)
         for k, q in enumerate(peers):
             other = everyone[q]
             handles[k * 320:(k + 1) * 320] = np.frombuffer(other["handles"], dtype=np.uint8)
-            r0, nr = other["recv"].get(self.rank, (0, 0))
-            ns = int(part.send_local[q].size)
-            if nr != ns:
-                raise RuntimeError(f"halo mismatch: rank {self.rank} sends {ns} elements to {q}, which expects {nr}")
-            ghost_first[k] = other["n_owned"] + r0
+            ns = self.halo.send_count[q]
+            if self.rows:
+                rows = np.asarray(other["recv_rows"].get(self.rank, np.zeros((0, 2), dtype=np.int64)), dtype=np.int64).reshape(-1, 2)
+                if rows.shape[0] != ns:
+                    raise RuntimeError(f"halo mismatch: rank {self.rank} sends {ns} rows to {q}, which expects {rows.shape[0]}")
+                dst_units[self.halo.send_off[q]:self.halo.send_off[q] + ns] = rows[:, 0] * 6 + rows[:, 1]   # ghost rows keep their caller index
+            else:
+                r0, nr = other["recv"].get(self.rank, (0, 0))
+                if nr != ns:
+                    raise RuntimeError(f"halo mismatch: rank {self.rank} sends {ns} elements to {q}, which expects {nr}")
+                ghost_first[k] = other["n_owned"] + r0
             send_first[k] = self.halo.send_off[q]; send_count[k] = ns
             slot[k] = other["peers"].index(self.rank)
         self._chk(lib.sdg_ipc_connect(self.S.h, n, handles.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
                                       ghost_first.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), send_first.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                                       send_count.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), slot.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        if self.rows:
+            self._chk(lib.sdg_ipc_set_destination_units(self.S.h, int(self.halo.n_send), dst_units.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
 
     def _exchange(self, what):
         """Refresh the ghost copies of field `what` (0 state, 1 volume gradient); returns after ENQUEUEING the work on the
@@ -293,6 +342,7 @@ class DistributedSolver:
             per_elem = int(self.lib.sdg_halo_doubles_per_element(self.S.h, what))
             reqs = self.halo.start(send, recv, per_elem)
             self.halo.finish(reqs)      # stream-ordered for NCCL: the communication stream waits, the host does not
+            self._chk(self.lib.sdg_halo_unpack(self.S.h, self.etype, what, ctypes.c_void_p(self.comm.cuda_stream)))   # trace rows: staging -> rows
             self.ev_halo.record(self.comm)
 
     # -- Solver interface ---------------------------------------------------------------------------------------------------
@@ -372,13 +422,12 @@ class InProcessCluster:
         self.world = world
         self.device = device
         self.parts = [partition(mesh, r, world) for r in range(world)]
-        self.halos = [HaloExchange(p) for p in self.parts]
         self.etype = self.parts[0].etype
         self.S = [Solver(cfg, p.mesh, device=device, n_ghost={self.etype: p.n_ghost}, reorder=reorder) for p in self.parts]
+        self.rows = bool(self.lib.sdg_uses_trace_rows(self.S[0].h)) and os.environ.get("SDG_HALO_ROWS", "1") != "0"
+        self.halos = [HaloExchange(p, rows=self.rows) for p in self.parts]
         for S, h in zip(self.S, self.halos):
-            rc = self.lib.sdg_set_halo_send(S.h, self.etype, int(h.n_send), h.send_elems.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
-            if rc != 0:
-                raise RuntimeError(self.lib.sdg_last_error().decode())
+            _set_halo(self.lib, S, self.etype, h)
         sz = self.S[0].sizes(self.etype)
         self.elem_doubles = sz.Nv * sz.Nb
         self.dim = self.S[0].dim
@@ -407,11 +456,15 @@ class InProcessCluster:
         bufs = [self._buffers(r, what) for r in range(self.world)]
         for r, p in enumerate(self.parts):
             for q in p.peers:
-                r0, nr = p.recv_range[q]
+                r0, nr = self.halos[r].recv_off[q], self.halos[r].recv_count[q]
                 if nr:
                     s0 = self.halos[q].send_off[r]
+                    assert self.halos[q].send_count[r] == nr
                     bufs[r][1][r0 * per:(r0 + nr) * per].copy_(bufs[q][0][s0 * per:(s0 + nr) * per])
         self.torch.cuda.synchronize()
+        for S in self.S:
+            self._chk(self.lib.sdg_halo_unpack(S.h, self.etype, what, None))
+            S.synchronize()
 
     def initializeSolver(self, ic, bc=None):
         for S in self.S:
@@ -440,7 +493,7 @@ class InProcessCluster:
 
 
 # ---- bench.py entry for N > 1 ---------------------------------------------------------------------------------------------------
-def bench_main(a, workload, metric, unit, bytes_per_dof, peaks, ClockSampler, ic, cfg_base):
+def bench_main(a, workload, metric, unit, bytes_per_dof, peaks, ClockSampler, ic, cfg_base, ns_cfg=None, ns_bytes_per_dof=144.0):
     """One rank of `torchrun ... bench.py --gpus N`: strong scaling of the same global mesh over N GPUs."""
     import torch
     import torch.distributed as dist
@@ -512,7 +565,7 @@ def bench_main(a, workload, metric, unit, bytes_per_dof, peaks, ClockSampler, ic
         value = dof_global * nst * a.steps / sec / 1e9
         stage_ms = ms / (a.steps * nst)
         achieved = bytes_per_dof * dof_global / world / (stage_ms * 1e-3) / 1e9
-        halo_bytes = int(D.halo.n_send) * D.elem_doubles * 8
+        halo_bytes = int(D.halo.n_send) * int(D.lib.sdg_halo_doubles_per_element(D.S.h, 0)) * 8
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": warmup, "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": workload, "elements": D.n_global, "scalar_dof": dof_global, "dt": dt,
@@ -525,6 +578,37 @@ def bench_main(a, workload, metric, unit, bytes_per_dof, peaks, ClockSampler, ic
                             "algorithmic_bytes_per_launch": bytes_per_dof * dof_global / world, "peak_source": how, "note": "per GPU"}}
         if e2e:
             out["e2e"] = e2e
+    ns_line = None
+    if ns_cfg is not None:
+        # north_star's Navier-Stokes target cube (96^3 P3 hexahedra, BR2) on the same N GPUs: strong scaling of the NS stage, same timing rules
+        D.S.close(); del D
+        torch.cuda.empty_cache()
+        cfg2 = dict(ns_cfg); cfg2["p"] = a.p
+        D2 = DistributedSolver(cfg2, M.periodic_box_fast(3, 96), device=local)
+        D2.initializeSolver(ic)
+        dt2 = D2.calculateDeltaTime(1.0)
+        D2.stepSolver(dt2, 3)
+        steps2 = max(3, min(a.steps, 5))
+        D2.synchronize(); torch.cuda.synchronize(); dist.barrier()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(D2.main)
+        D2.stepSolver(dt2, steps2, want_error=False)
+        f1.record(D2.main)
+        D2.synchronize(); torch.cuda.synchronize()
+        ms2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        ms2 = float(ms2.item())
+        dof2 = D2.n_global * D2.sizes.Nb * D2.sizes.Nv
+        stage2 = ms2 / (steps2 * D2.n_stage)
+        ach2 = ns_bytes_per_dof * dof2 / world / (stage2 * 1e-3) / 1e9
+        ns_line = {"workload": f"periodic cube of configs[3] with CompresibleNS, HLLC, BR2, constant mu=1.4e-3, 96^3 hexes, p={a.p}, SSPRK3, {world} GPUs (strong scaling)",
+                   "value": dof2 * D2.n_stage * steps2 / (ms2 * 1e-3) / 1e9, "unit": unit, "ms_per_stage": stage2,
+                   "roofline": {"bound": "hbm", "achieved": ach2, "peak": peaks()[0], "unit": "GB/s", "frac": ach2 / peaks()[0], "note": "per GPU"},
+                   "halo": f"{int(D2.halo.n_send) * int(D2.lib.sdg_halo_doubles_per_element(D2.S.h, 0)) * 8 / 1e6:.1f} MB per rank per stage pass"}
+    if rank == 0:
+        if ns_line:
+            out["ns_target"] = ns_line
         print(json.dumps(out))
     dist.barrier()
     dist.destroy_process_group()

@@ -45,7 +45,8 @@ EXPORTS = [
     "sdg_compute_dt", "sdg_step", "sdg_step_timed", "sdg_residual", "sdg_set_halo_send", "sdg_halo_pack", "sdg_halo_buffers_device", "sdg_step_begin",
     "sdg_stage_pass", "sdg_step_end", "sdg_num_passes", "sdg_num_stages", "sdg_stream", "sdg_synchronize", "sdg_set_state_device",
     "sdg_get_state_device", "sdg_launch_count", "sdg_debug_plan", "sdg_ipc_export", "sdg_ipc_connect", "sdg_halo_push", "sdg_halo_wait",
-    "sdg_halo_doubles_per_element", "sdg_debug_physics",
+    "sdg_halo_doubles_per_element", "sdg_debug_physics", "sdg_uses_trace_rows", "sdg_set_halo_rows", "sdg_halo_unpack",
+    "sdg_ipc_set_destination_units",
 ]
 
 _lib = None

@@ -136,3 +136,31 @@ def test_push_targets_match_ghost_ranges(dim, n, world):
             assert nr == sent_global.size
             assert np.array_equal(pq.ghost_global[r0:r0 + nr], sent_global)
             assert sorted(pq.peers).index(r) < 64                  # flag slot bound of the library
+
+
+@pytest.mark.parametrize("make,world", [(lambda: M.periodic_box_fast(3, 6), 3), (lambda: M.periodic_box_fast(3, 4), 2), (lambda: M.sphere_in_box(3, 3, 2), 4),
+                                        (lambda: M.box(3, (4, 3, 5), 0.0, 1.0), 5)])
+def test_trace_row_lists_agree_between_peers(make, world):
+    """trace-row halo: what rank r sends to rank q — (owned element, local face) rows in ascending global face order — is, row for row,
+    what q expects to receive into its (ghost element, local face) rows; every cut face appears exactly once per direction."""
+    mesh = make()
+    parts = [P.partition(mesh, r, world) for r in range(world)]
+    f = mesh.faces
+    n_cut = 0
+    for r, p in enumerate(parts):
+        for q in p.peers:
+            send = p.send_rows[q]
+            recv = parts[q].recv_rows[r]
+            assert send.shape == recv.shape
+            glob_sent = np.stack([send[:, 0] + p.lo, send[:, 1]], axis=1)                                  # global element, local face
+            ghost = recv[:, 0] - parts[q].n_owned
+            assert np.all(ghost >= 0)
+            glob_recv = np.stack([parts[q].ghost_global[ghost], recv[:, 1]], axis=1)
+            assert np.array_equal(glob_sent, glob_recv)
+            assert len({tuple(x) for x in glob_sent.tolist()}) == send.shape[0]                           # no row twice
+            n_cut += send.shape[0]
+    b = P.block_bounds(mesh.n_elements, world)
+    owner = lambda e: np.searchsorted(b, e, side="right") - 1
+    ni = int(f["n_int"])
+    expected = int(np.sum(owner(np.asarray(f["le"][:ni])) != owner(np.asarray(f["re"][:ni]))))
+    assert n_cut == 2 * expected

@@ -24,7 +24,7 @@ def main():
     ok = True
     NS = dict(model=1, transport=1, mu=0.01)
     for dim, n, cfg in [(3, 8, dict(p=3, conv_flux=2, rk=2)), (2, 16, dict(p=3, conv_flux=3, rk=2)), (3, 8, dict(NS, p=2, conv_flux=2, rk=2, visc_flux=2)),
-                        (3, 6, dict(NS, p=3, conv_flux=2, rk=2, visc_flux=1))]:
+                        (3, 6, dict(NS, p=3, conv_flux=2, rk=2, visc_flux=1)), (3, 8, dict(NS, p=3, conv_flux=2, rk=2, visc_flux=2))]:
         mesh = M.periodic_box_fast(dim, n)
         ic = cases.ic_density_wave([0.7, 0.3] if dim == 2 else [0.5, 0.3, 0.2])
         D = DistributedSolver(dict(cfg), mesh, device=local)
