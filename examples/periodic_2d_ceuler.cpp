@@ -4,8 +4,9 @@
  * Mirrors /root/reference/examples/periodic_2d_ceuler.cpp line for line where the surface allows: same SimulationControl
  * typedef (:19-26), same InitialCondition / BoundaryCondition specialisations (:28-44), same System setter sequence (:49-59).
  * Differences: the include, and generateMesh() (gmsh transfinite 10x10 recombined square with periodic sides, :64-96) is
- * replaced by the in-code producer makePeriodicBox (Gmsh is not available here); setTimeIntegration / setViewConfig get their
- * iteration count explicitly because the reference reads it from std::cin.
+ * written with the in-code producer makePeriodicBox into the flat mesh format (Gmsh is not available here); setTimeIntegration /
+ * setViewConfig get their iteration count explicitly because the reference reads it from std::cin.  Output (raw/<prefix>_<step>.zst, error.txt)
+ * goes to build/out/periodic_2d_ceuler under the working directory.
  *
  * usage: periodic_2d_ceuler [iterations=100] [state_out.bin]
  */
@@ -15,6 +16,10 @@
 #include <iostream>
 
 inline const std::string kExampleName{"periodic_2d_ceuler"};
+
+inline const std::filesystem::path kExampleDirectory{std::filesystem::path("build/out") / kExampleName};
+
+void generateMesh(const std::filesystem::path& mesh_file_path);
 
 using SimulationControl = SubrosaDG::SimulationControl<SubrosaDG::SolveControl<SubrosaDG::DimensionEnum::D2,
     SubrosaDG::PolynomialOrderEnum::P3, SubrosaDG::BoundaryTimeEnum::Steady, SubrosaDG::SourceTermEnum::None>,
@@ -44,12 +49,12 @@ inline Primitive<SimulationControl> SubrosaDG::BoundaryCondition<SimulationContr
 int main(int argc, char* argv[]) {
   const int iterations = argc > 1 ? std::atoi(argv[1]) : 100;
   SubrosaDG::System<SimulationControl> system;
-  system.setMesh(SubrosaDG::makePeriodicBox(SimulationControl::kDimension, 10, 0.0, 2.0));
+  system.setMesh(kExampleDirectory / "periodic_2d_ceuler.sdgm", generateMesh);
   system.addBoundaryCondition<SubrosaDG::BoundaryConditionEnum::Periodic>(1);
   system.setThermodynamicModel<SimulationControl::kThermodynamicModel>(2.5_r, 25.0_r / 14.0_r);
   system.setTimeIntegration(1.0_r, {0, iterations});
   system.setDeltaTime(1.0e-03_r);
-  system.setViewConfig("build/out/" + kExampleName, kExampleName, -1);
+  system.setViewConfig(kExampleDirectory, kExampleName, -1);
   system.addViewVariable({SubrosaDG::ViewVariableEnum::Density, SubrosaDG::ViewVariableEnum::Velocity,
       SubrosaDG::ViewVariableEnum::Pressure});
   system.synchronize();
@@ -74,4 +79,11 @@ int main(int argc, char* argv[]) {
     f.write(reinterpret_cast<const char*>(u.data()), static_cast<std::streamsize>(u.size() * sizeof(double)));
   }
   return EXIT_SUCCESS;
+}
+
+// the reference meshes the [0,2]^2 square with a 10 x 10 transfinite recombined Gmsh grid with periodic sides (:64-96); here the same
+// grid comes from the in-code producer, through the mesh file like in the reference
+void generateMesh(const std::filesystem::path& mesh_file_path) {
+  std::filesystem::create_directories(mesh_file_path.parent_path());
+  SubrosaDG::makePeriodicBox(SimulationControl::kDimension, 10, 0.0, 2.0).writeFlat(mesh_file_path);
 }

@@ -16,6 +16,12 @@
 
 inline const std::string kExampleName{"periodic_3d_ceuler"};
 
+inline const std::filesystem::path kExampleDirectory{std::filesystem::path("build/out") / kExampleName};
+
+inline int mesh_cells{16};
+
+void generateMesh(const std::filesystem::path& mesh_file_path);
+
 using SimulationControl = SubrosaDG::SimulationControl<SubrosaDG::SolveControl<SubrosaDG::DimensionEnum::D3,
     SubrosaDG::PolynomialOrderEnum::P3, SubrosaDG::BoundaryTimeEnum::Steady, SubrosaDG::SourceTermEnum::None>,
     SubrosaDG::NumericalControl<SubrosaDG::MeshModelEnum::Hexahedron, SubrosaDG::ShockCapturingEnum::None,
@@ -43,13 +49,13 @@ inline Primitive<SimulationControl> SubrosaDG::BoundaryCondition<SimulationContr
 int main(int argc, char* argv[]) {
   const int iterations = argc > 1 ? std::atoi(argv[1]) : 100;
   SubrosaDG::System<SimulationControl> system;
-  const int cells = argc > 3 ? std::atoi(argv[3]) : 16;
-  system.setMesh(SubrosaDG::makePeriodicBox(SimulationControl::kDimension, cells, 0.0, 2.0));
+  mesh_cells = argc > 3 ? std::atoi(argv[3]) : 16;
+  system.setMesh(kExampleDirectory / "periodic_3d_ceuler.sdgm", generateMesh);
   system.addBoundaryCondition<SubrosaDG::BoundaryConditionEnum::Periodic>(1);
   system.setThermodynamicModel<SimulationControl::kThermodynamicModel>(2.5_r, 25.0_r / 14.0_r);
   system.setTimeIntegration(1.0_r, {0, iterations});
   system.setDeltaTime(5.0e-04_r);
-  system.setViewConfig("build/out/" + kExampleName, kExampleName, -1);
+  system.setViewConfig(kExampleDirectory, kExampleName, -1);
   system.addViewVariable({SubrosaDG::ViewVariableEnum::Density, SubrosaDG::ViewVariableEnum::Velocity,
       SubrosaDG::ViewVariableEnum::Pressure});
   system.synchronize();
@@ -74,4 +80,10 @@ int main(int argc, char* argv[]) {
     f.write(reinterpret_cast<const char*>(u.data()), static_cast<std::streamsize>(u.size() * sizeof(double)));
   }
   return EXIT_SUCCESS;
+}
+
+// the reference's Gmsh box with periodic faces, from the in-code producer through the mesh file
+void generateMesh(const std::filesystem::path& mesh_file_path) {
+  std::filesystem::create_directories(mesh_file_path.parent_path());
+  SubrosaDG::makePeriodicBox(SimulationControl::kDimension, mesh_cells, 0.0, 2.0).writeFlat(mesh_file_path);
 }

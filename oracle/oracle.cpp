@@ -930,6 +930,40 @@ int orc_get_gradient_at_quadrature(void* h, int type, double* out) {
     gemmNT(s.G, s.Nq, s.Nb, 1.0, &C[(size_t)e * s.G * s.Nb], s.G, B.tab.Phi.data(), s.Nq, 0.0, &out[(size_t)e * s.Nq * s.G], s.G);
   ORC_CATCH
 }
+// RawBinary payload (RawBinary.cpp:75-88): variable_gradient_basis_function_coefficient_ of every element, [n][Nb][Nv*D]
+int orc_get_gradient_state(void* h, int type, double* out) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  if (!O.blk[type]) throw std::runtime_error("oracle: no such element block");
+  ElemBlock& B = *O.blk[type];
+  const std::vector<double>& C = O.P.ns() ? B.gcoef : B.gcoefVol;
+  std::copy(C.begin(), C.end(), out);
+  ORC_CATCH
+}
+// RawBinary payload (RawBinary.cpp:89-154): per boundary face, in face order, the gradient coefficients written next to the parent's
+// state: BR1 the total gradient, BR2 variable_volume_gradient_ + variable_interface_gradient_ of THAT face.  Rows are Nb(parent) x Nv*D.
+int orc_get_boundary_gradient_state(void* h, double* out) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  const FaceSet& F = O.F;
+  const int G = O.P.Nv * O.P.D;
+  size_t at = 0;
+  for (int b = 0; b < F.nBnd; b++) {
+    const int i = F.nInt + b, t = F.etype[0][i], e = F.elem[0][i], f = F.lface[0][i];
+    const ElemBlock& B = *O.blk[t]; const int Nb = B.tab.Nb;
+    const size_t len = (size_t)G * Nb;
+    if (O.P.visc == kBR2) {
+      const double* a = &B.gcoefVol[(size_t)e * len];
+      const double* c = &B.gicoef[((size_t)e * B.tab.Nf + f) * len];
+      for (size_t k = 0; k < len; k++) out[at + k] = a[k] + c[k];
+    } else {
+      const double* a = &(O.P.ns() ? B.gcoef : B.gcoefVol)[(size_t)e * len];
+      for (size_t k = 0; k < len; k++) out[at + k] = a[k];
+    }
+    at += len;
+  }
+  ORC_CATCH
+}
 // Pointwise physics of the oracle behind the SAME entry point as oracle/ref_physics.cpp (the reference's own functions): what = 0 Riemann
 // flux, 1 boundary face point, 2 viscous terms, 3 conversions / raw flux / source.  cfg = {dim, model, eos, transport, conv_flux, source},
 // params = {cp, cv, mu, c0, rho0, beta, t_ref}; input / output layouts as documented there.  Pins the restatement against

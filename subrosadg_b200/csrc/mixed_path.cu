@@ -682,6 +682,61 @@ void MixedSolver::gradientAtQuadrature(int type, double* Gq) {
   CUDA_OK(cudaStreamSynchronize(stream_));
 }
 
+// gradient coefficients of the CURRENT state in every block (Gvol, Gtot, Gf)
+void MixedSolver::refreshGradient() {
+  if (!phys_.ns) throw std::runtime_error("gradient state exists for Navier-Stokes models only");
+  Args a; fill(a);
+  const int nfp = (F_.nInt + F_.nBnd) * (p_ + 1);
+  mxFaceKernel<0><<<std::max(1, (nfp + 127) / 128), 128, 0, stream_>>>(a); launches++;
+  for (int t : {(int)kTriangle, (int)kQuadrangle}) if (blk_[t]) { mxGradElemKernel<<<elemBlocks(blk_[t]->n), kElemThreads, gradSmemBytes(blk_[t]->T), stream_>>>(a, t == kTriangle ? 0 : 1); launches++; }
+  CUDA_OK(cudaGetLastError());
+}
+
+// RawBinary.cpp:75-88: variable_gradient_basis_function_coefficient_, [n][Nb][Nv*D]
+void MixedSolver::gradientState(int type, double* G) {
+  needDevice(); CUDA_OK(cudaSetDevice(device_));
+  refreshGradient();
+  MixedBlock& B = block(type);
+  CUDA_OK(cudaMemcpyAsync(G, B.Gtot.p, B.Gtot.n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+}
+
+// RawBinary.cpp:89-154: per boundary face the parent's gradient block (BR1 total; BR2 volume part + the lift of that face)
+static __global__ void mxBoundaryGradientKernel(const double* __restrict__ base, const double* __restrict__ lift, const int* __restrict__ rec /* {e, f, offset} */,
+                                                int nRec, int Nf, int len, double* __restrict__ out) {
+  const int r = blockIdx.x;
+  if (r >= nRec) return;
+  const int e = rec[3 * r], f = rec[3 * r + 1]; double* dst = out + rec[3 * r + 2];
+  const double* a = base + (size_t)e * len;
+  const double* b = lift ? lift + ((size_t)e * Nf + f) * len : nullptr;
+  for (int k = threadIdx.x; k < len; k += blockDim.x) dst[k] = a[k] + (b ? b[k] : 0.0);
+}
+void MixedSolver::boundaryGradientState(double* Gb) {
+  needDevice(); CUDA_OK(cudaSetDevice(device_));
+  refreshGradient();
+  if (F_.nBnd == 0) return;
+  std::vector<int> rec[7]; size_t at = 0;
+  for (int b = 0; b < F_.nBnd; b++) {
+    const int i = F_.nInt + b, t = F_.lt[i];
+    rec[t].push_back(F_.le[i]); rec[t].push_back(F_.lf[i]); rec[t].push_back((int)at);
+    at += (size_t)block(t).T.Nb * kG;
+  }
+  DevBuf<double> out; out.alloc(at);
+  DevBuf<int> d;
+  for (int t = 0; t < 7; t++) if (!rec[t].empty()) {
+    MixedBlock& B = block(t);
+    d.alloc(rec[t].size());
+    CUDA_OK(cudaMemcpyAsync(d.p, rec[t].data(), rec[t].size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    const int nRec = (int)(rec[t].size() / 3);
+    const bool br2 = phys_.visc == kBR2;
+    mxBoundaryGradientKernel<<<nRec, 64, 0, stream_>>>(br2 ? B.Gvol.p : B.Gtot.p, br2 ? B.Gf.p : nullptr, d.p, nRec, B.T.Nf, B.T.Nb * kG, out.p); launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(stream_));
+  }
+  CUDA_OK(cudaMemcpyAsync(Gb, out.p, at * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+}
+
 double MixedSolver::computeDt(double cfl) {
   needDevice(); CUDA_OK(cudaSetDevice(device_));
   double best = 1.7976931348623157e308;

@@ -47,6 +47,9 @@ class MixedSolver {
   void getStateDevice(int type, void* U);
   void stateAtQuadrature(int type, double* Uq);
   void gradientAtQuadrature(int type, double* Gq);
+  void gradientState(int type, double* G);
+  void boundaryGradientState(double* Gb);
+  void refreshGradient();
   double computeDt(double cfl);
   void step(double dt, int nSteps, double* relErr, float* ms);
   void residual(int type, double* Rmodal, double* rhsq);

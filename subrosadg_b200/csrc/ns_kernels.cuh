@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
       if (br2) {
 #pragma unroll
         for (int f = 0; f < NF; f++) {
+          if (A.mode == 3 && A.faceSel >= 0 && f != A.faceSel) continue;
           const int dn = faceDirOf<D>(f), side = faceSideOf<D>(f);
           const int st = strideOf<N, D>(dn);
           const int id = (q / st) % N;

@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
 
   // ---- G1-G4, one conserved variable at a time (a rolled loop: the body is ~600 instructions); the line and the face values of the
   //      NEXT variable are requested before this one is worked on ---------------------------------------------------------------------
+  const unsigned selBits = A.faceSel < 0 ? 63u : 1u << A.faceSel;   // diagnostics: the lift of one face only
   double fmine[6], fother[6];
   auto loadFaceValues = [&](int v) {
 #pragma unroll
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
       const double mine = cmine[f];
       const double other = cother[f];
       const double avg = 0.5 * (mine + other), jmp = 0.5 * (amR ? mine - other : other - mine);   // ViscousFlux.cpp:33-56
-      const double aV = (amR ? -avg : avg) * jw[f], aT = aV + jmp * jw[f];                        // SpatialDiscrete.cpp:885-906
+      const double aV = (amR ? -avg : avg) * jw[f], aT = aV + ((selBits >> f) & 1 ? jmp * jw[f] : 0.0);   // SpatialDiscrete.cpp:885-906
       constexpr int dnTab[6] = {2, 1, 0, 0, 1, 2};
       const int dn = dnTab[f], side = f >= 3 ? 1 : 0;
       if (dn == 2 || !AFFINE) {

@@ -89,7 +89,7 @@ void fillArgs(sdg_ctx* c, StageArgs& a) {
   a.geoE = c->geoE.p; a.invjw = c->invjw.p; a.geoF = c->geoF.p; a.cfGeo = c->cfGeo.p;
   a.faceRec = reinterpret_cast<const int4*>(c->faceRec.p); a.chunkFaceOff = c->chunkOff.p; a.chunkList = nullptr;
   a.dummy = c->dummy.p; a.tab = c->tab.p; a.normPartial = nullptr;
-  a.nOwned = B.nOwned; a.nInt = c->plan.F.nInt; a.mode = 0; a.phys = c->phys;
+  a.nOwned = B.nOwned; a.nInt = c->plan.F.nInt; a.mode = 0; a.faceSel = -1; a.phys = c->phys;
   const int N = B.T.N;
   for (int i = 0; i < N * N; i++) { a.dm[i] = B.T.Dm[i]; a.k1[i] = B.T.K1[i]; }
   for (int i = 0; i < 2 * N; i++) a.lend[i] = B.T.Lend[i];
@@ -547,6 +547,25 @@ int sdg_get_state_at_quadrature(sdg_ctx* c, int32_t type, double* Uq) {
   SDG_CATCH
 }
 
+// Gradient of the CURRENT state at the nodes, on the device: all lifts (faceSel < 0: variable_gradient_basis_function_coefficient_)
+// or the volume part plus the BR2 lift of local face faceSel only (variable_volume_gradient_ + variable_interface_gradient_(f),
+// RawBinary.cpp:118-135).  Returns the device array [pos][NV*D][NN]; *zslow = node order of the line kernels.  c->G2 must be allocated.
+static const double* nodalGradient(sdg_ctx* c, int faceSel, int* zslow) {
+  StageArgs args; fillArgs(c, args);
+  args.Uin = c->U[c->cur].p; args.Ulast = c->U[c->cur].p; args.Uout = c->U[(c->cur + 1) % 3].p;
+  args.Gvol = c->G.p; args.Gout = c->G.p; args.faceSel = c->phys.visc == kBR2 ? faceSel : -1;
+  if (c->lineTrace) {   // pass G of the line kernels leaves the TOTAL gradient in G (zeta-slowest node order)
+    ensureTraces(c, c->cur, c->stream);
+    args.TUin = c->TU[c->cur].p; args.TUout = c->TU[(c->cur + 1) % 3].p;
+    lineBoundary(c, args, -1, c->stream);
+  }
+  runStage(c, args, -1, c->stream, 0);
+  const bool second = !c->lineTrace && c->phys.visc == kBR2;
+  if (second) { args.Gout = c->G2.p; args.mode = 3; runStage(c, args, -1, c->stream, 1); }
+  *zslow = c->lineTrace ? 1 : 0;
+  return second ? c->G2.p : c->G.p;
+}
+
 int sdg_get_gradient_at_quadrature(sdg_ctx* c, int32_t type, double* Gq) {
   SDG_TRY
   if (c->mx) { needFinal(c); c->mx->gradientAtQuadrature(type, Gq); return 0; }
@@ -557,20 +576,66 @@ int sdg_get_gradient_at_quadrature(sdg_ctx* c, int32_t type, double* Gq) {
   const int NG = c->NV * c->D;
   c->G2.alloc(c->G.n);
   DevBuf<double> tmp; tmp.alloc(c->G.n);
-  StageArgs args; fillArgs(c, args);
-  args.Uin = c->U[c->cur].p; args.Ulast = c->U[c->cur].p; args.Uout = c->U[(c->cur + 1) % 3].p;
-  args.Gvol = c->G.p; args.Gout = c->G.p;
-  if (c->lineTrace) {   // pass G of the line kernels leaves the TOTAL gradient in G (zeta-slowest node order)
-    ensureTraces(c, c->cur, c->stream);
-    args.TUin = c->TU[c->cur].p; args.TUout = c->TU[(c->cur + 1) % 3].p;
-    lineBoundary(c, args, -1, c->stream);
-  }
-  runStage(c, args, -1, c->stream, 0);
-  if (!c->lineTrace && c->phys.visc == kBR2) { args.Gout = c->G2.p; args.mode = 3; runStage(c, args, -1, c->stream, 1); }
-  seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>((!c->lineTrace && c->phys.visc == kBR2) ? c->G2.p : c->G.p, tmp.p, c->perm.p, B.n, NG, B.T.NN, c->lineTrace ? 3 : 1);
+  int zslow = 0;
+  const double* g = nodalGradient(c, -1, &zslow);
+  seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(g, tmp.p, c->perm.p, B.n, NG, B.T.NN, zslow ? 3 : 1);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(Gq, tmp.p, c->G.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->G2.release();
+  SDG_CATCH
+}
+
+int sdg_get_gradient_state(sdg_ctx* c, int32_t type, double* G) {
+  SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->gradientState(type, G); return 0; }
+  needFinal(c); needDevice(c); needType(c, type);
+  if (!c->phys.ns) throw std::runtime_error("gradient state exists for Navier-Stokes models only");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  const int NG = c->NV * c->D;
+  c->G2.alloc(c->G.n);
+  DevBuf<double> tmp; tmp.alloc(c->G.n);
+  int zslow = 0;
+  const double* g = nodalGradient(c, -1, &zslow);
+  modalRowsKernel<<<B.n, 128, sizeof(double) * NG * B.T.NN, c->stream>>>(g, tmp.p, c->PhiInv.p, c->perm.p, nullptr, B.n, NG, B.T.NN, zslow);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(G, tmp.p, c->G.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->G2.release();
+  SDG_CATCH
+}
+
+int sdg_get_boundary_gradient_state(sdg_ctx* c, double* Gb) {
+  SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->boundaryGradientState(Gb); return 0; }
+  needFinal(c); needDevice(c);
+  if (!c->phys.ns) throw std::runtime_error("gradient state exists for Navier-Stokes models only");
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk; const FaceInput& F = c->plan.F;
+  if (F.nBnd == 0) return 0;
+  const int NG = c->NV * c->D, NF = 2 * c->D;
+  const size_t row = (size_t)NG * B.T.NN;
+  c->G2.alloc(c->G.n);
+  DevBuf<double> out; out.alloc((size_t)F.nBnd * row);
+  DevBuf<int> list; list.alloc((size_t)F.nBnd * 2);
+  const bool perFace = c->phys.visc == kBR2;
+  for (int f = perFace ? 0 : -1; f < (perFace ? NF : 0); f++) {
+    std::vector<int> h;
+    for (int b = 0; b < F.nBnd; b++) if (!perFace || F.lf[F.nInt + b] == f) { h.push_back(B.perm[F.le[F.nInt + b]]); h.push_back(b); }
+    if (h.empty()) continue;
+    int zslow = 0;
+    const double* g = nodalGradient(c, f, &zslow);
+    CUDA_OK(cudaMemcpyAsync(list.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const int nl = (int)(h.size() / 2);
+    modalRowsKernel<<<nl, 128, sizeof(double) * row, c->stream>>>(g, out.p, c->PhiInv.p, nullptr, reinterpret_cast<const int2*>(list.p), nl, NG, B.T.NN, zslow);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(c->stream));   // h is reused
+  }
+  CUDA_OK(cudaMemcpyAsync(Gb, out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   c->G2.release();
   SDG_CATCH

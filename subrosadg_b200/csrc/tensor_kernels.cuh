@@ -68,6 +68,7 @@ struct StageArgs {
   double dm[kMaxN * kMaxN], lend[2 * kMaxN], k1[kMaxN * kMaxN];   // 1-D operators in the parameter (constant) bank: Dm[a*N+b], Lend[side*N+a], K1
   int nOwned, nInt;
   int mode;               // 0 RK update, 1 write dU/dt, 2 write R (nodal, un-inverted)
+  int faceSel;            // gradient diagnostics: -1 = lifts of all faces (total gradient), f = volume part + the lift of local face f only (RawBinary.cpp:110-135)
   PhysParams phys;
   // trace-based line kernels (nsl_kernels.cuh): published face traces [nTotal][6][5][16], per-(element, face) link / geometry records
   const double* TUin; double* TUout;   // traces of the state read / written by this stage
@@ -543,6 +544,30 @@ static __global__ void seamTransformKernel(const double* __restrict__ in, double
       const int i = o / NV, v = o - i * NV;
       for (int q = 0; q < NN; q++) s += M[(size_t)i * NN + q] * sbuf[v * NN + q];
     }
+    dst[o] = s;
+  }
+}
+
+// RawBinary payload rows: nodal fields [pos][C][NN] (zslow: internal node index (q % 4) * 16 + q / 4) -> modal coefficients
+// out[row][b][C] = Σ_q M[b][q] in[pos][c][q].  list == nullptr: every element e (pos = perm[e], row = e); else list[i] = {pos, row}.
+static __global__ void modalRowsKernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ M, const int* __restrict__ perm,
+                                       const int2* __restrict__ list, int n, int C, int NN, int zslow) {
+  extern __shared__ double sbuf[];  // one element: C*NN
+  const int e = blockIdx.x;
+  if (e >= n) return;
+  const int pos = list ? list[e].x : (perm ? perm[e] : e);
+  const int row = list ? list[e].y : e;
+  const double* src = in + (size_t)pos * C * NN;
+  for (int i = threadIdx.x; i < C * NN; i += blockDim.x) {
+    const int c = i / NN, q = i - c * NN;
+    sbuf[i] = src[c * NN + (zslow ? (q & 3) * 16 + (q >> 2) : q)];
+  }
+  __syncthreads();
+  double* dst = out + (size_t)row * C * NN;
+  for (int o = threadIdx.x; o < C * NN; o += blockDim.x) {
+    const int b = o / C, c = o - b * C;
+    double s = 0.0;
+    for (int q = 0; q < NN; q++) s += M[(size_t)b * NN + q] * sbuf[c * NN + q];
     dst[o] = s;
   }
 }

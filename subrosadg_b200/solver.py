@@ -46,7 +46,7 @@ EXPORTS = [
     "sdg_stage_pass", "sdg_step_end", "sdg_num_passes", "sdg_num_stages", "sdg_stream", "sdg_synchronize", "sdg_set_state_device",
     "sdg_get_state_device", "sdg_launch_count", "sdg_debug_plan", "sdg_ipc_export", "sdg_ipc_connect", "sdg_halo_push", "sdg_halo_wait",
     "sdg_halo_doubles_per_element", "sdg_debug_physics", "sdg_uses_trace_rows", "sdg_set_halo_rows", "sdg_halo_unpack",
-    "sdg_ipc_set_destination_units",
+    "sdg_ipc_set_destination_units", "sdg_get_gradient_state", "sdg_get_boundary_gradient_state",
 ]
 
 _lib = None
@@ -204,6 +204,24 @@ class Solver:
         s = self.sizes(t)
         out = np.zeros((s.n, s.Nq, s.Nv * self.dim))
         _chk(load_library().sdg_get_gradient_at_quadrature(self.h, t, _dp(out)))
+        return out
+
+    def gradient_state(self, t):
+        """variable_gradient_basis_function_coefficient_ [n][Nb][Nv*D] of the current state (RawBinary.cpp:75-88)."""
+        s = self.sizes(t)
+        out = np.zeros((s.n, s.Nb, s.Nv * self.dim))
+        _chk(load_library().sdg_get_gradient_state(self.h, t, _dp(out)))
+        return out
+
+    def boundary_gradient_state(self):
+        """Per boundary face (face order) the parent's gradient block as RawBinary.cpp:89-154 writes it (BR1 total, BR2 volume + that
+        face's lift): a flat array of Nb(parent type) x Nv*D rows."""
+        f = self.mesh.faces
+        lt = np.asarray(f["lt"])[int(f["n_int"]):int(f["n_int"]) + int(f["n_bnd"])]
+        n = sum(self.sizes(int(t)).Nb for t in lt) * self.Nv * self.dim
+        out = np.zeros(int(n))
+        if n:
+            _chk(load_library().sdg_get_boundary_gradient_state(self.h, _dp(out)))
         return out
 
     # -- Solver::calculateDeltaTime (TimeIntegration.cpp:133-179) -------------------------------------------------------------

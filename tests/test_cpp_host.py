@@ -20,13 +20,13 @@ def examples_built(built):
     return True
 
 
-def test_examples_build_and_fail_loudly_without_gpu(examples_built):
+def test_examples_build_and_fail_loudly_without_gpu(examples_built, tmp_path):
     exe = os.path.join(EX, "_build", "periodic_2d_ceuler")
     assert os.path.exists(exe)
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present: covered by the gpu test")
-    r = subprocess.run([exe, "1"], capture_output=True, text=True)
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode != 0 and "no usable CUDA device" in (r.stdout + r.stderr)
 
 
@@ -57,7 +57,7 @@ def test_cpp_driver_matches_ctypes_path(examples_built, tmp_path, name, dim, vel
     out = tmp_path / "state.bin"
     n = 10 if dim == 2 else 6
     args = [os.path.join(EX, "_build", name), "20", str(out)] + ([str(n)] if dim == 3 else [])
-    r = subprocess.run(args, capture_output=True, text=True)
+    r = subprocess.run(args, capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     err = float(r.stdout.strip().splitlines()[-1].split(":")[-1])
     assert err < 1e-4, r.stdout           # P3 on this grid: discretisation error of the travelling wave
@@ -84,7 +84,7 @@ def test_cpp_config_drivers_match_ctypes_path(examples_built, tmp_path, name, pr
     path = tmp_path / "mesh.sdgm"
     M.write_flat(mesh, path)
     out = tmp_path / "state"
-    r = subprocess.run([os.path.join(EX, "_build", name), str(path), "3", str(out)], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(EX, "_build", name), str(path), "3", str(out)], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     dim = mesh.dim
 
@@ -108,3 +108,53 @@ def test_cpp_config_drivers_match_ctypes_path(examples_built, tmp_path, name, pr
         assert np.isfinite(ref).all()
         assert np.array_equal(got, ref), f"{name} type {t}: C++ driver vs ctypes path rel-L2 {cases.rel_l2(got, ref):.3e}"
     assert dim == len(vel)
+
+
+def _compile(src, exe):
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++20", "-O1", "-Wall", "-Wextra", f"-I{ROOT}/include", str(src), "-o", str(exe), f"-L{ROOT}/subrosadg_b200",
+                        "-lsubrosadg_b200", f"-Wl,-rpath,{ROOT}/subrosadg_b200"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return str(exe)
+
+
+def test_boundary_time_driver_compiles(built, tmp_path):
+    _compile(os.path.join(ROOT, "tests", "cpp", "boundary_time_driver.cpp"), tmp_path / "bt")
+
+
+@pytest.mark.gpu
+def test_time_varying_boundary_sees_the_reference_times(built, tmp_path):
+    """System::solve assigns iteration_ AFTER stepSolver (SystemControl.cpp:175-177): the TimeVarying callback of step i is evaluated at
+    t = (i - 1) dt, the first step at t = 0."""
+    from subrosadg_b200.solver import Solver
+    exe = _compile(os.path.join(ROOT, "tests", "cpp", "boundary_time_driver.cpp"), tmp_path / "bt")
+    mesh = M.box(2, (5, 4), 0.0, 1.0, phys_bc={k: M.RIEMANN_FARFIELD for k in (1, 2, 3, 4)})
+    M.write_flat(mesh, tmp_path / "mesh.sdgm")
+    r = subprocess.run([exe, str(tmp_path / "mesh.sdgm"), str(tmp_path / "out"), "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    dt = 2.0e-3
+    times = [float(x) for x in r.stdout.strip().splitlines()[-1].split()[1:]]
+    assert np.allclose(times, [0.0, dt, 2 * dt], rtol=1e-5, atol=0), times
+
+    def ic(x):
+        one = np.ones(x.shape[:-1])
+        return np.stack([1.4 * one, 0.3 * one, 0.1 * one, one], axis=-1)
+
+    def bc(x, phys, time=0.0):
+        one = np.ones(x.shape[:-1])
+        return np.stack([1.4 * one, 0.3 * (1.0 + 5.0 * time) * one, 0.1 * one, one], axis=-1)
+
+    S = Solver(dict(p=2, conv_flux=2, rk=2), mesh, device=0)
+    S.initializeSolver(ic, bc)
+    for i in range(1, 4):
+        S.updateBoundaryVariable(bc, (i - 1) * dt)
+        S.stepSolver(dt, 1)
+    ref = S.state_at_quadrature(S.types[0])
+    got = np.fromfile(tmp_path / "out" / "state.bin", dtype=np.float64).reshape(ref.shape)
+    assert np.array_equal(got, ref), f"rel-L2 {cases.rel_l2(got, ref):.3e}"
+    S2 = Solver(dict(p=2, conv_flux=2, rk=2), mesh, device=0)      # one step late (t = i dt) is a different solution
+    S2.initializeSolver(ic, bc)
+    for i in range(1, 4):
+        S2.updateBoundaryVariable(bc, i * dt)
+        S2.stepSolver(dt, 1)
+    assert cases.rel_l2(S2.state_at_quadrature(S.types[0]), ref) > 1e-9
