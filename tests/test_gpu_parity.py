@@ -113,10 +113,13 @@ def compare_ns(O, S, dt, nsteps, label, cond=1.0):
     e_g = cases.rel_l2(gs, go)
     assert e_g < 1e-11 * cond, f"{label}: total gradient at quadrature points rel-L2 {e_g:.3e}"
     e_m = cases.rel_l2(S.gradient_state(t), O.gradient_state(t))    # the RawBinary gradient blocks (RawBinary.cpp:75-154)
-    assert e_m < 1e-11 * cond, f"{label}: modal gradient coefficients rel-L2 {e_m:.3e}"
+    # nodal -> modal goes through the inverse Vandermonde matrix of the H1-Legendre basis: the nodal error is amplified by up to its
+    # 2-norm condition number (59 for P3 quadrangles, 458 / 1633 / 3591 for P3 / P4 / P5 hexahedra; measured errors are 7e-14..3e-13 times it)
+    tol_m = max(1e-11, 1e-12 * np.linalg.cond(O.table(t, 0))) * cond
+    assert e_m < tol_m, f"{label}: modal gradient coefficients rel-L2 {e_m:.3e}"
     bo, bs = O.boundary_gradient_state(), S.boundary_gradient_state()
     if bo.size:
-        assert cases.rel_l2(bs, bo) < 1e-11 * cond, f"{label}: boundary-parent gradient blocks rel-L2 {cases.rel_l2(bs, bo):.3e}"
+        assert cases.rel_l2(bs, bo) < tol_m, f"{label}: boundary-parent gradient blocks rel-L2 {cases.rel_l2(bs, bo):.3e}"
     e_R, e_q = cases.rel_l2(Rs, Ro), cases.rel_l2(qs, qo)
     assert e_R < TOL_RES * cond, f"{label}: modal residual rel-L2 {e_R:.3e}"
     assert e_q < TOL_RHS * cond, f"{label}: dU/dt rel-L2 {e_q:.3e}"

@@ -115,8 +115,9 @@ def node_number(mesh):
 
 def parse_payload(buf, mesh, nb, ns):
     """Restated reader of Solver::writeRawBinary's stream: per element type (ascending ElementEnum) and element [Nb][Nv] (+ [Nb][Nv*D] for
-    Navier-Stokes, as InitialCondition.cpp:47-56 skips it); per boundary face the same blocks of its parent (RawBinary.cpp:89-154);
-    node_number_ reals.  nb = {type: Nb}.  Returns (U, G, [(type, parent, local face, U row, G row)], node artificial viscosity)."""
+    Navier-Stokes, as InitialCondition.cpp:47-56 skips it and ElementViewSolver::calcluateElementViewVariable reads it,
+    RawBinary.cpp:193-240); per boundary face the same blocks of its parent (RawBinary.cpp:89-154, read at :242-296); node_number_ reals
+    at the tail (ViewSolver::calcluateViewVariable seeks them first, :352-356).  nb = {type: Nb}.  Returns (U, G, [(type, parent, local face, U row, G row)], node artificial viscosity)."""
     a = np.frombuffer(buf, dtype=np.float64)
     D, Nv = mesh.dim, mesh.dim + 2
     pos = 0
@@ -176,6 +177,9 @@ def test_raw_binary_of_the_config_drivers(built, tmp_path, name, producer, cfg, 
     dt = S.calculateDeltaTime(1.0)
     nb = {t: S.sizes(t).Nb for t in S.types}
     raw = tmp_path / "build" / "out" / name / "raw"
+    import oracle
+    O = oracle.Oracle(dict(cfg), mesh)      # the modal basis at the quadrature points, to evaluate the file like the View reader does
+    phi = {t: O.table(t, 0) for t in S.types}                # [Nq][Nb]: the reader's `coefficient * modal_value_` (RawBinary.cpp:204-205)
     for step in (0, 3):
         if step:
             S.stepSolver(dt, step)
@@ -185,6 +189,8 @@ def test_raw_binary_of_the_config_drivers(built, tmp_path, name, producer, cfg, 
         assert np.all(av == 0.0) and av.size == node_number(mesh)
         for t in S.types:
             assert np.array_equal(U[t], S.get_state(t)), f"{name} step {step} type {t}: modal state"
+            uq = np.einsum("ebv,qb->eqv", U[t], phi[t])       # what the reference's view reader reconstructs from the file
+            assert cases.rel_l2(uq, S.state_at_quadrature(t)) < 1e-13
             if ns:
                 assert np.array_equal(G[t], S.gradient_state(t)), f"{name} step {step} type {t}: gradient coefficients"
         state = {t: S.get_state(t) for t in S.types}
