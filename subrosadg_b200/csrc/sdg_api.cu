@@ -36,12 +36,13 @@ struct sdg_ctx {
   bool hasDevice = false, finalized = false;
   MeshPlan plan;
   bool haveBlock = false, haveFaces = false;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copyStream = nullptr;
+  cudaEvent_t seamEvent[9] = {};
   int64_t launches = 0;
 
   // device state
-  DevBuf<double> U[3], geoE, invjw, minEdge, geoF, dummy, Phi, PhiInv, PhiT, normPartial, normSlices, normOut, dtPartial, scratch, sendBuf, cfGeo;
-  DevBuf<int> perm, faceRec, chunkOff, chunkInterior, chunkBoundary, sendList;
+  DevBuf<double> U[3], geoE, invjw, minEdge, geoF, dummy, Phi, PhiInv, PhiT, M1[3], normPartial, normSlices, normOut, dtPartial, scratch, sendBuf, cfGeo;
+  DevBuf<int> perm, faceRec, chunkOff, chunkInterior, chunkBoundary, sendList, lexOf;
   DevBuf<TensorDev> tab;
   int cur = 0;          // index of the buffer holding the current state
   int latest = 0;       // buffer written last (halo source / target)
@@ -244,6 +245,7 @@ void sdg_destroy(sdg_ctx* c) {
   if (c->hasDevice) { cudaSetDevice(c->cfg.device); cudaDeviceSynchronize(); }
   if (c->stepGraph) cudaGraphExecDestroy(c->stepGraph);
   for (void* q : c->ipcOpened) cudaIpcCloseMemHandle(q);
+  if (c->copyStream) { cudaStreamDestroy(c->copyStream); for (cudaEvent_t e : c->seamEvent) if (e) cudaEventDestroy(e); }
   cudaStream_t s = c->stream; const bool dev = c->hasDevice;
   delete c;
   if (dev && s) cudaStreamDestroy(s);
@@ -368,6 +370,16 @@ int sdg_finalize(sdg_ctx* c) {
     c->chunkInterior.upload(B.chunkInterior, c->stream); c->chunkBoundary.upload(B.chunkBoundary, c->stream);
     c->Phi.upload(B.T.Phi, c->stream); c->PhiInv.upload(B.T.PhiInv, c->stream);
     { std::vector<double> PT(B.T.Phi.size()); const int NN = B.T.NN; for (int q = 0; q < NN; q++) for (int b = 0; b < NN; b++) PT[(size_t)b * NN + q] = B.T.Phi[(size_t)q * NN + b]; c->PhiT.upload(PT, c->stream); }
+    {   // 1-D factors of the modal transforms (tensorTransformKernel): Phi1, Phi1^-1, Phi1^T, and the lexicographic index of every mode
+      const int N = B.T.N, D = B.T.D;
+      std::vector<double> inv = B.T.Phi1, tr((size_t)N * N);
+      invertDense(inv, N);
+      for (int a = 0; a < N; a++) for (int k = 0; k < N; k++) tr[(size_t)k * N + a] = B.T.Phi1[(size_t)a * N + k];
+      c->M1[0].upload(B.T.Phi1, c->stream); c->M1[1].upload(inv, c->stream); c->M1[2].upload(tr, c->stream);
+      std::vector<int> lex(B.T.NN);
+      for (int b = 0; b < B.T.NN; b++) { int q = 0; for (int d = 0; d < D; d++) q = q * N + B.T.modalIdx[b][d]; lex[b] = q; }
+      c->lexOf.upload(lex, c->stream);
+    }
     if (c->phys.ns) { c->G.alloc((size_t)B.n * c->NV * c->D * B.T.NN); CUDA_OK(cudaMemsetAsync(c->G.p, 0, c->G.n * sizeof(double), c->stream)); }
     c->normPartial.alloc((size_t)B.nChunks * c->NV); c->normSlices.alloc(128 * 8); c->normOut.alloc(8); c->dtPartial.alloc(1024);
     CUDA_OK(cudaMemsetAsync(c->normPartial.p, 0, c->normPartial.n * sizeof(double), c->stream));
@@ -476,12 +488,33 @@ int sdg_set_boundary_primitive(sdg_ctx* c, const double* prim) {
 
 // nElems < B.n: the state setters of a partitioned block touch the OWNED elements only — the trailing ghost range of U[cur]
 // belongs to the peers' halo pushes, which may land before or after this rank's setter (no receiver-ready handshake)
-static void transformModal(sdg_ctx* c, const double* in, double* out, const double* M, int dir, int nElems = -1) {
+enum { kToNodal = 0, kToModal = 1, kProject = 2 };   // which: Phi1 (dir 0), Phi1^-1 (dir 1), Phi1^T (dir 1)
+// elements [e0, e0 + ne) of the caller's order; the caller-order side of the transform is addressed by e, the internal side through perm
+static void transformModalRange(sdg_ctx* c, const double* in, double* out, int which, int e0, int ne, cudaStream_t st) {
   const BlockPlan& B = c->plan.blk;
-  const int n = nElems < 0 ? B.n : nElems;
-  seamTransformKernel<<<n, 128, sizeof(double) * c->NV * B.T.NN, c->stream>>>(in, out, M, c->perm.p, n, c->NV, B.T.NN, dir);
+  if (ne <= 0) return;
+  const int per = c->NV * B.T.NN, perP = c->NV * (B.T.NN + 1);
+  const int epb = std::max(1, (40 << 10) / (16 * perP));
+  const size_t smem = sizeof(double) * 2 * (size_t)epb * perP;
+  using Fn = void (*)(const double*, double*, const double*, const int*, const int*, int, int, int, int, int);
+  const Fn fn = (B.T.D == 3 && B.T.N == 4) ? tensorTransformKernel<3, 4> : (B.T.D == 2 && B.T.N == 4) ? tensorTransformKernel<2, 4> : tensorTransformKernel<0, 0>;
+  const int blocks = std::min((ne + epb - 1) / epb, 148 * 8);
+  const bool toNodal = which == kToNodal;
+  fn<<<blocks, 256, smem, st>>>(toNodal ? in + (size_t)e0 * per : in, toNodal ? out : out + (size_t)e0 * per, c->M1[which].p, c->lexOf.p, c->perm.p + e0, ne,
+                                B.T.N, B.T.D, toNodal ? 0 : 1, epb);
   c->launches++;
   CUDA_OK(cudaGetLastError());
+}
+static void transformModal(sdg_ctx* c, const double* in, double* out, int which, int nElems = -1) {
+  transformModalRange(c, in, out, which, 0, nElems < 0 ? c->plan.blk.n : nElems, c->stream);
+}
+// Host <-> device seam of sdg_set_state / sdg_get_state: the copy runs on its own stream in kSeamChunks pieces so that the transform of
+// one piece overlaps the PCIe transfer of the next (the transform is ~6-13 ms of a ~100 ms copy at 128^3 P3 hexahedra)
+constexpr int kSeamChunks = 8;
+static void seamStreams(sdg_ctx* c) {
+  if (c->copyStream) return;
+  CUDA_OK(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+  for (auto& e : c->seamEvent) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
 int sdg_set_state_device(sdg_ctx* c, int32_t type, const void* U_device) {
@@ -489,7 +522,7 @@ int sdg_set_state_device(sdg_ctx* c, int32_t type, const void* U_device) {
   if (c->mx) { needFinal(c); c->mx->setStateDevice(type, U_device); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  transformModal(c, (const double*)U_device, c->U[c->cur].p, c->Phi.p, 0, c->plan.blk.nOwned);
+  transformModal(c, (const double*)U_device, c->U[c->cur].p, kToNodal, c->plan.blk.nOwned);
   c->latest = c->cur; c->traceValid[c->cur] = false;
   SDG_CATCH
 }
@@ -498,7 +531,7 @@ int sdg_get_state_device(sdg_ctx* c, int32_t type, void* U_device) {
   if (c->mx) { needFinal(c); c->mx->getStateDevice(type, U_device); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  transformModal(c, c->U[c->cur].p, (double*)U_device, c->PhiInv.p, 1);
+  transformModal(c, c->U[c->cur].p, (double*)U_device, kToModal);
   SDG_CATCH
 }
 
@@ -507,11 +540,22 @@ int sdg_set_state(sdg_ctx* c, int32_t type, const double* U) {
   if (c->mx) { needFinal(c); c->mx->setState(type, U); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  const size_t nd = c->stateDoubles();
+  const BlockPlan& B = c->plan.blk;
+  const size_t per = (size_t)c->NV * B.T.NN;
   const int s = (c->cur + 1) % 3;  // scratch: a stage buffer that holds no live data between steps
   c->traceValid[s] = false;
-  CUDA_OK(cudaMemcpyAsync(c->U[s].p, U, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  transformModal(c, c->U[s].p, c->U[c->cur].p, c->Phi.p, 0, c->plan.blk.nOwned);
+  const int n = B.nOwned;          // ghosts are fed by the halo exchange only (see transformModal)
+  seamStreams(c);
+  CUDA_OK(cudaEventRecord(c->seamEvent[kSeamChunks], c->stream));              // earlier work on the scratch buffer
+  CUDA_OK(cudaStreamWaitEvent(c->copyStream, c->seamEvent[kSeamChunks], 0));
+  const int nc = n >= 8192 ? kSeamChunks : 1;
+  for (int k = 0; k < nc; k++) {
+    const int e0 = (int)((long long)n * k / nc), e1 = (int)((long long)n * (k + 1) / nc);
+    CUDA_OK(cudaMemcpyAsync(c->U[s].p + e0 * per, U + e0 * per, (size_t)(e1 - e0) * per * sizeof(double), cudaMemcpyHostToDevice, c->copyStream));
+    CUDA_OK(cudaEventRecord(c->seamEvent[k], c->copyStream));
+    CUDA_OK(cudaStreamWaitEvent(c->stream, c->seamEvent[k], 0));
+    transformModalRange(c, c->U[s].p, c->U[c->cur].p, kToNodal, e0, e1 - e0, c->stream);
+  }
   CUDA_OK(cudaStreamSynchronize(c->stream));
   c->latest = c->cur; c->traceValid[c->cur] = false;
   SDG_CATCH
@@ -521,11 +565,21 @@ int sdg_get_state(sdg_ctx* c, int32_t type, double* U) {
   if (c->mx) { needFinal(c); c->mx->getState(type, U); return 0; }
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  const size_t nd = c->stateDoubles();
+  const BlockPlan& B = c->plan.blk;
+  const size_t per = (size_t)c->NV * B.T.NN;
   const int s = (c->cur + 1) % 3;
   c->traceValid[s] = false;
-  transformModal(c, c->U[c->cur].p, c->U[s].p, c->PhiInv.p, 1);
-  CUDA_OK(cudaMemcpyAsync(U, c->U[s].p, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  const int n = B.n;
+  seamStreams(c);
+  const int nc = n >= 8192 ? kSeamChunks : 1;
+  for (int k = 0; k < nc; k++) {
+    const int e0 = (int)((long long)n * k / nc), e1 = (int)((long long)n * (k + 1) / nc);
+    transformModalRange(c, c->U[c->cur].p, c->U[s].p, kToModal, e0, e1 - e0, c->stream);
+    CUDA_OK(cudaEventRecord(c->seamEvent[k], c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->copyStream, c->seamEvent[k], 0));
+    CUDA_OK(cudaMemcpyAsync(U + e0 * per, c->U[s].p + e0 * per, (size_t)(e1 - e0) * per * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+  }
+  CUDA_OK(cudaStreamSynchronize(c->copyStream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   SDG_CATCH
 }
@@ -812,7 +866,7 @@ int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
       seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->U[a].p, c->U[b].p, c->perm.p, B.n, c->NV, B.T.NN, 1);
       c->launches++;
     } else {
-      transformModal(c, c->U[a].p, c->U[b].p, c->PhiT.p, 1);
+      transformModal(c, c->U[a].p, c->U[b].p, kProject);
     }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(host, c->U[b].p, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

