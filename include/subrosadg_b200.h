@@ -106,6 +106,20 @@ int sdg_get_gradient_at_quadrature(sdg_ctx* ctx, int32_t type, double* Gq);
 int sdg_get_gradient_state(sdg_ctx* ctx, int32_t type, double* G);
 int sdg_get_boundary_gradient_state(sdg_ctx* ctx, double* Gb);
 
+/* ShockCapturingEnum::ArtificialViscosity (Euler models).  System::setArtificialViscosity (SystemControl.cpp:105-108) + the mesh data the
+ * reference's Solver::calculateArtificialViscosity reads (SpatialDiscrete.cpp:37-192): node_number = Mesh::node_number_; per block the
+ * 0-based tags of the corner nodes, [n][kBasicNodeNumber] in gmsh node order (PerElementMesh::node_tag_, ReadControl.cpp:64), and
+ * inner_radius_ [n] (gmsh "innerRadius" element quality, Geometry.cpp:31-41).  All three calls precede sdg_finalize.  Every sdg_step then
+ * evaluates the element indicator, the node maximum and the corner values once per step and adds eps * grad(U) to the volume and face
+ * fluxes of every stage (SpatialDiscrete.cpp:210-253, 529-631, 694-746, 786-819; ViscousFlux.cpp:105-113,126-136,172-186). */
+int sdg_set_artificial_viscosity(sdg_ctx* ctx, double empirical_tolerance, double artificial_viscosity_factor, int32_t node_number);
+int sdg_set_element_nodes(sdg_ctx* ctx, int32_t type, const int32_t* node_tag, const double* inner_radius);
+/* Solver::node_artificial_viscosity_ [node_number] (the tail of the RawBinary payload) and variable_artificial_viscosity_ [n][kBasicNodeNumber]
+ * as of the last step; sdg_update_artificial_viscosity re-evaluates them for the current state (diagnostics / parity). */
+int sdg_get_node_artificial_viscosity(sdg_ctx* ctx, double* out);
+int sdg_get_element_artificial_viscosity(sdg_ctx* ctx, int32_t type, double* out);
+int sdg_update_artificial_viscosity(sdg_ctx* ctx);
+
 /* Solver::calculateDeltaTime (TimeIntegration.cpp:104-179) */
 int sdg_compute_dt(sdg_ctx* ctx, double cfl, double* dt);
 

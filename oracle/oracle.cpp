@@ -82,6 +82,8 @@ struct ElemTable {
   std::vector<double> GNf, dGNf;                // at face points (parent coordinates): Naq x nn, (Naq*D) x nn
   std::vector<double> ftan;                     // per face: d(xi)/d(s_a), Nf x (D-1) x D
   std::vector<double> fxi;                      // face points in parent reference coordinates, Naq x 3
+  int nbasic = 0;                               // kBasicNodeNumber: corner nodes (the first nodes of the gmsh order)
+  std::vector<double> NodalQ, NodalF;           // nodal_value_ (Nq x nbasic), nodal_adjacency_value_ (Naq x nbasic): order-1 Lagrange basis, BasisFunction.cpp:149-208
 
   void build(int type_, int p_, int g_) {
     type = type_; p = p_; g = g_; D = elemDim(type);
@@ -95,7 +97,9 @@ struct ElemTable {
     Naq = off[Nf];
     ModalBasis mb(type, p);
     LagrangeBasis lb(type, g);
-    nn = lb.n;
+    LagrangeBasis l1(type, 1);
+    nn = lb.n; nbasic = l1.n;
+    NodalQ.assign((size_t)Nq * nbasic, 0); NodalF.assign((size_t)Naq * nbasic, 0);
     std::vector<double> val; std::vector<std::array<double, 3>> grad;
     Phi.assign((size_t)Nq * Nb, 0); dPhi.assign((size_t)Nq * D * Nb, 0);
     GN.assign((size_t)Nq * nn, 0); dGN.assign((size_t)Nq * D * nn, 0);
@@ -103,6 +107,8 @@ struct ElemTable {
       const double* x = &quad.pts[3 * q];
       mb.eval(x[0], x[1], x[2], val, grad);
       for (int b = 0; b < Nb; b++) { Phi[(size_t)b * Nq + q] = val[b]; for (int d = 0; d < D; d++) dPhi[(size_t)b * Nq * D + q * D + d] = grad[b][d]; }
+      l1.eval(x[0], x[1], x[2], val, grad);
+      for (int b = 0; b < nbasic; b++) NodalQ[(size_t)b * Nq + q] = val[b];
       lb.eval(x[0], x[1], x[2], val, grad);
       for (int b = 0; b < nn; b++) { GN[(size_t)b * Nq + q] = val[b]; for (int d = 0; d < D; d++) dGN[(size_t)b * Nq * D + q * D + d] = grad[b][d]; }
     }
@@ -128,6 +134,8 @@ struct ElemTable {
         for (int k = 0; k < 3; k++) fxi[(size_t)row * 3 + k] = xi[k];
         mb.eval(xi[0], xi[1], xi[2], val, grad);
         for (int b = 0; b < Nb; b++) PhiF[(size_t)b * Naq + row] = val[b];
+        l1.eval(xi[0], xi[1], xi[2], val, grad);
+        for (int b = 0; b < nbasic; b++) NodalF[(size_t)b * Naq + row] = val[b];
         lb.eval(xi[0], xi[1], xi[2], val, grad);
         for (int b = 0; b < nn; b++) { GNf[(size_t)b * Naq + row] = val[b]; for (int d = 0; d < D; d++) dGNf[(size_t)b * Naq * D + row * D + d] = grad[b][d]; }
       }
@@ -146,6 +154,10 @@ struct ElemBlock {
   std::vector<double> coef, coefLast, vq, vaq, res, sq;
   std::vector<double> gvq, gvaq, gresVol, gcoefVol;   // PerElementVolumeGradientSolver
   std::vector<double> gcoef, giaq, gires, gicoef;     // NS: total gradient, interface quadrature, per-face (BR2) / single (BR1) lifts
+  // ShockCapturingEnum::ArtificialViscosity: mesh data (node_tag_ of the corner nodes, 0-based; inner_radius_) and
+  // variable_artificial_viscosity_ (n x nbasic), SolveControl.cpp:132
+  std::vector<int> nodeTag;
+  std::vector<double> innerRadius, avElem;
 };
 
 // AdjacencyElementMesh + AdjacencyElementSolver (ReadControl.cpp:72-83, SolveControl.cpp:223-289)
@@ -166,6 +178,9 @@ struct Oracle {
   FaceSet F;
   bool finalized = false;
   double relErr[kMaxV] = {0, 0, 0, 0, 0};
+  bool av = false;           // ShockCapturingEnum::ArtificialViscosity
+  double avTol = 0.0, avFactor = 1.0;   // Solver::empirical_tolerance_, artificial_viscosity_factor_ (SolveControl.cpp:293-294)
+  std::vector<double> nodeAV;           // Solver::node_artificial_viscosity_
   int totalElems() const { int s = 0; for (auto& b : blk) if (b) s += b->n; return s; }
 };
 
@@ -449,6 +464,11 @@ static void sweepR1(Oracle& O, ElemBlock& B) {
       gq.resize((size_t)s.G * s.Nq);
       gemmNT(s.G, s.Nq, s.Nb, 1.0, &B.gcoef[(size_t)e * s.G * s.Nb], s.G, T.Phi.data(), s.Nq, 0.0, gq.data(), s.G);
     }
+    std::vector<double> gvolq;
+    if (O.av) {  // ElementVariableGradient::get<ViscousFluxEnum::None>: the volume gradient coefficients
+      gvolq.resize((size_t)s.G * s.Nq);
+      gemmNT(s.G, s.Nq, s.Nb, 1.0, &B.gcoefVol[(size_t)e * s.G * s.Nb], s.G, T.Phi.data(), s.Nq, 0.0, gvolq.data(), s.G);
+    }
     double* out = &B.vq[(size_t)e * s.Nv * s.Nq * s.D];
     for (int q = 0; q < s.Nq; q++) {
       Var v;
@@ -462,6 +482,11 @@ static void sweepR1(Oracle& O, ElemBlock& B) {
         viscRawFlux(P, v.comp, gp, Fv);
         for (int k = 0; k < s.D * s.Nv; k++) Fc[k] -= Fv[k];
       }
+      if (O.av) {  // calculateArtificialViscousRawFlux, ViscousFlux.cpp:105-113: eps(q) * volume gradient of the conserved variables (SpatialDiscrete.cpp:210-228,249-253)
+        double eps = 0.0;
+        for (int k = 0; k < T.nbasic; k++) eps += T.NodalQ[(size_t)k * s.Nq + q] * B.avElem[(size_t)e * T.nbasic + k];
+        for (int k = 0; k < s.D * s.Nv; k++) Fc[k] -= eps * gvolq[(size_t)q * s.G + k];
+      }
       const double* mt = &B.mt[((size_t)e * s.Nq + q) * s.D * s.D];
       // flux^T (Nv x D) * Mt (D x D)
       for (int dd = 0; dd < s.D; dd++) for (int k = 0; k < s.Nv; k++) {
@@ -473,6 +498,20 @@ static void sweepR1(Oracle& O, ElemBlock& B) {
         for (int k = 0; k < s.Nv; k++) B.sq[((size_t)e * s.Nq + q) * s.Nv + k] = S[k] * B.jw[(size_t)e * s.Nq + q];
       }
     }
+  }
+}
+// AdjacencyElementVariableGradient::get<ViscousFluxEnum::None> (volume gradient trace) and calculateAdjacencyElementArtificialViscosity
+// (SpatialDiscrete.cpp:529-631): eps at the face points of local face f = nodal_adjacency_value_ rows of that face * corner values
+static inline void faceVolGradTrace(const Oracle& O, int type, int e, int f, double* out /* G x nq */, double* eps /* nq */) {
+  const ElemBlock& B = *O.blk[type]; const ElemTable& T = B.tab;
+  const int G = O.P.Nv * O.P.D, Nb = T.Nb, Naq = T.Naq, nq = T.nqf[f];
+  const double* C = &B.gcoefVol[(size_t)e * G * Nb];
+  for (int j = 0; j < nq; j++) {
+    const int row = T.off[f] + j;
+    for (int r = 0; r < G; r++) out[(size_t)j * G + r] = 0.0;
+    for (int b = 0; b < Nb; b++) { const double ph = T.PhiF[(size_t)b * Naq + row]; for (int r = 0; r < G; r++) out[(size_t)j * G + r] += C[b * G + r] * ph; }
+    eps[j] = 0.0;
+    for (int k = 0; k < T.nbasic; k++) eps[j] += T.NodalF[(size_t)k * Naq + row] * B.avElem[(size_t)e * T.nbasic + k];
   }
 }
 // R2 calculateInterior/BoundaryAdjacencyElementQuadrature, SpatialDiscrete.cpp:633-842
@@ -491,6 +530,11 @@ static void sweepR2(Oracle& O) {
       faceGradTrace(O, tL, eL, fL, gL.data()); faceGradTrace(O, tR, eR, fR, gR.data());
       for (int j = 0; j < Nqf; j++) { primGradFromConsGrad(P, L[j], &gL[(size_t)j * G], &pL[(size_t)j * G]); primGradFromConsGrad(P, R[j], &gR[(size_t)j * G], &pR[(size_t)j * G]); }
     }
+    std::vector<double> avgL, avgR, epsL, epsR;
+    if (O.av) {
+      avgL.resize((size_t)G * Nqf); avgR.resize((size_t)G * Nqf); epsL.resize(Nqf); epsR.resize(Nqf);
+      faceVolGradTrace(O, tL, eL, fL, avgL.data(), epsL.data()); faceVolGradTrace(O, tR, eR, fR, avgR.data(), epsR.data());
+    }
     const std::vector<int> seq = faceQuadratureSequence(F.ftype, O.p, F.rot[i]);
     ElemBlock& BL = *O.blk[tL]; ElemBlock& BR = *O.blk[tR];
     const int offL = BL.tab.off[fL], offR = BR.tab.off[fR];
@@ -504,6 +548,13 @@ static void sweepR2(Oracle& O) {
         viscNormalFlux(P, n, L[j].comp, &pL[(size_t)j * G], a);
         viscNormalFlux(P, n, R[jr].comp, &pR[(size_t)jr * G], b);
         for (int v = 0; v < Nv; v++) Fc[v] -= (a[v] + b[v]) / 2.0;
+      }
+      if (O.av) {  // calculateArtificialViscousFlux, ViscousFlux.cpp:172-186: average of eps * grad(U) . n of both sides
+        for (int v = 0; v < Nv; v++) {
+          double a = 0.0, b = 0.0;
+          for (int c = 0; c < D; c++) { a += epsL[j] * avgL[(size_t)j * G + v * D + c] * n[c]; b += epsR[jr] * avgR[(size_t)jr * G + v * D + c] * n[c]; }
+          Fc[v] -= (a + b) / 2.0;
+        }
       }
       double* aL = &BL.vaq[((size_t)eL * BL.tab.Naq + offL + j) * Nv];
       double* aR = &BR.vaq[((size_t)eR * BR.tab.Naq + offR + jr) * Nv];
@@ -522,6 +573,8 @@ static void sweepR2(Oracle& O) {
       faceGradTrace(O, tL, eL, fL, gL.data());
       for (int j = 0; j < Nqf; j++) primGradFromConsGrad(P, L[j], &gL[(size_t)j * G], &pL[(size_t)j * G]);
     }
+    std::vector<double> avgL, epsL;
+    if (O.av) { avgL.resize((size_t)G * Nqf); epsL.resize(Nqf); faceVolGradTrace(O, tL, eL, fL, avgL.data(), epsL.data()); }
     ElemBlock& BL = *O.blk[tL];
     const int offL = BL.tab.off[fL];
     for (int j = 0; j < Nqf; j++) {
@@ -541,6 +594,13 @@ static void sweepR2(Oracle& O) {
         viscNormalFlux(P, n, L[j].comp, &pL[(size_t)j * G], a);
         viscNormalFlux(P, n, b.comp, gb, c);
         for (int v = 0; v < Nv; v++) Fc[v] -= (a[v] + c[v]) / 2.0;
+      }
+      if (O.av) {  // boundary faces: the interior side alone, calculateArtificialViscousNormalFlux (SpatialDiscrete.cpp:813-819)
+        for (int v = 0; v < Nv; v++) {
+          double a = 0.0;
+          for (int c = 0; c < D; c++) a += epsL[j] * avgL[(size_t)j * G + v * D + c] * n[c];
+          Fc[v] -= a;
+        }
       }
       double* aL = &BL.vaq[((size_t)eL * BL.tab.Naq + offL + j) * Nv];
       for (int v = 0; v < Nv; v++) aL[v] = Fc[v] * w;
@@ -581,8 +641,50 @@ static void sweepR4(Oracle& O, ElemBlock& B, const double* c, double dt) {
   }
 }
 
+// Solver::calculateArtificialViscosity, SpatialDiscrete.cpp:37-192: per element the Persson-Peraire smoothness indicator of the density
+// (energy of the modes above order P-1 against the energy of all modes), a constant, zero or sine-ramped viscosity per element, the
+// maximum over the elements sharing each corner node, and the node values copied back to the elements' corners.
+static void artificialViscosity(Oracle& O) {
+  static const double kTol[5] = {0.0, -1.20411998266, -1.90848501888, -2.40823996531, -2.79588001734};   // SimulationControl.cpp:892-893
+  const double tol = kTol[O.p - 1];
+  const double kPi = 3.14159265358979323846;
+  for (auto& bp : O.blk) if (bp) {
+    ElemBlock& B = *bp; const Sizes s = sizes(O, B); const ElemTable& T = B.tab;
+    if ((int)B.nodeTag.size() != B.n * T.nbasic || (int)B.innerRadius.size() != B.n) throw std::runtime_error("oracle: artificial viscosity needs orc_set_element_nodes for every block");
+    const int nbLow = O.p == 1 ? 0 : numNodes(B.type, O.p - 1);   // getElementBasisFunctionNumber<type, P - 1>; P1: every mode is "high"
+    B.avElem.assign((size_t)B.n * T.nbasic, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < B.n; e++) {
+      const double* U = &B.coef[(size_t)e * s.Nv * s.Nb];
+      double num = 0.0, den = 0.0;
+      for (int q = 0; q < s.Nq; q++) {
+        double all = 0.0, high = 0.0;
+        for (int b = 0; b < s.Nb; b++) { const double t = T.Phi[(size_t)b * s.Nq + q] * U[b * s.Nv]; all += t; if (b >= nbLow) high += t; }
+        const double w = B.jw[(size_t)e * s.Nq + q];
+        num += high * (high * w); den += all * (all * w);
+      }
+      const double shock = std::log10(num / den);
+      const double full = O.avFactor * (B.innerRadius[e] / O.p);
+      double val;
+      if (shock < tol - O.avTol) val = 0.0;
+      else if (shock > tol + O.avTol) val = full;
+      else val = full * (1.0 + std::sin(kPi * (shock - tol) / (2.0 * O.avTol))) / 2.0;
+      for (int k = 0; k < T.nbasic; k++) B.avElem[(size_t)e * T.nbasic + k] = val;
+    }
+  }
+  std::fill(O.nodeAV.begin(), O.nodeAV.end(), 0.0);
+  for (auto& bp : O.blk) if (bp) {   // maxElementArtificialViscosity :89-108
+    ElemBlock& B = *bp; const int nb = B.tab.nbasic;
+    for (int e = 0; e < B.n; e++) for (int k = 0; k < nb; k++) { double& a = O.nodeAV[B.nodeTag[(size_t)e * nb + k]]; a = std::max(a, B.avElem[(size_t)e * nb + k]); }
+  }
+  for (auto& bp : O.blk) if (bp) {   // storeElementArtificialViscosity :110-122
+    ElemBlock& B = *bp; const int nb = B.tab.nbasic;
+    for (int e = 0; e < B.n; e++) for (int k = 0; k < nb; k++) B.avElem[(size_t)e * nb + k] = O.nodeAV[B.nodeTag[(size_t)e * nb + k]];
+  }
+}
+
 static void evalResidual(Oracle& O) {  // one full residual evaluation: G1-G4 (if needed) + R1-R3
-  const bool grad = O.P.ns() || O.deadGradient;
+  const bool grad = O.P.ns() || O.deadGradient || O.av;
   if (grad) {
     for (auto& b : O.blk) if (b) sweepG1(O, *b);
     sweepG2(O);
@@ -622,6 +724,7 @@ static void relativeError(Oracle& O) {
 // Solver::stepSolver, TimeIntegration.cpp:326-350
 static void step(Oracle& O, double dt) {
   for (auto& b : O.blk) if (b) b->coefLast = b->coef;  // copyBasisFunctionCoefficient :70-102
+  if (O.av) artificialViscosity(O);                    // once per step, before the stages (TimeIntegration.cpp:336-338)
   int ns; double c[3][3]; rkTable(O.rk, ns, c);
   for (int i = 0; i < ns; i++) {
     evalResidual(O);
@@ -896,6 +999,7 @@ int orc_eval_residual(void* h) {
   ORC_TRY
   Oracle& O = *(Oracle*)h;
   if (!O.finalized) throw std::runtime_error("oracle: not finalized");
+  if (O.av) artificialViscosity(O);   // parity hook: the viscosity of the CURRENT state (stepSolver evaluates it once per step)
   evalResidual(O);
   ORC_CATCH
 }
@@ -962,6 +1066,45 @@ int orc_get_boundary_gradient_state(void* h, double* out) {
     }
     at += len;
   }
+  ORC_CATCH
+}
+// System::setArtificialViscosity (SystemControl.cpp:105-108) with ShockCapturingEnum::ArtificialViscosity; n_nodes = Mesh::node_number_
+int orc_set_artificial_viscosity(void* h, double empirical_tolerance, double factor, int n_nodes) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  if (O.P.ns()) throw std::runtime_error("oracle: artificial viscosity is restated for the Euler models only");
+  O.av = true; O.avTol = empirical_tolerance; O.avFactor = factor; O.nodeAV.assign((size_t)n_nodes, 0.0);
+  ORC_CATCH
+}
+// mesh data of one block: node_tag_ of the corner nodes (0-based, n x nbasic) and inner_radius_ (n), ReadControl.cpp:64,91
+int orc_set_element_nodes(void* h, int type, const int32_t* tags, const double* inner_radius) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  if (!O.blk[type]) throw std::runtime_error("oracle: no such element block");
+  ElemBlock& B = *O.blk[type];
+  B.nodeTag.assign(tags, tags + (size_t)B.n * B.tab.nbasic);
+  B.innerRadius.assign(inner_radius, inner_radius + B.n);
+  B.avElem.assign((size_t)B.n * B.tab.nbasic, 0.0);
+  for (int t : B.nodeTag) if (t < 0 || t >= (int)O.nodeAV.size()) throw std::runtime_error("oracle: node tag out of range (call orc_set_artificial_viscosity first)");
+  ORC_CATCH
+}
+int orc_update_artificial_viscosity(void* h) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  if (O.av) artificialViscosity(O);
+  ORC_CATCH
+}
+int orc_get_node_artificial_viscosity(void* h, double* out) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  std::copy(O.nodeAV.begin(), O.nodeAV.end(), out);
+  ORC_CATCH
+}
+int orc_get_element_artificial_viscosity(void* h, int type, double* out) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  if (!O.blk[type]) throw std::runtime_error("oracle: no such element block");
+  std::copy(O.blk[type]->avElem.begin(), O.blk[type]->avElem.end(), out);
   ORC_CATCH
 }
 // Pointwise physics of the oracle behind the SAME entry point as oracle/ref_physics.cpp (the reference's own functions): what = 0 Riemann

@@ -737,6 +737,12 @@ void MixedSolver::boundaryGradientState(double* Gb) {
   CUDA_OK(cudaStreamSynchronize(stream_));
 }
 
+void MixedSolver::setArtificialViscosity(double, double, int) { throw std::runtime_error("artificial viscosity is not built on the dense-operator (triangle / mixed-type) path yet"); }
+void MixedSolver::setElementNodes(int, const int32_t*, const double*) { throw std::runtime_error("artificial viscosity is not built on the dense-operator path yet"); }
+void MixedSolver::updateArtificialViscosity() {}
+void MixedSolver::nodeArtificialViscosity(double*) {}
+void MixedSolver::elementArtificialViscosity(int, double*) {}
+
 double MixedSolver::computeDt(double cfl) {
   needDevice(); CUDA_OK(cudaSetDevice(device_));
   double best = 1.7976931348623157e308;

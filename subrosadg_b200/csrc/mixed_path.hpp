@@ -50,6 +50,12 @@ class MixedSolver {
   void gradientState(int type, double* G);
   void boundaryGradientState(double* Gb);
   void refreshGradient();
+  // ShockCapturingEnum::ArtificialViscosity (SpatialDiscrete.cpp:37-192)
+  void setArtificialViscosity(double empiricalTolerance, double factor, int nodeNumber);
+  void setElementNodes(int type, const int32_t* nodeTag, const double* innerRadius);
+  void updateArtificialViscosity();
+  void nodeArtificialViscosity(double* out);
+  void elementArtificialViscosity(int type, double* out);
   double computeDt(double cfl);
   void step(double dt, int nSteps, double* relErr, float* ms);
   void residual(int type, double* Rmodal, double* rhsq);

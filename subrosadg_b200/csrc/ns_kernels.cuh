@@ -323,6 +323,8 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
   const int nNodes = ne * NN;
   const Phys<PH> ph(A.phys);
   const bool br2 = A.phys.visc == kBR2;
+  const bool av = A.phys.av != 0;   // Euler + artificial viscosity: G is the volume gradient, the viscous terms are eps * grad(U)
+  constexpr int NB = 1 << D;
   const int f0 = A.chunkFaceOff[chunk], nfc = A.chunkFaceOff[chunk + 1] - f0;
   if (A.mode == 0 && A.aLast != 0.0) {   // U_last is consumed at the very end: pull its lines into L2 now
     const char* p = reinterpret_cast<const char*>(A.Ulast + (size_t)e0 * NV * NN);
@@ -386,8 +388,19 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
 #pragma unroll
             for (int c = 0; c < D; c++) g[v * D + c] += lamL * n[c] * jump[v];
         }
-        primGradFromConsGrad<D>(ph, consL, compL, g, gp);
-        viscNormalFlux<D>(ph, n, compL, gp, va);   // calculateViscousFlux, ViscousFlux.cpp:139-153: average of both sides
+        if (av) {   // calculateArtificialViscousNormalFlux, ViscousFlux.cpp:126-136
+          const double eps = avAt<NB>(A.avTabF + (size_t)(lfL * NQF + j) * NB, A.avElem + (size_t)eL * NB);
+#pragma unroll
+          for (int v = 0; v < NV; v++) {
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; c++) t += g[v * D + c] * n[c];
+            va[v] = eps * t;
+          }
+        } else {
+          primGradFromConsGrad<D>(ph, consL, compL, g, gp);
+          viscNormalFlux<D>(ph, n, compL, gp, va);   // calculateViscousFlux, ViscousFlux.cpp:139-153: average of both sides
+        }
       }
       {
         double g[NG], gp[NG], vb[NV];
@@ -402,10 +415,21 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
 #pragma unroll
             for (int c = 0; c < D; c++) g[v * D + c] += lamR * n[c] * jump[v];
         }
-        primGradFromConsGrad<D>(ph, consR, compR, g, gp);
-        viscNormalFlux<D>(ph, n, compR, gp, vb);
+        if (av) {
+          const double eps = avAt<NB>(A.avTabF + (size_t)(lfR * NQF + jr) * NB, A.avElem + (size_t)eR * NB);
 #pragma unroll
-        for (int v = 0; v < NV; v++) Fn[v] -= (va[v] + vb[v]) / 2.0;
+          for (int v = 0; v < NV; v++) {
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; c++) t += g[v * D + c] * n[c];
+            vb[v] = eps * t;
+          }
+        } else {
+          primGradFromConsGrad<D>(ph, consR, compR, g, gp);
+          viscNormalFlux<D>(ph, n, compR, gp, vb);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) Fn[v] -= (va[v] + vb[v]) / 2.0;   // calculateArtificialViscousFlux averages as well (ViscousFlux.cpp:172-186)
       }
     } else {
       double compR[D + 3], b[D + 3], volCons[NV], intCons[NV], g[NG];
@@ -424,9 +448,19 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
           for (int c = 0; c < D; c++) g[v * D + c] += lamL * n[c] * jump[v];
       }
       double pL[NG], gb[NG], vb[NV];
-      primGradFromConsGrad<D>(ph, consL, compL, g, pL);        // from the UNMODIFIED interior trace (SpatialDiscrete.cpp:792-796)
       bcBoundaryVariable<D>(ph, bc, n, compL, compR, b);
       convNormalFlux<D>(ph, n, b, Fn);                          // :797-803
+      if (av) {   // boundary faces: the interior side alone (SpatialDiscrete.cpp:813-819)
+        const double eps = avAt<NB>(A.avTabF + (size_t)(lfL * NQF + j) * NB, A.avElem + (size_t)eL * NB);
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          double t = 0.0;
+#pragma unroll
+          for (int c = 0; c < D; c++) t += g[v * D + c] * n[c];
+          Fn[v] -= eps * t;
+        }
+      } else {
+      primGradFromConsGrad<D>(ph, consL, compL, g, pL);        // from the UNMODIFIED interior trace (SpatialDiscrete.cpp:792-796)
       // modifyBoundaryVariable (BoundaryCondition.cpp:299-307,443-452,490-501,535-546): walls overwrite the interior computational
       // state; boundary gradient = interior primitive gradient, adiabatic walls drop the temperature gradient
       if (bcIsWall(bc)) {
@@ -443,6 +477,7 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
       viscNormalFlux<D>(ph, n, b, gb, vb);
 #pragma unroll
       for (int v = 0; v < NV; v++) Fn[v] -= (va[v] + vb[v]) / 2.0;
+      }
     }
     if (inL) {
       const int slot = lfL * NQF + j;
@@ -519,8 +554,14 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
         for (int r = 0; r < NG; r++) out[(size_t)r * NN] = g[r];
       } else {
         compFromCons<D>(ph, cons, comp);
-        primGradFromConsGrad<D>(ph, cons, comp, g, gp);
-        viscRawFlux<D>(ph, comp, gp, Fv);
+        if (av) {   // calculateArtificialViscousRawFlux, ViscousFlux.cpp:105-113: eps(q) * volume gradient of the conserved variables
+          const double eps = avAt<NB>(A.avTabQ + (size_t)q * NB, A.avElem + (size_t)(e0 + el) * NB);
+#pragma unroll
+          for (int r = 0; r < NG; r++) Fv[r] = eps * g[r];
+        } else {
+          primGradFromConsGrad<D>(ph, cons, comp, g, gp);
+          viscRawFlux<D>(ph, comp, gp, Fv);
+        }
 #pragma unroll
         for (int dd = 0; dd < D; dd++) {
           double m[D], Ft[NV];

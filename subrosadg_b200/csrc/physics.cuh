@@ -46,6 +46,7 @@ __device__ __forceinline__ double fsqrt(double x) {
 struct PhysParams {
   int model, eos, transport, conv, visc, source;
   int compressible, ns;
+  int av, pad_;   // ShockCapturingEnum::ArtificialViscosity (Euler models): the gradient pass runs and the viscous terms are eps * grad(U_conserved)
   double cp, cv, icv, kg, gamma, mu0, k0, c0, rho0, padd, beta, tref;
 };
 

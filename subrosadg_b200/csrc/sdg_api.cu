@@ -17,6 +17,7 @@
 #include "mixed_path.hpp"
 #include "nsl_kernels.cuh"
 #include "tensor_kernels.cuh"
+#include "av_kernels.cuh"
 
 using namespace sdg;
 
@@ -37,6 +38,11 @@ struct sdg_ctx {
   MeshPlan plan;
   bool haveBlock = false, haveFaces = false;
   cudaStream_t stream = nullptr, copyStream = nullptr;
+  // ShockCapturingEnum::ArtificialViscosity: Solver::empirical_tolerance_, artificial_viscosity_factor_, Mesh::node_number_; the mesh data of
+  // the block in caller order (node_tag_ of the corner nodes, inner_radius_); device copies in internal order
+  double avTol = 0.0, avFactor = 1.0; int avNodes = 0;
+  std::vector<int> avTagsHost; std::vector<double> avRadiusHost;
+  DevBuf<int> avTags; DevBuf<double> avRadius, avElem, avTabQ, avTabF, avH, avNode, avE;
   cudaEvent_t seamEvent[9] = {};
   int64_t launches = 0;
 
@@ -80,6 +86,7 @@ struct sdg_ctx {
 
 namespace {
 
+bool twoPass(const sdg_ctx* c);
 void needDevice(sdg_ctx* c) { if (!c->hasDevice) throw std::runtime_error("no CUDA device bound to this context (plan-only context); the product has no CPU path"); }
 void needFinal(sdg_ctx* c) { if (!c->finalized) throw std::runtime_error("sdg_finalize has not been called"); }
 void needType(sdg_ctx* c, int type) { if (!c->haveBlock || c->plan.blk.type != type) throw std::runtime_error("no element block of this type"); }
@@ -91,6 +98,7 @@ void fillArgs(sdg_ctx* c, StageArgs& a) {
   a.faceRec = reinterpret_cast<const int4*>(c->faceRec.p); a.chunkFaceOff = c->chunkOff.p; a.chunkList = nullptr;
   a.dummy = c->dummy.p; a.tab = c->tab.p; a.normPartial = nullptr;
   a.nOwned = B.nOwned; a.nInt = c->plan.F.nInt; a.mode = 0; a.faceSel = -1; a.phys = c->phys;
+  a.avElem = c->avElem.p; a.avTabQ = c->avTabQ.p; a.avTabF = c->avTabF.p;
   const int N = B.T.N;
   for (int i = 0; i < N * N; i++) { a.dm[i] = B.T.Dm[i]; a.k1[i] = B.T.K1[i]; }
   for (int i = 0; i < 2 * N; i++) a.lend[i] = B.T.Lend[i];
@@ -101,6 +109,24 @@ void fillArgs(sdg_ctx* c, StageArgs& a) {
     static const int ahead = std::max(1, getenv("SDG_AHEAD") ? atoi(getenv("SDG_AHEAD")) : 1 << 30);   // default: every block fetches its OWN ranges; fetching one wave ahead (444, 148) measured slower: 1.90 / 1.66 vs 1.42 ms per residual pass at 64^3 (L2 churn)
     a.ahead = ahead;
   }
+}
+
+bool twoPass(const sdg_ctx* c) { return c->phys.ns != 0 || c->phys.av != 0; }
+
+// Solver::calculateArtificialViscosity for the state in buffer `buf` (TimeIntegration.cpp:336-338: once per step, before the stages)
+void avUpdate(sdg_ctx* c, int buf, cudaStream_t st) {
+  static const double kTol[5] = {0.0, -1.20411998266, -1.90848501888, -2.40823996531, -2.79588001734};   // SimulationControl.cpp:892-893
+  const BlockPlan& B = c->plan.blk;
+  const int NB = 1 << c->D, n = B.nOwned;
+  const int REC = (c->D * c->D + 2) & ~1;
+  avIndicatorKernel<<<std::min((n + 7) / 8, 148 * 8), 256, 0, st>>>(c->U[buf].p, c->avH.p, c->geoE.p, c->invjw.p, c->tab.p->wq, B.affine ? 1 : 0, REC, c->D * c->D, n,
+                                                                    c->NV, B.T.NN, c->cfg.p, kTol[c->cfg.p - 1], c->avTol, c->avFactor, c->avRadius.p, c->avE.p);
+  CUDA_OK(cudaMemsetAsync(c->avNode.p, 0, c->avNode.n * sizeof(double), st));
+  const int blocks = std::min((n * NB + 255) / 256, 148 * 8);
+  avNodeMaxKernel<<<blocks, 256, 0, st>>>(c->avE.p, c->avTags.p, n, NB, reinterpret_cast<unsigned long long*>(c->avNode.p));
+  avStoreKernel<<<blocks, 256, 0, st>>>(c->avNode.p, c->avTags.p, n, NB, c->avElem.p);
+  c->launches += 3;
+  CUDA_OK(cudaGetLastError());
 }
 
 // traces of a state that did not come out of the residual pass (initial condition, state setters)
@@ -125,7 +151,7 @@ void runStage(sdg_ctx* c, const StageArgs& base, int part, cudaStream_t s, int p
   if (c->lineTrace) {
     if (pass == 0) c->lineFns.grad(a, nBlocks, s); else c->lineFns.stage(a, nBlocks, s);
   }
-  else if (!c->phys.ns) c->eulerFn(a, nBlocks, s);
+  else if (!twoPass(c)) c->eulerFn(a, nBlocks, s);
   else if (pass == 0) c->nsGradFn(a, nBlocks, s);
   else c->nsStageFn(a, nBlocks, s);
   c->launches++;
@@ -159,10 +185,10 @@ void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st, int pass = -1) {
   if (c->lineTrace) {
     ensureTraces(c, in, st);
     a.TUin = c->TU[in].p; a.TUout = c->TU[out].p;
-    if (c->phys.ns && (pass == -1 || pass == 0)) lineBoundary(c, a, c->stepCount * 4 + s, st);
+    if (twoPass(c) && (pass == -1 || pass == 0)) lineBoundary(c, a, c->stepCount * 4 + s, st);
   }
-  if (c->phys.ns && (pass == -1 || pass == 0)) { runStage(c, a, part, st, 0); if (pass == 0) return; }
-  if (!c->phys.ns && pass == 0) return;
+  if (twoPass(c) && (pass == -1 || pass == 0)) { runStage(c, a, part, st, 0); if (pass == 0) return; }
+  if (!twoPass(c) && pass == 0) return;
   a.aLast = s == 0 ? 0.0 : c->rkc[s][0];
   a.aCur = s == 0 ? 1.0 : c->rkc[s][1];
   a.bdt = c->rkc[s][2] * c->stepDt;
@@ -261,7 +287,10 @@ int sdg_add_elements(sdg_ctx* c, int32_t type, int32_t n, int32_t n_ghost, int32
   // cfg.chunk == -1 (diagnostics): dense-operator path in the reference's modal representation (mixed_path.cu).
   if (type == kTriangle || c->haveBlock || c->mx || c->cfg.chunk == -1) {
     if (c->D != 2) throw std::runtime_error("several element types in one mesh: 2-D (triangle / quadrangle) only");
-    if (!c->mx) c->mx = std::make_unique<MixedSolver>(c->cfg.p, c->phys, c->nStages, c->rkc, c->stream, c->hasDevice, c->cfg.device);
+    if (!c->mx) {
+      c->mx = std::make_unique<MixedSolver>(c->cfg.p, c->phys, c->nStages, c->rkc, c->stream, c->hasDevice, c->cfg.device);
+      if (c->phys.av) c->mx->setArtificialViscosity(c->avTol, c->avFactor, c->avNodes);
+    }
     if (c->haveBlock) {  // a tensor block was registered first: hand it over
       BlockPlan& B = c->plan.blk;
       c->mx->addBlock(B.type, B.n, B.nGhost, B.g, B.X.data());
@@ -322,10 +351,11 @@ int sdg_finalize(sdg_ctx* c) {
   // without viscous terms, partners gathered from their nodal states) | trace (the same with published traces: twice the HBM traffic)
   const char* ek = getenv("SDG_EULER_KERNEL");
   const std::string eulerKernel = ek ? ek : "trace";   // measured at 128^3 (ms per stage): trace 8.12, line 8.80, link 8.83; 2 GPUs: 6.14 vs 6.85
-  c->lineTrace = c->D == 3 && N == 4 && (c->phys.ns ? getenv("SDG_NS_NODE_KERNEL") == nullptr : eulerKernel != "line");
+  // artificial viscosity runs on the node-per-thread kernels of ns_kernels.cuh (gradient pass + residual pass with eps * grad(U))
+  c->lineTrace = c->D == 3 && N == 4 && !c->phys.av && (c->phys.ns ? getenv("SDG_NS_NODE_KERNEL") == nullptr : eulerKernel != "line");
   c->traceTU = c->lineTrace && (c->phys.ns || eulerKernel == "trace");
   if (c->lineTrace) pickNslFns(B.affine, ph, c->phys.ns != 0, !c->traceTU, c->lineFns, K);
-  else if (c->phys.ns) pickNsFn(c->D, N, B.affine, ph, c->nsGradFn, c->nsStageFn, K);
+  else if (twoPass(c)) pickNsFn(c->D, N, B.affine, ph, c->nsGradFn, c->nsStageFn, K);
   else c->eulerFn = pickEulerFn(c->D, N, B.affine, ph, K);
   if (c->cfg.chunk > 0 && c->cfg.chunk != K) throw std::runtime_error("chunk override not available: kernels are compiled for K = " + std::to_string(K));
   B.K = K; B.nChunks = (B.nOwned + K - 1) / K;
@@ -380,7 +410,7 @@ int sdg_finalize(sdg_ctx* c) {
       for (int b = 0; b < B.T.NN; b++) { int q = 0; for (int d = 0; d < D; d++) q = q * N + B.T.modalIdx[b][d]; lex[b] = q; }
       c->lexOf.upload(lex, c->stream);
     }
-    if (c->phys.ns) { c->G.alloc((size_t)B.n * c->NV * c->D * B.T.NN); CUDA_OK(cudaMemsetAsync(c->G.p, 0, c->G.n * sizeof(double), c->stream)); }
+    if (twoPass(c)) { c->G.alloc((size_t)B.n * c->NV * c->D * B.T.NN); CUDA_OK(cudaMemsetAsync(c->G.p, 0, c->G.n * sizeof(double), c->stream)); }
     c->normPartial.alloc((size_t)B.nChunks * c->NV); c->normSlices.alloc(128 * 8); c->normOut.alloc(8); c->dtPartial.alloc(1024);
     CUDA_OK(cudaMemsetAsync(c->normPartial.p, 0, c->normPartial.n * sizeof(double), c->stream));
     std::vector<TensorDev> td(1);
@@ -398,6 +428,34 @@ int sdg_finalize(sdg_ctx* c) {
       for (int j = 0; j < B.T.NQF; j++) t.seq[r * B.T.NQF + j] = s[j];
     }
     c->tab.upload(td, c->stream);
+    if (c->phys.av) {
+      // H = Phi[:, high] Phi^-1[high, :] (the part of a nodal field carried by the modes above order P-1; P1: every mode), the order-1 nodal
+      // basis at the volume nodes and at the face points (nodal_value_ / nodal_adjacency_value_, BasisFunction.cpp:149-208), mesh data by position
+      const int NN = B.T.NN, D = c->D, NB = 1 << D, p = c->cfg.p;
+      int nbLow = 1; for (int d = 0; d < D; d++) nbLow *= p;       // getElementBasisFunctionNumber<type, P - 1> of line / quadrangle / hexahedron
+      if (p == 1) nbLow = 0;
+      std::vector<double> H((size_t)NN * NN, 0.0);
+      for (int q = 0; q < NN; q++) for (int r = 0; r < NN; r++) { double a = 0.0; for (int b = nbLow; b < NN; b++) a += B.T.Phi[(size_t)q * NN + b] * B.T.PhiInv[(size_t)b * NN + r]; H[(size_t)q * NN + r] = a; }
+      c->avH.upload(H, c->stream);
+      GeomEval P1(B.type, 1);
+      std::vector<double> wv, wd, tq((size_t)NN * NB), tf((size_t)B.T.NF * B.T.NQF * NB);
+      auto coordOf = [&](int q, double* xi) { int s = NN; for (int d = 0; d < D; d++) { s /= N; xi[d] = B.T.x[(q / s) % N]; } };
+      for (int q = 0; q < NN; q++) { double xi[3] = {0, 0, 0}; coordOf(q, xi); P1.weights(xi, wv, wd); for (int k = 0; k < NB; k++) tq[(size_t)q * NB + k] = wv[k]; }
+      for (int f = 0; f < B.T.NF; f++) for (int j = 0; j < B.T.NQF; j++) {
+        double xi[3] = {0, 0, 0}; coordOf(B.T.faceBase[f * B.T.NQF + j], xi);
+        xi[B.T.faceDir[f]] = B.T.faceSide[f] ? 1.0 : -1.0;
+        P1.weights(xi, wv, wd);
+        for (int k = 0; k < NB; k++) tf[(size_t)(f * B.T.NQF + j) * NB + k] = wv[k];
+      }
+      c->avTabQ.upload(tq, c->stream); c->avTabF.upload(tf, c->stream);
+      if ((int)c->avTagsHost.size() != B.n * NB || (int)c->avRadiusHost.size() != B.n) throw std::runtime_error("artificial viscosity needs sdg_set_element_nodes before sdg_finalize");
+      std::vector<int> tg((size_t)B.n * NB); std::vector<double> rad(B.n);
+      for (int e = 0; e < B.n; e++) { const int pos = B.perm[e]; rad[pos] = c->avRadiusHost[e]; for (int k = 0; k < NB; k++) tg[(size_t)pos * NB + k] = c->avTagsHost[(size_t)e * NB + k]; }
+      c->avTags.upload(tg, c->stream); c->avRadius.upload(rad, c->stream);
+      c->avElem.alloc((size_t)B.n * NB); c->avElem.zero(c->stream);
+      c->avNode.alloc((size_t)std::max(c->avNodes, 1)); c->avNode.zero(c->stream);
+      c->avE.alloc((size_t)B.n); c->avE.zero(c->stream);
+    }
     if (c->lineTrace) {
       const LinePlan& LP = c->linePlan;
       c->links.upload(LP.links, c->stream); c->bndRec.upload(LP.bndRec, c->stream);
@@ -695,6 +753,67 @@ int sdg_get_boundary_gradient_state(sdg_ctx* c, double* Gb) {
   SDG_CATCH
 }
 
+// System::setArtificialViscosity (SystemControl.cpp:105-108) for ShockCapturingEnum::ArtificialViscosity; before sdg_finalize
+int sdg_set_artificial_viscosity(sdg_ctx* c, double empirical_tolerance, double artificial_viscosity_factor, int32_t node_number) {
+  SDG_TRY
+  if (c->finalized) throw std::runtime_error("sdg_set_artificial_viscosity must precede sdg_finalize");
+  if (c->phys.ns) throw std::runtime_error("artificial viscosity is built for the Euler models (every example of the reference that uses it)");
+  if (node_number < 1) throw std::runtime_error("node_number must be positive");
+  c->phys.av = 1; c->avTol = empirical_tolerance; c->avFactor = artificial_viscosity_factor; c->avNodes = node_number;
+  if (c->mx) c->mx->setArtificialViscosity(empirical_tolerance, artificial_viscosity_factor, node_number);
+  SDG_CATCH
+}
+int sdg_set_element_nodes(sdg_ctx* c, int32_t type, const int32_t* node_tag, const double* inner_radius) {
+  SDG_TRY
+  if (c->finalized) throw std::runtime_error("sdg_set_element_nodes must precede sdg_finalize");
+  if (!c->phys.av) throw std::runtime_error("sdg_set_artificial_viscosity first");
+  if (c->mx) { c->mx->setElementNodes(type, node_tag, inner_radius); return 0; }
+  needType(c, type);
+  const BlockPlan& B = c->plan.blk;
+  if (B.nGhost > 0) throw std::runtime_error("artificial viscosity is single-GPU (the node maximum is not exchanged between partitions)");
+  const int NB = 1 << c->D;
+  c->avTagsHost.assign(node_tag, node_tag + (size_t)B.n * NB);
+  c->avRadiusHost.assign(inner_radius, inner_radius + B.n);
+  for (int t : c->avTagsHost) if (t < 0 || t >= c->avNodes) throw std::runtime_error("node tag out of range");
+  SDG_CATCH
+}
+int sdg_get_node_artificial_viscosity(sdg_ctx* c, double* out) {
+  SDG_TRY
+  needFinal(c);
+  if (!c->phys.av) throw std::runtime_error("artificial viscosity is not enabled");
+  if (c->mx) { c->mx->nodeArtificialViscosity(out); return 0; }
+  needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  CUDA_OK(cudaMemcpyAsync(out, c->avNode.p, (size_t)c->avNodes * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  SDG_CATCH
+}
+int sdg_get_element_artificial_viscosity(sdg_ctx* c, int32_t type, double* out) {
+  SDG_TRY
+  needFinal(c);
+  if (!c->phys.av) throw std::runtime_error("artificial viscosity is not enabled");
+  if (c->mx) { c->mx->elementArtificialViscosity(type, out); return 0; }
+  needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk; const int NB = 1 << c->D;
+  std::vector<double> h((size_t)B.n * NB);
+  CUDA_OK(cudaMemcpyAsync(h.data(), c->avElem.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int e = 0; e < B.n; e++) for (int k = 0; k < NB; k++) out[(size_t)e * NB + k] = h[(size_t)B.perm[e] * NB + k];
+  SDG_CATCH
+}
+int sdg_update_artificial_viscosity(sdg_ctx* c) {
+  SDG_TRY
+  needFinal(c);
+  if (!c->phys.av) return 0;
+  if (c->mx) { c->mx->updateArtificialViscosity(); return 0; }
+  needDevice(c);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  avUpdate(c, c->cur, c->stream);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  SDG_CATCH
+}
+
 int sdg_compute_dt(sdg_ctx* c, double cfl, double* dt) {
   SDG_TRY
   if (c->mx) { needFinal(c); *dt = c->mx->computeDt(cfl); return 0; }
@@ -717,7 +836,7 @@ int sdg_compute_dt(sdg_ctx* c, double cfl, double* dt) {
 }
 
 int sdg_num_stages(sdg_ctx* c) { return c->nStages; }
-int sdg_num_passes(sdg_ctx* c) { return c->phys.ns ? 2 : 1; }
+int sdg_num_passes(sdg_ctx* c) { return twoPass(c) ? 2 : 1; }
 void* sdg_stream(sdg_ctx* c) { return (void*)c->stream; }
 int64_t sdg_launch_count(sdg_ctx* c) { return c->launches + (c->mx ? c->mx->launches : 0); }
 
@@ -734,6 +853,7 @@ int sdg_step_begin(sdg_ctx* c, double dt) {
   if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c);
   c->stepDt = dt;
+  if (c->phys.av) { CUDA_OK(cudaSetDevice(c->cfg.device)); avUpdate(c, c->cur, c->stream); }
   SDG_CATCH
 }
 
@@ -743,7 +863,7 @@ int sdg_stage_pass(sdg_ctx* c, int32_t stage, int32_t pass, int32_t part, void* 
   needFinal(c); needDevice(c);
   if (stage < 0 || stage >= c->nStages || pass < 0 || pass >= sdg_num_passes(c) || part < -1 || part > 1) throw std::runtime_error("bad stage/pass/part");
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  stageLaunch(c, stage, part, stream ? (cudaStream_t)stream : c->stream, c->phys.ns ? pass : 1);
+  stageLaunch(c, stage, part, stream ? (cudaStream_t)stream : c->stream, twoPass(c) ? pass : 1);
   SDG_CATCH
 }
 
@@ -767,6 +887,7 @@ namespace {
 constexpr int kGraphMaxChunks = 1 << 15;   // above this a stage kernel runs for >= 100 us and launch overhead is irrelevant
 
 void launchOneStep(sdg_ctx* c) {
+  if (c->phys.av) avUpdate(c, c->cur, c->stream);
   for (int s = 0; s < c->nStages; s++) stageLaunch(c, s, -1, c->stream);
   finishStep(c);
 }
@@ -847,6 +968,7 @@ int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
   const size_t nd = c->stateDoubles();
   const int a = (c->cur + 1) % 3, b = (c->cur + 2) % 3;
   c->traceValid[a] = c->traceValid[b] = false;   // both scratch buffers are overwritten below
+  if (c->phys.av) avUpdate(c, c->cur, c->stream);   // parity hook: the viscosity of the CURRENT state
   for (int mode = 1; mode <= 2; mode++) {
     double* host = mode == 1 ? rhsq : Rmodal;
     if (!host) continue;
@@ -858,9 +980,9 @@ int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
     if (c->lineTrace) {
       ensureTraces(c, c->cur, c->stream);
       args.TUin = c->TU[c->cur].p; args.TUout = c->TU[a].p;
-      if (c->phys.ns) lineBoundary(c, args, -1, c->stream);
+      if (twoPass(c)) lineBoundary(c, args, -1, c->stream);
     }
-    if (c->phys.ns) runStage(c, args, -1, c->stream, 0);
+    if (twoPass(c)) runStage(c, args, -1, c->stream, 0);
     runStage(c, args, -1, c->stream, 1);
     if (mode == 1) {
       seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->U[a].p, c->U[b].p, c->perm.p, B.n, c->NV, B.T.NN, 1);

@@ -80,7 +80,19 @@ struct StageArgs {
   double w1[kMaxN];                    // 1-D Gauss weights
   int ahead;                           // thread blocks per wave: how far ahead a block prefetches the contiguous ranges of a later block into L2
   double cLift;                        // sum_a l_a(-1)^2 / w_a: BR2 lift trace factor of a face point, without 1 / (detJ w_face)
+  // artificial viscosity (SpatialDiscrete.cpp:37-192): corner values per element [n][2^D] (variable_artificial_viscosity_), order-1 nodal
+  // basis at the volume nodes [NN][2^D] (nodal_value_) and at the face points [NF*NQF][2^D] (nodal_adjacency_value_)
+  const double* avElem; const double* avTabQ; const double* avTabF;
 };
+
+// eps at a point = nodal basis row * corner values (SpatialDiscrete.cpp:213-214, 539-546)
+template <int NB>
+__device__ __forceinline__ double avAt(const double* __restrict__ row, const double* __restrict__ corner) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < NB; k++) s += __ldg(row + k) * __ldg(corner + k);
+  return s;
+}
 
 template <int N, int D> struct Pow { static constexpr int v = N * Pow<N, D - 1>::v; };
 template <int N> struct Pow<N, 0> { static constexpr int v = 1; };

@@ -510,6 +510,73 @@ def sphere_in_box(n_mid=11, n_out=9, n_rad=9, half=5.0, r_sphere=0.5, geom_order
                             info=dict(kind="sphere_in_box", blocks=32, n_mid=n_mid, n_out=n_out, n_rad=n_rad))
 
 
+# ---- mesh data of ShockCapturingEnum::ArtificialViscosity (PerElementMesh::node_tag_, inner_radius_; ReadControl.cpp:64,91) ------------
+N_BASIC = {LINE: 2, TRIANGLE: 3, QUADRANGLE: 4, HEXAHEDRON: 8}   # kBasicNodeNumber: the corner nodes lead the gmsh node order
+
+
+def node_tags(mesh: Mesh):
+    """({type: int32 [n, kBasicNodeNumber] 0-based tags of the corner nodes}, node_number).  The flat mesh carries coordinates per
+    element, not gmsh tags: nodes are the distinct coordinate tuples over all blocks (the two copies of a periodic pair stay distinct,
+    as in a Gmsh mesh), numbered in lexicographic order of their coordinates — the same rule as MeshData::countNodes in the C++ shim."""
+    pts = np.concatenate([np.asarray(b["coords"], dtype=np.float64).reshape(-1, mesh.dim) for b in mesh.blocks.values()])
+    uniq, inv = np.unique(pts, axis=0, return_inverse=True)
+    inv = np.asarray(inv).reshape(-1)
+    out, at = {}, 0
+    for t, b in mesh.blocks.items():
+        n, nn = np.asarray(b["coords"]).shape[:2]
+        out[t] = np.ascontiguousarray(inv[at:at + n * nn].reshape(n, nn)[:, :N_BASIC[t]], dtype=np.int32)
+        at += n * nn
+    return out, int(uniq.shape[0])
+
+
+def _quad_inner_radius(P):
+    """P [n, 4, 2]: radius of the smallest circle tangent to three consecutive edge lines (centre = intersection of the interior angle
+    bisectors at the two vertices of the middle edge) — Gmsh's MQuadrangle::getInnerRadius (third party, Gmsh 4.x; restated from its
+    published algorithm, not checked against Gmsh here)."""
+    unit = lambda v: v / np.linalg.norm(v, axis=-1, keepdims=True)
+    cross = lambda a, b: a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]
+    best = np.full(P.shape[0], np.inf)
+    for i in range(4):
+        A, B, prev, nxt = P[:, i], P[:, (i + 1) % 4], P[:, (i - 1) % 4], P[:, (i + 2) % 4]
+        dA = unit(prev - A) + unit(B - A)
+        dB = unit(A - B) + unit(nxt - B)
+        den = cross(dA, dB)
+        ok = np.abs(den) > 1e-300
+        s_ = np.where(ok, cross(B - A, dB) / np.where(ok, den, 1.0), np.inf)
+        C = A + s_[:, None] * dA
+        r = np.abs(cross(B - A, C - A)) / np.linalg.norm(B - A, axis=-1)
+        best = np.minimum(best, np.where(ok, r, np.inf))
+    return best
+
+
+def inner_radius(mesh: Mesh, t: int) -> np.ndarray:
+    """inner_radius_ of every element of block t: gmsh::model::mesh::getElementQualities(..., "innerRadius") (Geometry.cpp:31-41).  Gmsh is
+    a third-party dependency that is not in this image; its definitions are restated: line = half length, triangle = area / half
+    perimeter (inscribed circle), quadrangle = see _quad_inner_radius, hexahedron = minimum of its six faces' quadrangle radii."""
+    X = np.asarray(mesh.blocks[t]["coords"], dtype=np.float64)[:, :N_BASIC[t], :]
+    if t == LINE:
+        return 0.5 * np.linalg.norm(X[:, 1] - X[:, 0], axis=-1)
+    if t == TRIANGLE:
+        a = np.linalg.norm(X[:, 1] - X[:, 0], axis=-1); b = np.linalg.norm(X[:, 2] - X[:, 1], axis=-1); c = np.linalg.norm(X[:, 0] - X[:, 2], axis=-1)
+        k = 0.5 * (a + b + c)
+        return np.sqrt(k * (k - a) * (k - b) * (k - c)) / k
+    if t == QUADRANGLE:
+        return _quad_inner_radius(X[:, :, :2])
+    if t == HEXAHEDRON:
+        best = np.full(X.shape[0], np.inf)
+        for fc in FACE_CORNERS[HEXAHEDRON]:
+            V = X[:, fc, :]                                      # [n, 4, 3]
+            nrm = np.cross(V[:, 2] - V[:, 0], V[:, 3] - V[:, 1])
+            nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+            e1 = V[:, 1] - V[:, 0]; e1 /= np.linalg.norm(e1, axis=-1, keepdims=True)
+            e2 = np.cross(nrm, e1)
+            c0 = V.mean(axis=1, keepdims=True)
+            P = np.stack([((V - c0) * e1[:, None, :]).sum(-1), ((V - c0) * e2[:, None, :]).sum(-1)], axis=-1)
+            best = np.minimum(best, _quad_inner_radius(P))
+        return best
+    raise ValueError("inner_radius: unsupported element type")
+
+
 def write_flat(mesh: Mesh, path) -> None:
     """Flat little-endian mesh file for the C++ host side (`SubrosaDG::MeshData::readFlat`,
     include/SubrosaDG_b200/SubrosaDG.hpp): magic "SDGM", dim, nblocks, per block {type, geom_order, n, nn, coords[n][nn][dim]},

@@ -46,7 +46,8 @@ EXPORTS = [
     "sdg_stage_pass", "sdg_step_end", "sdg_num_passes", "sdg_num_stages", "sdg_stream", "sdg_synchronize", "sdg_set_state_device",
     "sdg_get_state_device", "sdg_launch_count", "sdg_debug_plan", "sdg_ipc_export", "sdg_ipc_connect", "sdg_halo_push", "sdg_halo_wait",
     "sdg_halo_doubles_per_element", "sdg_debug_physics", "sdg_uses_trace_rows", "sdg_set_halo_rows", "sdg_halo_unpack",
-    "sdg_ipc_set_destination_units", "sdg_get_gradient_state", "sdg_get_boundary_gradient_state",
+    "sdg_ipc_set_destination_units", "sdg_get_gradient_state", "sdg_get_boundary_gradient_state", "sdg_set_artificial_viscosity",
+    "sdg_set_element_nodes", "sdg_get_node_artificial_viscosity", "sdg_get_element_artificial_viscosity", "sdg_update_artificial_viscosity",
 ]
 
 _lib = None
@@ -125,6 +126,13 @@ class Solver:
         f = mesh.faces
         arrs = [np.ascontiguousarray(f[k], dtype=np.int32) for k in ("le", "lt", "lf", "re", "rt", "rf", "rot", "bc", "phys")]
         _chk(lib.sdg_set_faces(self.h, int(f["n_int"]), int(f["n_bnd"]), *[_ip(a) for a in arrs]))
+        if cfg.get("av_tolerance") is not None:   # System::setArtificialViscosity with ShockCapturingEnum::ArtificialViscosity
+            from . import mesh as M
+            tags, self.n_nodes = M.node_tags(mesh)
+            _chk(lib.sdg_set_artificial_viscosity(self.h, ctypes.c_double(cfg["av_tolerance"]), ctypes.c_double(cfg.get("av_factor", 1.0)), int(self.n_nodes)))
+            for t in self.types:
+                r = np.ascontiguousarray(M.inner_radius(mesh, t), dtype=np.float64)
+                _chk(lib.sdg_set_element_nodes(self.h, t, _ip(tags[t]), _dp(r)))
         _chk(lib.sdg_finalize(self.h))
         self.relative_error_ = np.zeros(self.Nv)  # Solver::relative_error_, SolveControl.cpp:300
         self.delta_time_ = 0.0
@@ -222,6 +230,21 @@ class Solver:
         out = np.zeros(int(n))
         if n:
             _chk(load_library().sdg_get_boundary_gradient_state(self.h, _dp(out)))
+        return out
+
+    def update_artificial_viscosity(self):
+        _chk(load_library().sdg_update_artificial_viscosity(self.h))
+
+    def node_artificial_viscosity(self):
+        """Solver::node_artificial_viscosity_ [node_number] as of the last step (SpatialDiscrete.cpp:137-192)."""
+        out = np.zeros(self.n_nodes)
+        _chk(load_library().sdg_get_node_artificial_viscosity(self.h, _dp(out)))
+        return out
+
+    def element_artificial_viscosity(self, t):
+        from . import mesh as M
+        out = np.zeros((self.sizes(t).n, M.N_BASIC[t]))
+        _chk(load_library().sdg_get_element_artificial_viscosity(self.h, t, _dp(out)))
         return out
 
     # -- Solver::calculateDeltaTime (TimeIntegration.cpp:133-179) -------------------------------------------------------------
