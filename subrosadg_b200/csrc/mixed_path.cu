@@ -10,6 +10,7 @@
 // Meshes on this path are the small hybrid meshes of configs 2/3 (1e3-1e4 elements): launch-latency bound, operators stay
 // in L1/L2; the HBM-roofline work of the repository is the tensor path.
 #include "mixed_path.hpp"
+#include "av_kernels.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -26,6 +27,11 @@ struct MxType {
   int n, Nb, Nq, Nf, Nqf, Naq, normOff;
   const double *Phi, *dPhi, *PhiF, *Proj, *mt, *jw, *Minv, *minEdge;
   double *U, *Ulast, *R, *A, *RM, *AGv, *AGi, *Gvol, *Gtot, *Gf;
+  // artificial viscosity: corner values [n][NB], order-1 nodal basis at the volume / face points, mesh data, scratch
+  int NB, nbLow;
+  const double *avElem, *NodalQ, *NodalF, *radius;
+  const int* tags;
+  double* avE;
 };
 struct MxFaces {
   int nInt, nBnd, Nqf;
@@ -67,6 +73,23 @@ __device__ __forceinline__ void gradTraceOf(const MxType& T, int visc, int e, in
     const double ph = phi[b];
     for (int r = 0; r < kG; r++) g[r] = fma(C0[b * kG + r] + (C1 ? C1[b * kG + r] : 0.0), ph, g[r]);
   }
+}
+
+// eps at a point: order-1 nodal basis row * corner values (SpatialDiscrete.cpp:213-214, 529-631)
+__device__ __forceinline__ double mxEps(const MxType& T, const double* __restrict__ row, int e) {
+  double s = 0.0;
+  for (int k = 0; k < T.NB; k++) s = fma(row[k], T.avElem[(size_t)e * T.NB + k], s);
+  return s;
+}
+// eps * grad(U_conserved) . n with the VOLUME gradient (calculateArtificialViscousNormalFlux, ViscousFlux.cpp:126-136)
+__device__ __forceinline__ void mxAvNormalFlux(const MxType& T, int e, int row, const double* n, double* out) {
+  double g[kG];
+  for (int r = 0; r < kG; r++) g[r] = 0.0;
+  const double* C = T.Gvol + (size_t)e * T.Nb * kG;
+  const double* phi = T.PhiF + (size_t)row * T.Nb;
+  for (int b = 0; b < T.Nb; b++) { const double ph = phi[b]; for (int r = 0; r < kG; r++) g[r] = fma(C[b * kG + r], ph, g[r]); }
+  const double eps = mxEps(T, T.NodalF + (size_t)row * T.NB, e);
+  for (int v = 0; v < kNV; v++) out[v] = eps * (g[v * kD] * n[0] + g[v * kD + 1] * n[1]);
 }
 
 template <int PASS>
@@ -111,6 +134,11 @@ __global__ void __launch_bounds__(128) mxFaceKernel(const __grid_constant__ Args
           primGradFromConsGrad<kD>(ph, consR, compR, g, gp); viscNormalFlux<kD>(ph, n, compR, gp, b);
           for (int v = 0; v < kNV; v++) Fc[v] -= (a[v] + b[v]) / 2.0;
         }
+        if (A.phys.av) {  // calculateArtificialViscousFlux, ViscousFlux.cpp:172-186
+          double a[kNV], b[kNV];
+          mxAvNormalFlux(TL, eL, rowL, n, a); mxAvNormalFlux(TR, eR, rowR, n, b);
+          for (int v = 0; v < kNV; v++) Fc[v] -= (a[v] + b[v]) / 2.0;
+        }
         double* aL = TL.A + ((size_t)eL * TL.Naq + rowL) * kNV; double* aR = TR.A + ((size_t)eR * TR.Naq + rowR) * kNV;
         for (int v = 0; v < kNV; v++) { aL[v] = Fc[v] * w; aR[v] = -Fc[v] * w; }
       }
@@ -138,6 +166,11 @@ __global__ void __launch_bounds__(128) mxFaceKernel(const __grid_constant__ Args
           if (bc == kAdiabaticSlipWall || bc == kAdiabaticNonSlipWall) for (int d = 0; d < kD; d++) gb[(kD + 1) * kD + d] = 0.0;
           viscNormalFlux<kD>(ph, n, cl, gp, a); viscNormalFlux<kD>(ph, n, b, gb, c2);
           for (int v = 0; v < kNV; v++) Fc[v] -= (a[v] + c2[v]) / 2.0;
+        }
+        if (A.phys.av) {  // boundary faces: the interior side alone (SpatialDiscrete.cpp:813-819)
+          double a[kNV];
+          mxAvNormalFlux(TL, eL, rowL, n, a);
+          for (int v = 0; v < kNV; v++) Fc[v] -= a[v];
         }
         double* aL = TL.A + ((size_t)eL * TL.Naq + rowL) * kNV;
         for (int v = 0; v < kNV; v++) aL[v] = Fc[v] * w;
@@ -215,12 +248,13 @@ __global__ void __launch_bounds__(kElemThreads) mxElemKernel(const __grid_consta
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int e = blockIdx.x * (kElemThreads / 32) + wib, Nb = T.Nb, Nq = T.Nq, Naq = T.Naq;
   if (e >= T.n) return;   // whole warp
-  const bool ns = A.phys.ns != 0, src = A.phys.source != kSourceNone;
+  const bool ns = A.phys.ns != 0, src = A.phys.source != kSourceNone, av = A.phys.av != 0;
   extern __shared__ double sm[];
   const int per = Nb * kNV + Nb * kG + Nq * kD * kNV + Nq * kNV + Nb * kNV;
   double* sU = sm + (size_t)wib * per; double* sG = sU + Nb * kNV; double* sQ = sG + Nb * kG; double* sS = sQ + Nq * kD * kNV; double* sR = sS + Nq * kNV;
   for (int k = lane; k < Nb * kNV; k += 32) sU[k] = T.U[(size_t)e * Nb * kNV + k];
   if (ns) for (int k = lane; k < Nb * kG; k += 32) sG[k] = T.Gtot[(size_t)e * Nb * kG + k];
+  if (av) for (int k = lane; k < Nb * kG; k += 32) sG[k] = T.Gvol[(size_t)e * Nb * kG + k];   // Euler + artificial viscosity: the volume gradient
   __syncwarp();
   for (int q = lane; q < Nq; q += 32) {  // calculateElementQuadrature, SpatialDiscrete.cpp:194-266
     double cons[kNV] = {0, 0, 0, 0}, comp[kD + 3], Fc[kD * kNV];
@@ -234,6 +268,13 @@ __global__ void __launch_bounds__(kElemThreads) mxElemKernel(const __grid_consta
       primGradFromConsGrad<kD>(ph, cons, comp, g, gp);
       viscRawFlux<kD>(ph, comp, gp, Fv);
       for (int k = 0; k < kD * kNV; k++) Fc[k] -= Fv[k];
+    }
+    if (av) {  // calculateArtificialViscousRawFlux, ViscousFlux.cpp:105-113
+      double g[kG];
+      for (int r = 0; r < kG; r++) g[r] = 0.0;
+      for (int b = 0; b < Nb; b++) { const double f = T.Phi[q * Nb + b]; for (int r = 0; r < kG; r++) g[r] = fma(sG[b * kG + r], f, g[r]); }
+      const double eps = mxEps(T, T.NodalQ + (size_t)q * T.NB, e);
+      for (int k = 0; k < kD * kNV; k++) Fc[k] -= eps * g[k];
     }
     const double* mt = T.mt + ((size_t)e * Nq + q) * 4;
     for (int dd = 0; dd < kD; dd++) for (int k = 0; k < kNV; k++) {
@@ -280,6 +321,33 @@ __global__ void __launch_bounds__(kElemThreads) mxElemKernel(const __grid_consta
       double s = 0.0;
       for (int q = 0; q < Nq; q++) s += sQ[q * kNV + lane];
       A.normPartial[(size_t)(T.normOff + e) * kNV + lane] = s / Nq;
+    }
+  }
+}
+
+// calculateElementArtificialViscosity (SpatialDiscrete.cpp:37-87) in the modal representation: one warp per element
+__global__ void mxAvIndicatorKernel(const __grid_constant__ Args A, int slot, int p, double tol, double empTol, double factor) {
+  const MxType& T = A.t[slot];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+  for (int e = warp; e < T.n; e += nWarps) {
+    const double* U = T.U + (size_t)e * T.Nb * kNV;
+    double num = 0.0, den = 0.0;
+    for (int q = lane; q < T.Nq; q += 32) {
+      double all = 0.0, high = 0.0;
+      for (int b = 0; b < T.Nb; b++) { const double t = T.Phi[q * T.Nb + b] * U[b * kNV]; all += t; if (b >= T.nbLow) high += t; }
+      const double w = T.jw[(size_t)e * T.Nq + q];
+      num += high * (high * w); den += all * (all * w);
+    }
+    for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
+    if (lane == 0) {
+      const double shock = log10(num / den);
+      const double full = factor * (T.radius[e] / p);
+      double val;
+      if (shock < tol - empTol) val = 0.0;
+      else if (shock > tol + empTol) val = full;
+      else val = full * (1.0 + sin(3.14159265358979323846 * (shock - tol) / (2.0 * empTol))) / 2.0;
+      T.avE[e] = val;
     }
   }
 }
@@ -474,10 +542,16 @@ void MixedSolver::finalize() {
       const size_t ns4 = (size_t)B.n * T.Nb * kNV, ng = (size_t)B.n * T.Nb * kG;
       B.U.alloc(ns4); B.Ulast.alloc(ns4); B.R.alloc(ns4); B.RM.alloc(ns4); B.A.alloc((size_t)B.n * T.Naq * kNV);
       B.U.zero(stream_); B.Ulast.zero(stream_); B.R.zero(stream_); B.RM.zero(stream_); B.A.zero(stream_);
-      if (ns) {
+      if (ns || phys_.av) {
         B.AGv.alloc((size_t)B.n * T.Naq * kG); B.AGi.alloc((size_t)B.n * T.Naq * kG); B.Gvol.alloc(ng); B.Gtot.alloc(ng);
         B.AGv.zero(stream_); B.AGi.zero(stream_); B.Gvol.zero(stream_); B.Gtot.zero(stream_);
         if (phys_.visc == kBR2) { B.Gf.alloc(ng * T.Nf); B.Gf.zero(stream_); }
+      }
+      if (phys_.av) {
+        if ((int)B.tags.size() != B.n * T.nbasic || (int)B.radius.size() != B.n) throw std::runtime_error("artificial viscosity needs sdg_set_element_nodes for every block before sdg_finalize");
+        B.dTags.upload(B.tags, stream_); B.dRadius.upload(B.radius, stream_);
+        B.dNodalQ.upload(T.NodalQ, stream_); B.dNodalF.upload(T.NodalF, stream_);
+        B.dAvElem.alloc((size_t)B.n * T.nbasic); B.dAvElem.zero(stream_); B.dAvE.alloc((size_t)B.n); B.dAvE.zero(stream_);
       }
       const size_t sm = std::max(elemSmemBytes(T), gradSmemBytes(T));
       if (sm > 48 * 1024) throw std::runtime_error("internal: element tile exceeds the default shared-memory window");
@@ -487,6 +561,7 @@ void MixedSolver::finalize() {
     dNrm.upload(nrm_, stream_); dFjw.upload(fjw_, stream_);
     dDummy.alloc((size_t)std::max(F_.nBnd, 1) * (p_ + 1) * (kD + 3)); dDummy.zero(stream_);
     normPartial.alloc((size_t)totalElements() * kNV); normPartial.zero(stream_); normOut.alloc(8); dtPartial.alloc(1024);
+    if (phys_.av) { avNode_.alloc((size_t)std::max(avNodes_, 1)); avNode_.zero(stream_); }
     CUDA_OK(cudaStreamSynchronize(stream_));
   }
   finalized_ = true;
@@ -523,6 +598,8 @@ void MixedSolver::fill(Args& a) {
     t.Phi = B.dPhi_.p; t.dPhi = B.dDPhi.p; t.PhiF = B.dPhiF.p; t.Proj = B.dProj.p; t.mt = B.dMt.p; t.jw = B.dJw.p; t.Minv = B.dMinv.p; t.minEdge = B.dMinEdge.p;
     t.U = B.U.p; t.Ulast = B.Ulast.p; t.R = B.R.p; t.A = B.A.p; t.RM = B.RM.p;
     t.AGv = B.AGv.p; t.AGi = B.AGi.p; t.Gvol = B.Gvol.p; t.Gtot = B.Gtot.p; t.Gf = B.Gf.p;
+    t.NB = T.nbasic; t.nbLow = p_ == 1 ? 0 : mixedNumBasis(type, p_ - 1);
+    t.avElem = B.dAvElem.p; t.NodalQ = B.dNodalQ.p; t.NodalF = B.dNodalF.p; t.radius = B.dRadius.p; t.tags = B.dTags.p; t.avE = B.dAvE.p;
   }
   a.F.nInt = F_.nInt; a.F.nBnd = F_.nBnd; a.F.Nqf = p_ + 1;
   a.F.le = dLe.p; a.F.lt = dLt.p; a.F.lf = dLf.p; a.F.re = dRe.p; a.F.rt = dRt.p; a.F.rf = dRf.p; a.F.bc = dBc.p;
@@ -536,7 +613,7 @@ void MixedSolver::evalResidual(Args& a, int mode, bool wantNorm) {
   a.mode = mode; a.normPartial = wantNorm ? normPartial.p : nullptr;
   const int nfp = (F_.nInt + F_.nBnd) * (p_ + 1);
   const int fb = std::max(1, (nfp + 127) / 128);
-  if (phys_.ns) {
+  if (phys_.ns || phys_.av) {
     mxFaceKernel<0><<<fb, 128, 0, stream_>>>(a); launches++;
     for (int type : {(int)kTriangle, (int)kQuadrangle}) if (blk_[type]) {
       mxGradElemKernel<<<elemBlocks(blk_[type]->n), kElemThreads, gradSmemBytes(blk_[type]->T), stream_>>>(a, type == kTriangle ? 0 : 1); launches++;
@@ -557,6 +634,7 @@ void MixedSolver::step(double dt, int nSteps, double* relErr, float* ms) {
   if (ms) { CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1)); CUDA_OK(cudaStreamSynchronize(stream_)); CUDA_OK(cudaEventRecord(e0, stream_)); }
   auto oneStep = [&]() {
     if (nStages_ > 1) for (auto& b : blk_) if (b) CUDA_OK(cudaMemcpyAsync(b->Ulast.p, b->U.p, b->U.n * sizeof(double), cudaMemcpyDeviceToDevice, stream_));  // copyElementBasisFunctionCoefficient, TimeIntegration.cpp:70-78
+    if (phys_.av) avUpdate();   // once per step, before the stages (TimeIntegration.cpp:336-338)
     for (int s = 0; s < nStages_; s++) {
       a.aLast = s == 0 ? 0.0 : rkc_[s][0]; a.aCur = s == 0 ? 1.0 : rkc_[s][1]; a.bdt = rkc_[s][2] * dt;
       evalResidual(a, 0, s == nStages_ - 1);
@@ -597,6 +675,7 @@ void MixedSolver::residual(int type, double* Rmodal, double* rhsq) {
   CUDA_OK(cudaSetDevice(device_));
   MixedBlock& B = block(type); const MixedTable& T = B.T;
   Args a; fill(a);
+  if (phys_.av) avUpdate();   // parity hook: the viscosity of the CURRENT state
   evalResidual(a, 1, false);
   const size_t nd = (size_t)B.n * T.Nb * kNV;
   if (Rmodal) CUDA_OK(cudaMemcpyAsync(Rmodal, B.R.p, nd * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -737,11 +816,51 @@ void MixedSolver::boundaryGradientState(double* Gb) {
   CUDA_OK(cudaStreamSynchronize(stream_));
 }
 
-void MixedSolver::setArtificialViscosity(double, double, int) { throw std::runtime_error("artificial viscosity is not built on the dense-operator (triangle / mixed-type) path yet"); }
-void MixedSolver::setElementNodes(int, const int32_t*, const double*) { throw std::runtime_error("artificial viscosity is not built on the dense-operator path yet"); }
-void MixedSolver::updateArtificialViscosity() {}
-void MixedSolver::nodeArtificialViscosity(double*) {}
-void MixedSolver::elementArtificialViscosity(int, double*) {}
+void MixedSolver::setArtificialViscosity(double empiricalTolerance, double factor, int nodeNumber) {
+  if (finalized_) throw std::runtime_error("sdg_set_artificial_viscosity must precede sdg_finalize");
+  phys_.av = 1; avTol_ = empiricalTolerance; avFactor_ = factor; avNodes_ = nodeNumber;
+}
+void MixedSolver::setElementNodes(int type, const int32_t* nodeTag, const double* innerRadius) {
+  if (finalized_) throw std::runtime_error("sdg_set_element_nodes must precede sdg_finalize");
+  MixedBlock& B = block(type);
+  B.tags.assign(nodeTag, nodeTag + (size_t)B.n * B.T.nbasic);
+  B.radius.assign(innerRadius, innerRadius + B.n);
+  for (int t : B.tags) if (t < 0 || t >= avNodes_) throw std::runtime_error("node tag out of range");
+}
+// Solver::calculateArtificialViscosity, SpatialDiscrete.cpp:124-192
+void MixedSolver::avUpdate() {
+  static const double kTol[5] = {0.0, -1.20411998266, -1.90848501888, -2.40823996531, -2.79588001734};   // SimulationControl.cpp:892-893
+  Args a; fill(a);
+  for (int type : {(int)kTriangle, (int)kQuadrangle}) if (blk_[type]) {
+    mxAvIndicatorKernel<<<std::min((blk_[type]->n + 7) / 8, 148 * 8), 256, 0, stream_>>>(a, type == kTriangle ? 0 : 1, p_, kTol[p_ - 1], avTol_, avFactor_); launches++;
+  }
+  CUDA_OK(cudaMemsetAsync(avNode_.p, 0, avNode_.n * sizeof(double), stream_));
+  for (int type : {(int)kTriangle, (int)kQuadrangle}) if (blk_[type]) {
+    MixedBlock& B = *blk_[type]; const int NB = B.T.nbasic;
+    avNodeMaxKernel<<<std::min((B.n * NB + 255) / 256, 148 * 8), 256, 0, stream_>>>(B.dAvE.p, B.dTags.p, B.n, NB, reinterpret_cast<unsigned long long*>(avNode_.p)); launches++;
+  }
+  for (int type : {(int)kTriangle, (int)kQuadrangle}) if (blk_[type]) {
+    MixedBlock& B = *blk_[type]; const int NB = B.T.nbasic;
+    avStoreKernel<<<std::min((B.n * NB + 255) / 256, 148 * 8), 256, 0, stream_>>>(avNode_.p, B.dTags.p, B.n, NB, B.dAvElem.p); launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+}
+void MixedSolver::updateArtificialViscosity() {
+  needDevice(); CUDA_OK(cudaSetDevice(device_));
+  avUpdate();
+  CUDA_OK(cudaStreamSynchronize(stream_));
+}
+void MixedSolver::nodeArtificialViscosity(double* out) {
+  needDevice(); CUDA_OK(cudaSetDevice(device_));
+  CUDA_OK(cudaMemcpyAsync(out, avNode_.p, (size_t)avNodes_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+}
+void MixedSolver::elementArtificialViscosity(int type, double* out) {
+  needDevice(); CUDA_OK(cudaSetDevice(device_));
+  MixedBlock& B = block(type);
+  CUDA_OK(cudaMemcpyAsync(out, B.dAvElem.p, B.dAvElem.n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+}
 
 double MixedSolver::computeDt(double cfl) {
   needDevice(); CUDA_OK(cudaSetDevice(device_));

@@ -26,6 +26,9 @@ struct MixedBlock {
   DevBuf<double> dPhi_, dDPhi, dPhiF, dProj, dMt, dJw, dMinv, dMinEdge;
   DevBuf<double> U, Ulast, R, A, RM;                   // state, residual, face-flux slots, (R M^-1) scratch of the parity hook
   DevBuf<double> AGv, AGi, Gvol, Gtot, Gf;             // NS: gradient face slots, volume / total / per-face lifted gradient coefficients
+  // artificial viscosity: node_tag_ of the corner nodes (0-based), inner_radius_, variable_artificial_viscosity_ [n][nbasic]
+  std::vector<int> tags; std::vector<double> radius;
+  DevBuf<int> dTags; DevBuf<double> dRadius, dAvElem, dAvE, dNodalQ, dNodalF;
 };
 
 class MixedSolver {
@@ -95,6 +98,8 @@ class MixedSolver {
   std::vector<double> xf_, nrm_, fjw_;
   DevBuf<int> dLe, dLt, dLf, dRe, dRt, dRf, dBc;
   DevBuf<double> dNrm, dFjw, dDummy, normPartial, normOut, dtPartial;
+  double avTol_ = 0.0, avFactor_ = 1.0; int avNodes_ = 0; DevBuf<double> avNode_;
+  void avUpdate();
   cudaGraphExec_t stepGraph_ = nullptr; double graphDt_ = 0.0; bool graphWarm_ = false; int64_t launchesPerStep_ = 0;
 };
 

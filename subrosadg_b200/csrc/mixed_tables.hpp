@@ -162,6 +162,8 @@ struct MixedTable {
   std::vector<double> GN, dGN;           // geometry basis at volume points [Nq][nn], [Nq][2][nn]
   std::vector<double> GNf, dGNf;         // at face points [Naq][nn], [Naq][2][nn]
   std::vector<double> ftan;              // [Nf][2]: d(xi)/d(s) of the face's corner map
+  int nbasic = 0;                        // kBasicNodeNumber (corner nodes)
+  std::vector<double> NodalQ, NodalF;    // nodal_value_ [Nq][nbasic], nodal_adjacency_value_ [Naq][nbasic]: order-1 Lagrange basis (BasisFunction.cpp:149-208)
 
   void build(int type_, int p_, int g_) {
     type = type_; p = p_; g = g_;
@@ -178,12 +180,16 @@ struct MixedTable {
     }
     Nq = (int)wq.size();
     GeomBasis2 gb(type, g); nn = gb.nn;
+    GeomBasis2 g1(type, 1); nbasic = g1.nn;
+    NodalQ.assign((size_t)Nq * nbasic, 0.0); NodalF.assign((size_t)Naq * nbasic, 0.0);
     std::vector<double> val; std::vector<std::array<double, 2>> grad;
     Phi.assign((size_t)Nq * Nb, 0.0); dPhi.assign((size_t)Nq * 2 * Nb, 0.0); GN.assign((size_t)Nq * nn, 0.0); dGN.assign((size_t)Nq * 2 * nn, 0.0);
     for (int q = 0; q < Nq; q++) {
       modalEval(type, p, xi[2 * q], xi[2 * q + 1], val, grad);
       if ((int)val.size() != Nb) throw std::runtime_error("internal: modal basis size mismatch");
       for (int b = 0; b < Nb; b++) { Phi[(size_t)q * Nb + b] = val[b]; for (int d = 0; d < 2; d++) dPhi[((size_t)q * 2 + d) * Nb + b] = grad[b][d]; }
+      g1.eval(xi[2 * q], xi[2 * q + 1], val, grad);
+      for (int m = 0; m < nbasic; m++) NodalQ[(size_t)q * nbasic + m] = val[m];
       gb.eval(xi[2 * q], xi[2 * q + 1], val, grad);
       for (int m = 0; m < nn; m++) { GN[(size_t)q * nn + m] = val[m]; for (int d = 0; d < 2; d++) dGN[((size_t)q * 2 + d) * nn + m] = grad[m][d]; }
     }
@@ -204,6 +210,8 @@ struct MixedTable {
         const int row = f * Nqf + j;
         modalEval(type, p, u, v, val, grad);
         for (int b = 0; b < Nb; b++) PhiF[(size_t)row * Nb + b] = val[b];
+        g1.eval(u, v, val, grad);
+        for (int m = 0; m < nbasic; m++) NodalF[(size_t)row * nbasic + m] = val[m];
         gb.eval(u, v, val, grad);
         for (int m = 0; m < nn; m++) { GNf[(size_t)row * nn + m] = val[m]; for (int d = 0; d < 2; d++) dGNf[((size_t)row * 2 + d) * nn + m] = grad[m][d]; }
       }
