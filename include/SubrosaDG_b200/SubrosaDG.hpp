@@ -193,20 +193,96 @@ struct MeshData {
 
   // the flat format keeps coordinates per element, not node tags: nodes = distinct coordinate tuples (the copies of a periodic pair
   // stay distinct, as in the Gmsh mesh)
+  std::vector<std::array<double, 3>> node_point_;   // the distinct nodes, sorted: tag = position (0-based)
   void countNodes() {
-    std::vector<std::array<double, 3>> pts;
+    std::vector<std::array<double, 3>>& pts = node_point_;
+    pts.clear();
     element_number_ = 0;
     for (const Block& b : blocks) {
       element_number_ += b.n;
       const std::size_t np = static_cast<std::size_t>(b.n) * static_cast<std::size_t>(b.nn);
-      for (std::size_t i = 0; i < np; i++) {
-        std::array<double, 3> x{0.0, 0.0, 0.0};
-        for (int d = 0; d < dim; d++) x[static_cast<std::size_t>(d)] = b.coords[i * static_cast<std::size_t>(dim) + static_cast<std::size_t>(d)];
-        pts.push_back(x);
-      }
+      for (std::size_t i = 0; i < np; i++) pts.push_back(point(b, i));
     }
     std::sort(pts.begin(), pts.end());
-    node_number_ = static_cast<Isize>(std::unique(pts.begin(), pts.end()) - pts.begin());
+    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+    node_number_ = static_cast<Isize>(pts.size());
+  }
+  [[nodiscard]] std::array<double, 3> point(const Block& b, std::size_t node) const {
+    std::array<double, 3> x{0.0, 0.0, 0.0};
+    for (int d = 0; d < dim; d++) x[static_cast<std::size_t>(d)] = b.coords[node * static_cast<std::size_t>(dim) + static_cast<std::size_t>(d)];
+    return x;
+  }
+  [[nodiscard]] static int basicNodeNumber(int type) { return type == 1 ? 2 : type == 2 ? 3 : type == 3 ? 4 : 8; }   // kBasicNodeNumber: the corners lead the gmsh node order
+  // PerElementMesh::node_tag_ of the corner nodes (ReadControl.cpp:64), 0-based, [n][kBasicNodeNumber]
+  [[nodiscard]] std::vector<int32_t> nodeTags(const Block& b) const {
+    const int nb = basicNodeNumber(b.type);
+    std::vector<int32_t> tags(static_cast<std::size_t>(b.n) * static_cast<std::size_t>(nb));
+    for (int e = 0; e < b.n; e++)
+      for (int k = 0; k < nb; k++) {
+        const auto x = point(b, static_cast<std::size_t>(e) * static_cast<std::size_t>(b.nn) + static_cast<std::size_t>(k));
+        tags[static_cast<std::size_t>(e) * static_cast<std::size_t>(nb) + static_cast<std::size_t>(k)] =
+            static_cast<int32_t>(std::lower_bound(node_point_.begin(), node_point_.end(), x) - node_point_.begin());
+      }
+    return tags;
+  }
+  // smallest circle tangent to three consecutive edge lines of a planar quadrangle (Gmsh MQuadrangle::getInnerRadius, restated)
+  [[nodiscard]] static double quadInnerRadius(const std::array<std::array<double, 2>, 4>& P) {
+    auto unit = [](double x, double y) { const double l = std::sqrt(x * x + y * y); return std::array<double, 2>{x / l, y / l}; };
+    double best = 1.0e300;
+    for (std::size_t i = 0; i < 4; i++) {
+      const auto &A = P[i], &B = P[(i + 1) % 4], &prev = P[(i + 3) % 4], &nxt = P[(i + 2) % 4];
+      const auto a1 = unit(prev[0] - A[0], prev[1] - A[1]), a2 = unit(B[0] - A[0], B[1] - A[1]);
+      const auto b1 = unit(A[0] - B[0], A[1] - B[1]), b2 = unit(nxt[0] - B[0], nxt[1] - B[1]);
+      const double dA[2] = {a1[0] + a2[0], a1[1] + a2[1]}, dB[2] = {b1[0] + b2[0], b1[1] + b2[1]};
+      const double den = dA[0] * dB[1] - dA[1] * dB[0];
+      if (std::abs(den) < 1.0e-300) continue;
+      const double ab[2] = {B[0] - A[0], B[1] - A[1]};
+      const double t = (ab[0] * dB[1] - ab[1] * dB[0]) / den;
+      const double c[2] = {t * dA[0], t * dA[1]};   // centre - A
+      best = std::min(best, std::abs(ab[0] * c[1] - ab[1] * c[0]) / std::sqrt(ab[0] * ab[0] + ab[1] * ab[1]));
+    }
+    return best;
+  }
+  // PerElementMesh::inner_radius_ = gmsh "innerRadius" quality (Geometry.cpp:31-41), restated: line = half length, triangle = inscribed
+  // circle, quadrangle = quadInnerRadius, hexahedron = minimum over its faces
+  [[nodiscard]] std::vector<double> innerRadius(const Block& b) const {
+    std::vector<double> r(static_cast<std::size_t>(b.n));
+    static const int hexFace[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {0, 4, 7, 3}, {1, 2, 6, 5}, {2, 3, 7, 6}, {4, 5, 6, 7}};
+    for (int e = 0; e < b.n; e++) {
+      auto X = [&](int k) { return point(b, static_cast<std::size_t>(e) * static_cast<std::size_t>(b.nn) + static_cast<std::size_t>(k)); };
+      auto dist = [](const std::array<double, 3>& p, const std::array<double, 3>& q) { return std::sqrt((p[0] - q[0]) * (p[0] - q[0]) + (p[1] - q[1]) * (p[1] - q[1]) + (p[2] - q[2]) * (p[2] - q[2])); };
+      double v = 0.0;
+      if (b.type == 1) {
+        v = 0.5 * dist(X(0), X(1));
+      } else if (b.type == 2) {
+        const double a = dist(X(0), X(1)), c = dist(X(1), X(2)), d = dist(X(2), X(0)), k = 0.5 * (a + c + d);
+        v = std::sqrt(k * (k - a) * (k - c) * (k - d)) / k;
+      } else if (b.type == 3) {
+        v = quadInnerRadius({{{X(0)[0], X(0)[1]}, {X(1)[0], X(1)[1]}, {X(2)[0], X(2)[1]}, {X(3)[0], X(3)[1]}}});
+      } else {
+        v = 1.0e300;
+        for (const auto& f : hexFace) {
+          const auto p0 = X(f[0]), p1 = X(f[1]), p2 = X(f[2]), p3 = X(f[3]);
+          const double d1[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]}, d2[3] = {p3[0] - p1[0], p3[1] - p1[1], p3[2] - p1[2]};
+          double n[3] = {d1[1] * d2[2] - d1[2] * d2[1], d1[2] * d2[0] - d1[0] * d2[2], d1[0] * d2[1] - d1[1] * d2[0]};
+          const double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+          for (double& c : n) c /= nl;
+          double e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+          const double el = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+          for (double& c : e1) c /= el;
+          const double e2[3] = {n[1] * e1[2] - n[2] * e1[1], n[2] * e1[0] - n[0] * e1[2], n[0] * e1[1] - n[1] * e1[0]};
+          std::array<std::array<double, 2>, 4> P{};
+          const std::array<double, 3> q[4] = {p0, p1, p2, p3};
+          for (std::size_t m = 0; m < 4; m++) {
+            const double w[3] = {q[m][0] - p0[0], q[m][1] - p0[1], q[m][2] - p0[2]};
+            P[m] = {w[0] * e1[0] + w[1] * e1[1] + w[2] * e1[2], w[0] * e2[0] + w[1] * e2[1] + w[2] * e2[2]};
+          }
+          v = std::min(v, quadInnerRadius(P));
+        }
+      }
+      r[static_cast<std::size_t>(e)] = v;
+    }
+    return r;
   }
   void writeFlat(const std::filesystem::path& path) const {
     std::ofstream f(path, std::ios::binary | std::ios::trunc);
@@ -552,8 +628,8 @@ struct Solver : SolverBase<SimulationControl> {
   }
 
   inline void createContext(const Mesh<SimulationControl>& mesh, const PhysicalModel<SimulationControl>& physical_model) {
-    if constexpr (SimulationControl::kShockCapturing != ShockCapturingEnum::None || SimulationControl::kLimiter != LimiterEnum::None) {
-      throw std::runtime_error("subrosadg_b200: ShockCapturingEnum::ArtificialViscosity / LimiterEnum::PositivityPreserving are not built on the B200 path");
+    if constexpr (SimulationControl::kLimiter != LimiterEnum::None) {
+      throw std::runtime_error("subrosadg_b200: LimiterEnum::PositivityPreserving is not built on the B200 path");
     }
     sdg_config cfg{};
     cfg.dim = SimulationControl::kDimension; cfg.p = SimulationControl::kPolynomialOrder;
@@ -576,7 +652,19 @@ struct Solver : SolverBase<SimulationControl> {
       cfg.beta = SourceTerm<SimulationControl>::thermal_expansion_coefficient; cfg.t_ref = SourceTerm<SimulationControl>::reference_temperature;
     }
     check(sdg_create(&cfg, &ctx_));
-    for (const auto& b : mesh.blocks) { check(sdg_add_elements(ctx_, b.type, b.n, 0, b.geom_order, b.coords.data())); types_.push_back(b.type); }
+    constexpr bool kAV = SimulationControl::kShockCapturing == ShockCapturingEnum::ArtificialViscosity;
+    if constexpr (kAV) {   // System::setArtificialViscosity (SystemControl.cpp:105-108) -> empirical_tolerance_, artificial_viscosity_factor_
+      check(sdg_set_artificial_viscosity(ctx_, this->empirical_tolerance_, this->artificial_viscosity_factor_, static_cast<int32_t>(mesh.node_number_)));
+    }
+    for (const auto& b : mesh.blocks) {
+      check(sdg_add_elements(ctx_, b.type, b.n, 0, b.geom_order, b.coords.data()));
+      types_.push_back(b.type);
+      if constexpr (kAV) {   // mesh data of Solver::calculateArtificialViscosity: node_tag_ of the corners, inner_radius_
+        const std::vector<int32_t> tags = mesh.nodeTags(b);
+        const std::vector<double> radius = mesh.innerRadius(b);
+        check(sdg_set_element_nodes(ctx_, b.type, tags.data(), radius.data()));
+      }
+    }
     std::sort(types_.begin(), types_.end());
     check(sdg_set_faces(ctx_, mesh.n_int, mesh.n_bnd, mesh.le.data(), mesh.lt.data(), mesh.lf.data(), mesh.re.data(), mesh.rt.data(), mesh.rf.data(),
                         mesh.rot.data(), mesh.bc.data(), mesh.phys.data()));
@@ -709,6 +797,9 @@ struct Solver : SolverBase<SimulationControl> {
         put(U[t].data() + static_cast<std::size_t>(e) * row, row);
         if constexpr (kNS) { put(Gb.data() + at, row * D); at += row * D; }
       }
+    }
+    if constexpr (SimulationControl::kShockCapturing == ShockCapturingEnum::ArtificialViscosity) {
+      check(sdg_get_node_artificial_viscosity(ctx_, this->node_artificial_viscosity_.data()));   // as of the last step (zero before the first)
     }
     put(this->node_artificial_viscosity_.data(), static_cast<std::size_t>(mesh.node_number_));
     this->write_raw_binary_future_ = std::async(std::launch::async, RawBinaryCompress::write, raw_binary_path, std::ref(this->raw_binary_ss_));

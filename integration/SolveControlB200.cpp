@@ -50,8 +50,10 @@ struct SolverB200 : SolverBase<SimulationControl> {   // relative_error_, error_
   static_assert(kModel == MeshModelEnum::Line || kModel == MeshModelEnum::Triangle || kModel == MeshModelEnum::Quadrangle ||
                     kModel == MeshModelEnum::TriangleQuadrangle || kModel == MeshModelEnum::Hexahedron,
                 "the B200 path has no tetrahedron / pyramid kernels");
-  static_assert(SimulationControl::kShockCapturing == ShockCapturingEnum::None && SimulationControl::kLimiter == LimiterEnum::None,
-                "artificial viscosity and the positivity limiter are not built on the B200 path");
+  static_assert(SimulationControl::kLimiter == LimiterEnum::None, "the positivity limiter is not built on the B200 path");
+  static_assert(SimulationControl::kShockCapturing == ShockCapturingEnum::None || IsEuler<SimulationControl::kEquationModel>,
+                "artificial viscosity is built for the Euler models");
+  inline static constexpr bool kAV{SimulationControl::kShockCapturing == ShockCapturingEnum::ArtificialViscosity};
 
   sdg_ctx* ctx_{nullptr};
   int device_{0};
@@ -139,6 +141,9 @@ struct SolverB200 : SolverBase<SimulationControl> {   // relative_error_, error_
       cfg.t_ref = SourceTerm<SimulationControl>::reference_temperature;
     }
     check(sdg_create(&cfg, &ctx_));
+    if constexpr (kAV) {   // System::setArtificialViscosity has filled the two SolverBase fields (SystemControl.cpp:105-108)
+      check(sdg_set_artificial_viscosity(ctx_, this->empirical_tolerance_, this->artificial_viscosity_factor_, static_cast<int32_t>(mesh.node_number_)));
+    }
     // one block per element type: node coordinates in Gmsh node order (PerElementMesh::node_coordinate_, ReadControl.cpp:86-88)
     forEachElementMesh(mesh, [&]<typename ElementTrait>(const ElementMesh<ElementTrait>& element_mesh, ElementTrait) {
       std::vector<double> x(static_cast<std::size_t>(element_mesh.number_) * ElementTrait::kAllNodeNumber * kD);
@@ -149,6 +154,17 @@ struct SolverB200 : SolverBase<SimulationControl> {   // relative_error_, error_
         }
       }
       check(sdg_add_elements(ctx_, magic_enum::enum_integer(ElementTrait::kElementType), static_cast<int32_t>(element_mesh.number_), 0, kP, x.data()));
+      if constexpr (kAV) {   // what Solver::calculateArtificialViscosity reads of the mesh (SpatialDiscrete.cpp:75-78,96-99): node_tag_ (1-based) of the corners, inner_radius_
+        std::vector<int32_t> tags(static_cast<std::size_t>(element_mesh.number_) * ElementTrait::kBasicNodeNumber);
+        std::vector<double> radius(static_cast<std::size_t>(element_mesh.number_));
+        for (Isize i = 0; i < element_mesh.number_; i++) {
+          for (Isize j = 0; j < ElementTrait::kBasicNodeNumber; j++) {
+            tags[static_cast<std::size_t>(i * ElementTrait::kBasicNodeNumber + j)] = static_cast<int32_t>(element_mesh.element_(i).node_tag_(j) - 1);
+          }
+          radius[static_cast<std::size_t>(i)] = element_mesh.element_(i).inner_radius_;
+        }
+        check(sdg_set_element_nodes(ctx_, magic_enum::enum_integer(ElementTrait::kElementType), tags.data(), radius.data()));
+      }
     });
     // AdjacencyElementMesh records (ReadControl.cpp:72-83), interior faces first, then boundary faces
     const auto& adjacency = adjacencyMesh(mesh);
@@ -301,6 +317,7 @@ struct SolverB200 : SolverBase<SimulationControl> {   // relative_error_, error_
         }
       }
     }
+    if constexpr (kAV) check(sdg_get_node_artificial_viscosity(ctx_, this->node_artificial_viscosity_.data()));
     this->raw_binary_ss_.write(reinterpret_cast<const char*>(this->node_artificial_viscosity_.data()), mesh.node_number_ * kRealSize);
     this->write_raw_binary_future_ =
         std::async(std::launch::async, RawBinaryCompress::write, raw_binary_path, std::ref(this->raw_binary_ss_));

@@ -18,6 +18,13 @@ using Karman2d = Control<DimensionEnum::D2, MeshModelEnum::TriangleQuadrangle, N
 using Naca2d = Control<DimensionEnum::D2, MeshModelEnum::Triangle, EulerVariable>;                                         // configs[3]
 using Sphere3d = Control<DimensionEnum::D3, MeshModelEnum::Hexahedron, NSVariable, BoundaryTimeEnum::TimeVarying>;         // configs[4]
 using Restart2d = Control<DimensionEnum::D2, MeshModelEnum::Quadrangle, NSVariable, BoundaryTimeEnum::Steady, InitialConditionEnum::LastStep>;
+// the shock examples: sod_1d_ceuler (Line) and cylinder_2d_ceuler (TriangleQuadrangle) with ShockCapturingEnum::ArtificialViscosity
+template <DimensionEnum D, MeshModelEnum M>
+using ShockControl = SimulationControl<SolveControl<D, PolynomialOrderEnum::P3, BoundaryTimeEnum::Steady, SourceTermEnum::None>,
+                                       NumericalControl<M, ShockCapturingEnum::ArtificialViscosity, LimiterEnum::None, InitialConditionEnum::Function,
+                                                        TimeIntegrationEnum::SSPRK3>, EulerVariable>;
+using Sod1d = ShockControl<DimensionEnum::D1, MeshModelEnum::Line>;
+using Cylinder2d = ShockControl<DimensionEnum::D2, MeshModelEnum::TriangleQuadrangle>;
 
 template struct SubrosaDG::SolverB200<Periodic2d>;
 template struct SubrosaDG::SolverB200<Periodic3d>;
@@ -25,6 +32,8 @@ template struct SubrosaDG::SolverB200<Karman2d>;
 template struct SubrosaDG::SolverB200<Naca2d>;
 template struct SubrosaDG::SolverB200<Sphere3d>;
 template struct SubrosaDG::SolverB200<Restart2d>;
+template struct SubrosaDG::SolverB200<Sod1d>;
+template struct SubrosaDG::SolverB200<Cylinder2d>;
 
 // the call sequence of System<SC>::solve (SystemControl.cpp:159-195) against the replacement
 template <typename SC>

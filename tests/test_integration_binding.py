@@ -26,7 +26,8 @@ def test_reference_side_binding_compiles_against_the_reference_headers(tmp_path)
     undefined = {line.split()[-1] for line in nm.splitlines() if " U sdg_" in line}
     need = {"sdg_create", "sdg_destroy", "sdg_add_elements", "sdg_set_faces", "sdg_finalize", "sdg_sizes", "sdg_get_quadrature_coordinates",
             "sdg_get_boundary_quadrature_coordinates", "sdg_set_state_from_primitive", "sdg_set_state", "sdg_set_boundary_primitive", "sdg_compute_dt",
-            "sdg_step", "sdg_get_state", "sdg_get_gradient_state", "sdg_get_boundary_gradient_state", "sdg_last_error"}
+            "sdg_step", "sdg_get_state", "sdg_get_gradient_state", "sdg_get_boundary_gradient_state", "sdg_last_error",
+            "sdg_set_artificial_viscosity", "sdg_set_element_nodes", "sdg_get_node_artificial_viscosity"}
     assert need <= undefined, need - undefined
     # every member of the replacement was instantiated for the five configs' control types
     for member in ("initializeSolver", "updateBoundaryVariable", "calculateDeltaTime", "stepSolver", "writeRawBinary"):

@@ -252,3 +252,41 @@ def test_last_step_and_specific_file_restarts(built, tmp_path):
     c2 = np.fromfile(tmp_path / "c2.bin").reshape(36, 9, 4)
     scale = np.abs(c2).max()
     assert np.abs(U0[t][:, :9, :] - c2).max() < 1e-13 * scale and np.abs(U0[t][:, 9:, :]).max() < 1e-13 * scale
+
+
+def test_shock_driver_compiles(built, tmp_path):
+    compile_cpp(os.path.join(ROOT, "tests", "cpp", "shock_driver.cpp"), tmp_path / "shock")
+
+
+@pytest.mark.gpu
+def test_shock_capturing_run_and_its_raw_file(built, tmp_path):
+    """ShockCapturingEnum::ArtificialViscosity through System<SC> (setArtificialViscosity, SystemControl.cpp:105-108): same states as the
+    ctypes path, and the tail of the raw file is Solver::node_artificial_viscosity_ of the last step (RawBinary.cpp:187-188)."""
+    from subrosadg_b200.solver import Solver
+    exe = compile_cpp(os.path.join(ROOT, "tests", "cpp", "shock_driver.cpp"), tmp_path / "shock")
+    mesh = M.box(1, (24,), 0.0, 1.0, phys_bc={1: M.RIEMANN_FARFIELD, 2: M.RIEMANN_FARFIELD})
+    M.write_flat(mesh, tmp_path / "mesh.sdgm")
+    steps = 8
+    r = subprocess.run([str(exe), str(tmp_path / "mesh.sdgm"), str(tmp_path / "out"), str(steps)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+    def state(x, *_):
+        s = np.clip((x[..., 0] - 0.51) / 0.01, -1.0, 1.0)
+        rho, p = 0.5625 - 0.4375 * s, 0.55 - 0.45 * s
+        return np.stack([rho, np.zeros_like(rho), 1.4 * p / rho], axis=-1)
+
+    S = Solver(dict(p=2, conv_flux=2, rk=2, av_tolerance=0.5, av_factor=1.0), mesh, device=0)
+    S.initializeSolver(state, state)
+    dt = S.calculateDeltaTime(0.1)
+    assert abs(float(r.stdout.split()[-1]) - dt) <= 1e-5 * dt
+    S.stepSolver(dt, steps)
+    t = M.LINE
+    ref = S.state_at_quadrature(t)
+    got = np.fromfile(tmp_path / "out" / "state.bin").reshape(ref.shape)
+    assert np.array_equal(got, ref), f"rel-L2 {cases.rel_l2(got, ref):.3e}"
+    _, buf = read_raw_binary(tmp_path / "out" / "raw" / f"sod_{steps}.zst")
+    U, _, bnd, av = parse_payload(buf, mesh, {t: 3}, False)
+    assert np.array_equal(U[t], S.get_state(t)) and len(bnd) == 2
+    assert av.max() > 0.0 and np.array_equal(av, S.node_artificial_viscosity())
+    _, buf0 = read_raw_binary(tmp_path / "out" / "raw" / "sod_0.zst")
+    assert np.all(parse_payload(buf0, mesh, {t: 3}, False)[3] == 0.0)     # written before the first step: InitialCondition.cpp:156-157
