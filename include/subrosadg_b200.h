@@ -120,6 +120,13 @@ int sdg_get_node_artificial_viscosity(sdg_ctx* ctx, double* out);
 int sdg_get_element_artificial_viscosity(sdg_ctx* ctx, int32_t type, double* out);
 int sdg_update_artificial_viscosity(sdg_ctx* ctx);
 
+/* ViewVariable::get (src/Solver/VariableConvertor.cpp:754-872) on the device: the scalar field `variable` (ViewVariableEnum value,
+ * src/Utils/Enum.cpp: 0 Density, 1 Velocity, 2 Temperature, 3 Pressure, 4 SoundSpeed, 5 MachNumber, 6 Entropy, 7 Vorticity, 9
+ * ArtificialViscosity, 10-12 VelocityX/Y/Z, 13-15 MachNumberX/Y/Z, 16-18 VorticityX/Y/Z, 19-21 HeatFluxX/Y/Z) of the resident state at
+ * the volume quadrature points, [n][Nq].  Gradient-based entries use the total gradient of the current state (Navier-Stokes); entries
+ * that do not exist for the equation set return what the reference's switch falls through to. */
+int sdg_get_view_variable(sdg_ctx* ctx, int32_t type, int32_t variable, double* out);
+
 /* Solver::calculateDeltaTime (TimeIntegration.cpp:104-179) */
 int sdg_compute_dt(sdg_ctx* ctx, double cfl, double* dt);
 

@@ -1068,6 +1068,65 @@ int orc_get_boundary_gradient_state(void* h, double* out) {
   }
   ORC_CATCH
 }
+// ViewVariable::get (VariableConvertor.cpp:754-872) at the volume quadrature points, n x Nq.  variable = ViewVariableEnum value.  The
+// switch of the reference falls through where a variable does not exist for the equation set; `goto`-free restatement of that chain.
+int orc_view_variable(void* h, int type, int variable, double* out) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  if (!O.blk[type]) throw std::runtime_error("oracle: no such element block");
+  ElemBlock& B = *O.blk[type]; const Sizes s = sizes(O, B); const ElemTable& T = B.tab; const Phys& P = O.P;
+  const int D = s.D, Nv = s.Nv, G = s.G;
+  const bool ns = P.ns();
+  for (int e = 0; e < B.n; e++) {
+    std::vector<double> uq((size_t)Nv * s.Nq), gq((size_t)G * s.Nq, 0.0);
+    gemmNT(Nv, s.Nq, s.Nb, 1.0, &B.coef[(size_t)e * Nv * s.Nb], Nv, T.Phi.data(), s.Nq, 0.0, uq.data(), Nv);
+    if (ns) gemmNT(G, s.Nq, s.Nb, 1.0, &B.gcoef[(size_t)e * G * s.Nb], G, T.Phi.data(), s.Nq, 0.0, gq.data(), G);
+    for (int q = 0; q < s.Nq; q++) {
+      Var v;
+      for (int k = 0; k < Nv; k++) v.cons[k] = uq[(size_t)q * Nv + k];
+      compFromCons(P, v);
+      double gp[kMaxD * kMaxV] = {0};
+      if (ns) primGradFromConsGrad(P, v, &gq[(size_t)q * G], gp);
+      const double rho = v.comp[0], p = v.comp[D + 2];
+      double v2 = 0; for (int d = 0; d < D; d++) v2 += v.comp[1 + d] * v.comp[1 + d];
+      const double c = P.eos == kIdealGas ? std::sqrt(1.4 * p / rho) : P.c0;           // PhysicalModel.cpp:51-54,74-77
+      auto dU = [&](int comp, int dir) { return gp[(1 + comp) * D + dir]; };
+      double eps = 0.0;
+      if (O.av) for (int k = 0; k < T.nbasic; k++) eps += T.NodalQ[(size_t)k * s.Nq + q] * B.avElem[(size_t)e * T.nbasic + k];
+      double r = 0.0;
+      int w = variable;
+      for (;;) {
+        if (w == 0) { r = rho; break; }
+        if (w == 1) { r = std::sqrt(v2); break; }
+        if (w == 2) { r = v.comp[D + 1] / P.cv; break; }
+        if (w == 3) { r = p; break; }
+        if (w == 4) { r = c; break; }
+        if (w == 5) { r = std::sqrt(v2) / c; break; }
+        if (w == 6) { if (P.comp()) { r = p / std::pow(rho, 1.4); break; } w = 7; continue; }
+        if (w == 7) {
+          if (ns && D == 2) { r = dU(1, 0) - dU(0, 1); break; }
+          if (ns && D == 3) { const double a = dU(2, 1) - dU(1, 2), b = dU(0, 2) - dU(2, 0), cc = dU(1, 0) - dU(0, 1); r = std::sqrt(a * a + b * b + cc * cc); break; }
+          w = 9; continue;
+        }
+        if (w == 9) { r = eps; break; }
+        if (w >= 10 && w <= 12) { if (w - 10 >= D) throw std::runtime_error("oracle: view variable outside the dimension"); r = v.comp[1 + (w - 10)]; break; }
+        if (w >= 13 && w <= 15) { if (w - 13 >= D) throw std::runtime_error("oracle: view variable outside the dimension"); r = v.comp[1 + (w - 13)] / c; break; }
+        if (ns && w >= 16 && w <= 21) {
+          if ((w == 16 || w == 17 || w == 21) && D < 3) throw std::runtime_error("oracle: view variable outside the dimension");
+          if ((w == 18 || w == 20) && D < 2) throw std::runtime_error("oracle: view variable outside the dimension");
+          if (w == 16) r = dU(2, 1) - dU(1, 2);
+          else if (w == 17) r = dU(0, 2) - dU(2, 0);
+          else if (w == 18) r = dU(1, 0) - dU(0, 1);
+          else r = gp[(D + 1) * D + (w - 19)];
+          break;
+        }
+        r = 0.0; break;
+      }
+      out[(size_t)e * s.Nq + q] = r;
+    }
+  }
+  ORC_CATCH
+}
 // System::setArtificialViscosity (SystemControl.cpp:105-108) with ShockCapturingEnum::ArtificialViscosity; n_nodes = Mesh::node_number_
 int orc_set_artificial_viscosity(void* h, double empirical_tolerance, double factor, int n_nodes) {
   ORC_TRY

@@ -49,4 +49,17 @@ static __global__ void avStoreKernel(const double* __restrict__ node, const int*
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * NB; i += gridDim.x * blockDim.x) avElem[i] = node[tags[i]];
 }
 
+// artificial_viscosity_ at the volume nodes, caller element order: out[e][q] = sum_k tabQ[q][k] avElem[perm[e]][k]
+static __global__ void avAtNodesKernel(const double* __restrict__ avElem, const double* __restrict__ tabQ, const int* __restrict__ perm, int n, int NN, int NB,
+                                       double* __restrict__ out) {
+  const size_t total = (size_t)n * NN;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i / NN), q = (int)(i - (size_t)e * NN);
+    const int pos = perm ? perm[e] : e;
+    double s = 0.0;
+    for (int k = 0; k < NB; k++) s += tabQ[q * NB + k] * avElem[(size_t)pos * NB + k];
+    out[i] = s;
+  }
+}
+
 }  // namespace sdg

@@ -11,6 +11,7 @@
 // in L1/L2; the HBM-roofline work of the repository is the tensor path.
 #include "mixed_path.hpp"
 #include "av_kernels.cuh"
+#include "view_variable.hpp"
 
 #include <algorithm>
 #include <cstdlib>
@@ -859,6 +860,27 @@ void MixedSolver::elementArtificialViscosity(int type, double* out) {
   needDevice(); CUDA_OK(cudaSetDevice(device_));
   MixedBlock& B = block(type);
   CUDA_OK(cudaMemcpyAsync(out, B.dAvElem.p, B.dAvElem.n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+}
+
+void MixedSolver::viewVariable(int type, int variable, double* out) {
+  needDevice(); CUDA_OK(cudaSetDevice(device_));
+  MixedBlock& B = block(type); const MixedTable& T = B.T;
+  const size_t npts = (size_t)B.n * T.Nq;
+  DevBuf<double> cons, grad, eps, res;
+  cons.alloc(npts * kNV); res.alloc(npts);
+  mxToQuadratureKernel<<<148 * 4, 256, 0, stream_>>>(B.U.p, B.dPhi_.p, B.n, T.Nb, T.Nq, kNV, cons.p); launches++;
+  if (phys_.ns) {
+    refreshGradient();
+    grad.alloc(npts * kG);
+    mxToQuadratureKernel<<<148 * 4, 256, 0, stream_>>>(B.Gtot.p, B.dPhi_.p, B.n, T.Nb, T.Nq, kG, grad.p); launches++;
+  }
+  if (phys_.av) {
+    eps.alloc(npts);
+    avAtNodesKernel<<<148 * 4, 256, 0, stream_>>>(B.dAvElem.p, B.dNodalQ.p, nullptr, B.n, T.Nq, T.nbasic, eps.p); launches++;
+  }
+  launchViewVariable(kD, phys_, variable, npts, cons.p, phys_.ns ? grad.p : nullptr, phys_.av ? eps.p : nullptr, res.p, stream_); launches++;
+  CUDA_OK(cudaMemcpyAsync(out, res.p, npts * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   CUDA_OK(cudaStreamSynchronize(stream_));
 }
 

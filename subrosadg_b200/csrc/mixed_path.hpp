@@ -59,6 +59,7 @@ class MixedSolver {
   void updateArtificialViscosity();
   void nodeArtificialViscosity(double* out);
   void elementArtificialViscosity(int type, double* out);
+  void viewVariable(int type, int variable, double* out);   // ViewVariable::get at the quadrature points, VariableConvertor.cpp:754-872
   double computeDt(double cfl);
   void step(double dt, int nSteps, double* relErr, float* ms);
   void residual(int type, double* Rmodal, double* rhsq);

@@ -18,6 +18,7 @@
 #include "nsl_kernels.cuh"
 #include "tensor_kernels.cuh"
 #include "av_kernels.cuh"
+#include "view_variable.hpp"
 
 using namespace sdg;
 
@@ -811,6 +812,39 @@ int sdg_update_artificial_viscosity(sdg_ctx* c) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   avUpdate(c, c->cur, c->stream);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  SDG_CATCH
+}
+
+// ViewVariable::get (VariableConvertor.cpp:754-872) at the volume quadrature points of the resident state, [n][Nq]
+int sdg_get_view_variable(sdg_ctx* c, int32_t type, int32_t variable, double* out) {
+  SDG_TRY
+  if (c->mx) { needFinal(c); c->mx->viewVariable(type, variable, out); return 0; }
+  needFinal(c); needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  const size_t npts = (size_t)B.n * B.T.NN;
+  const int NG = c->NV * c->D;
+  DevBuf<double> cons, grad, eps, res;
+  cons.alloc(npts * c->NV); res.alloc(npts);
+  seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->U[c->cur].p, cons.p, c->perm.p, B.n, c->NV, B.T.NN, 1);
+  c->launches++;
+  if (c->phys.ns) {
+    c->G2.alloc(c->G.n); grad.alloc(npts * NG);
+    int zslow = 0;
+    const double* g = nodalGradient(c, -1, &zslow);
+    seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(g, grad.p, c->perm.p, B.n, NG, B.T.NN, zslow ? 3 : 1);
+    c->launches++;
+  }
+  if (c->phys.av) {   // artificial_viscosity_ at the points: nodal basis * corner values (RawBinary.cpp:206-211)
+    eps.alloc(npts);
+    avAtNodesKernel<<<148 * 4, 256, 0, c->stream>>>(c->avElem.p, c->avTabQ.p, c->perm.p, B.n, B.T.NN, 1 << c->D, eps.p);
+    c->launches++;
+  }
+  launchViewVariable(c->D, c->phys, variable, npts, cons.p, c->phys.ns ? grad.p : nullptr, c->phys.av ? eps.p : nullptr, res.p, c->stream);
+  c->launches++;
+  CUDA_OK(cudaMemcpyAsync(out, res.p, npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->G2.release();
   SDG_CATCH
 }
 

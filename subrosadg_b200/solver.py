@@ -48,6 +48,7 @@ EXPORTS = [
     "sdg_halo_doubles_per_element", "sdg_debug_physics", "sdg_uses_trace_rows", "sdg_set_halo_rows", "sdg_halo_unpack",
     "sdg_ipc_set_destination_units", "sdg_get_gradient_state", "sdg_get_boundary_gradient_state", "sdg_set_artificial_viscosity",
     "sdg_set_element_nodes", "sdg_get_node_artificial_viscosity", "sdg_get_element_artificial_viscosity", "sdg_update_artificial_viscosity",
+    "sdg_get_view_variable",
 ]
 
 _lib = None
@@ -230,6 +231,13 @@ class Solver:
         out = np.zeros(int(n))
         if n:
             _chk(load_library().sdg_get_boundary_gradient_state(self.h, _dp(out)))
+        return out
+
+    def view_variable(self, t, variable: int):
+        """ViewVariable::get (VariableConvertor.cpp:754-872) at the volume quadrature points, [n][Nq]; variable = ViewVariableEnum value."""
+        s = self.sizes(t)
+        out = np.zeros((s.n, s.Nq))
+        _chk(load_library().sdg_get_view_variable(self.h, t, int(variable), _dp(out)))
         return out
 
     def update_artificial_viscosity(self):
