@@ -26,8 +26,27 @@
 
 namespace sdg {
 
+// A/B switches of round 2 (64^3 NS / 96^3 Euler launch lists, profiles/r02_ns_line_ncu.md): the defaults are the measured winners
+#ifndef SDG_NSLG_NBRSEL
+#define SDG_NSLG_NBRSEL 1     // pass G, flux phase: partner rows from the offsets of phase one (select chain), no second table lookup
+#endif
+#ifndef SDG_NSLG_PRELOAD
+#define SDG_NSLG_PRELOAD 2    // pass G, flux phase: partner (1) and own (2) trace values requested before the 15-field trace of G_vol: 1.445 -> 1.397 ms
+#endif
+#ifndef SDG_NSL_LAZYJL
+#define SDG_NSL_LAZYJL 1
+#endif
+#ifndef SDG_NSLS_HOIST
+#define SDG_NSLS_HOIST 1      // pass R, inviscid: partner rows of all six faces before the direction loop: 2.88 / 3.05 / 3.73 -> 2.83 / 2.98 / 3.58 ms at 96^3
+#endif
+
+#if SDG_NSLG_PRELOAD && !SDG_NSLG_NBRSEL
+#error "SDG_NSLG_PRELOAD needs SDG_NSLG_NBRSEL"
+#endif
 constexpr int kLK = 8;                 // elements per thread block (a 2x2x2 brick of the internal Morton order)
 constexpr int kRow = 5 * 16;           // doubles per (element, face) row of TU / TV
+// (row * 16 + point) -> offset of the value of variable 0 inside a trace array
+__device__ __forceinline__ size_t nbrOffset(int packed) { return (size_t)(packed >> 4) * kRow + (packed & 15); }
 constexpr int kLG = 4;                 // affine per-(element, face) geometry record: face normal n[3] (left-outward), |J| scale
 
 // link record of (element, local face): .x = other parent (internal position, -1 = boundary face), .y = face id,
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
   }
 
   // ---- per-face set-up of this thread's face point (natural index t on each of the six faces) ---------------------------------------
-  int nbr[6];          // >= 0: offset of the partner's value of variable 0 inside TU; < 0: -(1 + offset inside TUb) for a boundary face
+  int nbr[6];          // >= 0: (partner's row in TU) * 16 + its point; < 0: -(1 + (boundary face row in TUb) * 16 + point).  Rows, not element offsets: 32 bits hold 2^27 rows = 22 M elements
   double jw[6];        // |J| w at the point
   unsigned amRightBits = 0;
   const double wij = A.w1[i] * A.w1[j];   // weight of the face point (t = two lattice indices) and of the line's nodes without w1[k]
@@ -299,8 +318,8 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
     const int4 lk = sLink[el * 6 + f];
     const int z = lk.z, lfo = linkLfo(z), rot = linkRot(z), amR = linkAmRight(z) ? 1 : 0;
     amRightBits |= (unsigned)amR << f;
-    if (lk.x >= 0) nbr[f] = (lk.x * 6 + lfo) * kRow + A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + amR) * 16 + t];
-    else nbr[f] = -1 - ((lk.y - A.nInt) * kRow + t);
+    if (lk.x >= 0) nbr[f] = (lk.x * 6 + lfo) * 16 + A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + amR) * 16 + t];
+    else nbr[f] = -1 - ((lk.y - A.nInt) * 16 + t);
     if constexpr (AFFINE) jw[f] = sLg[(el * 6 + f) * kLG + 3] * wij;
     else jw[f] = __ldg(A.geoF + ((size_t)lk.y * 4 + 3) * 16 + A.ltab->jLeft[((f * 4 + rot) * 2 + amR) * 16 + t]);
   }
@@ -333,7 +352,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
 #pragma unroll
     for (int f = 0; f < 6; f++) {
       fmine[f] = __ldg(gTU + (f * 5 + v) * 16);
-      fother[f] = nbr[f] >= 0 ? __ldg(A.TUin + (size_t)nbr[f] + v * 16) : A.TUb[(size_t)(-1 - nbr[f]) + v * 16];
+      fother[f] = nbr[f] >= 0 ? __ldg(A.TUin + nbrOffset(nbr[f]) + v * 16) : A.TUb[nbrOffset(-1 - nbr[f]) + v * 16];
     }
   };
   loadFaceValues(0);
@@ -488,6 +507,20 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
     int off[4];   // tile offsets of the four nodes of the normal line through this thread's point (natural index t) of the direction's faces
 #pragma unroll
     for (int a = 0; a < 4; a++) off[a] = d == 0 ? tIdx(a, i, j) : tIdx(i, a, j);   // (d == 2: the own line, read as two pairs below)
+#if SDG_NSLG_NBRSEL
+    // the partner rows of the direction's two faces: the offsets of phase one (a select chain instead of a second table lookup)
+    const int nb0 = d == 0 ? nbr[2] : d == 1 ? nbr[1] : nbr[0], nb1 = d == 0 ? nbr[3] : d == 1 ? nbr[4] : nbr[5];
+#endif
+#if SDG_NSLG_PRELOAD
+    double oth[2][5];   // requested before the 15-field trace below, consumed after it
+#pragma unroll
+    for (int v = 0; v < 5; v++) { oth[0][v] = nb0 >= 0 ? __ldg(A.TUin + nbrOffset(nb0) + v * 16) : 0.0; oth[1][v] = nb1 >= 0 ? __ldg(A.TUin + nbrOffset(nb1) + v * 16) : 0.0; }
+#endif
+#if SDG_NSLG_PRELOAD >= 2
+    double own[2][5];
+#pragma unroll
+    for (int v = 0; v < 5; v++) { own[0][v] = __ldg(gTU + (hexFaceRt(d, 0) * 5 + v) * 16); own[1][v] = __ldg(gTU + (hexFaceRt(d, 1) * 5 + v) * 16); }
+#endif
     double gm[15], gp[15];
 #pragma unroll
     for (int fld = 0; fld < 15; fld++) {
@@ -505,7 +538,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
       const int4 lk = sLink[el * 6 + f];
       const int z = lk.z;
       const bool amR = linkAmRight(z);
-      const int jL = A.ltab->jLeft[((f * 4 + linkRot(z)) * 2 + (amR ? 1 : 0)) * 16 + t];
+      const int jL = (!SDG_NSL_LAZYJL || !AFFINE || lk.x < 0) ? A.ltab->jLeft[((f * 4 + linkRot(z)) * 2 + (amR ? 1 : 0)) * 16 + t] : 0;   // curved geometry / boundary values only
       double n[3], jwf;
       if constexpr (AFFINE) {
         const double* lg = sLg + (el * 6 + f) * kLG;
@@ -526,15 +559,28 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
         }
       }
       double cm[5], va[5];
+#if SDG_NSLG_PRELOAD >= 2
+#pragma unroll
+      for (int v = 0; v < 5; v++) cm[v] = own[side][v];
+#else
 #pragma unroll
       for (int v = 0; v < 5; v++) cm[v] = __ldg(gTU + (f * 5 + v) * 16);
+#endif
       if (lk.x >= 0) {
+#if SDG_NSLG_NBRSEL
+        const size_t rowO = nbrOffset(side ? nb1 : nb0);
+#else
         const size_t rowO = ((size_t)lk.x * 6 + linkLfo(z)) * kRow + A.ltab->partner[(((f * 6 + linkLfo(z)) * 4 + linkRot(z)) * 2 + (amR ? 1 : 0)) * 16 + t];
+#endif
         double comp[6];
         compFromCons<3>(ph, cm, comp);
 #pragma unroll
         for (int v = 0; v < 5; v++) {
+#if SDG_NSLG_PRELOAD
+          const double other = oth[side][v];
+#else
           const double other = __ldg(A.TUin + rowO + v * 16);
+#endif
           const double jl = 0.5 * (amR ? cm[v] - other : other - cm[v]) * jwf * lam;
 #pragma unroll
           for (int c = 0; c < 3; c++) g[v * 3 + c] += jl * n[c];
@@ -662,6 +708,20 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
     lineTracesOut(A, u, sFl + el * 480, i, j, t, wm, sTr + el * 480);   // tile = the (not yet used) flux slots of the element
     __syncthreads();                                                     // partners inside the block live in other warps
   }
+#if SDG_NSLS_HOIST
+  // partner rows of all six faces, (row * 16 + point) packed: the table lookups leave the direction loop (one latency instead of three).
+  // Inviscid pass only: the viscous pass has no registers to spare (64 bytes of spills, 2.4 % slower when measured).
+  constexpr bool kHoist = !GATHER && !VISC;
+  int prow[6];
+  if constexpr (kHoist) {
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+      const int4 l = sLink[el * 6 + f];
+      const int z = l.z, lfo = linkLfo(z), rot = linkRot(z), amR = linkAmRight(z) ? 1 : 0;
+      prow[f] = l.x >= 0 ? (l.x * 6 + lfo) * 16 + A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + amR) * 16 + t] : (e * 6 + f) * 16 + t;
+    }
+  }
+#endif
 #pragma unroll 1
   for (int d = 0; d < 3; d++) {
     int4 lk[2];
@@ -673,8 +733,13 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
       const int f = hexFaceRt(d, side);
       lk[side] = sLink[el * 6 + f];
       const int z = lk[side].z, lfo = linkLfo(z), rot = linkRot(z), amR = linkAmRight(z) ? 1 : 0;
-      jL[side] = A.ltab->jLeft[((f * 4 + rot) * 2 + amR) * 16 + t];
+      // the left parent's point index of this face point: curved geometry and boundary values only (affine interior faces never read it)
+      jL[side] = (!SDG_NSL_LAZYJL || !AFFINE || lk[side].x < 0) ? A.ltab->jLeft[((f * 4 + rot) * 2 + amR) * 16 + t] : 0;
       // boundary face: the partner loads fall back on the own row (valid memory, values unused) so that no load sits behind a branch
+#if SDG_NSLS_HOIST
+      if constexpr (kHoist) rowO[side] = nbrOffset(side ? (d == 0 ? prow[3] : d == 1 ? prow[4] : prow[5]) : (d == 0 ? prow[2] : d == 1 ? prow[1] : prow[0]));
+      else
+#endif
       rowO[side] = lk[side].x >= 0 ? ((size_t)lk[side].x * 6 + lfo) * kRow + A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + amR) * 16 + t]
                                    : ((size_t)e * 6 + f) * kRow + t;
     }

@@ -11,5 +11,5 @@ for tu in sdg_api euler_launch ns_launch nsl_launch; do
 done
 wait
 [ -f _build/mixed_path.o ] || $NV -c mixed_path.cu -o _build/mixed_path.o 2> _build/mixed_path.ptxas.log
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fopenmp -o ../lib$NAME.so _build/sdg_api_$NAME.o _build/euler_launch_$NAME.o _build/ns_launch_$NAME.o _build/nsl_launch_$NAME.o _build/mixed_path.o -lgomp
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fopenmp -o ../lib$NAME.so _build/sdg_api_$NAME.o _build/euler_launch_$NAME.o _build/ns_launch_$NAME.o _build/nsl_launch_$NAME.o _build/mixed_path.o _build/physics_debug.o _build/view_variable.o -lgomp
 grep -A3 "nsStageKernelILi3ELi4ELi4ELb1ELi1E" _build/ns_launch_$NAME.ptxas.log | grep "spill\|Used" | head -2
