@@ -13,9 +13,12 @@
 // src/Solver/{VariableConvertor,ConvectiveFlux,ViscousFlux,BoundaryCondition,PhysicalModel,SourceTerm}.cpp where they lie (ref_physics.cpp
 // + the stand-in headers of ref_shim/), tests/golden/reference_physics.json holds their outputs and tests/test_reference_physics.py checks
 // orc_physics against every vector to 1e-13; and the integer tables embedded in the reference (tests/golden/reference_tables.json).
-// STILL UNPINNED w.r.t. a reference binary: the assembly around the physics (sweeps, face scatter, RK update) and the Gmsh-provided
-// tables (quadrature, H1Legendre basis, Jacobians) — pinned only by exactness properties, free-stream preservation, the exact
-// travelling-wave solution and the analytic viscous decay (tests/test_oracle_*.py).
+// ALSO PINNED AGAINST THE REFERENCE'S OWN CODE: the assembly around the physics — ref_sweeps.cpp runs the reference's initializeSolver,
+// calculateDeltaTime and stepSolver (all sweeps, RK update, relative error) on hand-filled Mesh<SC> objects; tests/golden/
+// reference_sweeps.json holds 8 control types and tests/test_reference_sweeps.py checks this restatement against them to 1e-12.
+// STILL UNPINNED w.r.t. a reference binary: the Gmsh-provided inputs (quadrature, H1Legendre / Lagrange basis values, Jacobians, the
+// "innerRadius" quality) — restated in tables.hpp / elementGeometry and pinned only by exactness properties, free-stream preservation,
+// the exact travelling wave, SSP-RK order and the analytic viscous decay (tests/test_oracle_*.py).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
 #include <omp.h>
@@ -715,7 +718,9 @@ static void relativeError(Oracle& O) {
 #pragma omp critical
       for (int v = 0; v < Nv; v++) acc[v] += loc[v];
     }
-    for (int v = 0; v < Nv; v++) tot[v] += acc[v];
+    // each calculateElementRelativeError ASSIGNS its sum to the shared vector (TimeIntegration.cpp:294-297): on a mixed mesh the last
+    // element type (ascending ElementEnum) wins, and the result is still divided by the number of all elements (:323)
+    for (int v = 0; v < Nv; v++) tot[v] = acc[v];
   }
   const int ne = O.totalElems();
   for (int v = 0; v < Nv; v++) O.relErr[v] = tot[v] / ne;

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <functional>
 #include <ranges>
+#include <type_traits>
 namespace tbb {
 template <typename T> struct blocked_range {
   T b_, e_;
@@ -14,9 +15,9 @@ template <typename T> struct blocked_range {
 template <typename Range, typename Body> void parallel_for(const Range& r, const Body& body) { body(r); }
 template <typename T> struct combinable {
   T v_{};
-  std::function<T()> init_;
   combinable() = default;
-  template <typename F> explicit combinable(F f) : v_(f()), init_(f) {}
+  // oneTBB: combinable(finit) with a callable, or an exemplar value to copy from
+  template <typename F> explicit combinable(F f) { if constexpr (std::is_invocable_v<F>) v_ = f(); else v_ = f; }
   T& local() { return v_; }
   template <typename F> T combine(F) { return v_; }
   template <typename F> void combine_each(F f) { f(v_); }

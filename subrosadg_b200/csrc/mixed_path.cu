@@ -663,7 +663,12 @@ void MixedSolver::step(double dt, int nSteps, double* relErr, float* ms) {
   if (ms) { CUDA_OK(cudaEventRecord(e1, stream_)); CUDA_OK(cudaEventSynchronize(e1)); CUDA_OK(cudaEventElapsedTime(ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
   if (relErr) {
     const int ne = totalElements();
-    mxNormReduceKernel<<<kNV, 256, 0, stream_>>>(normPartial.p, ne, normOut.p); launches++;
+    // Solver::calculateRelativeError (TimeIntegration.cpp:300-324) hands the SAME vector to every element type and each
+    // calculateElementRelativeError ASSIGNS its sum to it (:294-297): on a mixed mesh the value is the sum over the LAST element type
+    // only (quadrangles), divided by the number of ALL elements.  Reproduced as is (pinned by tests/golden/reference_sweeps.json).
+    const int lastType = blk_[kQuadrangle] ? kQuadrangle : kTriangle;
+    const int off = (lastType == kQuadrangle && blk_[kTriangle]) ? blk_[kTriangle]->n : 0;
+    mxNormReduceKernel<<<kNV, 256, 0, stream_>>>(normPartial.p + (size_t)off * kNV, blk_[lastType]->n, normOut.p); launches++;
     double h[kNV];
     CUDA_OK(cudaMemcpyAsync(h, normOut.p, sizeof(h), cudaMemcpyDeviceToHost, stream_));
     CUDA_OK(cudaStreamSynchronize(stream_));

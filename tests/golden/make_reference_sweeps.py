@@ -1,0 +1,116 @@
+"""Generates tests/golden/reference_sweeps.json from the REFERENCE'S OWN solver.
+
+oracle/Makefile (target `ref`) compiles /root/reference/src/Solver/{InitialCondition,SpatialDiscrete,TimeIntegration,...}.cpp and
+src/Mesh/{BasisFunction,Quadrature}.cpp — where they lie — behind oracle/ref_sweeps.cpp into oracle/_ref/libref_sweeps.so: the reference's
+initializeSolver, calculateDeltaTime and stepSolver (all eight sweeps, RK update, relative error) run on Mesh<SC> objects filled from the
+arrays below.  See the header of oracle/ref_sweeps.cpp for what is and what is not the reference's code.  Run in the development
+container (needs /root/reference); the committed JSON travels:
+
+    python tests/golden/make_reference_sweeps.py
+
+Consumers: tests/test_reference_sweeps.py (CPU: the oracle against these numbers; GPU: the CUDA path)."""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from subrosadg_b200 import mesh as M   # noqa: E402
+
+FAR, SLIP, NOSLIP, ISO = M.RIEMANN_FARFIELD, M.ADIABATIC_SLIP_WALL, M.ADIABATIC_NONSLIP_WALL, M.ISOTHERMAL_NONSLIP_WALL
+WARP2 = lambda x: x + 0.03 * np.sin(np.pi * x[:, ::-1])
+WARP3 = lambda x: x + 0.02 * np.sin(np.pi * np.roll(x, 1, axis=1))
+
+
+def cases():
+    """(name, compiled control type in oracle/ref_sweeps.cpp, oracle / product configuration, mesh, free-stream velocity, amplitude, steps, cfl)"""
+    mu = 0.01
+    return [
+        ("quad_p2_euler_hllc_ssprk3", 0, dict(p=2, conv_flux=2, rk=2),
+         M.box(2, (4, 3), 0.0, 1.0, geom_order=2, warp=WARP2, phys_bc={1: FAR, 2: FAR, 3: SLIP, 4: FAR}), [0.5, 0.1, 0.0], 0.02, 3, 0.5),
+        ("quad_p3_ns_br2_sutherland", 1, dict(p=3, model=1, transport=2, mu=mu, conv_flux=2, visc_flux=2, rk=2),
+         M.box(2, (3, 3), 0.0, 1.0, geom_order=3, warp=WARP2, phys_bc={1: FAR, 2: FAR, 3: NOSLIP, 4: ISO}), [0.3, 0.05, 0.0], 0.02, 2, 0.3),
+        ("quad_p2_ns_br1_roe_heun_periodic", 2, dict(p=2, model=1, transport=1, mu=mu, conv_flux=3, visc_flux=1, rk=1),
+         M.periodic_box(2, 4), [0.4, 0.2, 0.0], 0.05, 3, 0.3),
+        ("line_p3_euler_lf_forward_euler", 3, dict(p=3, conv_flux=1, rk=0),
+         M.box(1, (8,), 0.0, 1.0, phys_bc={1: FAR, 2: FAR}), [0.4, 0.0, 0.0], 0.05, 4, 0.2),
+        ("hex_p2_ns_br2_constant", 4, dict(p=2, model=1, transport=1, mu=mu, conv_flux=2, visc_flux=2, rk=2),
+         M.box(3, (2, 2, 3), 0.0, 1.0, geom_order=2, warp=WARP3, periodic_axes=(2,), phys_bc={1: FAR, 2: FAR, 3: NOSLIP, 4: SLIP}), [0.3, 0.1, 0.05], 0.02, 2, 0.3),
+        ("triangle_p2_euler_hllc", 5, dict(p=2, conv_flux=2, rk=2),
+         M.annulus(2, 8, r0=0.5, r1=2.0, geom_order=1, tri_rings=2), [0.4, 0.05, 0.0], 0.02, 3, 0.5),
+        ("hybrid_p3_ns_br2_sutherland", 6, dict(p=3, model=1, transport=2, mu=mu, conv_flux=2, visc_flux=2, rk=2),
+         M.annulus(3, 8, r0=0.5, r1=2.5, geom_order=3, tri_rings=1, phys_bc={1: FAR, 2: NOSLIP}), [0.2, 0.0, 0.0], 0.01, 2, 0.3),
+        ("hex_p3_euler_periodic", 7, dict(p=3, conv_flux=2, rk=2), M.periodic_box_fast(3, 3), [0.5, 0.3, 0.2], 0.05, 2, 0.5),
+    ]
+
+
+def fields(dim, vel, amp):
+    """the analytic fields compiled into oracle/ref_sweeps.cpp (fieldAt): initial condition and (amp = 0) boundary values"""
+    def make(a):
+        def f(x, *_):
+            s = np.sin(np.pi * x[..., 0])
+            if dim >= 2:
+                s = s * np.cos(np.pi * x[..., 1])
+            if dim >= 3:
+                s = s * np.cos(np.pi * x[..., 2])
+            g = 1.0 + a * s
+            return np.stack([1.4 * g] + [vel[d] * g + 0.0 * s for d in range(dim)] + [1.0 * g], axis=-1)
+        return f
+    return make(amp), make(0.0)
+
+
+def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl):
+    import oracle
+    O = oracle.Oracle(dict(cfg), mesh)          # geometry factors only (never stepped here)
+    types = O.types
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    geo = {t: [np.ascontiguousarray(O.element_geometry(t, w)) for w in range(5)] for t in types}
+    sizes = {t: O.sizes(t) for t in types}
+    coef = {t: np.zeros((sizes[t].n, sizes[t].Nb, mesh.dim + 2)) for t in types}
+    PP = ctypes.POINTER(ctypes.c_double) * len(types)
+    arr = lambda w: PP(*[dp(geo[t][w]) for t in types])
+    f = mesh.faces
+    fint = [np.ascontiguousarray(f[k], dtype=np.int32) for k in ("le", "lt", "lf", "re", "rt", "rf", "rot", "bc", "phys")]
+    FI = (ctypes.POINTER(ctypes.c_int32) * 9)(*[ip(a) for a in fint])
+    xf, nrm, fjw = (np.ascontiguousarray(O.face_geometry(w)) for w in range(3))
+    params = np.array([2.5, 25.0 / 14.0, cfg.get("mu", 0.0), amp, vel[0], vel[1], vel[2]])
+    relerr = np.zeros(mesh.dim + 2)
+    dt = ctypes.c_double(0)
+    tarr = np.array(types, dtype=np.int32); narr = np.array([sizes[t].n for t in types], dtype=np.int32)
+    lib.ref_sweeps.restype = ctypes.c_int
+    lib.ref_sweeps_error.restype = ctypes.c_char_p
+    rc = lib.ref_sweeps(case_id, dp(params), len(types), ip(tarr), ip(narr), arr(0), arr(1), arr(2), arr(3), arr(4), int(f["n_int"]), int(f["n_bnd"]), FI,
+                        dp(xf), dp(nrm), dp(fjw), int(steps), ctypes.c_double(cfl), ctypes.c_double(0.0), PP(*[dp(coef[t]) for t in types]), dp(relerr),
+                        ctypes.byref(dt))
+    assert rc == 0, lib.ref_sweeps_error().decode()
+    return coef, relerr, dt.value
+
+
+def main():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_sweeps.so"))
+    out = []
+    for name, case_id, cfg, mesh, vel, amp, steps, cfl in cases():
+        coef0, _, _ = run_reference(lib, case_id, cfg, mesh, vel, amp, 0, cfl)            # Solver::initializeSolver alone
+        coef, relerr, dt = run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl)
+        assert all(np.isfinite(c).all() for c in coef.values()), name
+        out.append(dict(name=name, steps=steps, cfl=cfl, dt=dt, relative_error=relerr.tolist(),
+                        initial={str(t): c.ravel().tolist() for t, c in coef0.items()}, state={str(t): c.ravel().tolist() for t, c in coef.items()},
+                        mesh_checksum={str(t): float(np.asarray(b["coords"]).sum()) for t, b in mesh.blocks.items()}))
+        print(f"{name}: dt {dt:.6e} relative_error {relerr}")
+    path = os.path.join(HERE, "reference_sweeps.json")
+    json.dump(dict(source="the reference's Solver<SC>::initializeSolver / calculateDeltaTime / stepSolver compiled from /root/reference/src (oracle/ref_sweeps.cpp)",
+                   cases=out), open(path, "w"))
+    print(f"{len(out)} cases -> {path} ({os.path.getsize(path) // 1024} KB)")
+
+
+if __name__ == "__main__":
+    main()
