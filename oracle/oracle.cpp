@@ -552,10 +552,12 @@ static void sweepR2(Oracle& O) {
         viscNormalFlux(P, n, R[jr].comp, &pR[(size_t)jr * G], b);
         for (int v = 0; v < Nv; v++) Fc[v] -= (a[v] + b[v]) / 2.0;
       }
-      if (O.av) {  // calculateArtificialViscousFlux, ViscousFlux.cpp:172-186: average of eps * grad(U) . n of both sides
+      if (O.av) {  // calculateArtificialViscousFlux, ViscousFlux.cpp:172-186: average of eps * grad(U) . n of both sides.  The reference
+        // passes right_quadrature_node_artificial_viscosity(j) (SpatialDiscrete.cpp:714-719): the right VISCOSITY is taken at the right
+        // element's own point j, not at the matching point sequence[j] its gradient column uses -- restated as it is
         for (int v = 0; v < Nv; v++) {
           double a = 0.0, b = 0.0;
-          for (int c = 0; c < D; c++) { a += epsL[j] * avgL[(size_t)j * G + v * D + c] * n[c]; b += epsR[jr] * avgR[(size_t)jr * G + v * D + c] * n[c]; }
+          for (int c = 0; c < D; c++) { a += epsL[j] * avgL[(size_t)j * G + v * D + c] * n[c]; b += epsR[j] * avgR[(size_t)jr * G + v * D + c] * n[c]; }
           Fc[v] -= (a + b) / 2.0;
         }
       }

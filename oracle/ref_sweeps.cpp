@@ -30,14 +30,38 @@ using namespace SubrosaDG;
 
 namespace {
 
-struct Params { double cp, cv, mu, amp, vel[3]; };
+struct Params { double cp, cv, mu, amp, vel[3]; double jump_width, jump_radius, av_tolerance, av_factor; };
 Params g_params;
 thread_local std::string g_error;
 
 // the analytic fields of tests/cases.py::ic_perturbed_freestream / bc_freestream (free stream rho = 1.4, T = 1, velocity vel, times a
 // smooth perturbation 1 + amp sin(pi x) cos(pi y) [cos(pi z)]; the boundary callback returns the unperturbed free stream)
+// shock-capturing cases: a steep density / pressure jump, fluid at rest — across the oblique plane sum_d x_d / sqrt(D) = 0.5 sqrt(D)
+// (jump_radius == 0) or across the circle |x| = jump_radius; tests/test_gpu_av.py::jump_ic / radial_jump_ic
+template <int D>
+Eigen::Vector<Real, D + 2> jumpAt(const Eigen::Vector<Real, D>& x) {
+  double a = 0.0;
+  if (g_params.jump_radius > 0.0) {
+    for (int d = 0; d < D; d++) a += x(d) * x(d);
+    a = (std::sqrt(a) - g_params.jump_radius) / g_params.jump_width;
+  } else {
+    const double c = 1.0 / std::sqrt(static_cast<double>(D));
+    for (int d = 0; d < D; d++) a += x(d) * c;
+    a = (a - 0.5 * c * D) / g_params.jump_width;
+  }
+  const double s = std::tanh(a);
+  const double rho = g_params.jump_radius > 0.0 ? 0.75 - 0.25 * s : 0.5625 - 0.4375 * s;
+  const double p = g_params.jump_radius > 0.0 ? 0.75 - 0.25 * s : 0.55 - 0.45 * s;
+  Eigen::Vector<Real, D + 2> q;
+  q(0) = rho;
+  for (int d = 0; d < D; d++) q(1 + d) = 0.0;
+  q(D + 1) = 1.4 * p / rho;
+  return q;
+}
+
 template <int D>
 Eigen::Vector<Real, D + 2> fieldAt(const Eigen::Vector<Real, D>& x, const double amp) {
+  if (g_params.jump_width > 0.0) return jumpAt<D>(x);
   double s = std::sin(kPi * x(0));
   if constexpr (D >= 2) s *= std::cos(kPi * x(1));
   if constexpr (D >= 3) s *= std::cos(kPi * x(2));
@@ -65,7 +89,7 @@ inline Eigen::Vector<Real, SimulationControl::kPrimitiveVariableNumber> SubrosaD
 namespace {
 
 // per element type: what the oracle's geometry getters hand out (oracle/__init__.py: element_geometry 0..4)
-struct BlockIn { int type, n; const double *xq, *jw, *mt, *minv, *min_edge; double* coef_out; };
+struct BlockIn { int type, n; const double *xq, *jw, *mt, *minv, *min_edge; double* coef_out; const int32_t* node_tag; const double* inner_radius; };
 struct FacesIn {
   int n_int, n_bnd;
   const int32_t *le, *lt, *lf, *re, *rt, *rf, *rot, *bc, *phys;
@@ -86,7 +110,8 @@ void fillElementMesh(ElementMesh<ElementTrait>& em, const BlockIn& b) {
     }
     for (int r = 0; r < Nb; r++) for (int c = 0; c < Nb; c++) e.local_mass_matrix_inverse_(r, c) = b.minv[((std::size_t)i * Nb + c) * Nb + r];   // column-major
     e.minimum_edge_ = b.min_edge[i];
-    e.inner_radius_ = 0.0;
+    e.inner_radius_ = b.inner_radius ? b.inner_radius[i] : 0.0;
+    if (b.node_tag) for (int k = 0; k < ElementTrait::kBasicNodeNumber; k++) e.node_tag_(k) = b.node_tag[(std::size_t)i * ElementTrait::kBasicNodeNumber + k] + 1;   // Gmsh tags are 1-based
   }
 }
 
@@ -118,7 +143,8 @@ void fillAdjacencyMesh(AdjacencyElementMesh<AdjacencyElementTrait>& am, const Fa
 }
 
 template <typename SC>
-int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nsteps, double cfl, double dt_in, double* relerr_out, double* dt_out) {
+int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nsteps, double cfl, double dt_in, double* relerr_out, double* dt_out, int node_number,
+            double* node_av_out) {
   constexpr int D = SC::kDimension, P = SC::kPolynomialOrder;
   auto mesh_p = std::make_unique<Mesh<SC>>();   // constructors assemble the reference-element tables (through the Gmsh stand-in)
   Mesh<SC>& mesh = *mesh_p;
@@ -142,7 +168,7 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
   if constexpr (D == 1) fillAdjacencyMesh<AdjacencyPointTrait<P>, D, P>(mesh.point_, faces);
   else if constexpr (D == 2) fillAdjacencyMesh<AdjacencyLineTrait<P>, D, P>(mesh.line_, faces);
   else fillAdjacencyMesh<AdjacencyQuadrangleTrait<P>, D, P>(mesh.quadrangle_, faces);
-  mesh.node_number_ = 1;
+  mesh.node_number_ = node_number;
 
   BoundaryCondition<SC> boundary_condition;
   InitialCondition<SC> initial_condition;
@@ -150,6 +176,8 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
   TimeIntegration<SC> time_integration;
   auto solver_p = std::make_unique<Solver<SC>>();
   Solver<SC>& solver = *solver_p;
+  solver.empirical_tolerance_ = g_params.av_tolerance;          // System::setArtificialViscosity, SystemControl.cpp:105-108
+  solver.artificial_viscosity_factor_ = g_params.av_factor;
   solver.initializeSolver(mesh, physical_model, boundary_condition, initial_condition);
   time_integration.courant_friedrichs_lewy_number_ = cfl;
   time_integration.delta_time_ = dt_in;
@@ -160,6 +188,7 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
     time_integration.iteration_ = i;
   }
   for (int v = 0; v < SC::kConservedVariableNumber; v++) relerr_out[v] = solver.relative_error_(v);
+  if (node_av_out) for (int k = 0; k < node_number; k++) node_av_out[k] = solver.node_artificial_viscosity_(k);
   for (int k = 0; k < n_blocks; k++) {
     const BlockIn& b = blocks[k];
     auto copyOut = [&](const auto& element_solver) {
@@ -175,9 +204,9 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
   return 0;
 }
 
-template <DimensionEnum D, PolynomialOrderEnum P, MeshModelEnum M, TimeIntegrationEnum RK, typename Variable>
+template <DimensionEnum D, PolynomialOrderEnum P, MeshModelEnum M, TimeIntegrationEnum RK, typename Variable, ShockCapturingEnum S = ShockCapturingEnum::None>
 using Control = SimulationControl<SolveControl<D, P, BoundaryTimeEnum::Steady, SourceTermEnum::None>,
-                                  NumericalControl<M, ShockCapturingEnum::None, LimiterEnum::None, InitialConditionEnum::Function, RK>, Variable>;
+                                  NumericalControl<M, S, LimiterEnum::None, InitialConditionEnum::Function, RK>, Variable>;
 template <ConvectiveFluxEnum F>
 using Euler = CompresibleEulerVariable<ThermodynamicModelEnum::Constant, EquationOfStateEnum::IdealGas, F>;
 template <TransportModelEnum T, ConvectiveFluxEnum F, ViscousFluxEnum V>
@@ -190,26 +219,32 @@ extern "C" {
 const char* ref_sweeps_error() { return g_error.c_str(); }
 
 // case_id selects one of the compiled control types (tests/golden/make_reference_sweeps.py lists them with their meshes);
-// params = {cp, cv, mu, amp, vel[3]}; blocks / faces: see BlockIn / FacesIn (faces in the order and meaning of sdg_set_faces)
+// params = {cp, cv, mu, amp, vel[3], jump_width, jump_radius, av_tolerance, av_factor}; node tags (0-based) / inner radii for the shock cases; blocks / faces: see BlockIn / FacesIn (faces in the order and meaning of sdg_set_faces)
 int ref_sweeps(int case_id, const double* params, int n_blocks, const int32_t* types, const int32_t* counts, const double* const* xq, const double* const* jw,
                const double* const* mt, const double* const* minv, const double* const* min_edge, int n_int, int n_bnd, const int32_t* const* face_int /* 9 arrays */,
                const double* xf, const double* nrm, const double* fjw, int nsteps, double cfl, double dt_in, double* const* coef_out, double* relerr_out,
-               double* dt_out) {
+               double* dt_out, int node_number, const int32_t* const* node_tag, const double* const* inner_radius, double* node_av_out) {
   try {
-    g_params = Params{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}};
+    g_params = Params{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}, params[7], params[8], params[9], params[10]};
     BlockIn blocks[4];
-    for (int k = 0; k < n_blocks; k++) blocks[k] = BlockIn{types[k], counts[k], xq[k], jw[k], mt[k], minv[k], min_edge[k], coef_out[k]};
+    for (int k = 0; k < n_blocks; k++) blocks[k] = BlockIn{types[k], counts[k], xq[k], jw[k], mt[k], minv[k], min_edge[k], coef_out[k], node_tag ? node_tag[k] : nullptr, inner_radius ? inner_radius[k] : nullptr};
     const FacesIn F{n_int, n_bnd, face_int[0], face_int[1], face_int[2], face_int[3], face_int[4], face_int[5], face_int[6], face_int[7], face_int[8], xf, nrm, fjw};
     using enum DimensionEnum; using enum PolynomialOrderEnum; using enum MeshModelEnum; using enum TimeIntegrationEnum;
     switch (case_id) {
-      case 0: return runCase<Control<D2, P2, Quadrangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out);
-      case 1: return runCase<Control<D2, P3, Quadrangle, SSPRK3, NS<TransportModelEnum::Sutherland, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out);
-      case 2: return runCase<Control<D2, P2, Quadrangle, HeunRK2, NS<TransportModelEnum::Constant, ConvectiveFluxEnum::Roe, ViscousFluxEnum::BR1>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out);
-      case 3: return runCase<Control<D1, P3, Line, ForwardEuler, Euler<ConvectiveFluxEnum::LaxFriedrichs>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out);
-      case 4: return runCase<Control<D3, P2, Hexahedron, SSPRK3, NS<TransportModelEnum::Constant, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out);
-      case 5: return runCase<Control<D2, P2, Triangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out);
-      case 6: return runCase<Control<D2, P3, TriangleQuadrangle, SSPRK3, NS<TransportModelEnum::Sutherland, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out);
-      case 7: return runCase<Control<D3, P3, Hexahedron, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out);
+      case 0: return runCase<Control<D2, P2, Quadrangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 1: return runCase<Control<D2, P3, Quadrangle, SSPRK3, NS<TransportModelEnum::Sutherland, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 2: return runCase<Control<D2, P2, Quadrangle, HeunRK2, NS<TransportModelEnum::Constant, ConvectiveFluxEnum::Roe, ViscousFluxEnum::BR1>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 3: return runCase<Control<D1, P3, Line, ForwardEuler, Euler<ConvectiveFluxEnum::LaxFriedrichs>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 4: return runCase<Control<D3, P2, Hexahedron, SSPRK3, NS<TransportModelEnum::Constant, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 5: return runCase<Control<D2, P2, Triangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 6: return runCase<Control<D2, P3, TriangleQuadrangle, SSPRK3, NS<TransportModelEnum::Sutherland, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 7: return runCase<Control<D3, P3, Hexahedron, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      // ShockCapturingEnum::ArtificialViscosity: sod_1d_ceuler / sedovblast_2d_ceuler / explosion_2d_ceuler / cylinder_2d_ceuler control types
+      case 8: return runCase<Control<D1, P2, Line, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 9: return runCase<Control<D2, P3, Quadrangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 10: return runCase<Control<D2, P2, Triangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 11: return runCase<Control<D2, P3, TriangleQuadrangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 12: return runCase<Control<D3, P2, Hexahedron, SSPRK3, Euler<ConvectiveFluxEnum::Roe>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
       default: throw std::runtime_error("ref_sweeps: unknown case");
     }
   } catch (const std::exception& ex) {

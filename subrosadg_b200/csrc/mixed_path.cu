@@ -83,13 +83,15 @@ __device__ __forceinline__ double mxEps(const MxType& T, const double* __restric
   return s;
 }
 // eps * grad(U_conserved) . n with the VOLUME gradient (calculateArtificialViscousNormalFlux, ViscousFlux.cpp:126-136)
-__device__ __forceinline__ void mxAvNormalFlux(const MxType& T, int e, int row, const double* n, double* out) {
+// epsRow: the face row the viscosity is taken at -- for the right side of an interior face the reference passes the LEFT loop index j
+// (right_quadrature_node_artificial_viscosity(j), SpatialDiscrete.cpp:714-719), not the matching point its gradient column uses
+__device__ __forceinline__ void mxAvNormalFlux(const MxType& T, int e, int row, int epsRow, const double* n, double* out) {
   double g[kG];
   for (int r = 0; r < kG; r++) g[r] = 0.0;
   const double* C = T.Gvol + (size_t)e * T.Nb * kG;
   const double* phi = T.PhiF + (size_t)row * T.Nb;
   for (int b = 0; b < T.Nb; b++) { const double ph = phi[b]; for (int r = 0; r < kG; r++) g[r] = fma(C[b * kG + r], ph, g[r]); }
-  const double eps = mxEps(T, T.NodalF + (size_t)row * T.NB, e);
+  const double eps = mxEps(T, T.NodalF + (size_t)epsRow * T.NB, e);
   for (int v = 0; v < kNV; v++) out[v] = eps * (g[v * kD] * n[0] + g[v * kD + 1] * n[1]);
 }
 
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(128) mxFaceKernel(const __grid_constant__ Args
         }
         if (A.phys.av) {  // calculateArtificialViscousFlux, ViscousFlux.cpp:172-186
           double a[kNV], b[kNV];
-          mxAvNormalFlux(TL, eL, rowL, n, a); mxAvNormalFlux(TR, eR, rowR, n, b);
+          mxAvNormalFlux(TL, eL, rowL, rowL, n, a); mxAvNormalFlux(TR, eR, rowR, fR * Nqf + j, n, b);
           for (int v = 0; v < kNV; v++) Fc[v] -= (a[v] + b[v]) / 2.0;
         }
         double* aL = TL.A + ((size_t)eL * TL.Naq + rowL) * kNV; double* aR = TR.A + ((size_t)eR * TR.Naq + rowR) * kNV;
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(128) mxFaceKernel(const __grid_constant__ Args
         }
         if (A.phys.av) {  // boundary faces: the interior side alone (SpatialDiscrete.cpp:813-819)
           double a[kNV];
-          mxAvNormalFlux(TL, eL, rowL, n, a);
+          mxAvNormalFlux(TL, eL, rowL, rowL, n, a);
           for (int v = 0; v < kNV; v++) Fc[v] -= a[v];
         }
         double* aL = TL.A + ((size_t)eL * TL.Naq + rowL) * kNV;

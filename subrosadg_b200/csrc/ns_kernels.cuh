@@ -416,7 +416,9 @@ __global__ void __launch_bounds__(TH, SDG_NSR_MINB) nsStageKernel(const __grid_c
             for (int c = 0; c < D; c++) g[v * D + c] += lamR * n[c] * jump[v];
         }
         if (av) {
-          const double eps = avAt<NB>(A.avTabF + (size_t)(lfR * NQF + jr) * NB, A.avElem + (size_t)eR * NB);
+          // the reference takes the right viscosity at the right face's own point j, not at the matching point sequence[j] that the
+          // gradient column uses (right_quadrature_node_artificial_viscosity(j), SpatialDiscrete.cpp:714-719): reproduced as it is
+          const double eps = avAt<NB>(A.avTabF + (size_t)(lfR * NQF + j) * NB, A.avElem + (size_t)eR * NB);
 #pragma unroll
           for (int v = 0; v < NV; v++) {
             double t = 0.0;

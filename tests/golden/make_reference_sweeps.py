@@ -30,8 +30,10 @@ WARP3 = lambda x: x + 0.02 * np.sin(np.pi * np.roll(x, 1, axis=1))
 
 
 def cases():
-    """(name, compiled control type in oracle/ref_sweeps.cpp, oracle / product configuration, mesh, free-stream velocity, amplitude, steps, cfl)"""
+    """(name, compiled control type in oracle/ref_sweeps.cpp, oracle / product configuration, mesh, free-stream velocity, amplitude, steps, cfl).
+    Shock-capturing cases carry av_tolerance / av_factor in the configuration and jump = (width, radius) instead of a velocity."""
     mu = 0.01
+    ann = dict(r0=0.5, r1=3.0)
     return [
         ("quad_p2_euler_hllc_ssprk3", 0, dict(p=2, conv_flux=2, rk=2),
          M.box(2, (4, 3), 0.0, 1.0, geom_order=2, warp=WARP2, phys_bc={1: FAR, 2: FAR, 3: SLIP, 4: FAR}), [0.5, 0.1, 0.0], 0.02, 3, 0.5),
@@ -48,11 +50,36 @@ def cases():
         ("hybrid_p3_ns_br2_sutherland", 6, dict(p=3, model=1, transport=2, mu=mu, conv_flux=2, visc_flux=2, rk=2),
          M.annulus(3, 8, r0=0.5, r1=2.5, geom_order=3, tri_rings=1, phys_bc={1: FAR, 2: NOSLIP}), [0.2, 0.0, 0.0], 0.01, 2, 0.3),
         ("hex_p3_euler_periodic", 7, dict(p=3, conv_flux=2, rk=2), M.periodic_box_fast(3, 3), [0.5, 0.3, 0.2], 0.05, 2, 0.5),
+        # ShockCapturingEnum::ArtificialViscosity (sod_1d / sedovblast_2d / explosion_2d / cylinder_2d control types): jump = (width, radius)
+        ("av_line_p2_sod", 8, dict(p=2, conv_flux=2, rk=2, av_tolerance=0.5, av_factor=1.0),
+         M.box(1, (24,), 0.0, 1.0, phys_bc={1: FAR, 2: FAR}), (0.02, 0.0), 0.0, 4, 0.2),
+        ("av_quad_p3_oblique_jump", 9, dict(p=3, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=2.0),
+         M.box(2, (8, 6), 0.0, 1.0, geom_order=2, warp=WARP2, phys_bc={1: FAR, 2: FAR, 3: SLIP, 4: SLIP}), (0.03, 0.0), 0.0, 3, 0.2),
+        ("av_triangle_p2_radial_jump", 10, dict(p=2, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=1.0),
+         M.annulus(6, 16, geom_order=1, tri_rings=6, **ann), (0.08, 1.5), 0.0, 3, 0.05),
+        ("av_hybrid_p3_radial_jump", 11, dict(p=3, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=2.0),
+         M.annulus(6, 16, geom_order=3, stretch=1.2, tri_rings=3, **ann), (0.05, 1.6), 0.0, 2, 0.2),
+        ("av_hex_p2_oblique_jump_roe", 12, dict(p=2, conv_flux=3, rk=2, av_tolerance=1.0, av_factor=1.0),
+         M.box(3, (4, 3, 3), 0.0, 1.0, periodic_axes=(2,), phys_bc={1: FAR, 2: FAR, 3: SLIP, 4: SLIP}), (0.05, 0.0), 0.0, 2, 0.2),
     ]
 
 
 def fields(dim, vel, amp):
-    """the analytic fields compiled into oracle/ref_sweeps.cpp (fieldAt): initial condition and (amp = 0) boundary values"""
+    """the analytic fields compiled into oracle/ref_sweeps.cpp (fieldAt / jumpAt): initial condition and (amp = 0) boundary values"""
+    if isinstance(vel, tuple):          # shock-capturing cases: (jump width, jump radius)
+        width, radius = vel
+
+        def jump(x, *_):
+            if radius > 0.0:
+                s = np.tanh((np.sqrt((x * x).sum(axis=-1)) - radius) / width)
+                rho, p = 0.75 - 0.25 * s, 0.75 - 0.25 * s
+            else:
+                c = 1.0 / np.sqrt(float(dim))
+                s = np.tanh(((x * c).sum(axis=-1) - 0.5 * c * dim) / width)
+                rho, p = 0.5625 - 0.4375 * s, 0.55 - 0.45 * s
+            return np.stack([rho] + [np.zeros_like(rho)] * dim + [1.4 * p / rho], axis=-1)
+        return jump, jump
+
     def make(a):
         def f(x, *_):
             s = np.sin(np.pi * x[..., 0])
@@ -81,7 +108,13 @@ def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl):
     fint = [np.ascontiguousarray(f[k], dtype=np.int32) for k in ("le", "lt", "lf", "re", "rt", "rf", "rot", "bc", "phys")]
     FI = (ctypes.POINTER(ctypes.c_int32) * 9)(*[ip(a) for a in fint])
     xf, nrm, fjw = (np.ascontiguousarray(O.face_geometry(w)) for w in range(3))
-    params = np.array([2.5, 25.0 / 14.0, cfg.get("mu", 0.0), amp, vel[0], vel[1], vel[2]])
+    shock = isinstance(vel, tuple)
+    params = np.array([2.5, 25.0 / 14.0, cfg.get("mu", 0.0), amp] + ([0.0, 0.0, 0.0, vel[0], vel[1], cfg["av_tolerance"], cfg["av_factor"]] if shock
+                      else [vel[0], vel[1], vel[2], 0.0, 0.0, 0.0, 1.0]))
+    tags, n_nodes = M.node_tags(mesh) if shock else ({}, 1)
+    radius = {t: np.ascontiguousarray(M.inner_radius(mesh, t)) for t in types} if shock else {}
+    IP = ctypes.POINTER(ctypes.c_int32) * len(types)
+    node_av = np.zeros(n_nodes)
     relerr = np.zeros(mesh.dim + 2)
     dt = ctypes.c_double(0)
     tarr = np.array(types, dtype=np.int32); narr = np.array([sizes[t].n for t in types], dtype=np.int32)
@@ -89,9 +122,10 @@ def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl):
     lib.ref_sweeps_error.restype = ctypes.c_char_p
     rc = lib.ref_sweeps(case_id, dp(params), len(types), ip(tarr), ip(narr), arr(0), arr(1), arr(2), arr(3), arr(4), int(f["n_int"]), int(f["n_bnd"]), FI,
                         dp(xf), dp(nrm), dp(fjw), int(steps), ctypes.c_double(cfl), ctypes.c_double(0.0), PP(*[dp(coef[t]) for t in types]), dp(relerr),
-                        ctypes.byref(dt))
+                        ctypes.byref(dt), int(n_nodes), IP(*[ip(tags[t]) for t in types]) if shock else None, PP(*[dp(radius[t]) for t in types]) if shock else None,
+                        dp(node_av) if shock else None)
     assert rc == 0, lib.ref_sweeps_error().decode()
-    return coef, relerr, dt.value
+    return coef, relerr, dt.value, (node_av if shock else None)
 
 
 def main():
@@ -99,10 +133,12 @@ def main():
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_sweeps.so"))
     out = []
     for name, case_id, cfg, mesh, vel, amp, steps, cfl in cases():
-        coef0, _, _ = run_reference(lib, case_id, cfg, mesh, vel, amp, 0, cfl)            # Solver::initializeSolver alone
-        coef, relerr, dt = run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl)
+        coef0, _, _, _ = run_reference(lib, case_id, cfg, mesh, vel, amp, 0, cfl)            # Solver::initializeSolver alone
+        coef, relerr, dt, node_av = run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl)
         assert all(np.isfinite(c).all() for c in coef.values()), name
-        out.append(dict(name=name, steps=steps, cfl=cfl, dt=dt, relative_error=relerr.tolist(),
+        if node_av is not None:
+            assert node_av.max() > 0.0 and (node_av == 0.0).any(), name      # the case switches the viscosity on somewhere, not everywhere
+        out.append(dict(name=name, steps=steps, cfl=cfl, dt=dt, relative_error=relerr.tolist(), node_artificial_viscosity=None if node_av is None else node_av.tolist(),
                         initial={str(t): c.ravel().tolist() for t, c in coef0.items()}, state={str(t): c.ravel().tolist() for t, c in coef.items()},
                         mesh_checksum={str(t): float(np.asarray(b["coords"]).sum()) for t, b in mesh.blocks.items()}))
         print(f"{name}: dt {dt:.6e} relative_error {relerr}")

@@ -3,7 +3,8 @@ the RK update and the relative error, compiled from /root/reference/src (oracle/
 the CUDA path (GPU).  tests/golden/reference_sweeps.json was written by tests/golden/make_reference_sweeps.py in the development
 container; here only the committed numbers are read.  Eight control types: line / quadrangle / triangle / hybrid / hexahedron meshes,
 Euler and Navier-Stokes (BR1, BR2; constant and Sutherland viscosity), Lax-Friedrichs / HLLC / Roe, ForwardEuler / HeunRK2 / SSPRK3,
-affine, curved and periodic meshes, far-field and wall boundaries."""
+affine, curved and periodic meshes, far-field and wall boundaries; five more with ShockCapturingEnum::ArtificialViscosity (the reference's
+calculateArtificialViscosity and its eps * grad(U) flux terms; the inner radius of the elements is an input on both sides)."""
 import json
 import os
 import sys
@@ -41,6 +42,13 @@ def _check(solver_state, solver_initial, dt, relerr, gold, types, shapes, tol_st
     assert np.allclose(relerr, gold["relative_error"], rtol=1e-8, atol=1e-300), f"relative_error_ {relerr} vs {gold['relative_error']}"
 
 
+def _check_viscosity(node_av, gold):
+    """Solver::node_artificial_viscosity_ of the last step (calculateArtificialViscosity, SpatialDiscrete.cpp:124-192)"""
+    ref = np.asarray(gold["node_artificial_viscosity"])
+    assert ref.max() > 0.0 and np.array_equal(ref == 0.0, node_av == 0.0), "different elements are flagged"
+    assert cases.rel_l2(node_av, ref) < 1e-9, f"node_artificial_viscosity_ rel-L2 {cases.rel_l2(node_av, ref):.3e}"
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_oracle_reproduces_the_reference_solver(case):
     import oracle
@@ -57,6 +65,8 @@ def test_oracle_reproduces_the_reference_solver(case):
     state = {t: O.get_state(t) for t in O.types}
     tol_ic = _projection_tolerance(cfg, mesh)
     _check(state, initial, dt, relerr, gold, O.types, {t: initial[t].shape for t in O.types}, max(1e-12, max(tol_ic.values())), tol_ic)
+    if gold["node_artificial_viscosity"] is not None:
+        _check_viscosity(O.node_artificial_viscosity(), gold)
 
 
 @pytest.mark.gpu
@@ -73,3 +83,5 @@ def test_cuda_path_reproduces_the_reference_solver(built, case):
     relerr = S.stepSolver(dt, steps)
     state = {t: S.get_state(t) for t in S.types}
     _check(state, initial, dt, relerr, gold, S.types, {t: initial[t].shape for t in S.types}, 1e-10, _projection_tolerance(cfg, mesh))   # 1e-10: BASELINE.json, fields after N steps
+    if gold["node_artificial_viscosity"] is not None:
+        _check_viscosity(S.node_artificial_viscosity(), gold)
