@@ -40,6 +40,14 @@ namespace sdg {
 #define SDG_NSLS_HOIST 1      // pass R, inviscid: partner rows of all six faces before the direction loop: 2.88 / 3.05 / 3.73 -> 2.83 / 2.98 / 3.58 ms at 96^3
 #endif
 
+// DIAGNOSTIC builds only (wrong numbers, tools/gpu_diag_euler.sh): what the face phase of the inviscid residual pass costs.
+//   1 = the lower face of every direction is skipped (upper bound of evaluating every face once)
+//   2 = the Riemann solve is replaced by the average of the two states (loads and slot traffic stay)
+//   3 = the partner row is not loaded (own trace on both sides; the Riemann solve stays)
+#ifndef SDG_NSL_DIAG
+#define SDG_NSL_DIAG 0
+#endif
+
 #if SDG_NSLG_PRELOAD && !SDG_NSLG_NBRSEL
 #error "SDG_NSLG_PRELOAD needs SDG_NSLG_NBRSEL"
 #endif
@@ -744,7 +752,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
                                    : ((size_t)e * 6 + f) * kRow + t;
     }
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
+    for (int side = (SDG_NSL_DIAG == 1 && !VISC) ? 1 : 0; side < 2; side++) {
       const int f = hexFaceRt(d, side);
       if constexpr (GATHER) {
         const int z = lk[side].z, lfo = linkLfo(z);
@@ -773,7 +781,14 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
         }
       } else {
 #pragma unroll
-        for (int v = 0; v < 5; v++) { cm[side][v] = __ldg(gTU + (f * 5 + v) * 16); co[side][v] = __ldg(A.TUin + rowO[side] + v * 16); }
+        for (int v = 0; v < 5; v++) {
+          cm[side][v] = __ldg(gTU + (f * 5 + v) * 16);
+#if SDG_NSL_DIAG == 3
+          co[side][v] = cm[side][v];
+#else
+          co[side][v] = __ldg(A.TUin + rowO[side] + v * 16);
+#endif
+        }
         if constexpr (VISC) {
 #pragma unroll
           for (int v = 0; v < 5; v++) { tm[side][v] = __ldg(gTV + (f * 5 + v) * 16); to[side][v] = __ldg(A.TVin + rowO[side] + v * 16); }
@@ -781,7 +796,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
       }
     }
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
+    for (int side = (SDG_NSL_DIAG == 1 && !VISC) ? 1 : 0; side < 2; side++) {
       const int f = hexFaceRt(d, side);
       const int z = lk[side].z;
       const bool amR = linkAmRight(z);
@@ -805,8 +820,16 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
         double consL[5], consR[5], compL[6], compR[6];
 #pragma unroll
         for (int v = 0; v < 5; v++) { consL[v] = amR ? co[side][v] : cm[side][v]; consR[v] = amR ? cm[side][v] : co[side][v]; }
+#if SDG_NSL_DIAG == 2
+        if constexpr (!VISC) {
+#pragma unroll
+          for (int v = 0; v < 5; v++) Fn[v] = 0.5 * (consL[v] + consR[v]) * n[v % 3];
+        } else
+#endif
+        {
         const double irL = compFromCons<3>(ph, consL, compL), irR = compFromCons<3>(ph, consR, compR);
         convFlux<3>(ph, n, consL, compL, irL, consR, compR, irR, Fn);
+        }
         if constexpr (VISC) {
 #pragma unroll
           for (int v = 0; v < 5; v++) Fn[v] -= 0.5 * (tm[side][v] + to[side][v]);   // calculateViscousFlux, ViscousFlux.cpp:139-153
@@ -817,6 +840,12 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
       }
     }
   }
+#if SDG_NSL_DIAG == 1
+  if constexpr (!VISC) {
+    for (int f = 0; f < 3; f++)
+      for (int v = 0; v < 5; v++) sFl[((el * 6 + f) * 5 + v) * 16 + t] = 0.0;
+  }
+#endif
   if constexpr (GATHER) __syncthreads();   // every warp has finished reading the trace tiles: the exchange region is free
   else __syncwarp(wm);
 
