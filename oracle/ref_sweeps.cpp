@@ -30,7 +30,11 @@ using namespace SubrosaDG;
 
 namespace {
 
-struct Params { double cp, cv, mu, amp, vel[3]; double jump_width, jump_radius, av_tolerance, av_factor; };
+struct Params {
+  double cp, cv, mu, amp, vel[3]; double jump_width, jump_radius, av_tolerance, av_factor;
+  double c0, rho0, beta, t_ref;   // EquationOfState<WeakCompressibleFluid> (PhysicalModel.cpp:57-78), SourceTermBase<Boussinesq> (SourceTerm.cpp:30-33)
+  int weak;                       // 1: the weakly compressible field below (incompressible examples' variable set)
+};
 Params g_params;
 thread_local std::string g_error;
 
@@ -67,6 +71,12 @@ Eigen::Vector<Real, D + 2> fieldAt(const Eigen::Vector<Real, D>& x, const double
   if constexpr (D >= 3) s *= std::cos(kPi * x(2));
   const double g = 1.0 + amp * s;
   Eigen::Vector<Real, D + 2> p;
+  if (g_params.weak) {   // density close to the reference density (p = c0^2 (rho - rho0) + p_add), smooth velocity, temperature field for the buoyancy
+    p(0) = g_params.rho0 * (1.0 + 0.01 * amp * s);
+    for (int d = 0; d < D; d++) p(1 + d) = g_params.vel[d] * g;
+    p(D + 1) = 1.0 + 2.0 * amp * s;
+    return p;
+  }
   p(0) = 1.4 * g;
   for (int d = 0; d < D; d++) p(1 + d) = g_params.vel[d] * g + 0.0 * s;
   p(D + 1) = 1.0 * g;
@@ -151,6 +161,11 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
   PhysicalModel<SC> physical_model;
   physical_model.thermodynamic_model_.specific_heat_constant_pressure = g_params.cp;
   physical_model.thermodynamic_model_.specific_heat_constant_volume = g_params.cv;
+  if constexpr (SC::kEquationOfState == EquationOfStateEnum::WeakCompressibleFluid) {   // System::setEquationOfState, SystemControl.cpp
+    physical_model.equation_of_state_.reference_sound_speed = g_params.c0;
+    physical_model.equation_of_state_.reference_density = g_params.rho0;
+    physical_model.equation_of_state_.calculatePressureAdditionFromSoundSpeedDensity();
+  }
   if constexpr (SC::kTransportModel != TransportModelEnum::None) {
     physical_model.transport_model_.dynamic_viscosity = g_params.mu;
     physical_model.calculateThermalConductivityFromDynamicViscosity();
@@ -173,6 +188,10 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
   BoundaryCondition<SC> boundary_condition;
   InitialCondition<SC> initial_condition;
   SourceTerm<SC> source_term;
+  if constexpr (SC::kSourceTerm == SourceTermEnum::Boussinesq) {   // System::setSourceTerm
+    source_term.thermal_expansion_coefficient = g_params.beta;
+    source_term.reference_temperature = g_params.t_ref;
+  }
   TimeIntegration<SC> time_integration;
   auto solver_p = std::make_unique<Solver<SC>>();
   Solver<SC>& solver = *solver_p;
@@ -204,9 +223,14 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
   return 0;
 }
 
-template <DimensionEnum D, PolynomialOrderEnum P, MeshModelEnum M, TimeIntegrationEnum RK, typename Variable, ShockCapturingEnum S = ShockCapturingEnum::None>
-using Control = SimulationControl<SolveControl<D, P, BoundaryTimeEnum::Steady, SourceTermEnum::None>,
+template <DimensionEnum D, PolynomialOrderEnum P, MeshModelEnum M, TimeIntegrationEnum RK, typename Variable, ShockCapturingEnum S = ShockCapturingEnum::None,
+          SourceTermEnum Src = SourceTermEnum::None>
+using Control = SimulationControl<SolveControl<D, P, BoundaryTimeEnum::Steady, Src>,
                                   NumericalControl<M, S, LimiterEnum::None, InitialConditionEnum::Function, RK>, Variable>;
+template <ConvectiveFluxEnum F>
+using IncEuler = IncompresibleEulerVariable<ThermodynamicModelEnum::Constant, EquationOfStateEnum::WeakCompressibleFluid, F>;
+template <ConvectiveFluxEnum F, ViscousFluxEnum V>
+using IncNS = IncompresibleNSVariable<ThermodynamicModelEnum::Constant, EquationOfStateEnum::WeakCompressibleFluid, TransportModelEnum::Constant, F, V>;
 template <ConvectiveFluxEnum F>
 using Euler = CompresibleEulerVariable<ThermodynamicModelEnum::Constant, EquationOfStateEnum::IdealGas, F>;
 template <TransportModelEnum T, ConvectiveFluxEnum F, ViscousFluxEnum V>
@@ -219,13 +243,14 @@ extern "C" {
 const char* ref_sweeps_error() { return g_error.c_str(); }
 
 // case_id selects one of the compiled control types (tests/golden/make_reference_sweeps.py lists them with their meshes);
-// params = {cp, cv, mu, amp, vel[3], jump_width, jump_radius, av_tolerance, av_factor}; node tags (0-based) / inner radii for the shock cases; blocks / faces: see BlockIn / FacesIn (faces in the order and meaning of sdg_set_faces)
+// params = {cp, cv, mu, amp, vel[3], jump_width, jump_radius, av_tolerance, av_factor, c0, rho0, beta, t_ref, weak}; node tags (0-based) / inner radii for the shock cases; blocks / faces: see BlockIn / FacesIn (faces in the order and meaning of sdg_set_faces)
 int ref_sweeps(int case_id, const double* params, int n_blocks, const int32_t* types, const int32_t* counts, const double* const* xq, const double* const* jw,
                const double* const* mt, const double* const* minv, const double* const* min_edge, int n_int, int n_bnd, const int32_t* const* face_int /* 9 arrays */,
                const double* xf, const double* nrm, const double* fjw, int nsteps, double cfl, double dt_in, double* const* coef_out, double* relerr_out,
                double* dt_out, int node_number, const int32_t* const* node_tag, const double* const* inner_radius, double* node_av_out) {
   try {
-    g_params = Params{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}, params[7], params[8], params[9], params[10]};
+    g_params = Params{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}, params[7], params[8], params[9], params[10],
+                      params[11], params[12], params[13], params[14], params[15] != 0.0};
     BlockIn blocks[4];
     for (int k = 0; k < n_blocks; k++) blocks[k] = BlockIn{types[k], counts[k], xq[k], jw[k], mt[k], minv[k], min_edge[k], coef_out[k], node_tag ? node_tag[k] : nullptr, inner_radius ? inner_radius[k] : nullptr};
     const FacesIn F{n_int, n_bnd, face_int[0], face_int[1], face_int[2], face_int[3], face_int[4], face_int[5], face_int[6], face_int[7], face_int[8], xf, nrm, fjw};
@@ -245,6 +270,21 @@ int ref_sweeps(int case_id, const double* params, int n_blocks, const int32_t* t
       case 10: return runCase<Control<D2, P2, Triangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
       case 11: return runCase<Control<D2, P3, TriangleQuadrangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
       case 12: return runCase<Control<D3, P2, Hexahedron, SSPRK3, Euler<ConvectiveFluxEnum::Roe>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      // the incompressible (weakly compressible) examples: lidcavity_2d / cylinder_2d / kovasznay_2d_incns, thermalcavity_2d_incns (Boussinesq),
+      // shearlayer_2d_inceuler, lidcavity_3d / cylinder_3d / square_3d_incns, thermalcavity_3d_incns (sphere_3d_incns without the source), taylorvortex_2d_incns
+      case 13: return runCase<Control<D2, P3, Quadrangle, SSPRK3, IncNS<ConvectiveFluxEnum::LaxFriedrichs, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 14: return runCase<Control<D2, P1, Quadrangle, SSPRK3, IncNS<ConvectiveFluxEnum::Exact, ViscousFluxEnum::BR2>, ShockCapturingEnum::None, SourceTermEnum::Boussinesq>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 15: return runCase<Control<D2, P1, Quadrangle, SSPRK3, IncEuler<ConvectiveFluxEnum::LaxFriedrichs>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 16: return runCase<Control<D3, P1, Hexahedron, SSPRK3, IncNS<ConvectiveFluxEnum::LaxFriedrichs, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 17: return runCase<Control<D3, P3, Hexahedron, SSPRK3, IncNS<ConvectiveFluxEnum::Exact, ViscousFluxEnum::BR2>, ShockCapturingEnum::None, SourceTermEnum::Boussinesq>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 18: return runCase<Control<D2, P4, Quadrangle, SSPRK3, IncNS<ConvectiveFluxEnum::Exact, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      // the remaining compressible control types of examples/: sphere_3d_cns (the north-star kernel family: P3 hexahedra, NS, BR2), blasius_3d / delta_3d_cns,
+      // rae2822_2d_cns (P5), khinstability_2d_ceuler (P5 + artificial viscosity), sod_1d / shuosher_1d_ceuler (P3 + artificial viscosity)
+      case 19: return runCase<Control<D3, P3, Hexahedron, SSPRK3, NS<TransportModelEnum::Constant, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 20: return runCase<Control<D3, P1, Hexahedron, SSPRK3, NS<TransportModelEnum::Constant, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 21: return runCase<Control<D2, P5, Quadrangle, SSPRK3, NS<TransportModelEnum::Sutherland, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 22: return runCase<Control<D2, P5, Quadrangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      case 23: return runCase<Control<D1, P3, Line, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
       default: throw std::runtime_error("ref_sweeps: unknown case");
     }
   } catch (const std::exception& ex) {

@@ -134,8 +134,19 @@ inline Quadrature makeQuadrature(int type, int order) {
     const int n = order / 2 + 1;
     std::vector<double> x, w; gaussLegendre(n, x, w);
     const int D = elemDim(type);
-    // DEVIATION (documented in DESIGN.md): gmsh uses a 7-point rule for quad order 2 and 3/6-point rules for
-    // quad/hex order 1; we use the tensor rule of the same degree.  None of the BASELINE configs hits these.
+    // Quadrangle order 2 (P1 quadrangles: thermalcavity_2d / naca0010_2d / shearlayer_2d of the reference's examples): Gmsh answers "Gauss2"
+    // with a SEVEN-point rule (kQuadrangleQuadratureNumber[2] = 7, SimulationControl.cpp:270; the reference's fixed-size tables are sized by it) --
+    // Radon's degree-5 formula for the square (Stroud C2 5-1): the centre with weight 8/7, (0, +-sqrt(14/15)) with 20/63 and
+    // (+-sqrt(3/5), +-sqrt(1/3)) with 5/9.  Values from the formula; the point ORDER follows Gmsh's table as far as it is remembered
+    // (it only permutes the quadrature arrays).  Orders 1 (3 / 6 points, quadrangle / hexahedron) are never requested (order = 2 P >= 2).
+    if (type == kQuadrangle && order == 2) {
+      const double r = std::sqrt(14.0 / 15.0), a = std::sqrt(3.0 / 5.0), b = std::sqrt(1.0 / 3.0);
+      const double P7[7][2] = {{0, 0}, {0, r}, {0, -r}, {a, b}, {a, -b}, {-a, b}, {-a, -b}};
+      const double W7[7] = {8.0 / 7.0, 20.0 / 63.0, 20.0 / 63.0, 5.0 / 9.0, 5.0 / 9.0, 5.0 / 9.0, 5.0 / 9.0};
+      q.n = 7;
+      for (int i = 0; i < 7; i++) { q.pts.insert(q.pts.end(), {P7[i][0], P7[i][1], 0}); q.wts.push_back(W7[i]); }
+      return q;
+    }
     if (D == 1) { q.n = n; for (int i = 0; i < n; i++) { q.pts.insert(q.pts.end(), {x[i], 0, 0}); q.wts.push_back(w[i]); } }
     if (D == 2) { q.n = n * n; for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { q.pts.insert(q.pts.end(), {x[i], x[j], 0}); q.wts.push_back(w[i] * w[j]); } }
     if (D == 3) { q.n = n * n * n; for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) { q.pts.insert(q.pts.end(), {x[i], x[j], x[k]}); q.wts.push_back(w[i] * w[j] * w[k]); } }

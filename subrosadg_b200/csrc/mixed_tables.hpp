@@ -175,6 +175,15 @@ struct MixedTable {
     if (type == kTriangle) {
       std::vector<std::array<double, 2>> pts; triangleRule(2 * p, pts, wq);
       for (auto& q : pts) { xi.push_back(q[0]); xi.push_back(q[1]); }
+    } else if (p == 1) {
+      // "Gauss2" on a quadrangle is Gmsh's SEVEN-point rule (kQuadrangleQuadratureNumber[2] = 7, SimulationControl.cpp:270): Radon's degree-5
+      // formula for the square (Stroud C2 5-1) -- centre 8/7, (0, +-sqrt(14/15)) 20/63, (+-sqrt(3/5), +-sqrt(1/3)) 5/9.  P1 quadrangle blocks
+      // (thermalcavity_2d / naca0010_2d / shearlayer_2d of the reference's examples) therefore run on this dense-operator path, not on the
+      // collocation tensor kernels, whose nodes would be the 2 x 2 Gauss points.
+      const double r = std::sqrt(14.0 / 15.0), a = std::sqrt(3.0 / 5.0), b = std::sqrt(1.0 / 3.0);
+      const double P7[7][2] = {{0, 0}, {0, r}, {0, -r}, {a, b}, {a, -b}, {-a, b}, {-a, -b}};
+      const double W7[7] = {8.0 / 7.0, 20.0 / 63.0, 20.0 / 63.0, 5.0 / 9.0, 5.0 / 9.0, 5.0 / 9.0, 5.0 / 9.0};
+      for (int i = 0; i < 7; i++) { xi.push_back(P7[i][0]); xi.push_back(P7[i][1]); wq.push_back(W7[i]); }
     } else {
       for (int i = 0; i <= p; i++) for (int j = 0; j <= p; j++) { xi.push_back(x1[i]); xi.push_back(x1[j]); wq.push_back(w1[i] * w1[j]); }   // first coordinate slowest
     }

@@ -284,9 +284,10 @@ int sdg_add_elements(sdg_ctx* c, int32_t type, int32_t n, int32_t n_ghost, int32
   if (!(type == kLine || type == kTriangle || type == kQuadrangle || type == kHexahedron)) throw std::runtime_error("device path implements line, triangle, quadrangle and hexahedron blocks");
   if (elemDim(type) != c->D) throw std::runtime_error("element dimension mismatch");
   if (n <= 0 || n_ghost < 0 || n_ghost >= n || geom_order < 1 || geom_order > 5) throw std::runtime_error("bad element block arguments");
-  // Single quadrangle / hexahedron block: collocation tensor path.  Triangles, several element types in one mesh, or
-  // cfg.chunk == -1 (diagnostics): dense-operator path in the reference's modal representation (mixed_path.cu).
-  if (type == kTriangle || c->haveBlock || c->mx || c->cfg.chunk == -1) {
+  // Single quadrangle / hexahedron block: collocation tensor path.  Triangles, several element types in one mesh, P1 quadrangles (Gmsh's
+  // "Gauss2" on a quadrangle is a seven-point rule, not the 2 x 2 tensor rule: mixed_tables.hpp) or cfg.chunk == -1 (diagnostics):
+  // dense-operator path in the reference's modal representation (mixed_path.cu).
+  if (type == kTriangle || c->haveBlock || c->mx || c->cfg.chunk == -1 || (type == kQuadrangle && c->cfg.p == 1)) {
     if (c->D != 2) throw std::runtime_error("several element types in one mesh: 2-D (triangle / quadrangle) only");
     if (!c->mx) {
       c->mx = std::make_unique<MixedSolver>(c->cfg.p, c->phys, c->nStages, c->rkc, c->stream, c->hasDevice, c->cfg.device);

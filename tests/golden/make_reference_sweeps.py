@@ -25,6 +25,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from subrosadg_b200 import mesh as M   # noqa: E402
 
 FAR, SLIP, NOSLIP, ISO = M.RIEMANN_FARFIELD, M.ADIABATIC_SLIP_WALL, M.ADIABATIC_NONSLIP_WALL, M.ISOTHERMAL_NONSLIP_WALL
+INFLOW, OUTFLOW = M.VELOCITY_INFLOW, M.PRESSURE_OUTFLOW
+WC = dict(eos=1, c0=10.0, rho0=1.0)   # EquationOfState<WeakCompressibleFluid> of the incompressible examples
 WARP2 = lambda x: x + 0.03 * np.sin(np.pi * x[:, ::-1])
 WARP3 = lambda x: x + 0.02 * np.sin(np.pi * np.roll(x, 1, axis=1))
 
@@ -61,11 +63,35 @@ def cases():
          M.annulus(6, 16, geom_order=3, stretch=1.2, tri_rings=3, **ann), (0.05, 1.6), 0.0, 2, 0.2),
         ("av_hex_p2_oblique_jump_roe", 12, dict(p=2, conv_flux=3, rk=2, av_tolerance=1.0, av_factor=1.0),
          M.box(3, (4, 3, 3), 0.0, 1.0, periodic_axes=(2,), phys_bc={1: FAR, 2: FAR, 3: SLIP, 4: SLIP}), (0.05, 0.0), 0.0, 2, 0.2),
+        # the incompressible (weakly compressible) control types of examples/*_incns.cpp / shearlayer_2d_inceuler.cpp
+        ("inc_quad_p3_ns_lf_br2_inflow_outflow", 13, dict(WC, p=3, model=3, transport=1, mu=mu, conv_flux=1, visc_flux=2, rk=2),
+         M.box(2, (5, 4), 0.0, 1.0, geom_order=2, warp=WARP2, phys_bc={1: INFLOW, 2: OUTFLOW, 3: ISO, 4: NOSLIP}), [0.3, 0.05, 0.0], 0.02, 3, 0.3),
+        ("inc_quad_p1_ns_exact_boussinesq_cavity", 14, dict(WC, p=1, model=3, transport=1, mu=mu, conv_flux=4, visc_flux=2, source=1, beta=0.5, t_ref=1.0, rk=2),
+         M.box(2, (6, 5), 0.0, 1.0, phys_bc={1: ISO, 2: ISO, 3: NOSLIP, 4: NOSLIP}), [0.1, 0.05, 0.0], 0.02, 4, 0.3),
+        ("inc_quad_p1_euler_lf_periodic", 15, dict(WC, p=1, model=2, conv_flux=1, rk=2), M.periodic_box(2, 6), [0.3, -0.2, 0.0], 0.05, 4, 0.5),
+        ("inc_hex_p1_ns_lf_br2", 16, dict(WC, p=1, model=3, transport=1, mu=mu, conv_flux=1, visc_flux=2, rk=2),
+         M.box(3, (3, 3, 2), 0.0, 1.0, phys_bc={1: INFLOW, 2: OUTFLOW, 3: NOSLIP, 4: SLIP, 5: ISO, 6: NOSLIP}), [0.3, 0.05, 0.1], 0.02, 3, 0.3),
+        ("inc_hex_p3_ns_exact_boussinesq", 17, dict(WC, p=3, model=3, transport=1, mu=mu, conv_flux=4, visc_flux=2, source=1, beta=0.5, t_ref=1.0, rk=2),
+         M.box(3, (3, 3, 2), 0.0, 1.0, geom_order=2, warp=WARP3, periodic_axes=(1,), phys_bc={1: ISO, 2: ISO, 5: NOSLIP, 6: NOSLIP}), [0.1, 0.05, 0.1], 0.02, 2, 0.3),
+        ("inc_quad_p4_ns_exact_periodic", 18, dict(WC, p=4, model=3, transport=1, mu=mu, conv_flux=4, visc_flux=2, rk=2), M.periodic_box(2, 4), [0.3, -0.2, 0.0], 0.05, 2, 0.3),
+        # the remaining compressible control types of examples/ (sphere_3d_cns = the north-star kernel family; blasius_3d / delta_3d_cns; rae2822_2d_cns;
+        # khinstability_2d_ceuler; sod_1d / shuosher_1d_ceuler)
+        ("hex_p3_ns_br2_constant_curved", 19, dict(p=3, model=1, transport=1, mu=mu, conv_flux=2, visc_flux=2, rk=2),
+         M.box(3, (3, 3, 2), 0.0, 1.0, geom_order=2, warp=WARP3, phys_bc={1: FAR, 2: FAR, 3: NOSLIP, 4: FAR, 5: ISO, 6: SLIP}), [0.3, 0.1, 0.05], 0.02, 2, 0.3),
+        ("hex_p1_ns_br2_constant", 20, dict(p=1, model=1, transport=1, mu=mu, conv_flux=2, visc_flux=2, rk=2),
+         M.box(3, (4, 3, 3), 0.0, 1.0, phys_bc={1: FAR, 2: FAR, 3: NOSLIP, 4: FAR, 5: FAR, 6: FAR}), [0.3, 0.1, 0.05], 0.02, 3, 0.3),
+        ("quad_p5_ns_br2_sutherland", 21, dict(p=5, model=1, transport=2, mu=mu, conv_flux=2, visc_flux=2, rk=2),
+         M.box(2, (3, 3), 0.0, 1.0, geom_order=2, warp=WARP2, phys_bc={1: FAR, 2: FAR, 3: NOSLIP, 4: FAR}), [0.5, 0.1, 0.0], 0.02, 2, 0.3),
+        ("av_quad_p5_oblique_jump", 22, dict(p=5, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=2.0),
+         M.box(2, (6, 5), 0.0, 1.0, phys_bc={1: FAR, 2: FAR, 3: SLIP, 4: SLIP}), (0.04, 0.0), 0.0, 2, 0.2),
+        ("av_line_p3_sod", 23, dict(p=3, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=1.0),
+         M.box(1, (24,), 0.0, 1.0, phys_bc={1: FAR, 2: FAR}), (0.01, 0.0), 0.0, 4, 0.2),
     ]
 
 
-def fields(dim, vel, amp):
+def fields(dim, vel, amp, cfg=None):
     """the analytic fields compiled into oracle/ref_sweeps.cpp (fieldAt / jumpAt): initial condition and (amp = 0) boundary values"""
+    weak = bool(cfg) and cfg.get("eos", 0) == 1
     if isinstance(vel, tuple):          # shock-capturing cases: (jump width, jump radius)
         width, radius = vel
 
@@ -88,6 +114,8 @@ def fields(dim, vel, amp):
             if dim >= 3:
                 s = s * np.cos(np.pi * x[..., 2])
             g = 1.0 + a * s
+            if weak:
+                return np.stack([cfg["rho0"] * (1.0 + 0.01 * a * s)] + [vel[d] * g for d in range(dim)] + [1.0 + 2.0 * a * s], axis=-1)
             return np.stack([1.4 * g] + [vel[d] * g + 0.0 * s for d in range(dim)] + [1.0 * g], axis=-1)
         return f
     return make(amp), make(0.0)
@@ -110,7 +138,8 @@ def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl):
     xf, nrm, fjw = (np.ascontiguousarray(O.face_geometry(w)) for w in range(3))
     shock = isinstance(vel, tuple)
     params = np.array([2.5, 25.0 / 14.0, cfg.get("mu", 0.0), amp] + ([0.0, 0.0, 0.0, vel[0], vel[1], cfg["av_tolerance"], cfg["av_factor"]] if shock
-                      else [vel[0], vel[1], vel[2], 0.0, 0.0, 0.0, 1.0]))
+                      else [vel[0], vel[1], vel[2], 0.0, 0.0, 0.0, 1.0])
+                      + [cfg.get("c0", 1.0), cfg.get("rho0", 1.0), cfg.get("beta", 0.0), cfg.get("t_ref", 0.0), 1.0 if cfg.get("eos", 0) == 1 else 0.0])
     tags, n_nodes = M.node_tags(mesh) if shock else ({}, 1)
     radius = {t: np.ascontiguousarray(M.inner_radius(mesh, t)) for t in types} if shock else {}
     IP = ctypes.POINTER(ctypes.c_int32) * len(types)

@@ -34,7 +34,8 @@ def test_face_point_permutations_match_reference(built, p):
         assert oracle.face_sequence(oracle.QUADRANGLE, p, rot).tolist() == t[f"Quadrangle/P{p}/case{rot}"], (p, rot)
 
 
-@pytest.mark.parametrize("dim,p", [(2, 1), (2, 2), (2, 3), (3, 1), (3, 2), (3, 3)])
+# P1 quadrangles run on the dense-operator path (Gmsh's seven-point "Gauss2" rule; the line faces there are reversed in place, mixed_path.cu)
+@pytest.mark.parametrize("dim,p", [(2, 2), (2, 3), (3, 1), (3, 2), (3, 3)])
 def test_product_face_point_permutations_match_reference(built, dim, p):
     from subrosadg_b200.solver import Solver
     S = Solver(dict(p=p), M.periodic_box(dim, 3), device=-1)
@@ -141,4 +142,6 @@ def test_product_modal_convention_equals_oracle(built):
             S = Solver(dict(p=p), m, device=-1)
             O = oracle.Oracle(dict(p=p), m)
             s = S.sizes(et)
-            assert np.abs(S.debug_plan(4).reshape(s.Nq, s.Nb) - O.table(et, 0)).max() < 1e-15
+            dense = dim == 2 and p == 1      # P1 quadrangles: seven-point rule, dense-operator tables (100 * type + 0 = Phi)
+            assert s.Nq == (7 if dense else (p + 1) ** dim)
+            assert np.abs(S.debug_plan(100 * et if dense else 4).reshape(s.Nq, s.Nb) - O.table(et, 0)).max() < 1e-15

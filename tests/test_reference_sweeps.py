@@ -56,7 +56,7 @@ def test_oracle_reproduces_the_reference_solver(case):
     gold = GOLD[name]
     for t, b in mesh.blocks.items():
         assert abs(float(np.asarray(b["coords"]).sum()) - gold["mesh_checksum"][str(t)]) < 1e-9, "the mesh producer changed: regenerate the golden file"
-    ic, bc = gen.fields(mesh.dim, vel, amp)
+    ic, bc = gen.fields(mesh.dim, vel, amp, cfg)
     O = oracle.Oracle(dict(cfg, accurate=0), mesh)      # the reference's plain-double M^-1 apply
     O.initialize(ic, bc)
     initial = {t: O.get_state(t) for t in O.types}
@@ -75,7 +75,7 @@ def test_cuda_path_reproduces_the_reference_solver(built, case):
     from subrosadg_b200.solver import Solver
     name, _, cfg, mesh, vel, amp, steps, cfl = case
     gold = GOLD[name]
-    ic, bc = gen.fields(mesh.dim, vel, amp)
+    ic, bc = gen.fields(mesh.dim, vel, amp, cfg)
     S = Solver(dict(cfg), mesh, device=0)
     S.initializeSolver(ic, bc)
     initial = {t: S.get_state(t) for t in S.types}
