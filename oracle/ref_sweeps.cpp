@@ -25,6 +25,7 @@
 #include "Solver/SourceTerm.cpp"
 #include "Solver/SpatialDiscrete.cpp"
 #include "Solver/TimeIntegration.cpp"
+#include "View/RawBinary.cpp"   // Solver<SC>::writeRawBinary + RawBinaryCompress::write (:42-57, :75-191); linked against the system's libzstd.so.1
 
 using namespace SubrosaDG;
 
@@ -37,6 +38,7 @@ struct Params {
 };
 Params g_params;
 thread_local std::string g_error;
+std::string g_raw_path;   // non-empty: the reference's writeRawBinary writes its .zst file there after the last step
 
 // the analytic fields of tests/cases.py::ic_perturbed_freestream / bc_freestream (free stream rho = 1.4, T = 1, velocity vel, times a
 // smooth perturbation 1 + amp sin(pi x) cos(pi y) [cos(pi z)]; the boundary callback returns the unperturbed free stream)
@@ -206,6 +208,10 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
     solver.stepSolver(mesh, source_term, physical_model, boundary_condition, time_integration);
     time_integration.iteration_ = i;
   }
+  if (!g_raw_path.empty()) {   // System::solve at an output step, SystemControl.cpp:178-183
+    solver.writeRawBinary(mesh, g_raw_path);
+    solver.write_raw_binary_future_.get();
+  }
   for (int v = 0; v < SC::kConservedVariableNumber; v++) relerr_out[v] = solver.relative_error_(v);
   if (node_av_out) for (int k = 0; k < node_number; k++) node_av_out[k] = solver.node_artificial_viscosity_(k);
   for (int k = 0; k < n_blocks; k++) {
@@ -241,6 +247,7 @@ using NS = CompresibleNSVariable<ThermodynamicModelEnum::Constant, EquationOfSta
 extern "C" {
 
 const char* ref_sweeps_error() { return g_error.c_str(); }
+void ref_sweeps_set_raw_path(const char* path) { g_raw_path = path ? path : ""; }
 
 // case_id selects one of the compiled control types (tests/golden/make_reference_sweeps.py lists them with their meshes);
 // params = {cp, cv, mu, amp, vel[3], jump_width, jump_radius, av_tolerance, av_factor, c0, rho0, beta, t_ref, weak}; node tags (0-based) / inner radii for the shock cases; blocks / faces: see BlockIn / FacesIn (faces in the order and meaning of sdg_set_faces)

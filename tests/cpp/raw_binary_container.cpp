@@ -1,9 +1,11 @@
 // The raw/<prefix>_<step>.zst container of include/SubrosaDG_b200/SubrosaDG.hpp (RawBinaryCompress, after src/View/RawBinary.cpp:42-74):
 // every payload is written with libzstd (as the reference does) and with the self-contained raw-block frame writer, and every file is
 // read back with both readers.  usage: raw_binary_container DIR SIZE...   (payload = SIZE bytes of a fixed pattern; files DIR/{lib,raw}_SIZE.zst)
+//                                        raw_binary_container decode FILE OUT   (the payload of a file written elsewhere, e.g. by the reference)
 #include "SubrosaDG_b200/SubrosaDG.hpp"
 
 #include <cstdlib>
+#include <fstream>
 #include <iostream>
 
 static std::string pattern(std::size_t n) {
@@ -20,6 +22,15 @@ static std::string pattern(std::size_t n) {
 int main(int argc, char* argv[]) {
   using SubrosaDG::RawBinaryCompress;
   if (argc < 3) return 2;
+  if (std::string(argv[1]) == "decode") {   // raw_binary_container decode FILE OUT: RawBinaryCompress::read of a file someone else wrote
+    if (argc < 4) return 2;
+    std::stringstream back;
+    RawBinaryCompress::read(argv[2], back);
+    const std::string payload = back.str();
+    std::ofstream(argv[3], std::ios::binary).write(payload.data(), static_cast<std::streamsize>(payload.size()));
+    std::cout << "decoded " << payload.size() << " bytes\n";
+    return 0;
+  }
   const std::filesystem::path dir(argv[1]);
   const bool have_lib = RawBinaryCompress::zstd().ok();
   std::cout << "libzstd " << (have_lib ? "found" : "absent") << "\n";

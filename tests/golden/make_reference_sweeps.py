@@ -31,6 +31,11 @@ WARP2 = lambda x: x + 0.03 * np.sin(np.pi * x[:, ::-1])
 WARP3 = lambda x: x + 0.02 * np.sin(np.pi * np.roll(x, 1, axis=1))
 
 
+# cases whose final state the reference's Solver::writeRawBinary (RawBinary.cpp:42-57,75-191) also writes to a committed .zst file:
+# BR2 (boundary parents carry volume + lift of that face), BR1, and a shock-capturing run on a hybrid mesh (two element types, viscosity tail)
+RAW_FILES = ("quad_p3_ns_br2_sutherland", "quad_p2_ns_br1_roe_heun_periodic", "av_hybrid_p3_radial_jump", "hex_p2_ns_br2_constant")
+
+
 def cases():
     """(name, compiled control type in oracle/ref_sweeps.cpp, oracle / product configuration, mesh, free-stream velocity, amplitude, steps, cfl).
     Shock-capturing cases carry av_tolerance / av_factor in the configuration and jump = (width, radius) instead of a velocity."""
@@ -121,7 +126,7 @@ def fields(dim, vel, amp, cfg=None):
     return make(amp), make(0.0)
 
 
-def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl):
+def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl, raw_path=None):
     import oracle
     O = oracle.Oracle(dict(cfg), mesh)          # geometry factors only (never stepped here)
     types = O.types
@@ -140,7 +145,7 @@ def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl):
     params = np.array([2.5, 25.0 / 14.0, cfg.get("mu", 0.0), amp] + ([0.0, 0.0, 0.0, vel[0], vel[1], cfg["av_tolerance"], cfg["av_factor"]] if shock
                       else [vel[0], vel[1], vel[2], 0.0, 0.0, 0.0, 1.0])
                       + [cfg.get("c0", 1.0), cfg.get("rho0", 1.0), cfg.get("beta", 0.0), cfg.get("t_ref", 0.0), 1.0 if cfg.get("eos", 0) == 1 else 0.0])
-    tags, n_nodes = M.node_tags(mesh) if shock else ({}, 1)
+    tags, n_nodes = M.node_tags(mesh) if (shock or raw_path) else ({}, 1)     # Mesh::node_number_ sizes the tail of the raw file
     radius = {t: np.ascontiguousarray(M.inner_radius(mesh, t)) for t in types} if shock else {}
     IP = ctypes.POINTER(ctypes.c_int32) * len(types)
     node_av = np.zeros(n_nodes)
@@ -148,6 +153,7 @@ def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl):
     dt = ctypes.c_double(0)
     tarr = np.array(types, dtype=np.int32); narr = np.array([sizes[t].n for t in types], dtype=np.int32)
     lib.ref_sweeps.restype = ctypes.c_int
+    lib.ref_sweeps_set_raw_path(raw_path.encode() if raw_path else None)   # the reference's Solver::writeRawBinary after the last step
     lib.ref_sweeps_error.restype = ctypes.c_char_p
     rc = lib.ref_sweeps(case_id, dp(params), len(types), ip(tarr), ip(narr), arr(0), arr(1), arr(2), arr(3), arr(4), int(f["n_int"]), int(f["n_bnd"]), FI,
                         dp(xf), dp(nrm), dp(fjw), int(steps), ctypes.c_double(cfl), ctypes.c_double(0.0), PP(*[dp(coef[t]) for t in types]), dp(relerr),
@@ -167,6 +173,11 @@ def main():
         assert all(np.isfinite(c).all() for c in coef.values()), name
         if node_av is not None:
             assert node_av.max() > 0.0 and (node_av == 0.0).any(), name      # the case switches the viscosity on somewhere, not everywhere
+        if name in RAW_FILES:     # the reference's own writer and the system's libzstd: tests/golden/reference_raw_<name>.zst
+            raw = os.path.join(HERE, f"reference_raw_{name}.zst")
+            again, _, _, _ = run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl, raw_path=raw)
+            assert all(np.array_equal(again[t], coef[t]) for t in coef)
+            print(f"  raw file {raw} ({os.path.getsize(raw)} bytes)")
         out.append(dict(name=name, steps=steps, cfl=cfl, dt=dt, relative_error=relerr.tolist(), node_artificial_viscosity=None if node_av is None else node_av.tolist(),
                         initial={str(t): c.ravel().tolist() for t, c in coef0.items()}, state={str(t): c.ravel().tolist() for t, c in coef.items()},
                         mesh_checksum={str(t): float(np.asarray(b["coords"]).sum()) for t, b in mesh.blocks.items()}))

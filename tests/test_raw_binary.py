@@ -106,6 +106,23 @@ def test_container_both_writers_both_readers(built, tmp_path):
             assert os.path.getsize(tmp_path / f"lib_{n}.zst") < os.path.getsize(tmp_path / f"raw_{n}.zst")
 
 
+def test_host_reader_decodes_files_written_by_the_reference(built, tmp_path):
+    """RawBinaryCompress::read of the C++ host side (what InitialConditionEnum::LastStep / SpecificFile call) on the .zst files the REFERENCE'S
+    own Solver::writeRawBinary wrote with libzstd (tests/golden/reference_raw_*.zst, tests/golden/make_reference_sweeps.py)"""
+    if _libzstd() is None:
+        pytest.skip("compressed blocks need libzstd.so.1, as in the reference")
+    exe = compile_cpp(os.path.join(ROOT, "tests", "cpp", "raw_binary_container.cpp"), tmp_path / "container")
+    files = sorted(f for f in os.listdir(os.path.join(ROOT, "tests", "golden")) if f.startswith("reference_raw_") and f.endswith(".zst"))
+    assert len(files) >= 4
+    for f in files:
+        src = os.path.join(ROOT, "tests", "golden", f)
+        r = subprocess.run([str(exe), "decode", src, str(tmp_path / "payload.bin")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        cap, want = read_raw_binary(src)
+        assert open(tmp_path / "payload.bin", "rb").read() == want and len(want) % 8 == 0 and cap == compress_bound(len(want))
+        assert os.path.getsize(src) - 8 < len(want)        # really compressed: the reference's ZSTD_compress at level 1
+
+
 # ---- payload (RawBinary.cpp:75-191) -------------------------------------------------------------------------------------------------------
 def node_number(mesh):
     """Mesh::node_number_ as the C++ host side counts it: distinct coordinate tuples over all blocks"""

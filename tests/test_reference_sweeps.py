@@ -85,3 +85,76 @@ def test_cuda_path_reproduces_the_reference_solver(built, case):
     _check(state, initial, dt, relerr, gold, S.types, {t: initial[t].shape for t in S.types}, 1e-10, _projection_tolerance(cfg, mesh))   # 1e-10: BASELINE.json, fields after N steps
     if gold["node_artificial_viscosity"] is not None:
         _check_viscosity(S.node_artificial_viscosity(), gold)
+
+
+# ---- raw files written by the reference's own Solver::writeRawBinary + the system's libzstd (RawBinary.cpp:42-57,75-191) ----------------------
+RAW_CASES = [c for c in CASES if c[0] in gen.RAW_FILES]
+
+
+def _reference_raw_file(case, sizes):
+    """(capacity header, state, gradient blocks, boundary rows, viscosity tail) of tests/golden/reference_raw_<name>.zst, decoded by the
+    restated reader of tests/test_raw_binary.py; the modal state in the file must be the golden state to the last bit."""
+    from test_raw_binary import compress_bound, parse_payload, read_raw_binary
+    name, _, cfg, mesh, *_ = case
+    cap, buf = read_raw_binary(os.path.join(HERE, "golden", f"reference_raw_{name}.zst"))
+    assert cap == compress_bound(len(buf))           # the header the reference writes: ZSTD_compressBound(payload size)
+    ns = cfg.get("model", 0) in (1, 3)
+    U, G, bnd, av = parse_payload(buf, mesh, {t: sizes[t].Nb for t in sizes}, ns)
+    gold = GOLD[name]
+    for t in sizes:
+        assert np.array_equal(U[t].ravel(), np.asarray(gold["state"][str(t)])), "the file and the golden state come from the same reference run"
+    if gold["node_artificial_viscosity"] is None:
+        assert np.all(av == 0.0)
+    else:
+        assert np.array_equal(av, np.asarray(gold["node_artificial_viscosity"]))
+    return U, G, bnd, av, ns
+
+
+def _check_raw(file, state, gradient, boundary_gradient, node_av, types, tol):
+    """what a solver would write (its state, gradient coefficients, boundary-parent rows, node viscosity) against the reference-written file"""
+    U, G, bnd, av, ns = file
+    for t in types:
+        assert cases.rel_l2(state[t], U[t]) < tol
+        if ns:
+            assert cases.rel_l2(gradient[t], G[t]) < 10 * tol, f"type {t}: variable_gradient_basis_function_coefficient_ {cases.rel_l2(gradient[t], G[t]):.3e}"
+    at = 0
+    for (t, e, lf, u_row, g_row) in bnd:
+        assert cases.rel_l2(state[t][e], u_row) < tol
+        if ns:
+            mine = boundary_gradient[at:at + g_row.size]
+            at += g_row.size
+            scale = max(np.abs(G[t]).max(), 1e-300)      # a row can be all but zero (uniform flow next to a far-field face)
+            assert np.abs(mine - g_row).max() < 10 * tol * scale, f"boundary parent {e} face {lf}: {np.abs(mine - g_row).max() / scale:.3e}"
+    if node_av is not None:
+        assert cases.rel_l2(node_av, av) < 1e-9 if av.max() > 0 else np.all(node_av == 0.0)
+
+
+@pytest.mark.parametrize("case", RAW_CASES, ids=[c[0] for c in RAW_CASES])
+def test_oracle_matches_the_reference_written_raw_file(case):
+    import oracle
+    name, _, cfg, mesh, vel, amp, steps, cfl = case
+    ic, bc = gen.fields(mesh.dim, vel, amp, cfg)
+    O = oracle.Oracle(dict(cfg, accurate=0), mesh)
+    O.initialize(ic, bc)
+    O.step(O.compute_dt(cfl), steps)
+    file = _reference_raw_file(case, {t: O.sizes(t) for t in O.types})
+    ns = file[4]
+    _check_raw(file, {t: O.get_state(t) for t in O.types}, {t: O.gradient_state(t) for t in O.types} if ns else None,
+               O.boundary_gradient_state() if ns else None, O.node_artificial_viscosity() if cfg.get("av_tolerance") is not None else None, O.types, 1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", RAW_CASES, ids=[c[0] for c in RAW_CASES])
+def test_cuda_path_matches_the_reference_written_raw_file(built, case):
+    """the arrays Solver::writeRawBinary of the C++ host side streams out (sdg_get_state, sdg_get_gradient_state,
+    sdg_get_boundary_gradient_state, sdg_get_node_artificial_viscosity) against the file the reference wrote for the same run"""
+    from subrosadg_b200.solver import Solver
+    name, _, cfg, mesh, vel, amp, steps, cfl = case
+    ic, bc = gen.fields(mesh.dim, vel, amp, cfg)
+    S = Solver(dict(cfg), mesh, device=0)
+    S.initializeSolver(ic, bc)
+    S.stepSolver(S.calculateDeltaTime(cfl), steps)
+    file = _reference_raw_file(case, {t: S.sizes(t) for t in S.types})
+    ns = file[4]
+    _check_raw(file, {t: S.get_state(t) for t in S.types}, {t: S.gradient_state(t) for t in S.types} if ns else None,
+               S.boundary_gradient_state() if ns else None, S.node_artificial_viscosity() if cfg.get("av_tolerance") is not None else None, S.types, 1e-10)
