@@ -97,8 +97,10 @@ int sdg_get_state(sdg_ctx* ctx, int32_t type, double* U);
 /* conserved variables / total gradient at the volume quadrature points, [n][Nq][Nv] / [n][Nq][Nv*D] (row var*D+dir) */
 int sdg_get_state_at_quadrature(sdg_ctx* ctx, int32_t type, double* Uq);
 int sdg_get_gradient_at_quadrature(sdg_ctx* ctx, int32_t type, double* Gq);
-/* The gradient blocks Solver::writeRawBinary serialises for Navier-Stokes models (src/View/RawBinary.cpp:75-88, 89-154), evaluated
- * for the CURRENT state:
+/* The gradient blocks Solver::writeRawBinary serialises for Navier-Stokes models (src/View/RawBinary.cpp:75-88, 89-154).  As in the
+ * reference, whose arrays keep what the LAST RK STAGE computed, after sdg_step they are the gradient of the INPUT of the last stage of the
+ * last step (not of the new state; pinned by the reference-written files tests/golden/reference_raw_*.zst); after a state setter, before any
+ * step, they are evaluated for the current state (the reference's arrays are uninitialised at that point):
  *   sdg_get_gradient_state           variable_gradient_basis_function_coefficient_ of every element, [n][Nb][Nv*D] (row var*D+dir);
  *   sdg_get_boundary_gradient_state  per boundary face, in the order of sdg_set_faces, the block written next to the parent's state:
  *                                    BR1 the total gradient, BR2 variable_volume_gradient_ + variable_interface_gradient_ of THAT

@@ -662,6 +662,7 @@ void MixedSolver::step(double dt, int nSteps, double* relErr, float* ms) {
     for (; it < nSteps; it++) { CUDA_OK(cudaGraphLaunch(stepGraph_, stream_)); launches += launchesPerStep_; }
   }
   for (; it < nSteps; it++) oneStep();
+  if (nSteps > 0) gradFromStep_ = true;
   if (ms) { CUDA_OK(cudaEventRecord(e1, stream_)); CUDA_OK(cudaEventSynchronize(e1)); CUDA_OK(cudaEventElapsedTime(ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
   if (relErr) {
     const int ne = totalElements();
@@ -679,7 +680,7 @@ void MixedSolver::step(double dt, int nSteps, double* relErr, float* ms) {
 }
 
 void MixedSolver::residual(int type, double* Rmodal, double* rhsq) {
-  needDevice();
+  needDevice(); gradFromStep_ = false;
   CUDA_OK(cudaSetDevice(device_));
   MixedBlock& B = block(type); const MixedTable& T = B.T;
   Args a; fill(a);
@@ -698,7 +699,7 @@ void MixedSolver::residual(int type, double* Rmodal, double* rhsq) {
 }
 
 void MixedSolver::setStateFromPrimitive(int type, const double* prim) {
-  needDevice();
+  needDevice(); gradFromStep_ = false;
   CUDA_OK(cudaSetDevice(device_));
   MixedBlock& B = block(type); const MixedTable& T = B.T;
   DevBuf<double> tmp; tmp.alloc((size_t)B.n * T.Nq * kNV);
@@ -722,7 +723,7 @@ void MixedSolver::setBoundaryPrimitive(const double* prim) {
 }
 
 void MixedSolver::setState(int type, const double* U) {
-  needDevice(); CUDA_OK(cudaSetDevice(device_));
+  needDevice(); gradFromStep_ = false; CUDA_OK(cudaSetDevice(device_));
   MixedBlock& B = block(type);
   CUDA_OK(cudaMemcpyAsync(B.U.p, U, B.U.n * sizeof(double), cudaMemcpyHostToDevice, stream_));
   CUDA_OK(cudaStreamSynchronize(stream_));
@@ -734,7 +735,7 @@ void MixedSolver::getState(int type, double* U) {
   CUDA_OK(cudaStreamSynchronize(stream_));
 }
 void MixedSolver::setStateDevice(int type, const void* U) {
-  needDevice(); CUDA_OK(cudaSetDevice(device_));
+  needDevice(); gradFromStep_ = false; CUDA_OK(cudaSetDevice(device_));
   MixedBlock& B = block(type);
   CUDA_OK(cudaMemcpyAsync(B.U.p, U, B.U.n * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
 }
@@ -769,7 +770,7 @@ void MixedSolver::gradientAtQuadrature(int type, double* Gq) {
   CUDA_OK(cudaStreamSynchronize(stream_));
 }
 
-// gradient coefficients of the CURRENT state in every block (Gvol, Gtot, Gf)
+// gradient coefficients of the CURRENT state in every block (Gvol, Gtot, Gf); after a step the getters keep what the last stage left (gradFromStep_)
 void MixedSolver::refreshGradient() {
   if (!phys_.ns) throw std::runtime_error("gradient state exists for Navier-Stokes models only");
   Args a; fill(a);
@@ -782,7 +783,7 @@ void MixedSolver::refreshGradient() {
 // RawBinary.cpp:75-88: variable_gradient_basis_function_coefficient_, [n][Nb][Nv*D]
 void MixedSolver::gradientState(int type, double* G) {
   needDevice(); CUDA_OK(cudaSetDevice(device_));
-  refreshGradient();
+  if (!gradFromStep_) refreshGradient();
   MixedBlock& B = block(type);
   CUDA_OK(cudaMemcpyAsync(G, B.Gtot.p, B.Gtot.n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   CUDA_OK(cudaStreamSynchronize(stream_));
@@ -800,7 +801,7 @@ static __global__ void mxBoundaryGradientKernel(const double* __restrict__ base,
 }
 void MixedSolver::boundaryGradientState(double* Gb) {
   needDevice(); CUDA_OK(cudaSetDevice(device_));
-  refreshGradient();
+  if (!gradFromStep_) refreshGradient();
   if (F_.nBnd == 0) return;
   std::vector<int> rec[7]; size_t at = 0;
   for (int b = 0; b < F_.nBnd; b++) {
@@ -878,7 +879,7 @@ void MixedSolver::viewVariable(int type, int variable, double* out) {
   cons.alloc(npts * kNV); res.alloc(npts);
   mxToQuadratureKernel<<<148 * 4, 256, 0, stream_>>>(B.U.p, B.dPhi_.p, B.n, T.Nb, T.Nq, kNV, cons.p); launches++;
   if (phys_.ns) {
-    refreshGradient();
+    if (!gradFromStep_) refreshGradient();
     grad.alloc(npts * kG);
     mxToQuadratureKernel<<<148 * 4, 256, 0, stream_>>>(B.Gtot.p, B.dPhi_.p, B.n, T.Nb, T.Nq, kG, grad.p); launches++;
   }

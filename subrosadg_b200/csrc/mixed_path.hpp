@@ -94,6 +94,9 @@ class MixedSolver {
   double rkc_[3][3];
   cudaStream_t stream_;
   bool hasDevice_, finalized_ = false;
+  // true after a step: Gvol / Gtot / Gf hold what the LAST RK STAGE computed (the gradient of that stage's input) -- what the reference writes
+  // to its raw files (Solver::writeRawBinary after stepSolver); false after a state setter: the getters evaluate the current state first
+  bool gradFromStep_ = false;
   std::unique_ptr<MixedBlock> blk_[7];
   FaceInput F_;
   std::vector<double> xf_, nrm_, fjw_;

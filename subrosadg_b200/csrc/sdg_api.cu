@@ -52,6 +52,10 @@ struct sdg_ctx {
   DevBuf<int> perm, faceRec, chunkOff, chunkInterior, chunkBoundary, sendList, lexOf;
   DevBuf<TensorDev> tab;
   int cur = 0;          // index of the buffer holding the current state
+  // buffer that held the INPUT of the last RK stage of the last completed step (-1: no step since the state was last set).  The reference
+  // writes variable_gradient_basis_function_coefficient_ as the last stage left it (Solver::writeRawBinary after stepSolver,
+  // SystemControl.cpp:166-183): the gradient of that stage's input, not of the new state; the gradient getters evaluate the same state.
+  int gradSrc = -1;
   int latest = 0;       // buffer written last (halo source / target)
   StageFn eulerFn = nullptr, nsGradFn = nullptr, nsStageFn = nullptr;
   DevBuf<double> G, G2;   // NS: gradient field [n][NV*D][NN] (+ scratch for diagnostics)
@@ -90,6 +94,8 @@ namespace {
 bool twoPass(const sdg_ctx* c);
 void needDevice(sdg_ctx* c) { if (!c->hasDevice) throw std::runtime_error("no CUDA device bound to this context (plan-only context); the product has no CPU path"); }
 void needFinal(sdg_ctx* c) { if (!c->finalized) throw std::runtime_error("sdg_finalize has not been called"); }
+// a stage buffer that holds neither the current state nor the input of the last stage (see gradSrc)
+int scratchBuffer(const sdg_ctx* c) { const int a = (c->cur + 1) % 3; return a == c->gradSrc ? (c->cur + 2) % 3 : a; }
 void needType(sdg_ctx* c, int type) { if (!c->haveBlock || c->plan.blk.type != type) throw std::runtime_error("no element block of this type"); }
 
 void fillArgs(sdg_ctx* c, StageArgs& a) {
@@ -199,7 +205,13 @@ void stageLaunch(sdg_ctx* c, int s, int part, cudaStream_t st, int pass = -1) {
   if (c->traceTU) c->traceValid[out] = true;   // the residual pass publishes the traces of the state it writes
 }
 
-void finishStep(sdg_ctx* c) { if (c->nStages == 1) c->cur = (c->cur + 1) % 3; c->latest = c->cur; c->stepCount++; }
+// where the input of the last stage of the step that has just finished lives (see sdg_ctx::gradSrc); `cur` is already rotated
+void markLastStageInput(sdg_ctx* c) {
+  if (c->nStages == 1) { c->gradSrc = (c->cur + 2) % 3; return; }
+  int in, out; stageBuffers(c, c->nStages - 1, in, out);
+  c->gradSrc = in;
+}
+void finishStep(sdg_ctx* c) { if (c->nStages == 1) c->cur = (c->cur + 1) % 3; c->latest = c->cur; c->stepCount++; markLastStageInput(c); }
 
 void reduceNorm(sdg_ctx* c, double* sums) {
   constexpr int kSlices = 128;
@@ -523,7 +535,7 @@ int sdg_set_state_from_primitive(sdg_ctx* c, int32_t type, const double* prim) {
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(c->stream));
   c->scratch.release();
-  c->latest = c->cur; c->traceValid[c->cur] = false;
+  c->latest = c->cur; c->traceValid[c->cur] = false; c->gradSrc = -1;
   SDG_CATCH
 }
 
@@ -583,7 +595,7 @@ int sdg_set_state_device(sdg_ctx* c, int32_t type, const void* U_device) {
   needFinal(c); needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   transformModal(c, (const double*)U_device, c->U[c->cur].p, kToNodal, c->plan.blk.nOwned);
-  c->latest = c->cur; c->traceValid[c->cur] = false;
+  c->latest = c->cur; c->traceValid[c->cur] = false; c->gradSrc = -1;
   SDG_CATCH
 }
 int sdg_get_state_device(sdg_ctx* c, int32_t type, void* U_device) {
@@ -602,7 +614,7 @@ int sdg_set_state(sdg_ctx* c, int32_t type, const double* U) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
   const size_t per = (size_t)c->NV * B.T.NN;
-  const int s = (c->cur + 1) % 3;  // scratch: a stage buffer that holds no live data between steps
+  const int s = scratchBuffer(c);  // scratch: a stage buffer that holds no live data between steps
   c->traceValid[s] = false;
   const int n = B.nOwned;          // ghosts are fed by the halo exchange only (see transformModal)
   seamStreams(c);
@@ -617,7 +629,7 @@ int sdg_set_state(sdg_ctx* c, int32_t type, const double* U) {
     transformModalRange(c, c->U[s].p, c->U[c->cur].p, kToNodal, e0, e1 - e0, c->stream);
   }
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  c->latest = c->cur; c->traceValid[c->cur] = false;
+  c->latest = c->cur; c->traceValid[c->cur] = false; c->gradSrc = -1;
   SDG_CATCH
 }
 int sdg_get_state(sdg_ctx* c, int32_t type, double* U) {
@@ -627,7 +639,7 @@ int sdg_get_state(sdg_ctx* c, int32_t type, double* U) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
   const size_t per = (size_t)c->NV * B.T.NN;
-  const int s = (c->cur + 1) % 3;
+  const int s = scratchBuffer(c);
   c->traceValid[s] = false;
   const int n = B.n;
   seamStreams(c);
@@ -651,7 +663,7 @@ int sdg_get_state_at_quadrature(sdg_ctx* c, int32_t type, double* Uq) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const BlockPlan& B = c->plan.blk;
   const size_t nd = c->stateDoubles();
-  const int s = (c->cur + 1) % 3;
+  const int s = scratchBuffer(c);
   c->traceValid[s] = false;
   seamTransposeKernel<<<148 * 8, 256, 0, c->stream>>>(c->U[c->cur].p, c->U[s].p, c->perm.p, B.n, c->NV, B.T.NN, 1);
   c->launches++;
@@ -661,16 +673,18 @@ int sdg_get_state_at_quadrature(sdg_ctx* c, int32_t type, double* Uq) {
   SDG_CATCH
 }
 
-// Gradient of the CURRENT state at the nodes, on the device: all lifts (faceSel < 0: variable_gradient_basis_function_coefficient_)
+// Gradient at the nodes, on the device, of the state the reference's gradient coefficients belong to -- the input of the last RK stage
+// after a step (gradSrc), the current state otherwise: all lifts (faceSel < 0: variable_gradient_basis_function_coefficient_)
 // or the volume part plus the BR2 lift of local face faceSel only (variable_volume_gradient_ + variable_interface_gradient_(f),
 // RawBinary.cpp:118-135).  Returns the device array [pos][NV*D][NN]; *zslow = node order of the line kernels.  c->G2 must be allocated.
 static const double* nodalGradient(sdg_ctx* c, int faceSel, int* zslow) {
   StageArgs args; fillArgs(c, args);
-  args.Uin = c->U[c->cur].p; args.Ulast = c->U[c->cur].p; args.Uout = c->U[(c->cur + 1) % 3].p;
+  const int src = c->gradSrc >= 0 ? c->gradSrc : c->cur, spare = scratchBuffer(c);
+  args.Uin = c->U[src].p; args.Ulast = c->U[src].p; args.Uout = c->U[spare].p;
   args.Gvol = c->G.p; args.Gout = c->G.p; args.faceSel = c->phys.visc == kBR2 ? faceSel : -1;
   if (c->lineTrace) {   // pass G of the line kernels leaves the TOTAL gradient in G (zeta-slowest node order)
-    ensureTraces(c, c->cur, c->stream);
-    args.TUin = c->TU[c->cur].p; args.TUout = c->TU[(c->cur + 1) % 3].p;
+    ensureTraces(c, src, c->stream);
+    args.TUin = c->TU[src].p; args.TUout = c->TU[spare].p;
     lineBoundary(c, args, -1, c->stream);
   }
   runStage(c, args, -1, c->stream, 0);
@@ -949,6 +963,7 @@ void runSteps(sdg_ctx* c, double dt, int n_steps) {
       c->graphDt = dt; c->graphCur = c->cur;
     }
     for (; it < n_steps; it++) { CUDA_OK(cudaGraphLaunch(c->stepGraph, c->stream)); c->launches += c->graphLaunches; }
+    if (n_steps > 0) markLastStageInput(c);   // a replay runs no host code: a setter may have cleared the mark since the capture
     return;
   }
   for (; it < n_steps; it++) launchOneStep(c);
@@ -1003,6 +1018,7 @@ int sdg_residual(sdg_ctx* c, int32_t type, double* Rmodal, double* rhsq) {
   const size_t nd = c->stateDoubles();
   const int a = (c->cur + 1) % 3, b = (c->cur + 2) % 3;
   c->traceValid[a] = c->traceValid[b] = false;   // both scratch buffers are overwritten below
+  c->gradSrc = -1;
   if (c->phys.av) avUpdate(c, c->cur, c->stream);   // parity hook: the viscosity of the CURRENT state
   for (int mode = 1; mode <= 2; mode++) {
     double* host = mode == 1 ? rhsq : Rmodal;

@@ -33,7 +33,8 @@ WARP3 = lambda x: x + 0.02 * np.sin(np.pi * np.roll(x, 1, axis=1))
 
 # cases whose final state the reference's Solver::writeRawBinary (RawBinary.cpp:42-57,75-191) also writes to a committed .zst file:
 # BR2 (boundary parents carry volume + lift of that face), BR1, and a shock-capturing run on a hybrid mesh (two element types, viscosity tail)
-RAW_FILES = ("quad_p3_ns_br2_sutherland", "quad_p2_ns_br1_roe_heun_periodic", "av_hybrid_p3_radial_jump", "hex_p2_ns_br2_constant")
+RAW_FILES = ("quad_p3_ns_br2_sutherland", "quad_p2_ns_br1_roe_heun_periodic", "av_hybrid_p3_radial_jump", "hex_p2_ns_br2_constant", "hybrid_p3_ns_br2_sutherland",
+             "hex_p3_ns_br2_constant_curved")
 
 
 def cases():
