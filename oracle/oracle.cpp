@@ -1075,31 +1075,13 @@ int orc_get_boundary_gradient_state(void* h, double* out) {
   }
   ORC_CATCH
 }
-// ViewVariable::get (VariableConvertor.cpp:754-872) at the volume quadrature points, n x Nq.  variable = ViewVariableEnum value.  The
-// switch of the reference falls through where a variable does not exist for the equation set; `goto`-free restatement of that chain.
-int orc_view_variable(void* h, int type, int variable, double* out) {
-  ORC_TRY
-  Oracle& O = *(Oracle*)h;
-  if (!O.blk[type]) throw std::runtime_error("oracle: no such element block");
-  ElemBlock& B = *O.blk[type]; const Sizes s = sizes(O, B); const ElemTable& T = B.tab; const Phys& P = O.P;
-  const int D = s.D, Nv = s.Nv, G = s.G;
-  const bool ns = P.ns();
-  for (int e = 0; e < B.n; e++) {
-    std::vector<double> uq((size_t)Nv * s.Nq), gq((size_t)G * s.Nq, 0.0);
-    gemmNT(Nv, s.Nq, s.Nb, 1.0, &B.coef[(size_t)e * Nv * s.Nb], Nv, T.Phi.data(), s.Nq, 0.0, uq.data(), Nv);
-    if (ns) gemmNT(G, s.Nq, s.Nb, 1.0, &B.gcoef[(size_t)e * G * s.Nb], G, T.Phi.data(), s.Nq, 0.0, gq.data(), G);
-    for (int q = 0; q < s.Nq; q++) {
-      Var v;
-      for (int k = 0; k < Nv; k++) v.cons[k] = uq[(size_t)q * Nv + k];
-      compFromCons(P, v);
-      double gp[kMaxD * kMaxV] = {0};
-      if (ns) primGradFromConsGrad(P, v, &gq[(size_t)q * G], gp);
+// ViewVariable::get (VariableConvertor.cpp:754-872) at one point: computational variables, primitive gradient (zeros for Euler models), the
+// interpolated artificial viscosity.  The switch of the reference falls through where a variable does not exist for the equation set.
+static double viewValue(const Phys& P, int D, bool ns, const Var& v, const double* gp, double eps, int variable) {
       const double rho = v.comp[0], p = v.comp[D + 2];
       double v2 = 0; for (int d = 0; d < D; d++) v2 += v.comp[1 + d] * v.comp[1 + d];
       const double c = P.eos == kIdealGas ? std::sqrt(1.4 * p / rho) : P.c0;           // PhysicalModel.cpp:51-54,74-77
       auto dU = [&](int comp, int dir) { return gp[(1 + comp) * D + dir]; };
-      double eps = 0.0;
-      if (O.av) for (int k = 0; k < T.nbasic; k++) eps += T.NodalQ[(size_t)k * s.Nq + q] * B.avElem[(size_t)e * T.nbasic + k];
       double r = 0.0;
       int w = variable;
       for (;;) {
@@ -1129,6 +1111,30 @@ int orc_view_variable(void* h, int type, int variable, double* out) {
         }
         r = 0.0; break;
       }
+      return r;
+}
+// ViewVariable::get (VariableConvertor.cpp:754-872) at the volume quadrature points, n x Nq.  variable = ViewVariableEnum value.  The
+// switch of the reference falls through where a variable does not exist for the equation set; `goto`-free restatement of that chain.
+int orc_view_variable(void* h, int type, int variable, double* out) {
+  ORC_TRY
+  Oracle& O = *(Oracle*)h;
+  if (!O.blk[type]) throw std::runtime_error("oracle: no such element block");
+  ElemBlock& B = *O.blk[type]; const Sizes s = sizes(O, B); const ElemTable& T = B.tab; const Phys& P = O.P;
+  const int D = s.D, Nv = s.Nv, G = s.G;
+  const bool ns = P.ns();
+  for (int e = 0; e < B.n; e++) {
+    std::vector<double> uq((size_t)Nv * s.Nq), gq((size_t)G * s.Nq, 0.0);
+    gemmNT(Nv, s.Nq, s.Nb, 1.0, &B.coef[(size_t)e * Nv * s.Nb], Nv, T.Phi.data(), s.Nq, 0.0, uq.data(), Nv);
+    if (ns) gemmNT(G, s.Nq, s.Nb, 1.0, &B.gcoef[(size_t)e * G * s.Nb], G, T.Phi.data(), s.Nq, 0.0, gq.data(), G);
+    for (int q = 0; q < s.Nq; q++) {
+      Var v;
+      for (int k = 0; k < Nv; k++) v.cons[k] = uq[(size_t)q * Nv + k];
+      compFromCons(P, v);
+      double gp[kMaxD * kMaxV] = {0};
+      if (ns) primGradFromConsGrad(P, v, &gq[(size_t)q * G], gp);
+      double eps = 0.0;
+      if (O.av) for (int k = 0; k < T.nbasic; k++) eps += T.NodalQ[(size_t)k * s.Nq + q] * B.avElem[(size_t)e * T.nbasic + k];
+      const double r = viewValue(P, D, ns, v, gp, eps, variable);
       out[(size_t)e * s.Nq + q] = r;
     }
   }
@@ -1235,6 +1241,17 @@ int orc_physics(const int32_t* cfg, const double* params, int what, int bc, int 
       convRawFlux(P, V.comp, o + NC + Nv);
       for (int k = 0; k < Nv; k++) o[NC + Nv + G + k] = 0.0;
       if (P.source != kSourceNone) sourceTerm(P, V.comp, o + NC + Nv + G);
+    } else if (what == 4) {   // the 22 ViewVariableEnum values at one point: in = cons[Nv], conserved gradient[G], artificial viscosity
+      const double* a = in + (size_t)i * (Nv + G + 1); double* o = out + (size_t)i * 22;
+      Var V;
+      for (int k = 0; k < Nv; k++) V.cons[k] = a[k];
+      compFromCons(P, V);
+      double gp[kMaxD * kMaxV] = {0};
+      if (P.ns()) primGradFromConsGrad(P, V, a + Nv, gp);
+      for (int w = 0; w < 22; w++) {
+        const bool needs3 = w == 12 || w == 15 || w == 16 || w == 17 || w == 21, needs2 = w == 11 || w == 14 || w == 18 || w == 20;
+        o[w] = ((needs3 && D < 3) || (needs2 && D < 2)) ? 0.0 : viewValue(P, D, P.ns(), V, gp, a[Nv + G], w);
+      }
     } else {
       throw std::runtime_error("orc_physics: bad selector");
     }

@@ -11,6 +11,7 @@
 // restated there as plain loops in expression order, compiled with -ffp-contract=off.
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 
 #include "Solver/BoundaryCondition.cpp"
 #include "Solver/ConvectiveFlux.cpp"
@@ -168,6 +169,27 @@ int run(const Params& p, int what, int bc, int n, const double* in, double* out)
         FluxNormalVariable<SC> s;
         st.calculateSourceTerm(pm, V, s, 0);
         for (int k = 0; k < NV; k++) o[NC + NV + NV * D + k] = s.normal_variable_(k);
+      }
+    } else if (what == 4) {
+      // ViewVariable::get (VariableConvertor.cpp:754-872) as ElementViewSolver::calcluateElementViewVariable fills it (RawBinary.cpp:193-240):
+      // in = cons[NV], conserved gradient[NV*D] (row var*D+dir), artificial viscosity; out = the 22 ViewVariableEnum values (0 where the
+      // variable names a direction the dimension does not have: the reference never asks for those)
+      using ET = std::conditional_t<D == 1, LineTrait<3>, std::conditional_t<D == 2, QuadrangleTrait<3>, HexahedronTrait<3>>>;
+      constexpr int NB = ET::kBasisFunctionNumber;
+      const int ni = NV + NV * D + 1, no = 22;
+      const double* a = in + (size_t)i * ni;
+      ViewVariable<ET, SC> vv;
+      for (int c = 0; c < NB; c++) for (int k = 0; k < NV; k++) vv.variable_.conserved_(k, c) = a[k];
+      vv.variable_.calculateComputationalFromConserved(pm);
+      if constexpr (IsNS<SC::kEquationModel>) {
+        for (int c = 0; c < NB; c++) for (int k = 0; k < NV * D; k++) vv.variable_gradient_.conserved_(k, c) = a[NV + k];
+        vv.variable_gradient_.calculatePrimitiveFromConserved(pm, vv.variable_);            // RawBinary.cpp:228-232
+      }
+      for (int c = 0; c < NB; c++) vv.artificial_viscosity_(c) = a[NV + NV * D];
+      double* o = out + (size_t)i * no;
+      for (int w = 0; w < no; w++) {
+        const bool needs3 = w == 12 || w == 15 || w == 16 || w == 17 || w == 21, needs2 = w == 11 || w == 14 || w == 18 || w == 20;
+        o[w] = ((needs3 && D < 3) || (needs2 && D < 2)) ? 0.0 : vv.get(pm, static_cast<ViewVariableEnum>(w), 0);
       }
     } else {
       return 4;

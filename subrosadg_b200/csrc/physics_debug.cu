@@ -9,10 +9,13 @@
 #include "../../include/subrosadg_b200.h"
 #include "dev_util.cuh"
 #include "physics.cuh"
+#include "view_variable.hpp"
+#include <vector>
 
 namespace sdg {
 
-// what: 0 Riemann flux, 1 boundary face point, 2 viscous terms, 3 conversions / raw flux / source (layouts: reference_physics.json "layout")
+// what: 0 Riemann flux, 1 boundary face point, 2 viscous terms, 3 conversions / raw flux / source (layouts: reference_physics.json "layout");
+// what 4 (view variables) runs the product's viewVariableKernel instead, see sdg_debug_physics
 template <int D, int PH>
 __global__ void physicsDebugKernel(PhysParams P, int what, int bc, int n, const double* __restrict__ in, double* __restrict__ out) {
   constexpr int NV = D + 2, NC = D + 3, G = NV * D;
@@ -90,7 +93,7 @@ extern "C" int sdg_debug_physics(const int32_t* cfg, const double* params, int32
   static thread_local std::string err;
   try {
     const int D = cfg[0];
-    if (D < 1 || D > 3 || what < 0 || what > 3 || n < 0) throw std::runtime_error("sdg_debug_physics: bad arguments");
+    if (D < 1 || D > 3 || what < 0 || what > 4 || n < 0) throw std::runtime_error("sdg_debug_physics: bad arguments");
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw std::runtime_error("sdg_debug_physics: no CUDA device — this library has no CPU path");
     PhysParams P{};
@@ -102,6 +105,31 @@ extern "C" int sdg_debug_physics(const int32_t* cfg, const double* params, int32
     P.mu0 = params[2]; P.k0 = params[0] * params[2] / 0.71; P.c0 = params[3]; P.rho0 = params[4]; P.padd = 0.01 * params[4] * params[3] * params[3];
     P.beta = params[5]; P.tref = params[6];
     const int NV = D + 2, NC = D + 3, G = NV * D;
+    if (what == 4) {
+      // the 22 ViewVariableEnum values at caller-supplied points through the product's viewVariableKernel (view_variable.cu):
+      // in = cons[NV], conserved gradient[G], artificial viscosity; 0 where the variable names a direction the dimension lacks
+      std::vector<double> hc((size_t)n * NV), hg((size_t)n * G), he((size_t)n), col((size_t)n);
+      for (int i = 0; i < n; i++) {
+        const double* a = in + (size_t)i * (NV + G + 1);
+        for (int k = 0; k < NV; k++) hc[(size_t)i * NV + k] = a[k];
+        for (int k = 0; k < G; k++) hg[(size_t)i * G + k] = a[NV + k];
+        he[i] = a[NV + G];
+      }
+      DevBuf<double> dc, dg, de, dr;
+      dc.alloc(hc.size() + 1); dg.alloc(hg.size() + 1); de.alloc(he.size() + 1); dr.alloc((size_t)n + 1);
+      CUDA_OK(cudaMemcpy(dc.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(dg.p, hg.data(), hg.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(de.p, he.data(), he.size() * sizeof(double), cudaMemcpyHostToDevice));
+      for (int w = 0; w < 22; w++) {
+        const bool needs3 = w == 12 || w == 15 || w == 16 || w == 17 || w == 21, needs2 = w == 11 || w == 14 || w == 18 || w == 20;
+        if ((needs3 && D < 3) || (needs2 && D < 2)) { for (int i = 0; i < n; i++) out[(size_t)i * 22 + w] = 0.0; continue; }
+        if (n > 0) launchViewVariable(D, P, w, (size_t)n, dc.p, P.ns ? dg.p : nullptr, de.p, dr.p, nullptr);
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpy(col.data(), dr.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) out[(size_t)i * 22 + w] = col[i];
+      }
+      return 0;
+    }
     const int ni = what == 0 ? D + 2 * NV : what == 1 ? D + 2 * NV + G : what == 2 ? D + NV + G : NV;
     const int no = what == 0 ? NV : what == 1 ? NC + 3 * NV + (P.ns ? NC + NV : 0) : what == 2 ? 2 * G + NV : NC + NV + G + NV;
     if (what == 2 && !P.ns) throw std::runtime_error("sdg_debug_physics: viscous terms need a Navier-Stokes model");

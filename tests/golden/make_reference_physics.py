@@ -61,6 +61,7 @@ def main():
         return inp, out
 
     rng = np.random.default_rng(20261017)
+    rng4 = np.random.default_rng(20261018)      # its own stream: the cases above keep their inputs
     n = 8
     mach = np.array([0.1, 0.5, 0.9, 1.6, 2.5, 0.3, 0.7, 0.05])
     for dim in (1, 2, 3):
@@ -107,13 +108,21 @@ def main():
             source = 1 if (dim >= 2 and model in (1, 3)) else 0
             inp, out = call(dim, model, eos, transport, conv, source, 3, 0, L, nc + nv + nv * dim + nv)
             cases.append(dict(name=name, dim=dim, cfg=[dim, model, eos, transport, conv, source], what=3, bc=0, input=inp.tolist(), output=out.tolist()))
+            # what 4: ViewVariable::get, all 22 ViewVariableEnum values (the fall-through chain of its switch included)
+            if conv in (2, 4):
+                grad = 0.5 * rng4.normal(size=(n, nv * dim))
+                eps = np.abs(rng4.normal(size=(n, 1))) * 0.01
+                inp, out = call(dim, model, eos, transport, conv, 0, 4, 0, np.concatenate([L, grad, eps], axis=1), 22)
+                cases.append(dict(name=name, dim=dim, cfg=[dim, model, eos, transport, conv, 0], what=4, bc=0, input=inp.tolist(), output=out.tolist()))
     doc = dict(source="reference sources compiled by oracle/Makefile target `ref` (oracle/ref_physics.cpp, oracle/ref_shim/, oracle/ref_patch.py); "
                       "g++ -std=c++23 -O2 -ffp-contract=off", params=PARAMS,
                layout={"0": "in: normal[D], consL[NV], consR[NV]; out: Riemann flux[NV]",
                        "1": "in: normal[D], consL[NV], user primitive[NV], conserved gradient[NV*D]; out: boundary comp[D+3], volCons[NV], intCons[NV], "
                             "convective boundary flux[NV], NS: interior comp after modifyBoundaryVariable[D+3], averaged viscous flux[NV]",
                        "2": "in: normal[D], cons[NV], conserved gradient[NV*D]; out: primitive gradient[NV*D], raw viscous flux[NV*D], normal viscous flux[NV]",
-                       "3": "in: cons[NV]; out: comp[D+3], primitive[NV], raw convective flux[NV*D], source[NV]"},
+                       "3": "in: cons[NV]; out: comp[D+3], primitive[NV], raw convective flux[NV*D], source[NV]",
+                       "4": "in: cons[NV], conserved gradient[NV*D], artificial viscosity; out: ViewVariable::get for the 22 ViewVariableEnum values "
+                            "(0 where the variable names a direction the dimension lacks)"},
                cases=cases)
     path = os.path.join(HERE, "reference_physics.json")
     with open(path, "w") as f:

@@ -48,6 +48,8 @@ def test_golden_file_covers_the_physics_rows():
     assert any(c["what"] == 2 and c["cfg"][3] == 2 for c in GOLD["cases"])         # P5: Sutherland
     assert any(c["what"] == 3 and c["cfg"][5] == 1 for c in GOLD["cases"])         # P8: Boussinesq
     assert {c["dim"] for c in GOLD["cases"]} == {1, 2, 3}
+    view = [c for c in GOLD["cases"] if c["what"] == 4]              # ViewVariable::get: Euler and NS, ideal gas and weakly compressible, 1-3 D
+    assert {c["cfg"][1] for c in view} == {0, 1, 2, 3} and {c["dim"] for c in view} == {1, 2, 3}
 
 
 @pytest.mark.parametrize("case", GOLD["cases"], ids=IDS)
