@@ -81,6 +81,10 @@ __device__ __forceinline__ void bulkPrefetchL2(const void* p, unsigned bytes) {
   if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef SDG_NSLS_PF_L1
+#define SDG_NSLS_PF_L1 0      // A/B: the partners' rows of the residual pass requested into L1 instead of L2 at block start: measured 7.83 -> 7.88 ms (Euler 128^3), 10.16 -> 10.34 ms (NS 96^3): off
+#endif
 // The few KB a block waits for before it can do anything (link records, affine metric and face geometry) are fetched into L2 one wave of
 // thread blocks ahead, by the block that currently occupies the slot: unlike the bulk data (measured: fetching THAT ahead only churns
 // L2), they are small enough to stay, and the block-start wait on DRAM (6 % of the stall samples) becomes an L2 hit.
@@ -696,7 +700,11 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
     const int4 lk = sLink[el * 6 + f];
     if (lk.x >= 0) {
       const size_t row = ((size_t)lk.x * 6 + linkLfo(lk.z)) * kRow;
+#if SDG_NSLS_PF_L1
+      prefetchL1(r < 5 ? A.TUin + row + r * 16 : A.TVin + row + (r - 5) * 16);
+#else
       prefetchL2(r < 5 ? A.TUin + row + r * 16 : A.TVin + row + (r - 5) * 16);
+#endif
     }
   }
 
