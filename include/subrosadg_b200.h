@@ -121,6 +121,13 @@ int sdg_set_element_nodes(sdg_ctx* ctx, int32_t type, const int32_t* node_tag, c
 int sdg_get_node_artificial_viscosity(sdg_ctx* ctx, double* out);
 int sdg_get_element_artificial_viscosity(sdg_ctx* ctx, int32_t type, double* out);
 int sdg_update_artificial_viscosity(sdg_ctx* ctx);
+/* Partitioned runs (one context per GPU): the node maximum of Solver::calculateArtificialViscosity -- in the reference the cwiseMax
+ * combine over the TBB threads' node arrays, SpatialDiscrete.cpp:89-108 -- spans the ranks, the one collective on this path.
+ * sdg_step_begin leaves the maximum over the context's OWNED elements in the device array sdg_av_node_buffer returns ([node_number],
+ * node tags global); the caller max-reduces it over the ranks in place (ncclAllReduce, ncclMax) and calls sdg_av_store, which rewrites
+ * variable_artificial_viscosity_ of owned and ghost elements from it. */
+int sdg_av_node_buffer(sdg_ctx* ctx, void** device_nodes, int64_t* count);
+int sdg_av_store(sdg_ctx* ctx, void* stream);
 
 /* ViewVariable::get (src/Solver/VariableConvertor.cpp:754-872) on the device: the scalar field `variable` (ViewVariableEnum value,
  * src/Utils/Enum.cpp: 0 Density, 1 Velocity, 2 Temperature, 3 Pressure, 4 SoundSpeed, 5 MachNumber, 6 Entropy, 7 Vorticity, 9

@@ -131,7 +131,9 @@ void avUpdate(sdg_ctx* c, int buf, cudaStream_t st) {
   CUDA_OK(cudaMemsetAsync(c->avNode.p, 0, c->avNode.n * sizeof(double), st));
   const int blocks = std::min((n * NB + 255) / 256, 148 * 8);
   avNodeMaxKernel<<<blocks, 256, 0, st>>>(c->avE.p, c->avTags.p, n, NB, reinterpret_cast<unsigned long long*>(c->avNode.p));
-  avStoreKernel<<<blocks, 256, 0, st>>>(c->avNode.p, c->avTags.p, n, NB, c->avElem.p);
+  // corner values of EVERY element of the context: between partitions the node array is first completed by a max-reduction over the
+  // ranks (sdg_av_node_buffer / sdg_av_store), and the ghost elements' values enter the right-hand side of the cut faces
+  avStoreKernel<<<std::min((B.n * NB + 255) / 256, 148 * 8), 256, 0, st>>>(c->avNode.p, c->avTags.p, B.n, NB, c->avElem.p);
   c->launches += 3;
   CUDA_OK(cudaGetLastError());
 }
@@ -786,7 +788,6 @@ int sdg_set_element_nodes(sdg_ctx* c, int32_t type, const int32_t* node_tag, con
   if (c->mx) { c->mx->setElementNodes(type, node_tag, inner_radius); return 0; }
   needType(c, type);
   const BlockPlan& B = c->plan.blk;
-  if (B.nGhost > 0) throw std::runtime_error("artificial viscosity is single-GPU (the node maximum is not exchanged between partitions)");
   const int NB = 1 << c->D;
   c->avTagsHost.assign(node_tag, node_tag + (size_t)B.n * NB);
   c->avRadiusHost.assign(inner_radius, inner_radius + B.n);
@@ -827,6 +828,31 @@ int sdg_update_artificial_viscosity(sdg_ctx* c) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   avUpdate(c, c->cur, c->stream);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  SDG_CATCH
+}
+
+// Partitioned runs: the node maximum of Solver::calculateArtificialViscosity (the cwiseMax combine of SpatialDiscrete.cpp:89-108) spans the
+// ranks.  sdg_step_begin leaves each rank's maximum over its OWNED elements in the node array; the caller max-reduces that array over
+// the ranks in place (it lives on the device: NCCL all-reduce) and sdg_av_store rewrites the corner values of owned and ghost elements.
+int sdg_av_node_buffer(sdg_ctx* c, void** device_nodes, int64_t* count) {
+  SDG_TRY
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
+  needFinal(c); needDevice(c);
+  if (!c->phys.av) throw std::runtime_error("artificial viscosity is not enabled");
+  *device_nodes = c->avNode.p; *count = (int64_t)c->avNode.n;
+  SDG_CATCH
+}
+int sdg_av_store(sdg_ctx* c, void* stream) {
+  SDG_TRY
+  if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
+  needFinal(c); needDevice(c);
+  if (!c->phys.av) return 0;
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const BlockPlan& B = c->plan.blk;
+  const int NB = 1 << c->D;
+  avStoreKernel<<<std::min((B.n * NB + 255) / 256, 148 * 8), 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(c->avNode.p, c->avTags.p, B.n, NB, c->avElem.p);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
   SDG_CATCH
 }
 
@@ -1100,7 +1126,7 @@ int sdg_set_halo_send(sdg_ctx* c, int32_t type, int32_t n_send, const int32_t* e
   for (int i = 0; i < n_send; i++) { if (elems[i] < 0 || elems[i] >= B.nOwned) throw std::runtime_error("halo send element out of range"); pos[i] = B.perm[elems[i]]; }
   c->sendList.upload(pos, c->stream);
   c->nSend = n_send;
-  c->sendBuf.alloc((size_t)std::max(n_send, 1) * std::max(haloStride(c, 0), c->phys.ns ? haloStride(c, 1) : 0));
+  c->sendBuf.alloc((size_t)std::max(n_send, 1) * std::max(haloStride(c, 0), twoPass(c) ? haloStride(c, 1) : 0));
   SDG_CATCH
 }
 
@@ -1155,7 +1181,7 @@ int sdg_halo_pack(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
   SDG_TRY
   if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c); needType(c, type);
-  if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
+  if (what != 0 && !(what == 1 && twoPass(c))) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes models and shock-capturing runs)");
   CUDA_OK(cudaSetDevice(c->cfg.device));
   if (what == 0) ensureTraces(c, c->latest, stream ? (cudaStream_t)stream : c->stream);
   if (c->nSend == 0) return 0;
@@ -1172,7 +1198,7 @@ int sdg_halo_buffers_device(sdg_ctx* c, int32_t type, int32_t what, void** send,
   SDG_TRY
   if (c->mx) throw std::runtime_error("not available on the dense-operator (triangle / mixed-type) path: single GPU, sdg_step only");
   needFinal(c); needDevice(c); needType(c, type);
-  if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
+  if (what != 0 && !(what == 1 && twoPass(c))) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes models and shock-capturing runs)");
   const BlockPlan& B = c->plan.blk;
   const int64_t per = haloStride(c, what);
   double* base = haloField(c, what);
@@ -1222,7 +1248,7 @@ int sdg_ipc_connect(sdg_ctx* c, int32_t n_peers, const unsigned char* handles, c
 int sdg_halo_push(sdg_ctx* c, int32_t type, int32_t what, void* stream) {
   SDG_TRY
   needFinal(c); needDevice(c); needType(c, type);
-  if (what != 0 && !(what == 1 && c->phys.ns)) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes only)");
+  if (what != 0 && !(what == 1 && twoPass(c))) throw std::runtime_error("halo field: 0 = state, 1 = volume gradient (Navier-Stokes models and shock-capturing runs)");
   if (c->peerLinks.empty() && c->nSend > 0) throw std::runtime_error("sdg_ipc_connect has not been called");
   CUDA_OK(cudaSetDevice(c->cfg.device));
   if (what == 0) ensureTraces(c, c->latest, stream ? (cudaStream_t)stream : c->stream);

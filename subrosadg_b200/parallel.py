@@ -145,6 +145,15 @@ def partition(mesh: M.Mesh, rank: int, world: int) -> Partition:
     return part
 
 
+def partition_node_data(mesh: M.Mesh, part: Partition):
+    """Shock-capturing runs: (node tags, node number, inner radii) of a partition's owned + ghost elements with the tags of the GLOBAL mesh
+    (Mesh::node_number_, PerElementMesh::node_tag_ / inner_radius_), so that the ranks' node arrays can be max-reduced entry by entry."""
+    tags, n_nodes = M.node_tags(mesh)
+    ids = np.concatenate([np.arange(part.lo, part.hi, dtype=np.int64), np.asarray(part.ghost_global, dtype=np.int64)])
+    t = part.etype
+    return {t: np.ascontiguousarray(tags[t][ids])}, n_nodes, {t: np.ascontiguousarray(M.inner_radius(mesh, t)[ids])}
+
+
 # ---- halo exchange (any torch.distributed backend) ---------------------------------------------------------------------------
 class HaloExchange:
     """One message per peer and direction.  `send` holds the packed states of send_local[peer] for all peers back to
@@ -230,7 +239,9 @@ class DistributedSolver:
         torch.cuda.set_device(self.device)
         self.part = partition(mesh, self.rank, self.world)
         self.etype = self.part.etype
-        self.S = Solver(cfg, self.part.mesh, device=self.device, n_ghost={self.etype: self.part.n_ghost}, reorder=reorder)
+        self.av = cfg.get("av_tolerance") is not None
+        self.S = Solver(cfg, self.part.mesh, device=self.device, n_ghost={self.etype: self.part.n_ghost}, reorder=reorder,
+                        node_data=partition_node_data(mesh, self.part) if self.av else None)
         self.lib = load_library()
         # kernels that read published face traces (P3 hexahedra: Navier-Stokes, Euler through traces) exchange 640-byte trace rows
         self.rows = bool(self.lib.sdg_uses_trace_rows(self.S.h)) and os.environ.get("SDG_HALO_ROWS", "1") != "0"
@@ -345,6 +356,16 @@ class DistributedSolver:
             self._chk(self.lib.sdg_halo_unpack(self.S.h, self.etype, what, ctypes.c_void_p(self.comm.cuda_stream)))   # trace rows: staging -> rows
             self.ev_halo.record(self.comm)
 
+    def _reduce_node_viscosity(self):
+        """The node maximum of Solver::calculateArtificialViscosity across the partitions (the cwiseMax combine of SpatialDiscrete.cpp:89-108):
+        all-reduce(max) of the device node array on the library's stream, then the corner values of owned and ghost elements."""
+        ptr, cnt = ctypes.c_void_p(), ctypes.c_int64()
+        self._chk(self.lib.sdg_av_node_buffer(self.S.h, ctypes.byref(ptr), ctypes.byref(cnt)))
+        nodes = self._view(ptr.value, cnt.value)
+        with self.torch.cuda.stream(self.main):
+            self.dist.all_reduce(nodes, op=self.dist.ReduceOp.MAX, group=self.group)
+        self._chk(self.lib.sdg_av_store(self.S.h, ctypes.c_void_p(self.main.cuda_stream)))
+
     # -- Solver interface ---------------------------------------------------------------------------------------------------
     def initializeSolver(self, ic, bc=None):
         self.S.initializeSolver(ic, bc)
@@ -369,6 +390,8 @@ class DistributedSolver:
         self._exchange(0)                                               # prime: ghosts of the current state
         for it in range(nsteps):
             self._chk(lib.sdg_step_begin(h, ctypes.c_double(dt)))
+            if self.av:
+                self._reduce_node_viscosity()
             for s in range(self.n_stage):
                 for p in range(self.n_pass):
                     self.main.wait_event(self.ev_halo)
@@ -423,7 +446,9 @@ class InProcessCluster:
         self.device = device
         self.parts = [partition(mesh, r, world) for r in range(world)]
         self.etype = self.parts[0].etype
-        self.S = [Solver(cfg, p.mesh, device=device, n_ghost={self.etype: p.n_ghost}, reorder=reorder) for p in self.parts]
+        self.av = cfg.get("av_tolerance") is not None
+        self.S = [Solver(cfg, p.mesh, device=device, n_ghost={self.etype: p.n_ghost}, reorder=reorder, node_data=partition_node_data(mesh, p) if self.av else None)
+                  for p in self.parts]
         self.rows = bool(self.lib.sdg_uses_trace_rows(self.S[0].h)) and os.environ.get("SDG_HALO_ROWS", "1") != "0"
         self.halos = [HaloExchange(p, rows=self.rows) for p in self.parts]
         for S, h in zip(self.S, self.halos):
@@ -478,6 +503,19 @@ class InProcessCluster:
         for it in range(nsteps):
             for S in self.S:
                 self._chk(self.lib.sdg_step_begin(S.h, ctypes.c_double(dt)))
+            if self.av:      # the all-reduce(max) of DistributedSolver._reduce_node_viscosity, between contexts of one device
+                arrays = []
+                for S in self.S:
+                    S.synchronize()
+                    ptr, cnt = ctypes.c_void_p(), ctypes.c_int64()
+                    self._chk(self.lib.sdg_av_node_buffer(S.h, ctypes.byref(ptr), ctypes.byref(cnt)))
+                    arrays.append(self.torch.as_tensor(_DevArray(ptr.value, cnt.value), device=f"cuda:{self.device}"))
+                top = self.torch.stack(arrays).max(dim=0).values
+                for a in arrays:
+                    a.copy_(top)
+                self.torch.cuda.synchronize()
+                for S in self.S:
+                    self._chk(self.lib.sdg_av_store(S.h, None))
             for s in range(self.n_stage):
                 for p in range(self.n_pass):
                     self._exchange(p)

@@ -48,7 +48,7 @@ EXPORTS = [
     "sdg_halo_doubles_per_element", "sdg_debug_physics", "sdg_uses_trace_rows", "sdg_set_halo_rows", "sdg_halo_unpack",
     "sdg_ipc_set_destination_units", "sdg_get_gradient_state", "sdg_get_boundary_gradient_state", "sdg_set_artificial_viscosity",
     "sdg_set_element_nodes", "sdg_get_node_artificial_viscosity", "sdg_get_element_artificial_viscosity", "sdg_update_artificial_viscosity",
-    "sdg_get_view_variable",
+    "sdg_get_view_variable", "sdg_av_node_buffer", "sdg_av_store",
 ]
 
 _lib = None
@@ -101,10 +101,11 @@ class Solver:
     cfg keys mirror the SimulationControl template parameters as Enum.cpp integers: p, model, eos, transport, conv_flux,
     visc_flux, source, rk, plus the physical-model parameters cp, cv, mu, c0, rho0, beta, t_ref.
     `n_ghost`: {type: count} — trailing elements of each block that are halo copies (multi-GPU partitions).
+    `node_data`: ({type: global node tags of the block's elements}, global node number, {type: inner radii}) for shock-capturing runs of a partition.
     `device=-1` builds a plan-only context (host flattening, no compute) used by CPU tests of the host logic.
     """
 
-    def __init__(self, cfg: dict, mesh, device: int = 0, n_ghost: dict | None = None, reorder: int = 1):
+    def __init__(self, cfg: dict, mesh, device: int = 0, n_ghost: dict | None = None, reorder: int = 1, node_data=None):
         lib = load_library()
         c = SdgConfig()
         vals = dict(dim=mesh.dim, p=cfg["p"], model=0, eos=0, transport=0, conv_flux=2, visc_flux=0, source=0, rk=2, device=device,
@@ -129,11 +130,12 @@ class Solver:
         _chk(lib.sdg_set_faces(self.h, int(f["n_int"]), int(f["n_bnd"]), *[_ip(a) for a in arrs]))
         if cfg.get("av_tolerance") is not None:   # System::setArtificialViscosity with ShockCapturingEnum::ArtificialViscosity
             from . import mesh as M
-            tags, self.n_nodes = M.node_tags(mesh)
+            # node_data = (tags, node_number, inner radii): a partition passes the GLOBAL node tags of its owned + ghost elements
+            tags, self.n_nodes, radii = node_data if node_data is not None else (*M.node_tags(mesh), {t: M.inner_radius(mesh, t) for t in self.types})
             _chk(lib.sdg_set_artificial_viscosity(self.h, ctypes.c_double(cfg["av_tolerance"]), ctypes.c_double(cfg.get("av_factor", 1.0)), int(self.n_nodes)))
             for t in self.types:
-                r = np.ascontiguousarray(M.inner_radius(mesh, t), dtype=np.float64)
-                _chk(lib.sdg_set_element_nodes(self.h, t, _ip(tags[t]), _dp(r)))
+                r = np.ascontiguousarray(radii[t], dtype=np.float64)
+                _chk(lib.sdg_set_element_nodes(self.h, t, _ip(np.ascontiguousarray(tags[t], dtype=np.int32)), _dp(r)))
         _chk(lib.sdg_finalize(self.h))
         self.relative_error_ = np.zeros(self.Nv)  # Solver::relative_error_, SolveControl.cpp:300
         self.delta_time_ = 0.0

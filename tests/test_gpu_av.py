@@ -139,3 +139,35 @@ def test_hybrid_cylinder(built):
     # the node maximum crossed the element types: some quadrangle corner carries a value set by a triangle or vice versa
     nodes = S.node_artificial_viscosity()
     assert nodes.max() > 0.0
+
+
+# ---- shock capturing across partitions: the node maximum is reduced over the ranks (the one collective of the path) -----------------------
+@pytest.mark.parametrize("dim,shape,world,p,width", [(2, (12, 6), 2, 3, 0.04), (2, (9, 8), 3, 2, 0.04), (3, (6, 4, 3), 2, 2, 0.08), (3, (4, 3, 3), 2, 3, 0.04)])
+def test_partitioned_shock_capturing_matches_single_context(built, dim, shape, world, p, width):
+    """`world` contexts (ghost elements, part-0 / part-1 launches, element halo of U and of the volume gradient) with the node array
+    max-reduced between them after sdg_step_begin (sdg_av_node_buffer / sdg_av_store) against the single-context run"""
+    from subrosadg_b200.parallel import InProcessCluster
+    from subrosadg_b200.solver import Solver
+    far, slip = M.RIEMANN_FARFIELD, M.ADIABATIC_SLIP_WALL
+    mesh = M.box(dim, shape, 0.0, 1.0, phys_bc={1: far, 2: far, 3: slip, 4: slip, 5: slip, 6: slip} if dim == 3 else {1: far, 2: far, 3: slip, 4: slip})
+    cfg = dict(p=p, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=2.0)
+    ic = jump_ic(dim, width=width)
+    bc = lambda x, phys, time=None: ic(x)
+    S = Solver(dict(cfg), mesh, device=0)
+    S.initializeSolver(ic, bc)
+    C = InProcessCluster(dict(cfg), mesh, world, device=0)
+    C.initializeSolver(ic, bc)
+    t = S.types[0]
+    dt = 0.2 * S.calculateDeltaTime(1.0)
+    err_s = S.stepSolver(dt, 3)
+    err_c = C.stepSolver(dt, 3)
+    node = S.node_artificial_viscosity()
+    assert node.max() > 0.0 and (node == 0.0).any()
+    # every context ends with the complete node array: the maximum over ALL elements, wherever they live
+    first = C.S[0].node_artificial_viscosity()
+    for Sr in C.S:
+        assert np.array_equal(Sr.node_artificial_viscosity(), first)
+    assert np.array_equal(first == 0.0, node == 0.0) and cases.rel_l2(first, node) < 1e-12   # the states differ by round-off after two steps
+    a, b = C.state_at_quadrature(), S.state_at_quadrature(t)
+    assert cases.rel_l2(a, b) < 1e-14, f"partitioned vs single context: {cases.rel_l2(a, b):.3e}"
+    assert np.allclose(err_c, err_s, rtol=1e-11, atol=1e-300)

@@ -164,3 +164,25 @@ def test_trace_row_lists_agree_between_peers(make, world):
     ni = int(f["n_int"])
     expected = int(np.sum(owner(np.asarray(f["le"][:ni])) != owner(np.asarray(f["re"][:ni]))))
     assert n_cut == 2 * expected
+
+
+def test_partition_node_data_uses_global_tags():
+    """shock-capturing runs: a partition's elements (owned, then ghosts) carry the node tags and inner radii of the GLOBAL mesh"""
+    from subrosadg_b200.parallel import partition, partition_node_data
+    mesh = M.box(2, (6, 5), 0.0, 1.0)
+    tags, n_nodes = M.node_tags(mesh)
+    t = next(iter(mesh.blocks))
+    radius = M.inner_radius(mesh, t)
+    seen = np.zeros(n_nodes, dtype=bool)
+    for r in range(3):
+        part = partition(mesh, r, 3)
+        lt, nn, lr = partition_node_data(mesh, part)
+        assert nn == n_nodes == 7 * 6
+        ids = np.concatenate([np.arange(part.lo, part.hi), part.ghost_global])
+        assert lt[t].shape == (part.n_owned + part.n_ghost, 4) and np.array_equal(lt[t], tags[t][ids]) and np.array_equal(lr[t], radius[ids])
+        # same node, same coordinates: the local copy of an element has the corner coordinates the global tags stand for
+        pts = np.unique(np.asarray(mesh.blocks[t]["coords"]).reshape(-1, 2), axis=0)
+        corners = np.asarray(part.mesh.blocks[t]["coords"])[:, :4, :]
+        assert np.allclose(pts[lt[t]], corners)
+        seen[lt[t][:part.n_owned].ravel()] = True
+    assert seen.all()

@@ -43,6 +43,35 @@ def main():
             ok = ok and good
             print(f"mgpu_check world={world} dim={dim} n={n} cfg={cfg}: state rel-L2 {e:.2e} dt {dt:.6e}/{dt1:.6e} relerr {err[0]:.6e}/{err1[0]:.6e} {'OK' if good else 'MISMATCH'}", flush=True)
         dist.barrier()
+    # shock capturing across the ranks: the node maximum is all-reduced (ncclMax) after sdg_step_begin -- the one collective of the path
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_av import jump_ic
+    far, slip = M.RIEMANN_FARFIELD, M.ADIABATIC_SLIP_WALL
+    for dim, shape, p, width in [(2, (16, 8), 3, 0.04), (3, (8, 4, 3), 2, 0.08), (3, (8, 3, 3), 3, 0.04)]:
+        mesh = M.box(dim, shape, 0.0, 1.0, phys_bc={1: far, 2: far, 3: slip, 4: slip, 5: slip, 6: slip} if dim == 3 else {1: far, 2: far, 3: slip, 4: slip})
+        cfg = dict(p=p, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=2.0)
+        ic = jump_ic(dim, width=width)
+        bc = lambda x, phys, time=None: ic(x)
+        D = DistributedSolver(dict(cfg), mesh, device=local)
+        D.initializeSolver(ic, bc)
+        dt = 0.2 * D.calculateDeltaTime(1.0)
+        err = D.stepSolver(dt, 3)
+        got = D.gather_state_at_quadrature()
+        node = D.S.node_artificial_viscosity()
+        if rank == 0:
+            S = Solver(dict(cfg), mesh, device=local)
+            S.initializeSolver(ic, bc)
+            dt1 = 0.2 * S.calculateDeltaTime(1.0)
+            err1 = S.stepSolver(dt1, 3)
+            ref = S.state_at_quadrature(S.types[0])
+            node1 = S.node_artificial_viscosity()
+            e = cases.rel_l2(got, ref)
+            good = (e < 1e-14 and dt == dt1 and np.allclose(err, err1, rtol=1e-11, atol=1e-300) and node1.max() > 0 and np.array_equal(node == 0, node1 == 0)
+                    and cases.rel_l2(node, node1) < 1e-12)
+            ok = ok and good
+            print(f"mgpu_check world={world} shock capturing dim={dim} shape={shape} p={p}: state rel-L2 {e:.2e} node viscosity rel-L2 {cases.rel_l2(node, node1):.2e} "
+                  f"({int((node1 > 0).sum())} of {node1.size} nodes) relerr {err[0]:.6e}/{err1[0]:.6e} {'OK' if good else 'MISMATCH'}", flush=True)
+        dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
