@@ -602,6 +602,16 @@ EXAMPLE_MESHES = {
     "karmanvortex": lambda s: annulus(max(4, int(22 * s)), max(12, 4 * int(15 * s)), r0=0.5, r1=20.0, geom_order=3, stretch=2.0,
                                       tri_rings=max(2, int(11 * s)), phys_bc={1: RIEMANN_FARFIELD, 2: ADIABATIC_NONSLIP_WALL}),
     # config 5: cubed-sphere shell of curved P3 hexahedra (examples/sphere_3d_cns.cpp:259-296: 6 sphere blocks 11x11x9 + far blocks)
+    # examples/sod_1d_ceuler.cpp:71-86: [0, 1] in 100 lines, physical 1 = left end, 2 = right end (both RiemannFarfield)
+    "sod_1d": lambda s: box(1, (max(8, int(100 * s)),), 0.0, 1.0, phys_bc={1: RIEMANN_FARFIELD, 2: RIEMANN_FARFIELD}, geom_order=3),
+    # examples/lidcavity_2d_incns.cpp:72-98: unit square, 20 x 20 quadrangles, physical 1 = bottom / right / left walls, 2 = the lid (y = 1)
+    "lidcavity_2d": lambda s: box(2, (max(4, int(20 * s)),) * 2, 0.0, 1.0, phys_bc={1: ADIABATIC_NONSLIP_WALL, 2: ADIABATIC_NONSLIP_WALL}, geom_order=3,
+                                  tagger=lambda c: np.where(np.abs(c[:, 1] - 1.0) < 1e-9, 2, 1).astype(np.int32)),
+    # examples/thermalcavity_2d_incns.cpp:80-107: unit square, 80 x 80 P1 quadrangles, physical 1 = bottom / top (adiabatic), 2 = right wall (cold),
+    # 3 = left wall (hot)
+    "thermalcavity_2d": lambda s: box(2, (max(4, int(80 * s)),) * 2, 0.0, 1.0,
+                                      phys_bc={1: ADIABATIC_NONSLIP_WALL, 2: ISOTHERMAL_NONSLIP_WALL, 3: ISOTHERMAL_NONSLIP_WALL},
+                                      tagger=lambda c: np.where(np.abs(c[:, 0] - 1.0) < 1e-9, 2, np.where(np.abs(c[:, 0]) < 1e-9, 3, 1)).astype(np.int32)),
     "sphere": lambda s: cubed_sphere_shell(max(2, int(11 * s)), max(2, int(9 * s)), r0=0.5, r1=5.0, geom_order=3,
                                            phys_bc={1: RIEMANN_FARFIELD, 2: ADIABATIC_NONSLIP_WALL}),
 }

@@ -110,6 +110,70 @@ def test_cpp_config_drivers_match_ctypes_path(examples_built, tmp_path, name, pr
     assert dim == len(vel)
 
 
+def _sod_ic(x):
+    left = x[..., 0] <= 0.5
+    return np.stack([np.where(left, 1.0, 0.125), np.where(left, 0.75, 0.0), np.where(left, 1.4, 0.8 * 1.4)], axis=-1)
+
+
+def _sod_bc(x, phys, time=None):
+    return np.stack([np.where(phys == 1, 1.0, 0.125), np.where(phys == 1, 0.75, 0.0), np.where(phys == 1, 1.4, 0.8 * 1.4)], axis=-1)
+
+
+def _cavity(temperature, lid):
+    """(ic, bc) of the two cavity examples: fluid at rest, density 1; `temperature` = {physical index: wall value, None: interior}, lid = physical index
+    of the moving wall (u = 1) or None"""
+    def ic(x):
+        one = np.ones(x.shape[:-1])
+        return np.stack([one, 0 * one, 0 * one, temperature[None] * one], axis=-1)
+
+    def bc(x, phys, time=None):
+        one = np.ones(x.shape[:-1])
+        T = sum(np.where(phys == k, v, 0.0) for k, v in temperature.items() if k is not None)
+        return np.stack([one, np.where(phys == lid, 1.0, 0.0) * one if lid else 0 * one, 0 * one, T * one], axis=-1)
+    return ic, bc
+
+
+WC_CAVITY = dict(model=3, eos=1, rho0=1.0, transport=1, visc_flux=2, rk=2, cp=1.0, cv=1.0)
+MORE_DRIVERS = [
+    # examples/sod_1d_ceuler.cpp: ShockCapturingEnum::ArtificialViscosity on lines, setArtificialViscosity(0.5), CFL 0.001
+    ("sod_1d_ceuler", "sod_1d", 0.3, dict(p=3, conv_flux=2, rk=2, av_tolerance=0.5, av_factor=1.0), 0.001, (_sod_ic, _sod_bc)),
+    # examples/lidcavity_2d_incns.cpp: IncompresibleNS, WeakCompressibleFluid(10, 1), mu = 1 / 5000, Lax-Friedrichs + BR2, moving lid
+    ("lidcavity_2d_incns", "lidcavity_2d", 0.3, dict(WC_CAVITY, p=3, c0=10.0, mu=1.0 / 5000.0, conv_flux=1), 1.0, _cavity({None: 1.0, 1: 1.0, 2: 1.0}, 2)),
+    # examples/thermalcavity_2d_incns.cpp: P1 quadrangles (seven-point rule, dense-operator path), Exact flux, Boussinesq(1, 0.5), hot / cold walls
+    ("thermalcavity_2d_incns", "thermalcavity_2d", 0.1, dict(WC_CAVITY, p=1, c0=3.0, mu=float(np.sqrt(0.71 / 1e6)), conv_flux=4, source=1, beta=1.0, t_ref=0.5), 0.5,
+     _cavity({None: 0.5, 1: 0.5, 2: 0.0, 3: 1.0}, None)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,producer,scale,cfg,cfl,fields", MORE_DRIVERS, ids=[d[0] for d in MORE_DRIVERS])
+def test_cpp_drivers_of_more_reference_examples_match_ctypes_path(examples_built, tmp_path, name, producer, scale, cfg, cfl, fields):
+    """three more drivers that mirror examples of the reference (shock capturing in 1-D, weakly compressible Navier-Stokes with a moving wall,
+    Boussinesq convection on P1 quadrangles) over flat mesh files: the same numbers as the Python host mirror, bit for bit"""
+    from subrosadg_b200.solver import Solver
+    mesh = M.EXAMPLE_MESHES[producer](scale)
+    path = tmp_path / "mesh.sdgm"
+    M.write_flat(mesh, path)
+    out = tmp_path / "state"
+    r = subprocess.run([os.path.join(EX, "_build", name), str(path), "4", str(out)], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ic, bc = fields
+    S = Solver(cfg, mesh, device=0)
+    S.initializeSolver(ic, bc)
+    dt = S.calculateDeltaTime(cfl)
+    assert abs(float(r.stdout.strip().splitlines()[-1].split()[-1]) - dt) <= 1e-5 * dt   # printed with 6 significant digits
+    S.stepSolver(dt, 4)
+    for t in S.types:
+        ref = S.state_at_quadrature(t)
+        got = np.fromfile(f"{out}.{t}.bin", dtype=np.float64).reshape(ref.shape)
+        assert np.isfinite(ref).all()
+        assert np.array_equal(got, ref), f"{name} type {t}: C++ driver vs ctypes path rel-L2 {cases.rel_l2(got, ref):.3e}"
+    # something happened in four steps: the Sod jump moved, the lid / the hot wall set the fluid in motion
+    U0 = Solver(cfg, mesh, device=0)
+    U0.initializeSolver(ic, bc)
+    assert cases.rel_l2(S.state_at_quadrature(S.types[0]), U0.state_at_quadrature(S.types[0])) > 1e-7
+
+
 def _compile(src, exe):
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     r = subprocess.run([cxx, "-std=c++20", "-O1", "-Wall", "-Wextra", f"-I{ROOT}/include", str(src), "-o", str(exe), f"-L{ROOT}/subrosadg_b200",
