@@ -63,3 +63,48 @@ def test_gmsh_type_numbers():
     for (t, g), num in msh.GMSH_NUMBER.items():
         if t != M.POINT:
             assert len(M.gmsh_reference_nodes(t, g)) == {M.LINE: g + 1, M.TRIANGLE: (g + 1) * (g + 2) // 2, M.QUADRANGLE: (g + 1) ** 2, M.HEXAHEDRON: (g + 1) ** 3}[t]
+
+
+def test_file_in_gmsh_own_layout():
+    """tests/data/lidcavity_2x2_gmsh_layout.msh is written BY HAND in the layout Gmsh 4.13 itself produces for the reference's lid-cavity script
+    (examples/lidcavity_2d_incns.cpp:72-98 at 2 x 2 cells, order 1): $PhysicalNames, four point entities without physical tags, SEVERAL curves in
+    one physical group, signed bounding-entity lists, one node block per entity (corner nodes on the point entities), elements only for
+    entities in physical groups.  It is not a Gmsh-written file (no Gmsh here) — it checks that the reader does not lean on the simpler
+    layout of this repository's own writer."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lidcavity_2x2_gmsh_layout.msh")
+    r = msh.read_msh(path, {1: M.ADIABATIC_NONSLIP_WALL, 2: M.ISOTHERMAL_NONSLIP_WALL})
+    assert r.dim == 2 and sorted(r.blocks) == [M.QUADRANGLE] and r.blocks[M.QUADRANGLE]["geom_order"] == 1
+    xy = np.asarray(r.blocks[M.QUADRANGLE]["coords"])
+    assert xy.shape == (4, 4, 2)
+    ref = M.box(2, (2, 2), 0.0, 1.0)
+    cen = lambda c: sorted(map(tuple, np.round(np.asarray(c).mean(axis=1), 12)))
+    assert cen(xy) == cen(ref.blocks[M.QUADRANGLE]["coords"])
+    # counter-clockwise corners (positive area), as the reference's Jacobians need
+    a = 0.5 * np.abs(np.sum(xy[:, :, 0] * np.roll(xy[:, :, 1], -1, axis=1) - np.roll(xy[:, :, 0], -1, axis=1) * xy[:, :, 1], axis=1))
+    s = 0.5 * np.sum(xy[:, :, 0] * np.roll(xy[:, :, 1], -1, axis=1) - np.roll(xy[:, :, 0], -1, axis=1) * xy[:, :, 1], axis=1)
+    assert np.allclose(a, 0.25) and np.all(s > 0)
+    f = r.faces
+    n_int, n_bnd = int(f["n_int"]), int(f["n_bnd"])
+    assert (n_int, n_bnd) == (4, 8)
+    phys = np.asarray(f["phys"])[n_int:]; bc = np.asarray(f["bc"])[n_int:]
+    assert sorted(phys.tolist()) == [1] * 6 + [2] * 2 and np.array_equal(bc == M.ISOTHERMAL_NONSLIP_WALL, phys == 2)
+    # the two lid faces (curve 3, physical 2) lie on y = 1
+    for k in np.flatnonzero(phys == 2):
+        e, lf = int(f["le"][n_int + k]), int(f["lf"][n_int + k])
+        corners = xy[e][M.FACE_CORNERS[M.QUADRANGLE][lf]]
+        assert np.allclose(corners[:, 1], 1.0)
+
+
+def test_file_in_gmsh_own_layout_runs_through_the_oracle():
+    """a uniform flow on that mesh is steady (all four walls replaced by far-field faces): the face records the reader produced are consistent"""
+    import os
+    import oracle
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lidcavity_2x2_gmsh_layout.msh")
+    r = msh.read_msh(path, {1: M.RIEMANN_FARFIELD, 2: M.RIEMANN_FARFIELD})
+    O = oracle.Oracle(dict(p=2, conv_flux=2, rk=2), r)
+    one = lambda x, *a: np.stack([1.4 * np.ones(x.shape[:-1]), 0.3 * np.ones(x.shape[:-1]), 0.1 * np.ones(x.shape[:-1]), np.ones(x.shape[:-1])], axis=-1)
+    O.initialize(one, one)
+    before = O.get_state(M.QUADRANGLE).copy()
+    O.step(0.5 * O.compute_dt(1.0), 3)
+    assert np.abs(O.get_state(M.QUADRANGLE) - before).max() < 1e-13
