@@ -35,6 +35,7 @@ struct Params {
   double cp, cv, mu, amp, vel[3]; double jump_width, jump_radius, av_tolerance, av_factor;
   double c0, rho0, beta, t_ref;   // EquationOfState<WeakCompressibleFluid> (PhysicalModel.cpp:57-78), SourceTermBase<Boussinesq> (SourceTerm.cpp:30-33)
   int weak;                       // 1: the weakly compressible field below (incompressible examples' variable set)
+  double time_rate;               // BoundaryTimeEnum::TimeVarying: the boundary velocity grows like 1 + time_rate * t
 };
 Params g_params;
 thread_local std::string g_error;
@@ -96,6 +97,16 @@ template <typename SimulationControl>
 inline Eigen::Vector<Real, SimulationControl::kPrimitiveVariableNumber> SubrosaDG::BoundaryCondition<SimulationControl>::calculatePrimitiveFromCoordinate(
     const Eigen::Vector<Real, SimulationControl::kDimension>& coordinate, [[maybe_unused]] const Isize gmsh_physical_index) const {
   return fieldAt<SimulationControl::kDimension>(coordinate, 0.0);
+}
+
+// BoundaryTimeEnum::TimeVarying: Solver::updateBoundaryVariable calls this overload with t = iteration_ * delta_time_ at the start of every
+// stepSolver (BoundaryCondition.cpp:29-74, TimeIntegration.cpp:332-334)
+template <typename SimulationControl>
+inline Eigen::Vector<Real, SimulationControl::kPrimitiveVariableNumber> SubrosaDG::BoundaryCondition<SimulationControl>::calculatePrimitiveFromCoordinate(
+    const Eigen::Vector<Real, SimulationControl::kDimension>& coordinate, const Real time, [[maybe_unused]] const Isize gmsh_physical_index) const {
+  Eigen::Vector<Real, SimulationControl::kPrimitiveVariableNumber> p = fieldAt<SimulationControl::kDimension>(coordinate, 0.0);
+  for (int d = 0; d < SimulationControl::kDimension; d++) p(1 + d) = p(1 + d) * (1.0 + g_params.time_rate * time);
+  return p;
 }
 
 namespace {
@@ -230,8 +241,8 @@ int runCase(const BlockIn* blocks, int n_blocks, const FacesIn& faces, int nstep
 }
 
 template <DimensionEnum D, PolynomialOrderEnum P, MeshModelEnum M, TimeIntegrationEnum RK, typename Variable, ShockCapturingEnum S = ShockCapturingEnum::None,
-          SourceTermEnum Src = SourceTermEnum::None>
-using Control = SimulationControl<SolveControl<D, P, BoundaryTimeEnum::Steady, Src>,
+          SourceTermEnum Src = SourceTermEnum::None, BoundaryTimeEnum BT = BoundaryTimeEnum::Steady>
+using Control = SimulationControl<SolveControl<D, P, BT, Src>,
                                   NumericalControl<M, S, LimiterEnum::None, InitialConditionEnum::Function, RK>, Variable>;
 template <ConvectiveFluxEnum F>
 using IncEuler = IncompresibleEulerVariable<ThermodynamicModelEnum::Constant, EquationOfStateEnum::WeakCompressibleFluid, F>;
@@ -250,14 +261,14 @@ const char* ref_sweeps_error() { return g_error.c_str(); }
 void ref_sweeps_set_raw_path(const char* path) { g_raw_path = path ? path : ""; }
 
 // case_id selects one of the compiled control types (tests/golden/make_reference_sweeps.py lists them with their meshes);
-// params = {cp, cv, mu, amp, vel[3], jump_width, jump_radius, av_tolerance, av_factor, c0, rho0, beta, t_ref, weak}; node tags (0-based) / inner radii for the shock cases; blocks / faces: see BlockIn / FacesIn (faces in the order and meaning of sdg_set_faces)
+// params = {cp, cv, mu, amp, vel[3], jump_width, jump_radius, av_tolerance, av_factor, c0, rho0, beta, t_ref, weak, time_rate}; node tags (0-based) / inner radii for the shock cases; blocks / faces: see BlockIn / FacesIn (faces in the order and meaning of sdg_set_faces)
 int ref_sweeps(int case_id, const double* params, int n_blocks, const int32_t* types, const int32_t* counts, const double* const* xq, const double* const* jw,
                const double* const* mt, const double* const* minv, const double* const* min_edge, int n_int, int n_bnd, const int32_t* const* face_int /* 9 arrays */,
                const double* xf, const double* nrm, const double* fjw, int nsteps, double cfl, double dt_in, double* const* coef_out, double* relerr_out,
                double* dt_out, int node_number, const int32_t* const* node_tag, const double* const* inner_radius, double* node_av_out) {
   try {
     g_params = Params{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}, params[7], params[8], params[9], params[10],
-                      params[11], params[12], params[13], params[14], params[15] != 0.0};
+                      params[11], params[12], params[13], params[14], params[15] != 0.0, params[16]};
     BlockIn blocks[4];
     for (int k = 0; k < n_blocks; k++) blocks[k] = BlockIn{types[k], counts[k], xq[k], jw[k], mt[k], minv[k], min_edge[k], coef_out[k], node_tag ? node_tag[k] : nullptr, inner_radius ? inner_radius[k] : nullptr};
     const FacesIn F{n_int, n_bnd, face_int[0], face_int[1], face_int[2], face_int[3], face_int[4], face_int[5], face_int[6], face_int[7], face_int[8], xf, nrm, fjw};
@@ -292,6 +303,9 @@ int ref_sweeps(int case_id, const double* params, int n_blocks, const int32_t* t
       case 21: return runCase<Control<D2, P5, Quadrangle, SSPRK3, NS<TransportModelEnum::Sutherland, ConvectiveFluxEnum::HLLC, ViscousFluxEnum::BR2>>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
       case 22: return runCase<Control<D2, P5, Quadrangle, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
       case 23: return runCase<Control<D1, P3, Line, SSPRK3, Euler<ConvectiveFluxEnum::HLLC>, ShockCapturingEnum::ArtificialViscosity>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
+      // BoundaryTimeEnum::TimeVarying (the alternative control type of cylinder_2d_incns.cpp:31-41): boundary values re-evaluated before every step
+      case 24: return runCase<Control<D2, P2, Quadrangle, SSPRK3, IncNS<ConvectiveFluxEnum::LaxFriedrichs, ViscousFluxEnum::BR2>, ShockCapturingEnum::None, SourceTermEnum::None,
+                                      BoundaryTimeEnum::TimeVarying>>(blocks, n_blocks, F, nsteps, cfl, dt_in, relerr_out, dt_out, node_number, node_av_out);
       default: throw std::runtime_error("ref_sweeps: unknown case");
     }
   } catch (const std::exception& ex) {

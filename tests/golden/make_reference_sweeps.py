@@ -90,9 +90,17 @@ def cases():
          M.box(2, (3, 3), 0.0, 1.0, geom_order=2, warp=WARP2, phys_bc={1: FAR, 2: FAR, 3: NOSLIP, 4: FAR}), [0.5, 0.1, 0.0], 0.02, 2, 0.3),
         ("av_quad_p5_oblique_jump", 22, dict(p=5, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=2.0),
          M.box(2, (6, 5), 0.0, 1.0, phys_bc={1: FAR, 2: FAR, 3: SLIP, 4: SLIP}), (0.04, 0.0), 0.0, 2, 0.2),
+        # BoundaryTimeEnum::TimeVarying: vel[3] = growth rate of the boundary velocity, 1 + rate * t with t = iteration * dt (first step: t = 0)
+        ("inc_quad_p2_ns_time_varying_inflow", 24, dict(WC, p=2, model=3, transport=1, mu=mu, conv_flux=1, visc_flux=2, rk=2),
+         M.box(2, (5, 4), 0.0, 1.0, phys_bc={1: INFLOW, 2: OUTFLOW, 3: ISO, 4: NOSLIP}), [0.3, 0.05, 0.0, 400.0], 0.02, 4, 0.3),
         ("av_line_p3_sod", 23, dict(p=3, conv_flux=2, rk=2, av_tolerance=1.0, av_factor=1.0),
          M.box(1, (24,), 0.0, 1.0, phys_bc={1: FAR, 2: FAR}), (0.01, 0.0), 0.0, 4, 0.2),
     ]
+
+
+def time_varying(vel):
+    """True for the BoundaryTimeEnum::TimeVarying cases: the consumer re-evaluates the boundary callback at t = iteration * dt before every step"""
+    return not isinstance(vel, tuple) and len(vel) > 3 and vel[3] != 0.0
 
 
 def fields(dim, vel, amp, cfg=None):
@@ -112,8 +120,11 @@ def fields(dim, vel, amp, cfg=None):
             return np.stack([rho] + [np.zeros_like(rho)] * dim + [1.4 * p / rho], axis=-1)
         return jump, jump
 
+    rate = vel[3] if len(vel) > 3 else 0.0
+
     def make(a):
-        def f(x, *_):
+        def f(x, phys=None, time=None):
+            grow = 1.0 + rate * (time or 0.0) if phys is not None else 1.0       # boundary callback only (BoundaryTimeEnum::TimeVarying)
             s = np.sin(np.pi * x[..., 0])
             if dim >= 2:
                 s = s * np.cos(np.pi * x[..., 1])
@@ -121,8 +132,8 @@ def fields(dim, vel, amp, cfg=None):
                 s = s * np.cos(np.pi * x[..., 2])
             g = 1.0 + a * s
             if weak:
-                return np.stack([cfg["rho0"] * (1.0 + 0.01 * a * s)] + [vel[d] * g for d in range(dim)] + [1.0 + 2.0 * a * s], axis=-1)
-            return np.stack([1.4 * g] + [vel[d] * g + 0.0 * s for d in range(dim)] + [1.0 * g], axis=-1)
+                return np.stack([cfg["rho0"] * (1.0 + 0.01 * a * s)] + [vel[d] * g * grow for d in range(dim)] + [1.0 + 2.0 * a * s], axis=-1)
+            return np.stack([1.4 * g] + [(vel[d] * g + 0.0 * s) * grow for d in range(dim)] + [1.0 * g], axis=-1)
         return f
     return make(amp), make(0.0)
 
@@ -145,7 +156,8 @@ def run_reference(lib, case_id, cfg, mesh, vel, amp, steps, cfl, raw_path=None):
     shock = isinstance(vel, tuple)
     params = np.array([2.5, 25.0 / 14.0, cfg.get("mu", 0.0), amp] + ([0.0, 0.0, 0.0, vel[0], vel[1], cfg["av_tolerance"], cfg["av_factor"]] if shock
                       else [vel[0], vel[1], vel[2], 0.0, 0.0, 0.0, 1.0])
-                      + [cfg.get("c0", 1.0), cfg.get("rho0", 1.0), cfg.get("beta", 0.0), cfg.get("t_ref", 0.0), 1.0 if cfg.get("eos", 0) == 1 else 0.0])
+                      + [cfg.get("c0", 1.0), cfg.get("rho0", 1.0), cfg.get("beta", 0.0), cfg.get("t_ref", 0.0), 1.0 if cfg.get("eos", 0) == 1 else 0.0,
+                         vel[3] if (not shock and len(vel) > 3) else 0.0])
     tags, n_nodes = M.node_tags(mesh) if (shock or raw_path) else ({}, 1)     # Mesh::node_number_ sizes the tail of the raw file
     radius = {t: np.ascontiguousarray(M.inner_radius(mesh, t)) for t in types} if shock else {}
     IP = ctypes.POINTER(ctypes.c_int32) * len(types)

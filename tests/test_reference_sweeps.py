@@ -61,7 +61,12 @@ def test_oracle_reproduces_the_reference_solver(case):
     O.initialize(ic, bc)
     initial = {t: O.get_state(t) for t in O.types}
     dt = O.compute_dt(cfl)
-    relerr = O.step(dt, steps)
+    if gen.time_varying(vel):   # Solver::updateBoundaryVariable at t = iteration_ * delta_time_ before every step (first step: t = 0)
+        for i in range(steps):
+            O.update_boundary(bc, i * dt)
+            relerr = O.step(dt, 1)
+    else:
+        relerr = O.step(dt, steps)
     state = {t: O.get_state(t) for t in O.types}
     tol_ic = _projection_tolerance(cfg, mesh)
     _check(state, initial, dt, relerr, gold, O.types, {t: initial[t].shape for t in O.types}, max(1e-12, max(tol_ic.values())), tol_ic)
@@ -80,7 +85,12 @@ def test_cuda_path_reproduces_the_reference_solver(built, case):
     S.initializeSolver(ic, bc)
     initial = {t: S.get_state(t) for t in S.types}
     dt = S.calculateDeltaTime(cfl)
-    relerr = S.stepSolver(dt, steps)
+    if gen.time_varying(vel):
+        for i in range(steps):
+            S.updateBoundaryVariable(bc, i * dt)
+            relerr = S.stepSolver(dt, 1)
+    else:
+        relerr = S.stepSolver(dt, steps)
     state = {t: S.get_state(t) for t in S.types}
     _check(state, initial, dt, relerr, gold, S.types, {t: initial[t].shape for t in S.types}, 1e-10, _projection_tolerance(cfg, mesh))   # 1e-10: BASELINE.json, fields after N steps
     if gold["node_artificial_viscosity"] is not None:
