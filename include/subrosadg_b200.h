@@ -146,6 +146,20 @@ int sdg_step(sdg_ctx* ctx, double dt, int32_t n_steps, double* relative_error);
 /* Same as sdg_step, additionally returning the device time of the n_steps (CUDA events on the context's stream). */
 int sdg_step_timed(sdg_ctx* ctx, double dt, int32_t n_steps, double* relative_error, float* milliseconds);
 
+/* One call of Solver::stepSolver (TimeIntegration.cpp:326-350) on a state that lives in HOST memory: the modal coefficients
+ * U_in [n][Nb][Nv] (the layout of sdg_set_state) are the step's input, U_out receives the coefficients after the step, relative_error
+ * [Nv] (may be NULL) Solver::relative_error_.  Same result, bit for bit, as sdg_set_state -> sdg_step(dt, 1) -> sdg_get_state; for
+ * P3 hexahedra on the trace-based kernels (inviscid, one GPU) the three phases are STREAMED: the caller's element order is cut into
+ * upload groups, the stages of a thread-block chunk run as soon as the chunk's and its face neighbours' inputs have arrived, and a
+ * group travels back while later groups are still arriving (PCIe in both directions at once).  U_in and U_out may be the same buffer;
+ * pinned host memory is what makes the copies asynchronous.  SDG_NO_HOST_PIPE=1 forces the phase-after-phase composition,
+ * SDG_HOST_PIPE_GROUPS=<G> sets the number of upload groups (default n / 16384, 2..64). */
+int sdg_step_host(sdg_ctx* ctx, int32_t type, double dt, const double* U_in, double* U_out, double* relative_error);
+
+/* Diagnostics of sdg_step_host: number of upload groups (0: the context does not stream) and the fraction of them whose download starts
+ * before the last upload has arrived. */
+int sdg_step_host_info(sdg_ctx* ctx, int32_t* groups, double* early_fraction);
+
 /* Parity hook: one residual evaluation of the current state.  Rmodal [n][Nb][Nv] = variable_residual_
  * (SpatialDiscrete.cpp:1016-1032); rhsq [n][Nq][Nv] = (R M^-1) Phi^T, i.e. dU/dt at the quadrature points.
  * Either may be NULL. */

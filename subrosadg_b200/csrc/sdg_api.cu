@@ -17,6 +17,7 @@
 #include "mixed_path.hpp"
 #include "nsl_kernels.cuh"
 #include "tensor_kernels.cuh"
+#include <functional>
 #include "av_kernels.cuh"
 #include "view_variable.hpp"
 
@@ -84,6 +85,18 @@ struct sdg_ctx {
   LinePlan linePlan;   // host image (diagnostics: sdg_debug_plan 20-23)
   bool traceValid[3] = {false, false, false};
   int64_t stepCount = 0, bndKey = -1;
+  // sdg_step_host: one time step streamed through host buffers (upload, stages and download overlapped per dependency level)
+  const int* listOverride = nullptr; int listCount = 0;   // runStage: explicit chunk list of the launch (device pointer)
+  struct HostPipe {
+    int G = 0;                                   // upload groups = contiguous ranges of the caller's element order
+    std::vector<int> first;                      // [G + 1] caller-order element ranges
+    std::vector<int> off;                        // [(nStages + 1) * G + 1]: chunk lists of (kind, level); kind 0 = traces, 1.. = stage
+    std::vector<std::vector<int>> download;      // per level: the upload groups whose elements have all finished the last stage
+    DevBuf<int> lists; DevBuf<double> up, down;
+    std::vector<cudaEvent_t> upEv, downEv;
+    cudaStream_t d2h = nullptr;
+    double overlap = 0.0;                        // fraction of the upload groups downloaded before the last level (diagnostic)
+  } pipe;
 
   size_t stateDoubles() const { return (size_t)plan.blk.n * NV * plan.blk.T.NN; }
   size_t elemDoubles() const { return (size_t)NV * plan.blk.T.NN; }
@@ -156,6 +169,7 @@ void runStage(sdg_ctx* c, const StageArgs& base, int part, cudaStream_t s, int p
   int nBlocks = B.nChunks;
   if (part == 0) { a.chunkList = c->chunkInterior.p; nBlocks = (int)B.chunkInterior.size(); }
   else if (part == 1) { a.chunkList = c->chunkBoundary.p; nBlocks = (int)B.chunkBoundary.size(); }
+  if (c->listOverride) { a.chunkList = c->listOverride; nBlocks = c->listCount; }
   if (nBlocks == 0) return;
   if (c->lineTrace) {
     if (pass == 0) c->lineFns.grad(a, nBlocks, s); else c->lineFns.stage(a, nBlocks, s);
@@ -287,6 +301,9 @@ void sdg_destroy(sdg_ctx* c) {
   if (c->stepGraph) cudaGraphExecDestroy(c->stepGraph);
   for (void* q : c->ipcOpened) cudaIpcCloseMemHandle(q);
   if (c->copyStream) { cudaStreamDestroy(c->copyStream); for (cudaEvent_t e : c->seamEvent) if (e) cudaEventDestroy(e); }
+  if (c->pipe.d2h) cudaStreamDestroy(c->pipe.d2h);
+  for (cudaEvent_t e : c->pipe.upEv) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->pipe.downEv) cudaEventDestroy(e);
   cudaStream_t s = c->stream; const bool dev = c->hasDevice;
   delete c;
   if (dev && s) cudaStreamDestroy(s);
@@ -1032,6 +1049,155 @@ int sdg_step_timed(sdg_ctx* c, double dt, int32_t n_steps, double* relative_erro
     reduceNorm(c, sums);
     for (int v = 0; v < c->NV; v++) relative_error[v] = sums[v] / c->plan.blk.nOwned;
   }
+  SDG_CATCH
+}
+
+namespace {
+
+// sdg_step_host can stream when the stage is ONE launch per chunk that reads, besides the chunk's own elements, only what the face
+// neighbours' previous stage published (trace rows): P3 hexahedra on the trace-based line kernels, inviscid, no shock capturing, one GPU.
+bool hostPipeEligible(const sdg_ctx* c) {
+  return c->lineTrace && c->traceTU && !twoPass(c) && !c->phys.av && c->plan.blk.nGhost == 0 && c->plan.blk.nOwned >= 8192 && !getenv("SDG_NO_HOST_PIPE");
+}
+
+// Dependency levels of the streamed step.  The caller's element order is cut into G contiguous upload groups; a chunk's traces can be
+// taken once its own elements have arrived (level t0), stage s of a chunk can run once stage s - 1 (stage 0: the traces) of the chunk
+// and of every face neighbour's chunk has run: r_s = max over {chunk, neighbours} of r_(s-1).  An upload group goes back to the host
+// at the level at which the last stage of all of its elements is done.  Launching level after level on ONE stream (traces, stage 1,
+// stage 2, ... of that level, in this order) satisfies every dependency without an event between kernels.
+void buildHostPipe(sdg_ctx* c) {
+  auto& P = c->pipe;
+  const BlockPlan& B = c->plan.blk;
+  const int n = B.nOwned, K = B.K, nCh = B.nChunks, S = c->nStages;
+  int G = std::max(2, std::min(64, n / 16384));
+  if (const char* e = getenv("SDG_HOST_PIPE_GROUPS")) G = std::max(1, std::min(256, atoi(e)));
+  P.G = G;
+  P.first.resize(G + 1);
+  for (int k = 0; k <= G; k++) P.first[k] = (int)((long long)n * k / G);
+  std::vector<int> groupOf(n);   // by internal position
+  for (int k = 0; k < G; k++) for (int ci = P.first[k]; ci < P.first[k + 1]; ci++) groupOf[B.perm[ci]] = k;
+  std::vector<std::vector<int>> lvl(S + 1, std::vector<int>(nCh, 0));
+  for (int e = 0; e < n; e++) lvl[0][e / K] = std::max(lvl[0][e / K], groupOf[e]);
+  const std::vector<int>& L = c->linePlan.links;
+  for (int s = 1; s <= S; s++) {
+    lvl[s] = lvl[s - 1];
+    for (int e = 0; e < n; e++)
+      for (int f = 0; f < 6; f++) {
+        const int o = L[((size_t)e * 6 + f) * 4];
+        if (o >= 0 && o < n) lvl[s][e / K] = std::max(lvl[s][e / K], lvl[s - 1][o / K]);
+      }
+  }
+  // chunk lists sorted by (kind, level); ascending chunk index inside a list
+  P.off.assign((size_t)(S + 1) * G + 1, 0);
+  std::vector<int> lists((size_t)(S + 1) * nCh);
+  for (int k = 0; k <= S; k++) {
+    std::vector<int> count(G, 0);
+    for (int ch = 0; ch < nCh; ch++) count[lvl[k][ch]]++;
+    int run = k * nCh;
+    for (int g = 0; g < G; g++) { P.off[(size_t)k * G + g] = run; run += count[g]; }
+    std::vector<int> fill(G);
+    for (int g = 0; g < G; g++) fill[g] = P.off[(size_t)k * G + g];
+    for (int ch = 0; ch < nCh; ch++) lists[fill[lvl[k][ch]]++] = ch;
+  }
+  P.off[(size_t)(S + 1) * G] = (S + 1) * nCh;
+  P.download.assign(G, {});
+  int early = 0;
+  for (int g = 0; g < G; g++) {
+    int d = 0;
+    for (int ci = P.first[g]; ci < P.first[g + 1]; ci++) d = std::max(d, lvl[S][B.perm[ci] / K]);
+    P.download[d].push_back(g);
+    if (d < G - 1) early++;
+  }
+  P.overlap = (double)early / G;
+  if (!c->hasDevice) return;   // plan-only context: the levels are all there is to inspect
+  P.lists.upload(lists);
+  const size_t per = (size_t)c->NV * B.T.NN;
+  P.up.alloc((size_t)n * per); P.down.alloc((size_t)n * per);
+  CUDA_OK(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
+  P.upEv.resize(G); P.downEv.resize(G);
+  for (auto& e : P.upEv) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : P.downEv) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+void pipeLaunchList(sdg_ctx* c, int kind, int level, const std::function<void()>& launch) {
+  const auto& P = c->pipe;
+  const int i = kind * P.G + level, a = P.off[i], b = (level == P.G - 1) ? (kind + 1) * c->plan.blk.nChunks : P.off[i + 1];
+  if (b <= a) return;
+  c->listOverride = P.lists.p + a; c->listCount = b - a;
+  launch();
+  c->listOverride = nullptr; c->listCount = 0;
+}
+
+}  // namespace
+
+int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, double* U_out, double* relative_error) {
+  SDG_TRY
+  needFinal(c);
+  if (!U_in || !U_out) throw std::runtime_error("null argument");
+  if (c->mx || !c->hasDevice || !hostPipeEligible(c)) {   // same result, one phase after the other
+    if (sdg_set_state(c, type, U_in)) throw std::runtime_error(g_err);
+    if (sdg_step(c, dt, 1, relative_error)) throw std::runtime_error(g_err);
+    if (sdg_get_state(c, type, U_out)) throw std::runtime_error(g_err);
+    return 0;
+  }
+  needDevice(c); needType(c, type);
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  auto& P = c->pipe;
+  if (P.G == 0) buildHostPipe(c);
+  seamStreams(c);
+  const BlockPlan& B = c->plan.blk;
+  const size_t per = (size_t)c->NV * B.T.NN;
+  const int G = P.G, S = c->nStages;
+  c->stepDt = dt;
+  int inLast, outLast; stageBuffers(c, S - 1, inLast, outLast);
+  // uploads: nothing on the device waits for them except the transform of the same group
+  CUDA_OK(cudaEventRecord(c->seamEvent[kSeamChunks], c->stream));   // an earlier call's transforms out of the staging array
+  CUDA_OK(cudaStreamWaitEvent(c->copyStream, c->seamEvent[kSeamChunks], 0));
+  for (int g = 0; g < G; g++) {
+    const size_t e0 = P.first[g], ne = P.first[g + 1] - P.first[g];
+    CUDA_OK(cudaMemcpyAsync(P.up.p + e0 * per, U_in + e0 * per, ne * per * sizeof(double), cudaMemcpyHostToDevice, c->copyStream));
+    CUDA_OK(cudaEventRecord(P.upEv[g], c->copyStream));
+  }
+  c->latest = c->cur; c->gradSrc = -1;
+  for (int b = 0; b < 3; b++) c->traceValid[b] = false;
+  for (int g = 0; g < G; g++) {
+    CUDA_OK(cudaStreamWaitEvent(c->stream, P.upEv[g], 0));
+    transformModalRange(c, P.up.p, c->U[c->cur].p, kToNodal, P.first[g], P.first[g + 1] - P.first[g], c->stream);
+    pipeLaunchList(c, 0, g, [&] {
+      StageArgs a; fillArgs(c, a);
+      a.Uin = c->U[c->cur].p; a.TUout = c->TU[c->cur].p; a.chunkList = c->listOverride;
+      c->lineFns.trace(a, c->listCount, c->stream);
+      c->launches++;
+      CUDA_OK(cudaGetLastError());
+    });
+    c->traceValid[c->cur] = true;   // level by level: every row a launch below reads has been written by a launch above
+    for (int s = 0; s < S; s++) pipeLaunchList(c, s + 1, g, [&] { stageLaunch(c, s, -1, c->stream); });
+    for (int h : P.download[g]) {
+      const size_t e0 = P.first[h], ne = P.first[h + 1] - P.first[h];
+      transformModalRange(c, c->U[outLast].p, P.down.p, kToModal, (int)e0, (int)ne, c->stream);
+      CUDA_OK(cudaEventRecord(P.downEv[h], c->stream));
+      CUDA_OK(cudaStreamWaitEvent(P.d2h, P.downEv[h], 0));
+      CUDA_OK(cudaMemcpyAsync(U_out + e0 * per, P.down.p + e0 * per, ne * per * sizeof(double), cudaMemcpyDeviceToHost, P.d2h));
+    }
+  }
+  finishStep(c);
+  if (relative_error) {
+    double sums[8];
+    reduceNorm(c, sums);
+    for (int v = 0; v < c->NV; v++) relative_error[v] = sums[v] / B.nOwned;
+  }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaStreamSynchronize(P.d2h));
+  SDG_CATCH
+}
+
+/* diagnostics of the streamed step: number of upload groups and the fraction of them that go back to the host before the last level */
+int sdg_step_host_info(sdg_ctx* c, int32_t* groups, double* early_fraction) {
+  SDG_TRY
+  needFinal(c);
+  if (!c->mx && hostPipeEligible(c) && c->pipe.G == 0) { if (c->hasDevice) CUDA_OK(cudaSetDevice(c->cfg.device)); buildHostPipe(c); }
+  if (groups) *groups = c->pipe.G;
+  if (early_fraction) *early_fraction = c->pipe.overlap;
   SDG_CATCH
 }
 

@@ -42,7 +42,7 @@ EXPORTS = [
     "sdg_last_error", "sdg_version", "sdg_create", "sdg_destroy", "sdg_add_elements", "sdg_set_faces", "sdg_finalize", "sdg_sizes",
     "sdg_get_quadrature_coordinates", "sdg_get_boundary_quadrature_coordinates", "sdg_set_state_from_primitive",
     "sdg_set_boundary_primitive", "sdg_set_state", "sdg_get_state", "sdg_get_state_at_quadrature", "sdg_get_gradient_at_quadrature",
-    "sdg_compute_dt", "sdg_step", "sdg_step_timed", "sdg_residual", "sdg_set_halo_send", "sdg_halo_pack", "sdg_halo_buffers_device", "sdg_step_begin",
+    "sdg_compute_dt", "sdg_step", "sdg_step_timed", "sdg_step_host", "sdg_step_host_info", "sdg_residual", "sdg_set_halo_send", "sdg_halo_pack", "sdg_halo_buffers_device", "sdg_step_begin",
     "sdg_stage_pass", "sdg_step_end", "sdg_num_passes", "sdg_num_stages", "sdg_stream", "sdg_synchronize", "sdg_set_state_device",
     "sdg_get_state_device", "sdg_launch_count", "sdg_debug_plan", "sdg_ipc_export", "sdg_ipc_connect", "sdg_halo_push", "sdg_halo_wait",
     "sdg_halo_doubles_per_element", "sdg_debug_physics", "sdg_uses_trace_rows", "sdg_set_halo_rows", "sdg_halo_unpack",
@@ -282,6 +282,27 @@ class Solver:
         _chk(load_library().sdg_step_timed(self.h, ctypes.c_double(dt), int(nsteps), _dp(err), ctypes.byref(ms)))
         self.relative_error_ = err
         return err, float(ms.value)
+
+    def step_host(self, t, U_in, dt=None, out=None):
+        """One stepSolver on a state held in host memory (sdg_step_host): modal coefficients in, modal coefficients out (into `out`,
+        which may be `U_in` itself), upload / stages / download streamed where the kernels allow it.  Returns (out, relative_error_)."""
+        dt = self.delta_time_ if dt is None else dt
+        s = self.sizes(t)
+        if U_in.dtype != np.float64 or not U_in.flags.c_contiguous or U_in.size != s.n * s.Nb * s.Nv:
+            raise ValueError("U_in must be a C-contiguous float64 array with n*Nb*Nv entries")
+        if out is None:
+            out = np.zeros((s.n, s.Nb, s.Nv))
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size != s.n * s.Nb * s.Nv:
+            raise ValueError("out must be a C-contiguous float64 array with n*Nb*Nv entries")
+        err = np.zeros(self.Nv)
+        _chk(load_library().sdg_step_host(self.h, t, ctypes.c_double(dt), _dp(U_in), _dp(out), _dp(err)))
+        self.relative_error_ = err
+        return out, err
+
+    def step_host_info(self):
+        g = ctypes.c_int32(0); f = ctypes.c_double(0)
+        _chk(load_library().sdg_step_host_info(self.h, ctypes.byref(g), ctypes.byref(f)))
+        return int(g.value), float(f.value)
 
     def step(self, dt, nsteps=1):
         return self.stepSolver(dt, nsteps)

@@ -1,0 +1,90 @@
+"""sdg_step_host: one stepSolver on a state held in host memory, streamed (upload groups -> dependency levels of the thread-block chunks
+-> downloads).  CPU: the levels of a plan-only context.  GPU: bit-identical to sdg_set_state -> sdg_step -> sdg_get_state."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from subrosadg_b200 import mesh as M
+from subrosadg_b200.solver import Solver
+
+HEX = M.HEXAHEDRON
+
+
+def _with_groups(g):
+    os.environ["SDG_HOST_PIPE_GROUPS"] = str(g)
+
+
+def test_levels_of_a_structured_cube_stream(built):
+    """24^3 periodic cube, 12 upload groups of two element layers = one layer of 2 x 2 x 2 chunks each: a stage moves the dependency by
+    one chunk layer, so group g goes back at level g + 3; the groups 0-2 next to the periodic wrap and the last ones wait for the end:
+    5 of the 12 groups travel back while later groups are still arriving."""
+    _with_groups(12)
+    try:
+        S = Solver(dict(p=3, conv_flux=2, rk=2), M.periodic_box_fast(3, 24), device=-1)
+        groups, early = S.step_host_info()
+        assert groups == 12
+        assert abs(early - 5.0 / 12.0) < 1e-12, early
+    finally:
+        del os.environ["SDG_HOST_PIPE_GROUPS"]
+
+
+def test_contexts_that_do_not_stream_report_zero_groups(built):
+    S = Solver(dict(p=2, conv_flux=2, rk=2), M.periodic_box_fast(3, 24), device=-1)   # P2: node-per-thread kernels
+    assert S.step_host_info()[0] == 0
+    S = Solver(dict(p=3, conv_flux=2, rk=2), M.periodic_box_fast(3, 8), device=-1)    # 512 elements: not worth streaming
+    assert S.step_host_info()[0] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rk,groups", [(2, 6), (2, 1), (1, 5), (0, 4)])
+def test_streamed_step_is_bit_identical(built, rk, groups):
+    _with_groups(groups)
+    try:
+        mesh = M.periodic_box_fast(3, 24)
+        cfg = dict(p=3, conv_flux=2, rk=rk)
+        S = Solver(cfg, mesh, device=0)
+        S.initializeSolver(cases.ic_density_wave([0.5, 0.3, 0.2]))
+        assert S.step_host_info()[0] == groups
+        dt = S.calculateDeltaTime(1.0)
+        U0 = S.get_state(HEX).copy()
+        # phase after phase
+        S.set_state(HEX, U0)
+        e_ref = S.stepSolver(dt, 1).copy()
+        U_ref = S.get_state(HEX).copy()
+        S.set_state(HEX, U_ref)                                   # the host round trip is part of what is compared
+        e_ref2 = S.stepSolver(dt, 1).copy()
+        U_ref2 = S.get_state(HEX).copy()
+        # streamed, twice in a row, the second time in place
+        buf, e1 = S.step_host(HEX, U0, dt)
+        assert np.array_equal(buf, U_ref) and np.array_equal(e1, e_ref)
+        assert np.array_equal(S.get_state(HEX), U_ref)            # the device state is the new state as well
+        _, e2 = S.step_host(HEX, buf, dt, out=buf)
+        assert np.array_equal(buf, U_ref2) and np.array_equal(e2, e_ref2)
+        # and the library carries on from there
+        e3 = S.stepSolver(dt, 1)                                   # from the resident (nodal) state
+        S.set_state(HEX, U_ref2)                                   # from its modal image: equal up to the round-off of the transform
+        assert np.allclose(S.stepSolver(dt, 1), e3, rtol=1e-9, atol=0.0)
+    finally:
+        del os.environ["SDG_HOST_PIPE_GROUPS"]
+
+
+@pytest.mark.gpu
+def test_streamed_step_with_boundaries(built):
+    """a box with far-field and wall faces (boundary faces carry no dependency) and the fallback composition for a context that does not stream"""
+    _with_groups(7)
+    try:
+        for cfg, mesh in [(dict(p=3, conv_flux=2, rk=2), M.box(3, (24, 20, 22), 0.0, 2.0, periodic_axes=(0,), phys_bc={3: M.RIEMANN_FARFIELD, 4: M.RIEMANN_FARFIELD, 5: M.ADIABATIC_SLIP_WALL, 6: M.ADIABATIC_SLIP_WALL})),
+                          (dict(p=2, conv_flux=2, rk=2), M.periodic_box_fast(3, 12))]:
+            S = Solver(cfg, mesh, device=0)
+            S.initializeSolver(cases.ic_density_wave([0.5, 0.3, 0.2]), cases.bc_freestream(0.4, 0.0, 3, wall_phys=(5, 6), vel=[0.5, 0.3, 0.2]) if mesh.faces["n_bnd"] else None)
+            dt = S.calculateDeltaTime(0.5)
+            U0 = S.get_state(HEX).copy()
+            S.set_state(HEX, U0)
+            e_ref = S.stepSolver(dt, 1).copy()
+            U_ref = S.get_state(HEX).copy()
+            buf, e1 = S.step_host(HEX, U0, dt)
+            assert np.array_equal(buf, U_ref) and np.array_equal(e1, e_ref)
+    finally:
+        del os.environ["SDG_HOST_PIPE_GROUPS"]
