@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(128, AFFINE ? 3 : 2) nslGradKernel(const __gri
 // =====================================================================================================================
 // pass R: residual, RK update, traces of the new state, relative error
 // =====================================================================================================================
-template <bool GATHER>
+template <bool GATHER, bool USM = false>
 struct NslStageLayout {
   static constexpr int XE = GATHER ? 480 : 320;              // doubles per element of the exchange region
   static constexpr int oFl = 0;                              // [K][6][5][16] face-flux slots (natural point order)
@@ -628,9 +628,18 @@ struct NslStageLayout {
   static constexpr int oLg = oGeoE + kLK * 10;               // affine: [K][6][kLG]
   static constexpr int oLink = oLg + kLK * 6 * kLG;          // [K][6] int4
   static constexpr int oRed = oLink + kLK * 6 * 2;           // [4][5]
-  static constexpr int nDoubles = oRed + 4 * 5 + 4;
+  static constexpr int oU = oRed + 4 * 5 + 4;                // USM: [K][5][64] the chunk's own states, staged by one TMA bulk copy
+  static constexpr int nDoubles = oU + (USM ? kLK * 5 * 64 : 0);
   static constexpr size_t bytes = sizeof(double) * nDoubles;
 };
+
+// 1 (inviscid pass, published traces): the chunk's own states arrive in shared memory by a TMA bulk copy issued at block start, on their
+// own mbarrier — the node phase and the update read them there instead of waiting for the L2 three times per line
+#ifndef SDG_NSL_U_SMEM
+#define SDG_NSL_U_SMEM 0
+#endif
+template <bool VISC, bool GATHER>
+struct NslStageUsm { static constexpr bool value = SDG_NSL_U_SMEM != 0 && !VISC && !GATHER; };
 
 #ifndef SDG_NSL_MINB
 #define SDG_NSL_MINB 3
@@ -643,13 +652,19 @@ struct NslStageLayout {
 #ifndef SDG_NSL_RELOAD_U
 #define SDG_NSL_RELOAD_U 1
 #endif
+// 1: the xi / eta factors of the relative-error transform move the data by transposition (4 shared-memory reads per variable and direction
+// instead of 16); 0: every thread keeps its zeta-line and reads the four lines it needs (round-2 first version)
+#ifndef SDG_NSL_NORM_TRANSPOSE
+#define SDG_NSL_NORM_TRANSPOSE 1
+#endif
 // GATHER (inviscid only): no published traces — the own traces are computed into shared memory, partners inside the block are read from
 // there, partners outside are interpolated from their nodal states in global memory (L2), as eulerLineKernel does; HBM traffic stays at
 // the state itself (read U, read U_last, write U).
 template <bool AFFINE, int PH, bool VISC, bool GATHER = false>
 __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER) nslStageKernel(const __grid_constant__ StageArgs A) {
   static_assert(!(GATHER && VISC), "the gathering variant is inviscid");
-  using L = NslStageLayout<GATHER>;
+  constexpr bool USM = NslStageUsm<VISC, GATHER>::value;
+  using L = NslStageLayout<GATHER, USM>;
   constexpr int K = kLK, XE = L::XE;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -665,9 +680,14 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
   const bool active = el < ne;
   const Phys<PH> ph(A.phys);
   const bool needLast = A.mode == 0 && A.aLast != 0.0;
-  if (tid == 0) mbarInit(&mbar, 1);
+  __shared__ __align__(8) unsigned long long mbarU;
+  if (tid == 0) { mbarInit(&mbar, 1); if constexpr (USM) mbarInit(&mbarU, 1); }
   __syncthreads();
   if (tid == 0) {
+    if constexpr (USM) {
+      mbarExpectTx(&mbarU, (unsigned)(ne * 5 * 64 * sizeof(double)));
+      bulkLoad(smem + L::oU, A.Uin + (size_t)e0 * 5 * 64, (unsigned)(ne * 5 * 64 * sizeof(double)), &mbarU);
+    }
     unsigned total = (unsigned)(ne * 6 * sizeof(int4));
     if constexpr (AFFINE) total += (unsigned)(ne * 10 * sizeof(double)) + (unsigned)(ne * 6 * kLG * sizeof(double));
     mbarExpectTx(&mbar, total);
@@ -858,8 +878,10 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
   else __syncwarp(wm);
 
   // ---- R1 + R3 volume part: fluxes at the own nodes, two nodes per round; zeta contraction in registers, xi / eta through half tiles ----
-  constexpr bool RELOAD = SDG_NSL_RELOAD_U != 0;
+  constexpr bool RELOAD = SDG_NSL_RELOAD_U != 0 || USM;
   const double* gUl = A.Uin + (size_t)e * 5 * 64 + t * 4;
+  const double* sUl = smem + L::oU + el * 5 * 64 + t * 4;   // USM only
+  if constexpr (USM) mbarWait(&mbarU, 0);
   if constexpr (!GATHER && !RELOAD) {
 #pragma unroll
     for (int v = 0; v < 5; v++)
@@ -884,7 +906,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
     double ur[5][2];
     if constexpr (RELOAD) {
 #pragma unroll
-      for (int v = 0; v < 5; v++) { const double2 x = ldg2(gUl + v * 64 + 2 * r); ur[v][0] = x.x; ur[v][1] = x.y; }
+      for (int v = 0; v < 5; v++) { const double2 x = USM ? lds2(sUl + v * 64 + 2 * r) : ldg2(gUl + v * 64 + 2 * r); ur[v][0] = x.x; ur[v][1] = x.y; }
     }
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {
@@ -971,7 +993,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
     for (int k = 0; k < 4; k++) {
       double cons[5], comp[6];
 #pragma unroll
-      for (int v = 0; v < 5; v++) cons[v] = RELOAD ? __ldg(gUl + v * 64 + k) : u[v][k];
+      for (int v = 0; v < 5; v++) cons[v] = USM ? sUl[v * 64 + k] : RELOAD ? __ldg(gUl + v * 64 + k) : u[v][k];
       compFromCons<3>(ph, cons, comp);
       R[3][k] += boussinesqSource<3>(ph, comp) / ijw[k];
     }
@@ -984,7 +1006,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
 #pragma unroll
         for (int k = 0; k < 4; k += 2) {
           double uk = u[v][k], uk1 = u[v][k + 1];
-          if constexpr (RELOAD) { const double2 x = ldg2(gUl + v * 64 + k); uk = x.x; uk1 = x.y; }
+          if constexpr (RELOAD) { const double2 x = USM ? lds2(sUl + v * 64 + k) : ldg2(gUl + v * 64 + k); uk = x.x; uk1 = x.y; }
           double ox = A.aCur * uk + A.bdt * (R[v][k] * ijw[k]), oy = A.aCur * uk1 + A.bdt * (R[v][k + 1] * ijw[k + 1]);
           if (needLast) { const double2 l = ldg2(A.Ulast + g + (size_t)v * 64 + k); ox += A.aLast * l.x; oy += A.aLast * l.y; }
           u[v][k] = ox; u[v][k + 1] = oy;
@@ -1023,6 +1045,38 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
 #pragma unroll
         for (int k = 0; k < 4; k++) R[v][k] = S[v][k];
     }
+#if SDG_NSL_NORM_TRANSPOSE
+    // xi, then eta, as TRANSPOSES through the element's [5][64] tile: the absolute sum does not care which thread holds which value, so
+    // after the write of the zeta-transformed lines thread (i, j) takes the xi-line (., j, k = i), transforms it in registers, writes it
+    // back and takes the eta-line (a = j, ., k = i): 4 reads per variable and direction instead of 16 (every value is read ONCE)
+    const int p0 = tPair(i, j, 0), p1 = tPair(i, j, 1);
+    __syncwarp(wm);
+#pragma unroll
+    for (int v = 0; v < 5; v++) { sts2(sXe + v * 64 + p0, R[v][0], R[v][1]); sts2(sXe + v * 64 + p1, R[v][2], R[v][3]); }
+    __syncwarp(wm);
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+      double x[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) x[a] = sXe[v * 64 + tIdx(a, j, i)];
+#pragma unroll
+      for (int q = 0; q < 4; q++) R[v][q] = A.k1[0 * 4 + q] * x[0] + A.k1[1 * 4 + q] * x[1] + A.k1[2 * 4 + q] * x[2] + A.k1[3 * 4 + q] * x[3];
+    }
+    __syncwarp(wm);
+#pragma unroll
+    for (int v = 0; v < 5; v++)
+#pragma unroll
+      for (int a = 0; a < 4; a++) sXe[v * 64 + tIdx(a, j, i)] = R[v][a];
+    __syncwarp(wm);
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+      double x[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) x[b] = sXe[v * 64 + tIdx(j, b, i)];
+#pragma unroll
+      for (int q = 0; q < 4; q++) R[v][q] = A.k1[0 * 4 + q] * x[0] + A.k1[1 * 4 + q] * x[1] + A.k1[2 * 4 + q] * x[2] + A.k1[3 * 4 + q] * x[3];
+    }
+#else
     const int p0 = tPair(i, j, 0), p1 = tPair(i, j, 1);
 #pragma unroll
     for (int d = 0; d < 2; d++) {   // xi, then eta: all five variables through the element's [5][64] tile
@@ -1043,6 +1097,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
         R[v][0] = x0; R[v][1] = x1; R[v][2] = x2; R[v][3] = x3;
       }
     }
+#endif
     // deterministic block reduction: warp shuffle (inactive lanes contribute zero), then one thread sums the warp partials in order
 #pragma unroll
     for (int v = 0; v < 5; v++) {

@@ -26,7 +26,7 @@ void launchNslGrad(const StageArgs& a, int nBlocks, cudaStream_t s) {
 
 template <bool AFFINE, int PH, bool VISC, bool GATHER>
 void launchNslStage(const StageArgs& a, int nBlocks, cudaStream_t s) {
-  using L = NslStageLayout<GATHER>;
+  using L = NslStageLayout<GATHER, NslStageUsm<VISC, GATHER>::value>;
   static std::atomic<unsigned long long> configured{0};
   if (firstUseOnThisDevice(configured)) CUDA_OK(cudaFuncSetAttribute(nslStageKernel<AFFINE, PH, VISC, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
   nslStageKernel<AFFINE, PH, VISC, GATHER><<<nBlocks, 128, L::bytes, s>>>(a);
