@@ -654,6 +654,14 @@ struct NslStageUsm { static constexpr bool value = SDG_NSL_U_SMEM != 0 && !VISC 
 #endif
 // 1: the xi / eta factors of the relative-error transform move the data by transposition (4 shared-memory reads per variable and direction
 // instead of 16); 0: every thread keeps its zeta-line and reads the four lines it needs (round-2 first version)
+// 1 (inviscid pass, published traces): a face between two elements of the same thread block in the eta / zeta direction of the 2 x 2 x 2
+// brick is evaluated by ONE of its parents, which also writes the opposite value into the other parent's slot; the parents alternate so
+// that every warp evaluates five of its six faces (the face between the two elements of a warp stays with both: no round would be saved).
+// Measured at 128^3 on one box: 7.52-7.60 ms per stage against 7.57-7.63 without (+0.5 %): the block barrier the shared slots need costs
+// what the sixth of the face evaluations saves (profiles/r02_ab_dedup.txt) — off
+#ifndef SDG_NSL_DEDUP
+#define SDG_NSL_DEDUP 0
+#endif
 #ifndef SDG_NSL_NORM_TRANSPOSE
 #define SDG_NSL_NORM_TRANSPOSE 1
 #endif
@@ -744,6 +752,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
     lineTracesOut(A, u, sFl + el * 480, i, j, t, wm, sTr + el * 480);   // tile = the (not yet used) flux slots of the element
     __syncthreads();                                                     // partners inside the block live in other warps
   }
+  constexpr bool kDedup = SDG_NSL_DEDUP != 0 && !GATHER && !VISC;
 #if SDG_NSLS_HOIST
   // partner rows of all six faces, (row * 16 + point) packed: the table lookups leave the direction loop (one latency instead of three).
   // Inviscid pass only: the viscous pass has no registers to spare (64 bytes of spills, 2.4 % slower when measured).
@@ -779,9 +788,24 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
       rowO[side] = lk[side].x >= 0 ? ((size_t)lk[side].x * 6 + lfo) * kRow + A.ltab->partner[(((f * 6 + lfo) * 4 + rot) * 2 + amR) * 16 + t]
                                    : ((size_t)e * 6 + f) * kRow + t;
     }
+    // role of this element on the face: 0 = evaluates it for itself; 1 = ... and for the other parent, which sits in the same block
+    // (its slot receives the opposite value); 2 = the other parent does.  Both parents derive the same answer from their block-local indices.
+    int role[2] = {0, 0};
+    if constexpr (kDedup) {
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        const int z = lk[side].z;
+        if (lk[side].x >= 0 && linkInChunk(z)) {
+          const int elP = lk[side].x - e0, lo = min(el, elP), hi = max(el, elP), diff = hi - lo;
+          const int handler = diff == 2 ? ((lo & 4) ? hi : lo) : diff == 4 ? ((lo & 2) ? lo : hi) : -1;
+          role[side] = handler < 0 ? 0 : handler == el ? 1 : 2;
+        }
+      }
+    }
 #pragma unroll
     for (int side = (SDG_NSL_DIAG == 1 && !VISC) ? 1 : 0; side < 2; side++) {
       const int f = hexFaceRt(d, side);
+      if (kDedup && role[side] == 2) continue;
       if constexpr (GATHER) {
         const int z = lk[side].z, lfo = linkLfo(z);
         const int natO = (int)(rowO[side] % kRow);   // partner's natural point index (own point for a boundary face)
@@ -828,6 +852,7 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
       const int f = hexFaceRt(d, side);
       const int z = lk[side].z;
       const bool amR = linkAmRight(z);
+      if (kDedup && role[side] == 2) continue;
       double n[3], jw, Fn[5];
       if constexpr (AFFINE) {
         const double* g = sLg + (el * 6 + f) * kLG;
@@ -865,6 +890,13 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
         const double sg = amR ? -jw : jw;   // left parent +, right parent - (SpatialDiscrete.cpp:738-744)
 #pragma unroll
         for (int v = 0; v < 5; v++) mine[v * 16] = Fn[v] * sg;
+        if constexpr (kDedup) {
+          if (role[side] == 1) {   // the other parent's slot: its local face, its point, the opposite role
+            double* theirs = sFl + (((lk[side].x - e0) * 6 + linkLfo(z)) * 5) * 16 + (int)(rowO[side] % kRow);
+#pragma unroll
+            for (int v = 0; v < 5; v++) theirs[v * 16] = -(Fn[v] * sg);
+          }
+        }
       }
     }
   }
@@ -874,7 +906,8 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
       for (int v = 0; v < 5; v++) sFl[((el * 6 + f) * 5 + v) * 16 + t] = 0.0;
   }
 #endif
-  if constexpr (GATHER) __syncthreads();   // every warp has finished reading the trace tiles: the exchange region is free
+  if constexpr (GATHER || kDedup) __syncthreads();   // GATHER: every warp has finished reading the trace tiles, the exchange region is free;
+                                                    // kDedup: slots of this element may have been written by another warp
   else __syncwarp(wm);
 
   // ---- R1 + R3 volume part: fluxes at the own nodes, two nodes per round; zeta contraction in registers, xi / eta through half tiles ----
