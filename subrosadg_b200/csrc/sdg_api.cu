@@ -90,7 +90,7 @@ struct sdg_ctx {
   struct HostPipe {
     int G = 0;                                   // upload groups = contiguous ranges of the caller's element order
     std::vector<int> first;                      // [G + 1] caller-order element ranges
-    std::vector<int> off;                        // [(nStages + 1) * G + 1]: chunk lists of (kind, level); kind 0 = traces, 1.. = stage
+    std::vector<int> off;                        // [(launches + 1) * G + 1]: chunk lists of (kind, level); kind 0 = traces, 1.. = the launches of a step in order
     std::vector<std::vector<int>> download;      // per level: the upload groups whose elements have all finished the last stage
     DevBuf<int> lists; DevBuf<double> up, down;
     std::vector<cudaEvent_t> upEv, downEv;
@@ -1054,21 +1054,25 @@ int sdg_step_timed(sdg_ctx* c, double dt, int32_t n_steps, double* relative_erro
 
 namespace {
 
-// sdg_step_host can stream when the stage is ONE launch per chunk that reads, besides the chunk's own elements, only what the face
-// neighbours' previous stage published (trace rows): P3 hexahedra on the trace-based line kernels, inviscid, no shock capturing, one GPU.
+// sdg_step_host can stream when a launch over a chunk reads, besides the chunk's own elements, only what the face neighbours' PREVIOUS
+// launch published (trace rows): P3 hexahedra on the trace-based line kernels — the inviscid stage (one launch), or the two passes of the
+// Navier-Stokes stage on a mesh without boundary faces (the virtual neighbour traces of boundary faces are one launch over all of them) —
+// without shock capturing, on one GPU.
 bool hostPipeEligible(const sdg_ctx* c) {
-  return c->lineTrace && c->traceTU && !twoPass(c) && !c->phys.av && c->plan.blk.nGhost == 0 && c->plan.blk.nOwned >= 8192 && !getenv("SDG_NO_HOST_PIPE");
+  return c->lineTrace && c->traceTU && (!twoPass(c) || c->plan.F.nBnd == 0) && !c->phys.av && c->plan.blk.nGhost == 0 && c->plan.blk.nOwned >= 8192 &&
+         !getenv("SDG_NO_HOST_PIPE");
 }
 
 // Dependency levels of the streamed step.  The caller's element order is cut into G contiguous upload groups; a chunk's traces can be
-// taken once its own elements have arrived (level t0), stage s of a chunk can run once stage s - 1 (stage 0: the traces) of the chunk
-// and of every face neighbour's chunk has run: r_s = max over {chunk, neighbours} of r_(s-1).  An upload group goes back to the host
+// taken once its own elements have arrived (level t0), launch k of a chunk (the stages in order; Navier-Stokes: gradient pass, then
+// residual pass of each stage) can run once launch k - 1 (launch 0: the traces) of the chunk and of every face neighbour's chunk has
+// run: r_k = max over {chunk, neighbours} of r_(k-1).  An upload group goes back to the host
 // at the level at which the last stage of all of its elements is done.  Launching level after level on ONE stream (traces, stage 1,
 // stage 2, ... of that level, in this order) satisfies every dependency without an event between kernels.
 void buildHostPipe(sdg_ctx* c) {
   auto& P = c->pipe;
   const BlockPlan& B = c->plan.blk;
-  const int n = B.nOwned, K = B.K, nCh = B.nChunks, S = c->nStages;
+  const int n = B.nOwned, K = B.K, nCh = B.nChunks, S = c->nStages * (twoPass(c) ? 2 : 1);   // launches per step after the traces
   int G = std::max(2, std::min(64, n / 16384));
   if (const char* e = getenv("SDG_HOST_PIPE_GROUPS")) G = std::max(1, std::min(256, atoi(e)));
   P.G = G;
@@ -1171,7 +1175,9 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
       CUDA_OK(cudaGetLastError());
     });
     c->traceValid[c->cur] = true;   // level by level: every row a launch below reads has been written by a launch above
-    for (int s = 0; s < S; s++) pipeLaunchList(c, s + 1, g, [&] { stageLaunch(c, s, -1, c->stream); });
+    const int passes = twoPass(c) ? 2 : 1;
+    for (int s = 0; s < S; s++)
+      for (int q = 0; q < passes; q++) pipeLaunchList(c, 1 + s * passes + q, g, [&] { stageLaunch(c, s, -1, c->stream, passes == 2 ? q : -1); });
     for (int h : P.download[g]) {
       const size_t e0 = P.first[h], ne = P.first[h + 1] - P.first[h];
       transformModalRange(c, c->U[outLast].p, P.down.p, kToModal, (int)e0, (int)ne, c->stream);

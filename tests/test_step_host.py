@@ -10,6 +10,7 @@ from subrosadg_b200 import mesh as M
 from subrosadg_b200.solver import Solver
 
 HEX = M.HEXAHEDRON
+NS = dict(model=1, transport=1, mu=1.4 * 0.2 / 200.0, visc_flux=2)   # CompresibleNS, constant viscosity, BR2 (the north-star kernel pair)
 
 
 def _with_groups(g):
@@ -30,6 +31,22 @@ def test_levels_of_a_structured_cube_stream(built):
         del os.environ["SDG_HOST_PIPE_GROUPS"]
 
 
+def test_two_pass_levels(built):
+    """Navier-Stokes: two launches per stage, so the dependency moves twice as far: group g of 12 goes back at level g + 6"""
+    _with_groups(12)
+    try:
+        S = Solver(dict(p=3, conv_flux=2, rk=2, **NS), M.periodic_box_fast(3, 24), device=-1)
+        groups, early = S.step_host_info()
+        assert groups == 12 and early == 0.0     # 24 cells are too few for six chunk layers each way: everything waits for the wrap
+        S = Solver(dict(p=3, conv_flux=2, rk=0, **NS), M.periodic_box_fast(3, 24), device=-1)   # forward Euler: two launches
+        assert abs(S.step_host_info()[1] - 7.0 / 12.0) < 1e-12
+        # a mesh with boundary faces needs the one-launch boundary-trace kernel per stage: phase after phase
+        S = Solver(dict(p=3, conv_flux=2, rk=2, **NS), M.box(3, (24, 24, 24), 0.0, 2.0), device=-1)
+        assert S.step_host_info()[0] == 0
+    finally:
+        del os.environ["SDG_HOST_PIPE_GROUPS"]
+
+
 def test_contexts_that_do_not_stream_report_zero_groups(built):
     S = Solver(dict(p=2, conv_flux=2, rk=2), M.periodic_box_fast(3, 24), device=-1)   # P2: node-per-thread kernels
     assert S.step_host_info()[0] == 0
@@ -38,12 +55,12 @@ def test_contexts_that_do_not_stream_report_zero_groups(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("rk,groups", [(2, 6), (2, 1), (1, 5), (0, 4)])
-def test_streamed_step_is_bit_identical(built, rk, groups):
+@pytest.mark.parametrize("rk,groups,extra", [(2, 6, {}), (2, 1, {}), (1, 5, {}), (0, 4, {}), (2, 6, NS), (1, 3, dict(NS, visc_flux=1))])
+def test_streamed_step_is_bit_identical(built, rk, groups, extra):
     _with_groups(groups)
     try:
         mesh = M.periodic_box_fast(3, 24)
-        cfg = dict(p=3, conv_flux=2, rk=rk)
+        cfg = dict(p=3, conv_flux=2, rk=rk, **extra)
         S = Solver(cfg, mesh, device=0)
         S.initializeSolver(cases.ic_density_wave([0.5, 0.3, 0.2]))
         assert S.step_host_info()[0] == groups
