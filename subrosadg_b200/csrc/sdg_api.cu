@@ -1127,9 +1127,9 @@ void pipeLaunchList(sdg_ctx* c, int kind, int level, const std::function<void()>
   const auto& P = c->pipe;
   const int i = kind * P.G + level, a = P.off[i], b = (level == P.G - 1) ? (kind + 1) * c->plan.blk.nChunks : P.off[i + 1];
   if (b <= a) return;
+  struct Guard { sdg_ctx* c; ~Guard() { c->listOverride = nullptr; c->listCount = 0; } } guard{c};   // also when a launch throws
   c->listOverride = P.lists.p + a; c->listCount = b - a;
   launch();
-  c->listOverride = nullptr; c->listCount = 0;
 }
 
 }  // namespace
@@ -1138,7 +1138,17 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
   SDG_TRY
   needFinal(c);
   if (!U_in || !U_out) throw std::runtime_error("null argument");
-  if (c->mx || !c->hasDevice || !hostPipeEligible(c)) {   // same result, one phase after the other
+  bool stream = !c->mx && c->hasDevice && hostPipeEligible(c) && c->pipe.G >= 0;
+  if (stream && c->pipe.G == 0) {
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    try { buildHostPipe(c); }
+    catch (const std::exception&) {   // no room for the two staging arrays: the phases reuse a stage buffer instead
+      cudaGetLastError();
+      c->pipe.lists.release(); c->pipe.up.release(); c->pipe.down.release();
+      c->pipe.G = -1; stream = false;
+    }
+  }
+  if (!stream) {   // same result, one phase after the other
     if (sdg_set_state(c, type, U_in)) throw std::runtime_error(g_err);
     if (sdg_step(c, dt, 1, relative_error)) throw std::runtime_error(g_err);
     if (sdg_get_state(c, type, U_out)) throw std::runtime_error(g_err);
@@ -1147,7 +1157,6 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
   needDevice(c); needType(c, type);
   CUDA_OK(cudaSetDevice(c->cfg.device));
   auto& P = c->pipe;
-  if (P.G == 0) buildHostPipe(c);
   seamStreams(c);
   const BlockPlan& B = c->plan.blk;
   const size_t per = (size_t)c->NV * B.T.NN;
@@ -1202,7 +1211,7 @@ int sdg_step_host_info(sdg_ctx* c, int32_t* groups, double* early_fraction) {
   SDG_TRY
   needFinal(c);
   if (!c->mx && hostPipeEligible(c) && c->pipe.G == 0) { if (c->hasDevice) CUDA_OK(cudaSetDevice(c->cfg.device)); buildHostPipe(c); }
-  if (groups) *groups = c->pipe.G;
+  if (groups) *groups = std::max(0, c->pipe.G);
   if (early_fraction) *early_fraction = c->pipe.overlap;
   SDG_CATCH
 }
