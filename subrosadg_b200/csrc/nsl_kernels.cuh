@@ -662,6 +662,10 @@ struct NslStageUsm { static constexpr bool value = SDG_NSL_U_SMEM != 0 && !VISC 
 #ifndef SDG_NSL_DEDUP
 #define SDG_NSL_DEDUP 0
 #endif
+// 1: L1 prefetch of the next direction's rows inside the face loop — measured 2.5 % SLOWER at 128^3 (profiles/r02_ab_pfnext.txt), off
+#ifndef SDG_NSLS_PF_NEXT
+#define SDG_NSLS_PF_NEXT 0
+#endif
 #ifndef SDG_NSL_NORM_TRANSPOSE
 #define SDG_NSL_NORM_TRANSPOSE 1
 #endif
@@ -847,6 +851,21 @@ __global__ void __launch_bounds__(128, VISC ? SDG_NSL_MINB : SDG_NSL_MINB_EULER)
         }
       }
     }
+#if SDG_NSLS_PF_NEXT
+    // the rows of the NEXT direction's two faces into L1 while this direction's Riemann solves run (the direction loop is rolled: the
+    // loads themselves cannot be hoisted across it without 40 more live registers)
+    if constexpr (kHoist) {
+      if (d < 2) {
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+          const int fn = hexFaceRt(d + 1, side);
+          const size_t ro = nbrOffset(side ? (d == 0 ? prow[4] : prow[5]) : (d == 0 ? prow[1] : prow[0]));
+#pragma unroll
+          for (int v = 0; v < 5; v++) { prefetchL1(gTU + (fn * 5 + v) * 16); prefetchL1(A.TUin + ro + v * 16); }
+        }
+      }
+    }
+#endif
 #pragma unroll
     for (int side = (SDG_NSL_DIAG == 1 && !VISC) ? 1 : 0; side < 2; side++) {
       const int f = hexFaceRt(d, side);
