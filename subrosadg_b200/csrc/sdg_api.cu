@@ -93,7 +93,8 @@ struct sdg_ctx {
     std::vector<int> off;                        // [(launches + 1) * G + 1]: chunk lists of (kind, level); kind 0 = traces, 1.. = the launches of a step in order
     std::vector<std::vector<int>> download;      // per level: the upload groups whose elements have all finished the last stage
     DevBuf<int> lists; DevBuf<double> up, down;
-    std::vector<cudaEvent_t> upEv, downEv;
+    std::vector<cudaEvent_t> upEv, downEv, doneEv;   // doneEv + t0: SDG_HOST_PIPE_TIMING=1 only (time line of the copies on stderr)
+    cudaEvent_t t0 = nullptr; bool timing = false;
     cudaStream_t d2h = nullptr;
     double overlap = 0.0;                        // fraction of the upload groups downloaded before the last level (diagnostic)
   } pipe;
@@ -304,6 +305,8 @@ void sdg_destroy(sdg_ctx* c) {
   if (c->pipe.d2h) cudaStreamDestroy(c->pipe.d2h);
   for (cudaEvent_t e : c->pipe.upEv) cudaEventDestroy(e);
   for (cudaEvent_t e : c->pipe.downEv) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->pipe.doneEv) cudaEventDestroy(e);
+  if (c->pipe.t0) cudaEventDestroy(c->pipe.t0);
   cudaStream_t s = c->stream; const bool dev = c->hasDevice;
   delete c;
   if (dev && s) cudaStreamDestroy(s);
@@ -1119,8 +1122,15 @@ void buildHostPipe(sdg_ctx* c) {
   P.up.alloc((size_t)n * per); P.down.alloc((size_t)n * per);
   CUDA_OK(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
   P.upEv.resize(G); P.downEv.resize(G);
-  for (auto& e : P.upEv) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto& e : P.downEv) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  P.timing = getenv("SDG_HOST_PIPE_TIMING") != nullptr;
+  const unsigned flags = P.timing ? cudaEventDefault : cudaEventDisableTiming;
+  for (auto& e : P.upEv) CUDA_OK(cudaEventCreateWithFlags(&e, flags));
+  for (auto& e : P.downEv) CUDA_OK(cudaEventCreateWithFlags(&e, flags));
+  if (P.timing) {
+    P.doneEv.resize(G);
+    for (auto& e : P.doneEv) CUDA_OK(cudaEventCreate(&e));
+    CUDA_OK(cudaEventCreate(&P.t0));
+  }
 }
 
 void pipeLaunchList(sdg_ctx* c, int kind, int level, const std::function<void()>& launch) {
@@ -1166,6 +1176,7 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
   // uploads: nothing on the device waits for them except the transform of the same group
   CUDA_OK(cudaEventRecord(c->seamEvent[kSeamChunks], c->stream));   // an earlier call's transforms out of the staging array
   CUDA_OK(cudaStreamWaitEvent(c->copyStream, c->seamEvent[kSeamChunks], 0));
+  if (P.timing) CUDA_OK(cudaEventRecord(P.t0, c->copyStream));
   for (int g = 0; g < G; g++) {
     const size_t e0 = P.first[g], ne = P.first[g + 1] - P.first[g];
     CUDA_OK(cudaMemcpyAsync(P.up.p + e0 * per, U_in + e0 * per, ne * per * sizeof(double), cudaMemcpyHostToDevice, c->copyStream));
@@ -1193,6 +1204,7 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
       CUDA_OK(cudaEventRecord(P.downEv[h], c->stream));
       CUDA_OK(cudaStreamWaitEvent(P.d2h, P.downEv[h], 0));
       CUDA_OK(cudaMemcpyAsync(U_out + e0 * per, P.down.p + e0 * per, ne * per * sizeof(double), cudaMemcpyDeviceToHost, P.d2h));
+      if (P.timing) CUDA_OK(cudaEventRecord(P.doneEv[h], P.d2h));
     }
   }
   finishStep(c);
@@ -1203,6 +1215,14 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
   }
   CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaStreamSynchronize(P.d2h));
+  if (P.timing) {   // time line of the copies, milliseconds after the first upload was queued
+    std::fprintf(stderr, "sdg_step_host time line (ms): group, upload done, download queued (last stage + transform done), download done\n");
+    for (int g = 0; g < G; g++) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, P.t0, P.upEv[g]); cudaEventElapsedTime(&b, P.t0, P.downEv[g]); cudaEventElapsedTime(&d, P.t0, P.doneEv[g]);
+      std::fprintf(stderr, "%3d %8.2f %8.2f %8.2f\n", g, a, b, d);
+    }
+  }
   SDG_CATCH
 }
 
