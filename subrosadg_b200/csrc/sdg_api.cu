@@ -1058,12 +1058,12 @@ int sdg_step_timed(sdg_ctx* c, double dt, int32_t n_steps, double* relative_erro
 namespace {
 
 // sdg_step_host can stream when a launch over a chunk reads, besides the chunk's own elements, only what the face neighbours' PREVIOUS
-// launch published (trace rows): P3 hexahedra on the trace-based line kernels — the inviscid stage (one launch), or the two passes of the
-// Navier-Stokes stage on a mesh without boundary faces (the virtual neighbour traces of boundary faces are one launch over all of them) —
-// without shock capturing, on one GPU.
+// launch wrote (their states or gradients, or the trace rows they published): every single-block context of the tensor kernels on one
+// GPU without shock capturing (its viscosity pass runs over the whole mesh) — except the trace-based Navier-Stokes passes on a mesh with
+// boundary faces, whose virtual neighbour traces are one launch over all of them.
 bool hostPipeEligible(const sdg_ctx* c) {
-  return c->lineTrace && c->traceTU && (!twoPass(c) || c->plan.F.nBnd == 0) && !c->phys.av && c->plan.blk.nGhost == 0 && c->plan.blk.nOwned >= 8192 &&
-         !getenv("SDG_NO_HOST_PIPE");
+  if (!c->haveBlock || c->phys.av || c->plan.blk.nGhost != 0 || c->plan.blk.nOwned < 8192 || getenv("SDG_NO_HOST_PIPE")) return false;
+  return !(c->lineTrace && c->traceTU && twoPass(c) && c->plan.F.nBnd > 0);
 }
 
 // Dependency levels of the streamed step.  The caller's element order is cut into G contiguous upload groups; a chunk's traces can be
@@ -1085,14 +1085,24 @@ void buildHostPipe(sdg_ctx* c) {
   for (int k = 0; k < G; k++) for (int ci = P.first[k]; ci < P.first[k + 1]; ci++) groupOf[B.perm[ci]] = k;
   std::vector<std::vector<int>> lvl(S + 1, std::vector<int>(nCh, 0));
   for (int e = 0; e < n; e++) lvl[0][e / K] = std::max(lvl[0][e / K], groupOf[e]);
-  const std::vector<int>& L = c->linePlan.links;
-  for (int s = 1; s <= S; s++) {
-    lvl[s] = lvl[s - 1];
+  // pairs of different chunks that share a face: link records of the line plan, else the chunks' face lists
+  std::vector<std::pair<int, int>> adj;
+  if (c->lineTrace) {
+    const std::vector<int>& L = c->linePlan.links;
     for (int e = 0; e < n; e++)
       for (int f = 0; f < 6; f++) {
         const int o = L[((size_t)e * 6 + f) * 4];
-        if (o >= 0 && o < n) lvl[s][e / K] = std::max(lvl[s][e / K], lvl[s - 1][o / K]);
+        if (o >= 0 && o < n && o / K != e / K) adj.emplace_back(e / K, o / K);
       }
+  } else {
+    for (size_t k = 0; k + 3 < B.faceRec.size(); k += 4) {
+      const int a = B.faceRec[k], b = B.faceRec[k + 1];
+      if (a >= 0 && b >= 0 && a < n && b < n && a / K != b / K) { adj.emplace_back(a / K, b / K); adj.emplace_back(b / K, a / K); }
+    }
+  }
+  for (int s = 1; s <= S; s++) {
+    lvl[s] = lvl[s - 1];
+    for (const auto& ab : adj) lvl[s][ab.first] = std::max(lvl[s][ab.first], lvl[s - 1][ab.second]);
   }
   // chunk lists sorted by (kind, level); ascending chunk index inside a list
   P.off.assign((size_t)(S + 1) * G + 1, 0);
@@ -1187,14 +1197,14 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
   for (int g = 0; g < G; g++) {
     CUDA_OK(cudaStreamWaitEvent(c->stream, P.upEv[g], 0));
     transformModalRange(c, P.up.p, c->U[c->cur].p, kToNodal, P.first[g], P.first[g + 1] - P.first[g], c->stream);
-    pipeLaunchList(c, 0, g, [&] {
+    if (c->traceTU) pipeLaunchList(c, 0, g, [&] {
       StageArgs a; fillArgs(c, a);
       a.Uin = c->U[c->cur].p; a.TUout = c->TU[c->cur].p; a.chunkList = c->listOverride;
       c->lineFns.trace(a, c->listCount, c->stream);
       c->launches++;
       CUDA_OK(cudaGetLastError());
     });
-    c->traceValid[c->cur] = true;   // level by level: every row a launch below reads has been written by a launch above
+    if (c->traceTU) c->traceValid[c->cur] = true;   // level by level: every row a launch below reads has been written by a launch above
     const int passes = twoPass(c) ? 2 : 1;
     for (int s = 0; s < S; s++)
       for (int q = 0; q < passes; q++) pipeLaunchList(c, 1 + s * passes + q, g, [&] { stageLaunch(c, s, -1, c->stream, passes == 2 ? q : -1); });

@@ -48,10 +48,24 @@ def test_two_pass_levels(built):
 
 
 def test_contexts_that_do_not_stream_report_zero_groups(built):
-    S = Solver(dict(p=2, conv_flux=2, rk=2), M.periodic_box_fast(3, 24), device=-1)   # P2: node-per-thread kernels
-    assert S.step_host_info()[0] == 0
     S = Solver(dict(p=3, conv_flux=2, rk=2), M.periodic_box_fast(3, 8), device=-1)    # 512 elements: not worth streaming
     assert S.step_host_info()[0] == 0
+    S = Solver(dict(p=2, conv_flux=2, rk=2, av_tolerance=1.0), M.periodic_box_fast(3, 24), device=-1)   # shock capturing: a pass over the whole mesh per step
+    assert S.step_host_info()[0] == 0
+
+
+def test_node_kernel_contexts_stream_too(built):
+    """the chunks' face lists give the same dependency for the node-per-thread kernels: P2 hexahedra, P3 quadrangles"""
+    _with_groups(8)
+    try:
+        S = Solver(dict(p=2, conv_flux=2, rk=2), M.periodic_box_fast(3, 24), device=-1)
+        groups, early = S.step_host_info()
+        assert groups == 8 and 0.0 < early < 1.0
+        S = Solver(dict(p=3, conv_flux=2, rk=2), M.periodic_box_fast(2, 128), device=-1)
+        groups, early = S.step_host_info()
+        assert groups == 8 and 0.0 < early < 1.0
+    finally:
+        del os.environ["SDG_HOST_PIPE_GROUPS"]
 
 
 @pytest.mark.gpu
@@ -88,12 +102,34 @@ def test_streamed_step_is_bit_identical(built, rk, groups, extra):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dim,cells,cfg", [(3, 24, dict(p=2, conv_flux=2, rk=2)), (2, 128, dict(p=3, conv_flux=3, rk=2)), (2, 100, dict(p=4, conv_flux=2, rk=1, **NS)),
+                                           (3, 22, dict(p=2, conv_flux=2, rk=2, **NS))])
+def test_streamed_step_on_the_node_kernels(built, dim, cells, cfg):
+    _with_groups(5)
+    try:
+        mesh = M.periodic_box_fast(dim, cells)
+        S = Solver(cfg, mesh, device=0)
+        t = S.types[0]
+        S.initializeSolver(cases.ic_density_wave([0.5, 0.3, 0.2][:dim]))
+        assert S.step_host_info()[0] == 5
+        dt = S.calculateDeltaTime(1.0)
+        U0 = S.get_state(t).copy()
+        S.set_state(t, U0)
+        e_ref = S.stepSolver(dt, 1).copy()
+        U_ref = S.get_state(t).copy()
+        buf, e1 = S.step_host(t, U0, dt)
+        assert np.array_equal(buf, U_ref) and np.array_equal(e1, e_ref)
+    finally:
+        del os.environ["SDG_HOST_PIPE_GROUPS"]
+
+
+@pytest.mark.gpu
 def test_streamed_step_with_boundaries(built):
-    """a box with far-field and wall faces (boundary faces carry no dependency) and the fallback composition for a context that does not stream"""
+    """a box with far-field and wall faces (boundary faces carry no dependency), and a small mesh that runs the phases one after the other"""
     _with_groups(7)
     try:
         for cfg, mesh in [(dict(p=3, conv_flux=2, rk=2), M.box(3, (24, 20, 22), 0.0, 2.0, periodic_axes=(0,), phys_bc={3: M.RIEMANN_FARFIELD, 4: M.RIEMANN_FARFIELD, 5: M.ADIABATIC_SLIP_WALL, 6: M.ADIABATIC_SLIP_WALL})),
-                          (dict(p=2, conv_flux=2, rk=2), M.periodic_box_fast(3, 12))]:
+                          (dict(p=2, conv_flux=2, rk=2), M.periodic_box_fast(3, 12))]:   # 1,728 elements: no streaming
             S = Solver(cfg, mesh, device=0)
             S.initializeSolver(cases.ic_density_wave([0.5, 0.3, 0.2]), cases.bc_freestream(0.4, 0.0, 3, wall_phys=(5, 6), vel=[0.5, 0.3, 0.2]) if mesh.faces["n_bnd"] else None)
             dt = S.calculateDeltaTime(0.5)
