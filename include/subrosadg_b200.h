@@ -149,8 +149,8 @@ int sdg_step_timed(sdg_ctx* ctx, double dt, int32_t n_steps, double* relative_er
 /* One call of Solver::stepSolver (TimeIntegration.cpp:326-350) on a state that lives in HOST memory: the modal coefficients
  * U_in [n][Nb][Nv] (the layout of sdg_set_state) are the step's input, U_out receives the coefficients after the step, relative_error
  * [Nv] (may be NULL) Solver::relative_error_.  Same result, bit for bit, as sdg_set_state -> sdg_step(dt, 1) -> sdg_get_state; for
- * a single line / quadrangle / hexahedron block of at least 8192 elements on one GPU (no shock capturing; the trace-based Navier-Stokes
- * passes only on a mesh without boundary faces) the three phases are STREAMED: the caller's element order is cut into
+ * a single line / quadrangle / hexahedron block of at least 8192 elements on one GPU, without shock capturing, the three phases are
+ * STREAMED: the caller's element order is cut into
  * upload groups, the stages of a thread-block chunk run as soon as the chunk's and its face neighbours' inputs have arrived, and a
  * group travels back while later groups are still arriving (PCIe in both directions at once).  U_in and U_out may be the same buffer;
  * pinned host memory is what makes the copies asynchronous.  SDG_NO_HOST_PIPE=1 forces the phase-after-phase composition,

@@ -158,8 +158,9 @@ static __global__ void __launch_bounds__(128) nslTraceKernel(const __grid_consta
 template <bool AFFINE>
 __global__ void __launch_bounds__(128) nslBoundaryKernel(const __grid_constant__ StageArgs A, const int4* __restrict__ bndRec, int nBnd) {
   const int idx = blockIdx.x * 128 + threadIdx.x;
-  const int fb = idx >> 4, t = idx & 15;
-  if (fb >= nBnd) return;
+  const int t = idx & 15;
+  if ((idx >> 4) >= nBnd) return;
+  const int fb = A.chunkList ? A.chunkList[idx >> 4] : idx >> 4;   // chunkList: here a list of boundary faces (sdg_step_host launches them by level)
   const Phys<0> ph(A.phys);
   const int4 r = bndRec[fb];   // left parent (internal position), its local face, boundary condition, face id
   const int jL = A.ltab->jLeft[((r.y * 4 + 0) * 2 + 0) * 16 + t];

@@ -92,7 +92,8 @@ struct sdg_ctx {
     std::vector<int> first;                      // [G + 1] caller-order element ranges
     std::vector<int> off;                        // [(launches + 1) * G + 1]: chunk lists of (kind, level); kind 0 = traces, 1.. = the launches of a step in order
     std::vector<std::vector<int>> download;      // per level: the upload groups whose elements have all finished the last stage
-    DevBuf<int> lists; DevBuf<double> up, down;
+    DevBuf<int> lists, bndLists; DevBuf<double> up, down;
+    std::vector<int> bndOff;                     // [nStages * G + 1]: boundary faces by (stage, level of the parent chunk's gradient pass)
     std::vector<cudaEvent_t> upEv, downEv, doneEv;   // doneEv + t0: SDG_HOST_PIPE_TIMING=1 only (time line of the copies on stderr)
     cudaEvent_t t0 = nullptr; bool timing = false;
     cudaStream_t d2h = nullptr;
@@ -1059,11 +1060,10 @@ namespace {
 
 // sdg_step_host can stream when a launch over a chunk reads, besides the chunk's own elements, only what the face neighbours' PREVIOUS
 // launch wrote (their states or gradients, or the trace rows they published): every single-block context of the tensor kernels on one
-// GPU without shock capturing (its viscosity pass runs over the whole mesh) — except the trace-based Navier-Stokes passes on a mesh with
-// boundary faces, whose virtual neighbour traces are one launch over all of them.
+// GPU without shock capturing (its viscosity pass runs over the whole mesh).  The virtual neighbour traces of the boundary faces, which
+// the trace-based Navier-Stokes gradient pass reads, are launched per level as well (face lists sorted by the level of the parent's chunk).
 bool hostPipeEligible(const sdg_ctx* c) {
-  if (!c->haveBlock || c->phys.av || c->plan.blk.nGhost != 0 || c->plan.blk.nOwned < 8192 || getenv("SDG_NO_HOST_PIPE")) return false;
-  return !(c->lineTrace && c->traceTU && twoPass(c) && c->plan.F.nBnd > 0);
+  return c->haveBlock && !c->phys.av && c->plan.blk.nGhost == 0 && c->plan.blk.nOwned >= 8192 && !getenv("SDG_NO_HOST_PIPE");
 }
 
 // Dependency levels of the streamed step.  The caller's element order is cut into G contiguous upload groups; a chunk's traces can be
@@ -1117,6 +1117,24 @@ void buildHostPipe(sdg_ctx* c) {
     for (int ch = 0; ch < nCh; ch++) lists[fill[lvl[k][ch]]++] = ch;
   }
   P.off[(size_t)(S + 1) * G] = (S + 1) * nCh;
+  // trace-based Navier-Stokes: the boundary faces whose virtual neighbour traces the gradient pass of (stage, level) reads
+  const bool bndLists = c->lineTrace && c->traceTU && twoPass(c) && c->plan.F.nBnd > 0;
+  std::vector<int> bnd;
+  if (bndLists) {
+    const int nB = c->plan.F.nBnd, nSt = c->nStages;
+    P.bndOff.assign((size_t)nSt * G + 1, 0);
+    bnd.resize((size_t)nSt * nB);
+    for (int st = 0; st < nSt; st++) {
+      const std::vector<int>& lv = lvl[1 + 2 * st];   // kind of the gradient pass of stage st
+      std::vector<int> count(G, 0);
+      for (int fb = 0; fb < nB; fb++) count[lv[c->linePlan.bndRec[(size_t)fb * 4] / K]]++;
+      int run = st * nB;
+      std::vector<int> fill(G);
+      for (int g = 0; g < G; g++) { P.bndOff[(size_t)st * G + g] = run; fill[g] = run; run += count[g]; }
+      for (int fb = 0; fb < nB; fb++) bnd[fill[lv[c->linePlan.bndRec[(size_t)fb * 4] / K]]++] = fb;
+    }
+    P.bndOff[(size_t)nSt * G] = nSt * nB;
+  }
   P.download.assign(G, {});
   int early = 0;
   for (int g = 0; g < G; g++) {
@@ -1128,6 +1146,7 @@ void buildHostPipe(sdg_ctx* c) {
   P.overlap = (double)early / G;
   if (!c->hasDevice) return;   // plan-only context: the levels are all there is to inspect
   P.lists.upload(lists);
+  if (bndLists) P.bndLists.upload(bnd);
   const size_t per = (size_t)c->NV * B.T.NN;
   P.up.alloc((size_t)n * per); P.down.alloc((size_t)n * per);
   CUDA_OK(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
@@ -1207,7 +1226,21 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
     if (c->traceTU) c->traceValid[c->cur] = true;   // level by level: every row a launch below reads has been written by a launch above
     const int passes = twoPass(c) ? 2 : 1;
     for (int s = 0; s < S; s++)
-      for (int q = 0; q < passes; q++) pipeLaunchList(c, 1 + s * passes + q, g, [&] { stageLaunch(c, s, -1, c->stream, passes == 2 ? q : -1); });
+      for (int q = 0; q < passes; q++) {
+        if (q == 0 && !P.bndOff.empty()) {   // virtual neighbour traces of this level's boundary faces, then no launch over all of them
+          const int b0 = P.bndOff[(size_t)s * G + g], b1 = P.bndOff[(size_t)s * G + g + 1];
+          int in, out; stageBuffers(c, s, in, out);
+          if (b1 > b0) {
+            StageArgs a; fillArgs(c, a);
+            a.Uin = c->U[in].p; a.TUin = c->TU[in].p; a.chunkList = P.bndLists.p + b0;
+            c->lineFns.boundary(a, reinterpret_cast<const int4*>(c->bndRec.p), b1 - b0, c->stream);
+            c->launches++;
+            CUDA_OK(cudaGetLastError());
+          }
+          c->bndKey = c->stepCount * 4 + s;
+        }
+        pipeLaunchList(c, 1 + s * passes + q, g, [&] { stageLaunch(c, s, -1, c->stream, passes == 2 ? q : -1); });
+      }
     for (int h : P.download[g]) {
       const size_t e0 = P.first[h], ne = P.first[h + 1] - P.first[h];
       transformModalRange(c, c->U[outLast].p, P.down.p, kToModal, (int)e0, (int)ne, c->stream);

@@ -40,9 +40,10 @@ def test_two_pass_levels(built):
         assert groups == 12 and early == 0.0     # 24 cells are too few for six chunk layers each way: everything waits for the wrap
         S = Solver(dict(p=3, conv_flux=2, rk=0, **NS), M.periodic_box_fast(3, 24), device=-1)   # forward Euler: two launches
         assert abs(S.step_host_info()[1] - 7.0 / 12.0) < 1e-12
-        # a mesh with boundary faces needs the one-launch boundary-trace kernel per stage: phase after phase
-        S = Solver(dict(p=3, conv_flux=2, rk=2, **NS), M.box(3, (24, 24, 24), 0.0, 2.0), device=-1)
-        assert S.step_host_info()[0] == 0
+        # a mesh with boundary faces: the virtual neighbour traces are launched per level too
+        S = Solver(dict(p=3, conv_flux=2, rk=0, **NS), M.box(3, (24, 24, 24), 0.0, 2.0), device=-1)
+        groups, early = S.step_host_info()
+        assert groups == 12 and early > 0.5     # no periodic wrap: only the last groups wait
     finally:
         del os.environ["SDG_HOST_PIPE_GROUPS"]
 
@@ -128,7 +129,11 @@ def test_streamed_step_with_boundaries(built):
     """a box with far-field and wall faces (boundary faces carry no dependency), and a small mesh that runs the phases one after the other"""
     _with_groups(7)
     try:
-        for cfg, mesh in [(dict(p=3, conv_flux=2, rk=2), M.box(3, (24, 20, 22), 0.0, 2.0, periodic_axes=(0,), phys_bc={3: M.RIEMANN_FARFIELD, 4: M.RIEMANN_FARFIELD, 5: M.ADIABATIC_SLIP_WALL, 6: M.ADIABATIC_SLIP_WALL})),
+        walls = {3: M.RIEMANN_FARFIELD, 4: M.RIEMANN_FARFIELD, 5: M.ADIABATIC_SLIP_WALL, 6: M.ADIABATIC_SLIP_WALL}
+        ns_walls = {3: M.RIEMANN_FARFIELD, 4: M.ISOTHERMAL_NONSLIP_WALL, 5: M.ADIABATIC_NONSLIP_WALL, 6: M.ADIABATIC_SLIP_WALL}
+        for cfg, mesh in [(dict(p=3, conv_flux=2, rk=2), M.box(3, (24, 20, 22), 0.0, 2.0, periodic_axes=(0,), phys_bc=walls)),
+                          (dict(p=3, conv_flux=2, rk=2, **NS), M.box(3, (24, 20, 22), 0.0, 2.0, periodic_axes=(0,), phys_bc=ns_walls)),
+                          (dict(p=3, conv_flux=2, rk=0, **dict(NS, visc_flux=1)), M.box(3, (22, 20, 24), 0.0, 2.0)),   # far field on all six sides, BR1
                           (dict(p=2, conv_flux=2, rk=2), M.periodic_box_fast(3, 12))]:   # 1,728 elements: no streaming
             S = Solver(cfg, mesh, device=0)
             S.initializeSolver(cases.ic_density_wave([0.5, 0.3, 0.2]), cases.bc_freestream(0.4, 0.0, 3, wall_phys=(5, 6), vel=[0.5, 0.3, 0.2]) if mesh.faces["n_bnd"] else None)
@@ -138,6 +143,7 @@ def test_streamed_step_with_boundaries(built):
             e_ref = S.stepSolver(dt, 1).copy()
             U_ref = S.get_state(HEX).copy()
             buf, e1 = S.step_host(HEX, U0, dt)
+            assert np.isfinite(U_ref).all() and np.isfinite(e_ref).all()
             assert np.array_equal(buf, U_ref) and np.array_equal(e1, e_ref)
     finally:
         del os.environ["SDG_HOST_PIPE_GROUPS"]
