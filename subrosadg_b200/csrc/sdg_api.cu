@@ -1202,6 +1202,8 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
   const int G = P.G, S = c->nStages;
   c->stepDt = dt;
   int inLast, outLast; stageBuffers(c, S - 1, inLast, outLast);
+  // whatever goes wrong below, no copy may still be reading or writing the caller's buffers when the call returns
+  struct Drain { sdg_ctx* c; bool armed = true; ~Drain() { if (armed) { cudaStreamSynchronize(c->copyStream); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->pipe.d2h); } } } drain{c};
   // uploads: nothing on the device waits for them except the transform of the same group
   CUDA_OK(cudaEventRecord(c->seamEvent[kSeamChunks], c->stream));   // an earlier call's transforms out of the staging array
   CUDA_OK(cudaStreamWaitEvent(c->copyStream, c->seamEvent[kSeamChunks], 0));
@@ -1258,6 +1260,7 @@ int sdg_step_host(sdg_ctx* c, int32_t type, double dt, const double* U_in, doubl
   }
   CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaStreamSynchronize(P.d2h));
+  drain.armed = false;
   if (P.timing) {   // time line of the copies, milliseconds after the first upload was queued
     std::fprintf(stderr, "sdg_step_host time line (ms): group, upload done, download queued (last stage + transform done), download done\n");
     for (int g = 0; g < G; g++) {
