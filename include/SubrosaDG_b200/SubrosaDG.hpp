@@ -754,6 +754,18 @@ struct Solver : SolverBase<SimulationControl> {
     check(sdg_step(ctx_, time_integration.delta_time_, 1, this->relative_error_.data()));
   }
 
+  // The same step for a caller that keeps the modal coefficients [n][Nb][Nv] of block `type` in HOST memory, as the reference's
+  // variable_basis_function_coefficient_ does (sdg_step_host: upload, stages and download streamed; coefficient_in and coefficient_out may
+  // be the same array; bit-identical to sdg_set_state -> stepSolver -> sdg_get_state).
+  inline void stepSolverHost(const Mesh<SimulationControl>& mesh, const PhysicalModel<SimulationControl>& physical_model,
+                             const BoundaryCondition<SimulationControl>& boundary_condition, const TimeIntegration<SimulationControl>& time_integration,
+                             int type, const double* coefficient_in, double* coefficient_out) {
+    if constexpr (SimulationControl::kBoundaryTime == BoundaryTimeEnum::TimeVarying) {
+      updateBoundaryVariable(mesh, physical_model, boundary_condition, time_integration);
+    }
+    check(sdg_step_host(ctx_, type, time_integration.delta_time_, coefficient_in, coefficient_out, this->relative_error_.data()));
+  }
+
   // Solver::writeRawBinary, RawBinary.cpp:156-191: per element type (ascending ElementEnum) and element the modal coefficients
   // [Nb][Nv] and, for Navier-Stokes, the gradient coefficients [Nb][Nv*D] (:75-88); per boundary face (face order) the same two
   // blocks of its parent, the gradient being BR1: total, BR2: volume part + the lift of that face (:89-154); node_number_ reals of

@@ -1,9 +1,10 @@
 // Pins the time a BoundaryTimeEnum::TimeVarying callback sees: step i runs with t = (i - 1) * delta_time_ because System::solve assigns
-// iteration_ after stepSolver (SystemControl.cpp:175-177, BoundaryCondition.cpp:29-74).  usage: boundary_time_driver MESH.sdgm OUT_DIR STEPS
+// iteration_ after stepSolver (SystemControl.cpp:175-177, BoundaryCondition.cpp:29-74).  usage: boundary_time_driver MESH.sdgm OUT_DIR STEPS [host]
 #include "SubrosaDG_b200/SubrosaDG.hpp"
 
 #include <cstdlib>
 #include <iostream>
+#include <string>
 
 using SimulationControl = SubrosaDG::SimulationControl<SubrosaDG::SolveControl<SubrosaDG::DimensionEnum::D2,
     SubrosaDG::PolynomialOrderEnum::P2, SubrosaDG::BoundaryTimeEnum::TimeVarying, SubrosaDG::SourceTermEnum::None>,
@@ -49,6 +50,14 @@ int main(int argc, char* argv[]) {
   std::cout << "times";
   for (double t : seen_times) std::cout << " " << t;
   std::cout << "\n";
+  if (argc > 4 && std::string(argv[4]) == "host") {
+    // one more step on coefficients held in host memory (Solver::stepSolverHost over sdg_step_host), in place
+    const int quad = static_cast<int>(SubrosaDG::ElementEnum::Quadrangle);
+    std::vector<double> c = system.solver_.getCoefficient(quad);
+    system.solver_.stepSolverHost(system.mesh_, system.physical_model_, system.boundary_condition_, system.time_integration_, quad, c.data(), c.data());
+    std::ofstream g(std::filesystem::path(argv[2]) / "coefficient_host.bin", std::ios::binary);
+    g.write(reinterpret_cast<const char*>(c.data()), static_cast<std::streamsize>(c.size() * sizeof(double)));
+  }
   const std::vector<double> u = system.solver_.getStateAtQuadrature(static_cast<int>(SubrosaDG::ElementEnum::Quadrangle));
   std::ofstream f(std::filesystem::path(argv[2]) / "state.bin", std::ios::binary);
   f.write(reinterpret_cast<const char*>(u.data()), static_cast<std::streamsize>(u.size() * sizeof(double)));

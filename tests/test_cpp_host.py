@@ -222,3 +222,37 @@ def test_time_varying_boundary_sees_the_reference_times(built, tmp_path):
         S2.updateBoundaryVariable(bc, i * dt)
         S2.stepSolver(dt, 1)
     assert cases.rel_l2(S2.state_at_quadrature(S.types[0]), ref) > 1e-9
+
+
+@pytest.mark.gpu
+def test_step_solver_host_of_the_cpp_shim(built, tmp_path):
+    """Solver<SC>::stepSolverHost (sdg_step_host behind the C++ mirror): one more step on coefficients held in host memory, in place,
+    after the three steps of the driver; the TimeVarying callback sees t = iteration_ * delta_time_ = 3 dt."""
+    from subrosadg_b200.solver import Solver
+    exe = _compile(os.path.join(ROOT, "tests", "cpp", "boundary_time_driver.cpp"), tmp_path / "bt")
+    mesh = M.box(2, (5, 4), 0.0, 1.0, phys_bc={k: M.RIEMANN_FARFIELD for k in (1, 2, 3, 4)})
+    M.write_flat(mesh, tmp_path / "mesh.sdgm")
+    r = subprocess.run([exe, str(tmp_path / "mesh.sdgm"), str(tmp_path / "out"), "3", "host"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    dt = 2.0e-3
+
+    def ic(x):
+        one = np.ones(x.shape[:-1])
+        return np.stack([1.4 * one, 0.3 * one, 0.1 * one, one], axis=-1)
+
+    def bc(x, phys, time=0.0):
+        one = np.ones(x.shape[:-1])
+        return np.stack([1.4 * one, 0.3 * (1.0 + 5.0 * time) * one, 0.1 * one, one], axis=-1)
+
+    S = Solver(dict(p=2, conv_flux=2, rk=2), mesh, device=0)
+    S.initializeSolver(ic, bc)
+    for i in range(1, 4):
+        S.updateBoundaryVariable(bc, (i - 1) * dt)
+        S.stepSolver(dt, 1)
+    t = S.types[0]
+    U = S.get_state(t)
+    S.updateBoundaryVariable(bc, 3 * dt)
+    ref, _ = S.step_host(t, U, dt)
+    got = np.fromfile(tmp_path / "out" / "coefficient_host.bin", dtype=np.float64).reshape(ref.shape)
+    assert np.isfinite(ref).all() and cases.rel_l2(ref, U) > 1e-9
+    assert np.array_equal(got, ref), f"rel-L2 {cases.rel_l2(got, ref):.3e}"
